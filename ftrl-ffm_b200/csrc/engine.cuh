@@ -1,0 +1,168 @@
+// engine.cuh -- the handle behind the C ABI: HBM tables, per-batch workspace, CSR staging slots,
+// streams/events, phase timing.  Host-side C++17; the kernels live in ffm.cuh / lr_fm.cuh /
+// exact.cuh / prep.cuh.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/ftrl_b200.h"
+#include "common.cuh"
+#include "prep.cuh"
+
+namespace ftrl {
+
+struct CudaFail {
+  cudaError_t e;
+  const char *what;
+  const char *file;
+  int line;
+};
+
+#define FTRL_CUDA(expr)                                         \
+  do {                                                          \
+    cudaError_t _e = (expr);                                    \
+    if (_e != cudaSuccess) throw CudaFail{_e, #expr, __FILE__, __LINE__}; \
+  } while (0)
+
+struct ArgFail {
+  std::string msg;
+};
+struct IoFail {
+  std::string msg;
+};
+struct StateFail {
+  std::string msg;
+};
+
+inline std::string fmt(const char *f, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, f);
+  vsnprintf(buf, sizeof(buf), f, ap);
+  va_end(ap);
+  return buf;
+}
+
+template <typename T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  void alloc(size_t count) {
+    release();
+    if (count) FTRL_CUDA(cudaMalloc(&p, count * sizeof(T)));
+    n = count;
+  }
+  void ensure(size_t count) {
+    if (count > n) alloc(count + count / 8);
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  ~DevBuf() { release(); }
+};
+
+template <typename T>
+struct PinBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  void ensure(size_t count) {
+    if (count <= n) return;
+    release();
+    FTRL_CUDA(cudaMallocHost(&p, (count + count / 8) * sizeof(T)));
+    n = count + count / 8;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    n = 0;
+  }
+  ~PinBuf() { release(); }
+};
+
+// one CSR staging slot of the host-pointer path (pinned/pageable host -> HBM, async)
+struct Slot {
+  DevBuf<int64_t> row_ptr;
+  DevBuf<int32_t> field, feat, label;
+  DevBuf<float> val, out;
+  DevBuf<double> loss;
+  PinBuf<float> h_out;
+  PinBuf<double> h_loss;
+  cudaEvent_t copied = nullptr, done = nullptr;
+  bool busy = false;
+  // deliveries performed when the slot retires (ftrl_sync or reuse)
+  float *user_out = nullptr;
+  double *user_loss = nullptr;
+  int64_t n_out = 0;
+};
+
+struct Phase {
+  const char *name;
+  double ms = 0.0;
+  int64_t launches = 0;
+};
+
+enum PhaseId { PH_PREP = 0, PH_SORT, PH_SEGMENT, PH_SAMPLE, PH_ROWS, PH_COMBINE, PH_REDUCE, PH_EXACT, PH_PREDICT, PH_H2D, PH_COUNT };
+
+struct PendingEvent {
+  int phase;
+  cudaEvent_t a, b;
+};
+
+}  // namespace ftrl
+
+struct ftrl_handle {
+  ftrl_config cfg{};
+  ftrl::Dims dims{};
+  ftrl::Hyper hyper{};
+  std::string err;
+  int n_sms = 148;
+
+  // HBM tables
+  float *tab = nullptr;     // [n_feats][3][ld]
+  float4 *lin = nullptr;    // [n_feats]
+  float4 *bias = nullptr;   // [1]
+  uint32_t *pair_lut = nullptr;
+  int32_t *d_err = nullptr;
+
+  // streams
+  cudaStream_t compute = nullptr, copy = nullptr;
+  bool own_compute = true;
+
+  // per-batch workspace (shared by consecutive batches: the compute stream is in-order)
+  int64_t rows_cap = 0, nnz_cap = 0;
+  ftrl::DevBuf<uint32_t> key, occ_idx, skey, socc;
+  ftrl::DevBuf<int32_t> occ_row, chunk_pos, n_chunks;
+  ftrl::DevBuf<uint8_t> sflags, occ_single, cub_tmp;
+  ftrl::DevBuf<ftrl::SegScan> scan;
+  ftrl::DevBuf<float> g, S, part;
+  ftrl::DevBuf<float2> part_lin;
+  ftrl::DevBuf<double> loss_s, loss_sum;
+  ftrl::DevBuf<float> xfer;  // staging for get/set rows
+  size_t cub_bytes = 0;
+  int32_t chunk = 32;
+
+  static constexpr int N_SLOTS = 3;
+  ftrl::Slot slots[N_SLOTS];
+  int next_slot = 0;
+
+  // measurement
+  bool profiling = false;
+  ftrl::Phase phases[ftrl::PH_COUNT];
+  std::vector<ftrl::PendingEvent> pending;
+  std::vector<cudaEvent_t> event_pool;
+  ftrl_batch_stats stats{};
+  int64_t launches_this_call = 0;
+  int64_t last_nnz = 0;
+
+  // tunables (env overrides for experiments)
+  int fuse = 1;
+  int sample_threads = 0;
+  int precise = 1;
+};

@@ -1,0 +1,1020 @@
+// ftrl_b200.cu -- C ABI (include/ftrl_b200.h) of the B200-native FTRL LR/FM/FFM trainer.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 (see build.py).
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+
+#include <thrust/iterator/counting_iterator.h>
+#include <thrust/iterator/transform_iterator.h>
+
+#include "engine.cuh"
+#include "exact.cuh"
+#include "ffm.cuh"
+#include "lr_fm.cuh"
+#include "model_io.h"
+
+using namespace ftrl;
+
+static thread_local std::string g_create_error;
+
+// ---------------------------------------------------------------------------------------------
+// small kernels: init, layout conversion, zero scan
+// ---------------------------------------------------------------------------------------------
+__global__ void k_init_tab(float *tab, int64_t n_rows, int32_t row_len, int32_t ld, float mean, float stddev,
+                           uint64_t seed) {
+  // one thread per 4 consecutive floats of the w plane of one row
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t per_row = ld / 4;
+  if (q >= n_rows * per_row) return;
+  const int64_t row = q / per_row;
+  const int v = (int)(q % per_row) * 4;
+  float *base = tab + row * 3 * (int64_t)ld;
+  const float4 gz = gaussian4((uint64_t)q, seed, 1u);
+  const float r[4] = {gz.x, gz.y, gz.z, gz.w};
+  for (int e = 0; e < 4; e++) {
+    base[v + e] = 0.f;
+    base[ld + v + e] = 0.f;
+    base[2 * ld + v + e] = (v + e < row_len) ? fmaf(stddev, r[e], mean) : 0.f;
+  }
+}
+
+__global__ void k_init_lin(float4 *lin, int64_t n, float mean, float stddev, uint64_t seed) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i0 = q * 4;
+  if (i0 >= n) return;
+  const float4 gz = gaussian4((uint64_t)q, seed, 2u);
+  const float r[4] = {gz.x, gz.y, gz.z, gz.w};
+  for (int e = 0; e < 4 && i0 + e < n; e++) lin[i0 + e] = make_float4(0.f, 0.f, fmaf(stddev, r[e], mean), 0.f);
+}
+
+__global__ void k_randomize(float *tab, float4 *lin, float4 *bias, int64_t n_rows, int32_t row_len, int32_t ld,
+                            uint64_t seed, float z_scale, float n_lo, float n_hi) {
+  // one thread per 4 consecutive coordinates; slot 0 of each row additionally handles the linear record
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t per_row = ld > 0 ? ld / 4 : 1;
+  if (q >= n_rows * per_row) return;
+  const int64_t row = q / per_row;
+  const int v = (int)(q % per_row) * 4;
+  const float4 gz = gaussian4((uint64_t)q, seed, 11u);
+  const uint4 u = philox4x32_10(make_uint4((uint32_t)q, (uint32_t)(q >> 32), 12u, 0u),
+                                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const float kk = 2.3283064365386963e-10f;
+  const float zr[4] = {gz.x, gz.y, gz.z, gz.w};
+  const float ur[4] = {u.x * kk, u.y * kk, u.z * kk, u.w * kk};
+  if (ld > 0) {
+    float *base = tab + row * 3 * (int64_t)ld;
+    for (int e = 0; e < 4; e++)
+      if (v + e < row_len) {
+        base[v + e] = z_scale * zr[e];
+        base[ld + v + e] = n_lo + (n_hi - n_lo) * ur[e];
+      }
+  }
+  if (v == 0) {
+    const float4 g2 = gaussian4((uint64_t)row, seed, 13u);
+    float4 e = lin[row];
+    e.x = z_scale * g2.x;
+    e.y = n_lo + (n_hi - n_lo) * fabsf(g2.y) * 0.25f;
+    lin[row] = e;
+    if (row == 0) *bias = make_float4(z_scale * 0.01f * g2.z, 0.5f * (n_lo + n_hi), 0.f, 0.f);
+  }
+}
+
+// dense[n_rows][row_len] <-> plane `plane` of tab rows [row0, row0+n_rows)
+__global__ void k_plane_copy(float *tab, float *dense, int64_t row0, int64_t n_rows, int32_t row_len, int32_t ld,
+                             int plane, int to_dense) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n_rows * row_len) return;
+  const int64_t r = q / row_len;
+  const int c = (int)(q % row_len);
+  float *t = tab + (row0 + r) * 3 * (int64_t)ld + (int64_t)plane * ld + c;
+  if (to_dense) dense[q] = *t; else *t = dense[q];
+}
+__global__ void k_lin_copy(float4 *lin, float *dense, int64_t row0, int64_t n_rows, int plane, int to_dense) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n_rows) return;
+  float *e = reinterpret_cast<float *>(lin + row0 + q) + plane;
+  if (to_dense) dense[q] = *e; else *e = dense[q];
+}
+
+__global__ void k_has_zero(const float *tab, const float4 *lin, int64_t n_rows, int32_t row_len, int32_t ld,
+                           int32_t *flag) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t per = (int64_t)row_len + 1;
+  if (q >= n_rows * per) return;
+  const int64_t r = q / per;
+  const int c = (int)(q % per);
+  const float w = c == 0 ? lin[r].z : tab[r * 3 * (int64_t)ld + 2 * (int64_t)ld + (c - 1)];
+  if (w == 0.0f) *flag = 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------------------------
+static inline int plane_of(int which) { return which == 0 ? PLANE_W : which == 1 ? PLANE_N : PLANE_Z; }
+
+static int env_int(const char *name, int dflt) {
+  const char *v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
+}
+
+static cudaEvent_t get_event(ftrl_handle *h) {
+  if (!h->event_pool.empty()) {
+    cudaEvent_t e = h->event_pool.back();
+    h->event_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  FTRL_CUDA(cudaEventCreate(&e));
+  return e;
+}
+
+struct PhaseScope {
+  ftrl_handle *h;
+  int id;
+  cudaEvent_t a = nullptr;
+  PhaseScope(ftrl_handle *h_, int id_) : h(h_), id(id_) {
+    if (h->profiling) {
+      a = get_event(h);
+      FTRL_CUDA(cudaEventRecord(a, h->compute));
+    }
+  }
+  ~PhaseScope() {
+    if (h->profiling && a) {
+      cudaEvent_t b = get_event(h);
+      cudaEventRecord(b, h->compute);
+      h->pending.push_back({id, a, b});
+    }
+  }
+};
+
+static void launched(ftrl_handle *h, int phase, int n = 1) {
+  h->phases[phase].launches += n;
+  h->launches_this_call += n;
+}
+
+static void drain_profile(ftrl_handle *h) {
+  for (auto &pe : h->pending) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(pe.b) == cudaSuccess && cudaEventElapsedTime(&ms, pe.a, pe.b) == cudaSuccess)
+      h->phases[pe.phase].ms += ms;
+    h->event_pool.push_back(pe.a);
+    h->event_pool.push_back(pe.b);
+  }
+  h->pending.clear();
+}
+
+static size_t cub_temp_bytes(int64_t nnz, int end_bit) {
+  size_t a = 0, b = 0, c = 0;
+  const int n = (int)nnz;
+  cub::DeviceRadixSort::SortPairs(nullptr, a, (const uint32_t *)nullptr, (uint32_t *)nullptr,
+                                  (const uint32_t *)nullptr, (uint32_t *)nullptr, n, 0, end_bit);
+  thrust::counting_iterator<int32_t> cnt(0);
+  auto it = thrust::make_transform_iterator(cnt, HeadFunctor{nullptr});
+  cub::DeviceScan::InclusiveScan(nullptr, b, it, (SegScan *)nullptr, SegScanOp(), n);
+  cub::DeviceSelect::If(nullptr, c, cnt, (int32_t *)nullptr, (int32_t *)nullptr, n, ChunkHeadPred{nullptr, nullptr, 0, 1});
+  return std::max(a, std::max(b, c)) + 256;
+}
+
+static int key_bits(int32_t n_feats) {
+  int bits = 1;
+  while (bits < 32 && (1ll << bits) <= (int64_t)n_feats) bits++;
+  return bits;
+}
+
+static void ensure_workspace(ftrl_handle *h, int64_t n_rows, int64_t nnz) {
+  if (n_rows <= h->rows_cap && nnz <= h->nnz_cap) return;
+  FTRL_CUDA(cudaStreamSynchronize(h->compute));
+  const int64_t rc = std::max<int64_t>(h->rows_cap, n_rows + n_rows / 8 + 16);
+  const int64_t nc = std::max<int64_t>(h->nnz_cap, nnz + nnz / 8 + 64);
+  if (nc >= (1ll << 31) - 64) throw ArgFail{"batch nnz must be < 2^31"};
+  h->g.ensure(rc);
+  h->loss_s.ensure(rc);
+  h->sflags.ensure(rc);
+  if (h->dims.model_type == FTRL_FM) h->S.ensure(rc * h->dims.k);
+  h->key.ensure(nc);
+  h->occ_idx.ensure(nc);
+  h->skey.ensure(nc);
+  h->socc.ensure(nc);
+  h->occ_row.ensure(nc);
+  h->occ_single.ensure(nc);
+  h->scan.ensure(nc);
+  h->chunk_pos.ensure(nc + 2);
+  const int64_t slots = 2 * (nc / h->chunk + 2);
+  if (h->dims.row_len) h->part.ensure((size_t)slots * 2 * h->dims.ld);
+  h->part_lin.ensure(slots);
+  h->cub_bytes = cub_temp_bytes(nc, key_bits(h->dims.n_feats));
+  h->cub_tmp.ensure(h->cub_bytes);
+  h->rows_cap = rc;
+  h->nnz_cap = nc;
+}
+
+template <typename F>
+static int guarded(ftrl_handle *h, F &&f) {
+  try {
+    if (h) FTRL_CUDA(cudaSetDevice(h->cfg.device));
+    f();
+    return FTRL_OK;
+  } catch (const CudaFail &e) {
+    std::string m = fmt("CUDA error %d (%s) at %s:%d: %s", (int)e.e, cudaGetErrorString(e.e), e.file, e.line, e.what);
+    if (h) h->err = m; else g_create_error = m;
+    cudaGetLastError();
+    return FTRL_ERR_CUDA;
+  } catch (const ArgFail &e) {
+    if (h) h->err = e.msg; else g_create_error = e.msg;
+    return FTRL_ERR_ARG;
+  } catch (const IoFail &e) {
+    if (h) h->err = e.msg; else g_create_error = e.msg;
+    return FTRL_ERR_IO;
+  } catch (const StateFail &e) {
+    if (h) h->err = e.msg; else g_create_error = e.msg;
+    return FTRL_ERR_STATE;
+  } catch (const std::exception &e) {
+    if (h) h->err = e.what(); else g_create_error = e.what();
+    return FTRL_ERR_ARG;
+  }
+}
+
+static int pick_vec(int k) { return k % 4 == 0 ? 4 : k % 2 == 0 ? 2 : 1; }
+
+// ---------------------------------------------------------------------------------------------
+// batch training, device-resident CSR
+// ---------------------------------------------------------------------------------------------
+template <int VEC, bool PRECISE>
+static void launch_ffm_sample(ftrl_handle *h, const Batch &b, float *logit_out) {
+  const Dims &d = h->dims;
+  const double fbar = b.n_rows ? (double)b.nnz / (double)b.n_rows : 0.0;
+  const double items = fbar * (fbar - 1) * 0.5 * (d.k / VEC);
+  int threads = h->sample_threads ? h->sample_threads : items <= 64 ? 64 : items <= 256 ? 128 : items <= 1024 ? 256 : 512;
+  const dim3 grid((unsigned)b.n_rows);
+#define FFM_SAMPLE(T)                                                                                          \
+  k_ffm_sample<VEC, PRECISE, T><<<grid, T, 0, h->compute>>>(b, d, h->hyper, h->tab, h->lin, h->bias, h->pair_lut, \
+                                                           h->occ_single.p, h->sflags.p, h->fuse, h->g.p, logit_out, \
+                                                           h->loss_s.p)
+  if (threads <= 64) FFM_SAMPLE(64);
+  else if (threads <= 128) FFM_SAMPLE(128);
+  else if (threads <= 256) FFM_SAMPLE(256);
+  else FFM_SAMPLE(512);
+#undef FFM_SAMPLE
+  FTRL_CUDA(cudaGetLastError());
+}
+
+template <int VEC, bool PRECISE>
+static void run_ffm_batch(ftrl_handle *h, const Batch &b, float *logit_out) {
+  const Dims &d = h->dims;
+  {
+    PhaseScope ps(h, PH_SAMPLE);
+    launch_ffm_sample<VEC, PRECISE>(h, b, logit_out);
+    launched(h, PH_SAMPLE);
+  }
+  if (b.nnz == 0) return;
+  const size_t smem8 = (size_t)8 * 2 * d.ld * sizeof(float);
+  const int grid = h->n_sms * 4;
+  {
+    PhaseScope ps(h, PH_ROWS);
+    if (smem8 <= 160 * 1024) {
+      auto kern = k_ffm_rows<VEC, PRECISE, 8>;
+      if (smem8 > 48 * 1024) FTRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
+      kern<<<grid, 256, smem8, h->compute>>>(b, d, h->hyper, h->tab, h->lin, h->chunk, h->n_chunks.p, h->chunk_pos.p,
+                                             h->skey.p, h->socc.p, h->scan.p, h->occ_row.p, h->sflags.p, h->fuse,
+                                             h->g.p, h->part.p, h->part_lin.p);
+    } else {
+      const size_t smem1 = (size_t)2 * d.ld * sizeof(float);
+      if (smem1 > 200 * 1024) throw ArgFail{"n_fields*n_factors too large for the row kernel"};
+      auto kern = k_ffm_rows<VEC, PRECISE, 1>;
+      FTRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+      kern<<<grid * 4, 32, smem1, h->compute>>>(b, d, h->hyper, h->tab, h->lin, h->chunk, h->n_chunks.p,
+                                                h->chunk_pos.p, h->skey.p, h->socc.p, h->scan.p, h->occ_row.p,
+                                                h->sflags.p, h->fuse, h->g.p, h->part.p, h->part_lin.p);
+    }
+    FTRL_CUDA(cudaGetLastError());
+    launched(h, PH_ROWS);
+  }
+  {
+    PhaseScope ps(h, PH_COMBINE);
+    k_ffm_combine<VEC, PRECISE, 8><<<grid, 256, 0, h->compute>>>(d, h->hyper, (int32_t)b.nnz, h->tab, h->lin, h->chunk,
+                                                                 h->n_chunks.p, h->chunk_pos.p, h->skey.p, h->scan.p,
+                                                                 h->part.p, h->part_lin.p);
+    FTRL_CUDA(cudaGetLastError());
+    launched(h, PH_COMBINE);
+  }
+}
+
+template <int VEC, bool PRECISE, bool IS_FM>
+static void run_lrfm_batch(ftrl_handle *h, const Batch &b, float *logit_out) {
+  const Dims &d = h->dims;
+  {
+    PhaseScope ps(h, PH_SAMPLE);
+    const int64_t warps = b.n_rows;
+    const unsigned grid = (unsigned)((warps * 32 + 255) / 256);
+    k_lrfm_sample<VEC, PRECISE, IS_FM><<<grid, 256, 0, h->compute>>>(b, d, h->hyper, h->tab, h->lin, h->bias, h->S.p,
+                                                                     h->g.p, logit_out, h->loss_s.p);
+    FTRL_CUDA(cudaGetLastError());
+    launched(h, PH_SAMPLE);
+  }
+  if (b.nnz == 0) return;
+  const int grid = h->n_sms * 4;
+  {
+    PhaseScope ps(h, PH_ROWS);
+    k_lrfm_rows<PRECISE, IS_FM, 8><<<grid, 256, 0, h->compute>>>(b, d, h->hyper, h->tab, h->lin, h->chunk, h->n_chunks.p,
+                                                                 h->chunk_pos.p, h->skey.p, h->socc.p, h->scan.p,
+                                                                 h->occ_row.p, h->g.p, h->S.p, h->part.p, h->part_lin.p);
+    FTRL_CUDA(cudaGetLastError());
+    launched(h, PH_ROWS);
+  }
+  {
+    PhaseScope ps(h, PH_COMBINE);
+    k_lrfm_combine<PRECISE, IS_FM, 8><<<grid, 256, 0, h->compute>>>(d, h->hyper, (int32_t)b.nnz, h->tab, h->lin, h->chunk,
+                                                                    h->n_chunks.p, h->chunk_pos.p, h->skey.p, h->scan.p,
+                                                                    h->part.p, h->part_lin.p);
+    FTRL_CUDA(cudaGetLastError());
+    launched(h, PH_COMBINE);
+  }
+}
+
+static void run_prep(ftrl_handle *h, const Batch &b) {
+  const Dims &d = h->dims;
+  const int32_t nnz = (int32_t)b.nnz;
+  const uint32_t sentinel = (uint32_t)d.n_feats;
+  {
+    PhaseScope ps(h, PH_PREP);
+    const unsigned grid = (unsigned)((b.n_rows * 32 + 255) / 256);
+    k_prep_rows<<<grid, 256, 0, h->compute>>>(b, d, INT32_MAX, pick_vec(d.k > 0 ? d.k : 4), h->key.p, h->occ_idx.p,
+                                              h->occ_row.p, h->sflags.p);
+    FTRL_CUDA(cudaGetLastError());
+    launched(h, PH_PREP);
+  }
+  if (nnz == 0) {
+    FTRL_CUDA(cudaMemsetAsync(h->n_chunks.p, 0, sizeof(int32_t), h->compute));
+    return;
+  }
+  {
+    PhaseScope ps(h, PH_SORT);
+    size_t bytes = h->cub_bytes;
+    FTRL_CUDA(cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, bytes, h->key.p, h->skey.p, h->occ_idx.p, h->socc.p, nnz, 0,
+                                              key_bits(d.n_feats), h->compute));
+  }
+  {
+    PhaseScope ps(h, PH_SEGMENT);
+    size_t bytes = h->cub_bytes;
+    thrust::counting_iterator<int32_t> cnt(0);
+    auto it = thrust::make_transform_iterator(cnt, HeadFunctor{h->skey.p});
+    FTRL_CUDA(cub::DeviceScan::InclusiveScan(h->cub_tmp.p, bytes, it, h->scan.p, SegScanOp(), nnz, h->compute));
+    bytes = h->cub_bytes;
+    FTRL_CUDA(cub::DeviceSelect::If(h->cub_tmp.p, bytes, cnt, h->chunk_pos.p, h->n_chunks.p, nnz,
+                                    ChunkHeadPred{h->skey.p, h->scan.p, sentinel, h->chunk}, h->compute));
+    k_terminate<<<1, 1, 0, h->compute>>>(h->chunk_pos.p, h->n_chunks.p, nnz);
+    launched(h, PH_SEGMENT);
+    if (d.model_type == FTRL_FFM && h->fuse) {
+      k_occ_class<<<(nnz + 255) / 256, 256, 0, h->compute>>>(nnz, sentinel, h->skey.p, h->socc.p, h->occ_single.p);
+      launched(h, PH_SEGMENT);
+    }
+    FTRL_CUDA(cudaGetLastError());
+  }
+}
+
+template <bool PRECISE>
+static void run_model(ftrl_handle *h, const Batch &b, float *logit_out) {
+  const Dims &d = h->dims;
+  const int vec = pick_vec(d.k);
+  if (d.model_type == FTRL_FFM) {
+    if (vec == 4) run_ffm_batch<4, PRECISE>(h, b, logit_out);
+    else if (vec == 2) run_ffm_batch<2, PRECISE>(h, b, logit_out);
+    else run_ffm_batch<1, PRECISE>(h, b, logit_out);
+  } else if (d.model_type == FTRL_FM) {
+    if (vec == 4) run_lrfm_batch<4, PRECISE, true>(h, b, logit_out);
+    else if (vec == 2) run_lrfm_batch<2, PRECISE, true>(h, b, logit_out);
+    else run_lrfm_batch<1, PRECISE, true>(h, b, logit_out);
+  } else {
+    run_lrfm_batch<1, PRECISE, false>(h, b, logit_out);
+  }
+}
+
+static void train_device(ftrl_handle *h, const Batch &b, float *logit_out, double *loss_sum_out) {
+  h->launches_this_call = 0;
+  h->stats = ftrl_batch_stats{};
+  h->stats.n_rows = b.n_rows;
+  h->last_nnz = b.nnz;
+  if (b.n_rows <= 0) {
+    if (loss_sum_out) FTRL_CUDA(cudaMemsetAsync(loss_sum_out, 0, sizeof(double), h->compute));
+    return;
+  }
+  ensure_workspace(h, b.n_rows, b.nnz);
+  const Dims &d = h->dims;
+  if (h->cfg.mode == FTRL_MODE_SEQUENTIAL) {
+    PhaseScope ps(h, PH_EXACT);
+    k_exact_train<<<1, EX_THREADS, 0, h->compute>>>(b, d, h->hyper, h->tab, h->lin, h->bias, logit_out, loss_sum_out,
+                                                    h->d_err);
+    FTRL_CUDA(cudaGetLastError());
+    launched(h, PH_EXACT);
+    h->stats.kernel_launches = h->launches_this_call;
+    return;
+  }
+  run_prep(h, b);
+  const bool pr = h->precise != 0;
+  if (pr) run_model<true>(h, b, logit_out); else run_model<false>(h, b, logit_out);
+  {
+    PhaseScope ps(h, PH_REDUCE);
+    if (pr) k_batch_reduce<true><<<1, 1024, 0, h->compute>>>(b.n_rows, h->hyper, h->g.p, h->loss_s.p, h->bias, 1, loss_sum_out);
+    else k_batch_reduce<false><<<1, 1024, 0, h->compute>>>(b.n_rows, h->hyper, h->g.p, h->loss_s.p, h->bias, 1, loss_sum_out);
+    FTRL_CUDA(cudaGetLastError());
+    launched(h, PH_REDUCE);
+  }
+  h->stats.kernel_launches = h->launches_this_call;
+}
+
+static void predict_device(ftrl_handle *h, const Batch &b, int output_prob, float *out, double *loss_sum_out) {
+  if (b.n_rows <= 0) {
+    if (loss_sum_out) FTRL_CUDA(cudaMemsetAsync(loss_sum_out, 0, sizeof(double), h->compute));
+    return;
+  }
+  ensure_workspace(h, b.n_rows, 0);
+  const Dims &d = h->dims;
+  double *loss_s = loss_sum_out ? h->loss_s.p : nullptr;
+  PhaseScope ps(h, PH_PREDICT);
+  if (h->cfg.mode == FTRL_MODE_SEQUENTIAL) {
+    k_exact_predict<<<(unsigned)((b.n_rows + 127) / 128), 128, 0, h->compute>>>(b, d, h->tab, h->lin, h->bias, output_prob,
+                                                                               out, loss_s);
+  } else if (d.model_type == FTRL_FFM) {
+    const int vec = pick_vec(d.k);
+    const dim3 grid((unsigned)b.n_rows);
+    if (vec == 4) k_ffm_predict<4, 256><<<grid, 256, 0, h->compute>>>(b, d, h->tab, h->lin, h->bias, h->pair_lut, output_prob, out, loss_s);
+    else if (vec == 2) k_ffm_predict<2, 256><<<grid, 256, 0, h->compute>>>(b, d, h->tab, h->lin, h->bias, h->pair_lut, output_prob, out, loss_s);
+    else k_ffm_predict<1, 256><<<grid, 256, 0, h->compute>>>(b, d, h->tab, h->lin, h->bias, h->pair_lut, output_prob, out, loss_s);
+  } else {
+    const unsigned grid = (unsigned)((b.n_rows * 32 + 255) / 256);
+    if (d.model_type == FTRL_FM) k_lrfm_predict<true><<<grid, 256, 0, h->compute>>>(b, d, h->tab, h->lin, h->bias, output_prob, out, loss_s);
+    else k_lrfm_predict<false><<<grid, 256, 0, h->compute>>>(b, d, h->tab, h->lin, h->bias, output_prob, out, loss_s);
+  }
+  FTRL_CUDA(cudaGetLastError());
+  launched(h, PH_PREDICT);
+  if (loss_sum_out) {
+    k_batch_reduce<true><<<1, 1024, 0, h->compute>>>(b.n_rows, h->hyper, nullptr, loss_s, h->bias, 0, loss_sum_out);
+    FTRL_CUDA(cudaGetLastError());
+    launched(h, PH_PREDICT);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-pointer path: CSR staged through slots, async copies on the copy stream
+// ---------------------------------------------------------------------------------------------
+static void retire_slot(ftrl_handle *h, Slot &s) {
+  if (!s.busy) return;
+  FTRL_CUDA(cudaEventSynchronize(s.done));
+  if (s.user_out && s.n_out) memcpy(s.user_out, s.h_out.p, sizeof(float) * (size_t)s.n_out);
+  if (s.user_loss) *s.user_loss = s.h_loss.p[0];
+  s.busy = false;
+  s.user_out = nullptr;
+  s.user_loss = nullptr;
+  s.n_out = 0;
+}
+
+static Slot &stage_batch(ftrl_handle *h, int64_t n_rows, const int64_t *row_ptr, const int32_t *field, const int32_t *feat,
+                         const float *val, const int32_t *label, Batch &b) {
+  Slot &s = h->slots[h->next_slot];
+  h->next_slot = (h->next_slot + 1) % ftrl_handle::N_SLOTS;
+  retire_slot(h, s);
+  if (!s.copied) {
+    FTRL_CUDA(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
+    FTRL_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+  }
+  if (n_rows < 0) throw ArgFail{"n_rows < 0"};
+  if (n_rows > 0 && (!row_ptr)) throw ArgFail{"row_ptr is NULL"};
+  const int64_t nnz = n_rows > 0 ? row_ptr[n_rows] - row_ptr[0] : 0;
+  if (n_rows > 0 && row_ptr[0] != 0) throw ArgFail{"row_ptr[0] must be 0"};
+  if (nnz < 0) throw ArgFail{"row_ptr not monotone"};
+  if (nnz > 0 && (!field || !feat || !val)) throw ArgFail{"field/feat/val is NULL"};
+  s.row_ptr.ensure(n_rows + 1);
+  s.label.ensure(n_rows);
+  s.out.ensure(n_rows);
+  s.loss.ensure(1);
+  s.h_out.ensure(n_rows);
+  s.h_loss.ensure(1);
+  s.field.ensure(nnz);
+  s.feat.ensure(nnz);
+  s.val.ensure(nnz);
+  if (n_rows > 0) {
+    FTRL_CUDA(cudaMemcpyAsync(s.row_ptr.p, row_ptr, sizeof(int64_t) * (n_rows + 1), cudaMemcpyHostToDevice, h->copy));
+    if (label) FTRL_CUDA(cudaMemcpyAsync(s.label.p, label, sizeof(int32_t) * n_rows, cudaMemcpyHostToDevice, h->copy));
+  }
+  if (nnz > 0) {
+    FTRL_CUDA(cudaMemcpyAsync(s.field.p, field, sizeof(int32_t) * nnz, cudaMemcpyHostToDevice, h->copy));
+    FTRL_CUDA(cudaMemcpyAsync(s.feat.p, feat, sizeof(int32_t) * nnz, cudaMemcpyHostToDevice, h->copy));
+    FTRL_CUDA(cudaMemcpyAsync(s.val.p, val, sizeof(float) * nnz, cudaMemcpyHostToDevice, h->copy));
+  }
+  FTRL_CUDA(cudaEventRecord(s.copied, h->copy));
+  FTRL_CUDA(cudaStreamWaitEvent(h->compute, s.copied, 0));
+  b.n_rows = n_rows;
+  b.nnz = nnz;
+  b.row_ptr = s.row_ptr.p;
+  b.field = s.field.p;
+  b.feat = s.feat.p;
+  b.val = s.val.p;
+  b.label = label ? s.label.p : nullptr;
+  return s;
+}
+
+static void finish_slot(ftrl_handle *h, Slot &s, int64_t n_rows, float *user_out, double *user_loss) {
+  if (user_out && n_rows > 0)
+    FTRL_CUDA(cudaMemcpyAsync(s.h_out.p, s.out.p, sizeof(float) * n_rows, cudaMemcpyDeviceToHost, h->compute));
+  if (user_loss) FTRL_CUDA(cudaMemcpyAsync(s.h_loss.p, s.loss.p, sizeof(double), cudaMemcpyDeviceToHost, h->compute));
+  FTRL_CUDA(cudaEventRecord(s.done, h->compute));
+  s.busy = true;
+  s.user_out = user_out;
+  s.user_loss = user_loss;
+  s.n_out = user_out ? n_rows : 0;
+}
+
+static void check_device_err(ftrl_handle *h) {
+  int32_t e = 0;
+  FTRL_CUDA(cudaMemcpy(&e, h->d_err, sizeof(e), cudaMemcpyDeviceToHost));
+  if (e) {
+    FTRL_CUDA(cudaMemset(h->d_err, 0, sizeof(e)));
+    throw ArgFail{"sequential mode: a sample exceeds the supported size (more than 96 valid features, or FM n_factors > 1024)"};
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+int ftrl_abi_version(void) { return FTRL_B200_ABI_VERSION; }
+
+void ftrl_config_default(ftrl_config *cfg) {
+  if (!cfg) return;
+  memset(cfg, 0, sizeof(*cfg));
+  cfg->model_type = FTRL_FFM;
+  cfg->n_feats = 10000;
+  cfg->n_fields = 8;
+  cfg->n_factors = 16;
+  cfg->init_mean = 0.0f;
+  cfg->init_stddev = 0.02f;
+  cfg->w_alpha = 1e-4f;
+  cfg->w_beta = 1.0f;
+  cfg->w_l1 = 0.1f;
+  cfg->w_l2 = 5.0f;
+  cfg->mode = FTRL_MODE_BATCH;
+  cfg->device = 0;
+  cfg->seed = 42;
+  cfg->world_size = 1;
+}
+
+const char *ftrl_last_error(const ftrl_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int ftrl_create(const ftrl_config *cfg, ftrl_handle **out) {
+  if (!cfg || !out) {
+    g_create_error = "cfg/out is NULL";
+    return FTRL_ERR_ARG;
+  }
+  *out = nullptr;
+  ftrl_handle *h = nullptr;
+  int rc = guarded(nullptr, [&] {
+    if (cfg->model_type < 0 || cfg->model_type > 2) throw ArgFail{fmt("Invalid model_type: %d, expect LR(0), FM(1) or FFM(2).", cfg->model_type)};
+    if (cfg->n_feats <= 0) throw ArgFail{"n_feats must be > 0"};
+    if (cfg->model_type != FTRL_LR && cfg->n_factors <= 0) throw ArgFail{"n_factors must be > 0"};
+    if (cfg->model_type == FTRL_FFM && cfg->n_fields <= 0) throw ArgFail{"n_fields must be > 0"};
+    if (cfg->model_type == FTRL_FM && cfg->n_factors > 32 * FM_MAX_REGS) throw ArgFail{"FM n_factors > 256 unsupported"};
+    if (cfg->mode != FTRL_MODE_BATCH && cfg->mode != FTRL_MODE_SEQUENTIAL) throw ArgFail{"bad mode"};
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0)
+      throw CudaFail{e == cudaSuccess ? cudaErrorNoDevice : e, "no usable CUDA device (this library has no CPU fallback)", __FILE__, __LINE__};
+    if (cfg->device < 0 || cfg->device >= n_dev) throw ArgFail{fmt("device %d out of range (%d devices)", cfg->device, n_dev)};
+    FTRL_CUDA(cudaSetDevice(cfg->device));
+    h = new ftrl_handle();
+    h->cfg = *cfg;
+    if (h->cfg.world_size < 1) h->cfg.world_size = 1;
+    Dims &d = h->dims;
+    d.model_type = cfg->model_type;
+    d.n_feats = cfg->n_feats;
+    d.n_fields = cfg->model_type == FTRL_FFM ? cfg->n_fields : 1;
+    d.k = cfg->model_type == FTRL_LR ? 0 : cfg->n_factors;
+    const int64_t rl = cfg->model_type == FTRL_FFM ? (int64_t)cfg->n_fields * cfg->n_factors : cfg->model_type == FTRL_FM ? cfg->n_factors : 0;
+    if (rl > (1 << 24)) throw ArgFail{"n_fields*n_factors too large"};
+    d.row_len = (int32_t)rl;
+    d.ld = (int32_t)((rl + 3) / 4 * 4);
+    h->hyper = Hyper{cfg->w_alpha, cfg->w_beta, cfg->w_l1, cfg->w_l2, 1.0f / cfg->w_alpha};
+    static const char *names[PH_COUNT] = {"prep_rows", "sort", "segment", "sample", "rows", "combine", "reduce", "exact", "predict", "h2d"};
+    for (int i = 0; i < PH_COUNT; i++) h->phases[i].name = names[i];
+    cudaDeviceProp prop;
+    FTRL_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+    h->n_sms = prop.multiProcessorCount;
+    h->fuse = env_int("FTRL_B200_FUSE", 1);
+    h->sample_threads = env_int("FTRL_B200_SAMPLE_THREADS", 0);
+    h->precise = env_int("FTRL_B200_PRECISE", 1);
+    h->chunk = env_int("FTRL_B200_CHUNK", cfg->model_type == FTRL_FFM ? 32 : cfg->model_type == FTRL_FM ? 256 : 2048);
+    if (h->chunk < 1) h->chunk = 1;
+    FTRL_CUDA(cudaStreamCreateWithFlags(&h->compute, cudaStreamNonBlocking));
+    FTRL_CUDA(cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking));
+    const int64_t n = d.n_feats;
+    FTRL_CUDA(cudaMalloc(&h->lin, sizeof(float4) * n));
+    FTRL_CUDA(cudaMalloc(&h->bias, sizeof(float4)));
+    FTRL_CUDA(cudaMemsetAsync(h->bias, 0, sizeof(float4), h->compute));
+    FTRL_CUDA(cudaMalloc(&h->d_err, sizeof(int32_t)));
+    FTRL_CUDA(cudaMemsetAsync(h->d_err, 0, sizeof(int32_t), h->compute));
+    FTRL_CUDA(cudaMalloc(&h->pair_lut, sizeof(uint32_t) * PAIR_LUT_N));
+    k_build_pair_lut<<<(PAIR_LUT_N + 255) / 256, 256, 0, h->compute>>>(h->pair_lut);
+    k_init_lin<<<(unsigned)(((n + 3) / 4 + 255) / 256), 256, 0, h->compute>>>(h->lin, n, cfg->init_mean, cfg->init_stddev, cfg->seed);
+    if (d.row_len) {
+      FTRL_CUDA(cudaMalloc(&h->tab, sizeof(float) * 3 * (size_t)d.ld * (size_t)n));
+      const int64_t q = n * (d.ld / 4);
+      k_init_tab<<<(unsigned)((q + 255) / 256), 256, 0, h->compute>>>(h->tab, n, d.row_len, d.ld, cfg->init_mean, cfg->init_stddev, cfg->seed);
+    }
+    FTRL_CUDA(cudaGetLastError());
+    if (cfg->max_batch_rows > 0) ensure_workspace(h, cfg->max_batch_rows, std::max<int64_t>(cfg->max_batch_nnz, 0));
+    FTRL_CUDA(cudaStreamSynchronize(h->compute));
+  });
+  if (rc != FTRL_OK) {
+    if (h) ftrl_destroy(h);
+    return rc;
+  }
+  *out = h;
+  return FTRL_OK;
+}
+
+void ftrl_destroy(ftrl_handle *h) {
+  if (!h) return;
+  cudaSetDevice(h->cfg.device);
+  cudaDeviceSynchronize();
+  for (auto &s : h->slots) {
+    if (s.copied) cudaEventDestroy(s.copied);
+    if (s.done) cudaEventDestroy(s.done);
+  }
+  for (auto &pe : h->pending) {
+    cudaEventDestroy(pe.a);
+    cudaEventDestroy(pe.b);
+  }
+  for (auto e : h->event_pool) cudaEventDestroy(e);
+  if (h->tab) cudaFree(h->tab);
+  if (h->lin) cudaFree(h->lin);
+  if (h->bias) cudaFree(h->bias);
+  if (h->pair_lut) cudaFree(h->pair_lut);
+  if (h->d_err) cudaFree(h->d_err);
+  if (h->compute && h->own_compute) cudaStreamDestroy(h->compute);
+  if (h->copy) cudaStreamDestroy(h->copy);
+  delete h;
+}
+
+int64_t ftrl_row_len(const ftrl_handle *h) { return h ? h->dims.row_len : 0; }
+
+int ftrl_train_batch_device(ftrl_handle *h, int64_t n_rows, int64_t nnz, const int64_t *row_ptr, const int32_t *field,
+                            const int32_t *feat, const float *val, const int32_t *label, float *logits_out,
+                            double *loss_sum_out) {
+  if (!h) return FTRL_ERR_ARG;
+  return guarded(h, [&] {
+    if (n_rows < 0 || nnz < 0) throw ArgFail{"negative size"};
+    if (n_rows > 0 && (!row_ptr || !label)) throw ArgFail{"row_ptr/label is NULL"};
+    if (nnz > 0 && (!field || !feat || !val)) throw ArgFail{"field/feat/val is NULL"};
+    Batch b{n_rows, nnz, row_ptr, field, feat, val, label};
+    train_device(h, b, logits_out, loss_sum_out);
+  });
+}
+
+int ftrl_train_batch(ftrl_handle *h, int64_t n_rows, const int64_t *row_ptr, const int32_t *field, const int32_t *feat,
+                     const float *val, const int32_t *label, float *logits_out, double *loss_sum_out) {
+  if (!h) return FTRL_ERR_ARG;
+  return guarded(h, [&] {
+    if (n_rows > 0 && !label) throw ArgFail{"label is NULL"};
+    Batch b{};
+    Slot &s = stage_batch(h, n_rows, row_ptr, field, feat, val, label, b);
+    train_device(h, b, logits_out ? s.out.p : nullptr, s.loss.p);
+    finish_slot(h, s, n_rows, logits_out, loss_sum_out);
+  });
+}
+
+int ftrl_predict_batch_device(ftrl_handle *h, int64_t n_rows, int64_t nnz, const int64_t *row_ptr, const int32_t *field,
+                              const int32_t *feat, const float *val, const int32_t *label, int output_prob, float *out,
+                              double *loss_sum_out) {
+  if (!h) return FTRL_ERR_ARG;
+  return guarded(h, [&] {
+    if (n_rows < 0 || nnz < 0) throw ArgFail{"negative size"};
+    if (n_rows > 0 && (!row_ptr || !out)) throw ArgFail{"row_ptr/out is NULL"};
+    if (loss_sum_out && !label && n_rows > 0) throw ArgFail{"loss requested without labels"};
+    Batch b{n_rows, nnz, row_ptr, field, feat, val, label};
+    predict_device(h, b, output_prob, out, loss_sum_out);
+  });
+}
+
+int ftrl_predict_batch(ftrl_handle *h, int64_t n_rows, const int64_t *row_ptr, const int32_t *field, const int32_t *feat,
+                       const float *val, const int32_t *label, int output_prob, float *out, double *loss_sum_out) {
+  if (!h) return FTRL_ERR_ARG;
+  return guarded(h, [&] {
+    if (n_rows > 0 && !out) throw ArgFail{"out is NULL"};
+    if (loss_sum_out && !label && n_rows > 0) throw ArgFail{"loss requested without labels"};
+    Batch b{};
+    Slot &s = stage_batch(h, n_rows, row_ptr, field, feat, val, label, b);
+    predict_device(h, b, output_prob, s.out.p, loss_sum_out ? s.loss.p : nullptr);
+    finish_slot(h, s, n_rows, out, loss_sum_out);
+  });
+}
+
+int ftrl_sync(ftrl_handle *h) {
+  if (!h) return FTRL_ERR_ARG;
+  return guarded(h, [&] {
+    FTRL_CUDA(cudaStreamSynchronize(h->copy));
+    FTRL_CUDA(cudaStreamSynchronize(h->compute));
+    for (auto &s : h->slots) retire_slot(h, s);
+    if (h->cfg.mode == FTRL_MODE_SEQUENTIAL) check_device_err(h);
+  });
+}
+
+// ---- state access ---------------------------------------------------------------------------
+static void xfer_rows(ftrl_handle *h, int which, int64_t row0, int64_t n_rows, float *lin, float *vec, bool get) {
+  const Dims &d = h->dims;
+  if (which < 0 || which > 2) throw ArgFail{"which must be 0 (w), 1 (n) or 2 (z)"};
+  if (row0 < 0 || n_rows < 0 || row0 + n_rows > d.n_feats) throw ArgFail{"row range out of bounds"};
+  const int plane = plane_of(which);
+  FTRL_CUDA(cudaStreamSynchronize(h->compute));
+  const int64_t chunk_rows = std::max<int64_t>(1, (int64_t)(16 << 20) / std::max<int32_t>(1, d.row_len));
+  h->xfer.ensure((size_t)std::min<int64_t>(n_rows, chunk_rows) * std::max<int32_t>(1, d.row_len));
+  for (int64_t r = 0; r < n_rows; r += chunk_rows) {
+    const int64_t nr = std::min(chunk_rows, n_rows - r);
+    if (lin) {
+      const unsigned grid = (unsigned)((nr + 255) / 256);
+      if (get) {
+        k_lin_copy<<<grid, 256, 0, h->compute>>>(h->lin, h->xfer.p, row0 + r, nr, plane, 1);
+        FTRL_CUDA(cudaMemcpyAsync(lin + r, h->xfer.p, sizeof(float) * nr, cudaMemcpyDeviceToHost, h->compute));
+      } else {
+        FTRL_CUDA(cudaMemcpyAsync(h->xfer.p, lin + r, sizeof(float) * nr, cudaMemcpyHostToDevice, h->compute));
+        k_lin_copy<<<grid, 256, 0, h->compute>>>(h->lin, h->xfer.p, row0 + r, nr, plane, 0);
+      }
+      FTRL_CUDA(cudaStreamSynchronize(h->compute));
+    }
+    if (vec && d.row_len) {
+      const int64_t q = nr * d.row_len;
+      const unsigned grid = (unsigned)((q + 255) / 256);
+      if (get) {
+        k_plane_copy<<<grid, 256, 0, h->compute>>>(h->tab, h->xfer.p, row0 + r, nr, d.row_len, d.ld, plane, 1);
+        FTRL_CUDA(cudaMemcpyAsync(vec + r * d.row_len, h->xfer.p, sizeof(float) * q, cudaMemcpyDeviceToHost, h->compute));
+      } else {
+        FTRL_CUDA(cudaMemcpyAsync(h->xfer.p, vec + r * d.row_len, sizeof(float) * q, cudaMemcpyHostToDevice, h->compute));
+        k_plane_copy<<<grid, 256, 0, h->compute>>>(h->tab, h->xfer.p, row0 + r, nr, d.row_len, d.ld, plane, 0);
+      }
+      FTRL_CUDA(cudaStreamSynchronize(h->compute));
+    }
+  }
+  FTRL_CUDA(cudaGetLastError());
+}
+
+static void xfer_bias(ftrl_handle *h, int which, float *v, bool get) {
+  if (!v) return;
+  FTRL_CUDA(cudaStreamSynchronize(h->compute));
+  float *p = reinterpret_cast<float *>(h->bias) + plane_of(which);
+  if (get) FTRL_CUDA(cudaMemcpy(v, p, sizeof(float), cudaMemcpyDeviceToHost));
+  else FTRL_CUDA(cudaMemcpy(p, v, sizeof(float), cudaMemcpyHostToDevice));
+}
+
+int ftrl_get_rows(ftrl_handle *h, int which, int64_t row0, int64_t n_rows, float *lin, float *vec) {
+  if (!h) return FTRL_ERR_ARG;
+  return guarded(h, [&] { xfer_rows(h, which, row0, n_rows, lin, vec, true); });
+}
+int ftrl_set_rows(ftrl_handle *h, int which, int64_t row0, int64_t n_rows, const float *lin, const float *vec) {
+  if (!h) return FTRL_ERR_ARG;
+  return guarded(h, [&] { xfer_rows(h, which, row0, n_rows, const_cast<float *>(lin), const_cast<float *>(vec), false); });
+}
+int ftrl_get_weights(ftrl_handle *h, float *bias, float *lin_w, float *vec_w) {
+  if (!h) return FTRL_ERR_ARG;
+  return guarded(h, [&] {
+    xfer_bias(h, 0, bias, true);
+    xfer_rows(h, 0, 0, h->dims.n_feats, lin_w, vec_w, true);
+  });
+}
+int ftrl_set_weights(ftrl_handle *h, const float *bias, const float *lin_w, const float *vec_w) {
+  if (!h) return FTRL_ERR_ARG;
+  return guarded(h, [&] {
+    xfer_bias(h, 0, const_cast<float *>(bias), false);
+    xfer_rows(h, 0, 0, h->dims.n_feats, const_cast<float *>(lin_w), const_cast<float *>(vec_w), false);
+  });
+}
+int ftrl_get_state(ftrl_handle *h, int which, float *bias_s, float *lin_s, float *vec_s) {
+  if (!h) return FTRL_ERR_ARG;
+  return guarded(h, [&] {
+    if (which != 1 && which != 2) throw ArgFail{"which must be 1 (n) or 2 (z)"};
+    xfer_bias(h, which, bias_s, true);
+    xfer_rows(h, which, 0, h->dims.n_feats, lin_s, vec_s, true);
+  });
+}
+int ftrl_set_state(ftrl_handle *h, int which, const float *bias_s, const float *lin_s, const float *vec_s) {
+  if (!h) return FTRL_ERR_ARG;
+  return guarded(h, [&] {
+    if (which != 1 && which != 2) throw ArgFail{"which must be 1 (n) or 2 (z)"};
+    xfer_bias(h, which, const_cast<float *>(bias_s), false);
+    xfer_rows(h, which, 0, h->dims.n_feats, const_cast<float *>(lin_s), const_cast<float *>(vec_s), false);
+  });
+}
+
+int ftrl_has_zero_weights(ftrl_handle *h, int *out) {
+  if (!h || !out) return FTRL_ERR_ARG;
+  return guarded(h, [&] {
+    const Dims &d = h->dims;
+    FTRL_CUDA(cudaMemsetAsync(h->d_err, 0, sizeof(int32_t), h->compute));
+    const int64_t q = (int64_t)d.n_feats * (d.row_len + 1);
+    k_has_zero<<<(unsigned)((q + 255) / 256), 256, 0, h->compute>>>(h->tab, h->lin, d.n_feats, d.row_len, d.ld, h->d_err);
+    FTRL_CUDA(cudaGetLastError());
+    int32_t f = 0;
+    FTRL_CUDA(cudaMemcpyAsync(&f, h->d_err, sizeof(f), cudaMemcpyDeviceToHost, h->compute));
+    FTRL_CUDA(cudaStreamSynchronize(h->compute));
+    FTRL_CUDA(cudaMemset(h->d_err, 0, sizeof(int32_t)));
+    float b = 0.f;
+    xfer_bias(h, 0, &b, true);
+    *out = f ? 1 : 0;
+  });
+}
+
+int ftrl_randomize_state(ftrl_handle *h, uint64_t seed, float z_scale, float n_lo, float n_hi) {
+  if (!h) return FTRL_ERR_ARG;
+  return guarded(h, [&] {
+    if (!(n_lo >= 0.f) || !(n_hi >= n_lo)) throw ArgFail{"need 0 <= n_lo <= n_hi"};
+    const Dims &d = h->dims;
+    const int64_t per_row = d.ld > 0 ? d.ld / 4 : 1;
+    const int64_t q = (int64_t)d.n_feats * per_row;
+    k_randomize<<<(unsigned)((q + 255) / 256), 256, 0, h->compute>>>(h->tab, h->lin, h->bias, d.n_feats, d.row_len, d.ld,
+                                                                    seed, z_scale, n_lo, n_hi);
+    FTRL_CUDA(cudaGetLastError());
+    FTRL_CUDA(cudaStreamSynchronize(h->compute));
+  });
+}
+
+// ---- model files ----------------------------------------------------------------------------
+int ftrl_save_model(ftrl_handle *h, const char *path, int compress_level) {
+  if (!h || !path) return FTRL_ERR_ARG;
+  return guarded(h, [&] {
+    const Dims &d = h->dims;
+    const uint64_t total = sizeof(float) * (1ull + (uint64_t)d.n_feats + (uint64_t)d.n_feats * d.row_len);
+    ModelWriter w(path, compress_level, total);
+    float b = 0.f;
+    xfer_bias(h, 0, &b, true);
+    w.write(&b, sizeof(float));
+    const int64_t chunk_rows = std::max<int64_t>(1, (int64_t)(16 << 20) / std::max<int32_t>(1, d.row_len));
+    std::vector<float> buf((size_t)chunk_rows * std::max<int32_t>(1, d.row_len));
+    for (int64_t r = 0; r < d.n_feats; r += chunk_rows) {
+      const int64_t nr = std::min<int64_t>(chunk_rows, d.n_feats - r);
+      xfer_rows(h, 0, r, nr, buf.data(), nullptr, true);
+      w.write(buf.data(), sizeof(float) * nr);
+    }
+    if (d.row_len)
+      for (int64_t r = 0; r < d.n_feats; r += chunk_rows) {
+        const int64_t nr = std::min<int64_t>(chunk_rows, d.n_feats - r);
+        xfer_rows(h, 0, r, nr, nullptr, buf.data(), true);
+        w.write(buf.data(), sizeof(float) * nr * d.row_len);
+      }
+    const uint64_t csize = w.finish();
+    printf("saving to %s, before: %zu -> after: %zu\n", path, (size_t)total, (size_t)csize);
+  });
+}
+
+int ftrl_load_model(ftrl_handle *h, const char *path) {
+  if (!h || !path) return FTRL_ERR_ARG;
+  return guarded(h, [&] {
+    const Dims &d = h->dims;
+    const uint64_t total = sizeof(float) * (1ull + (uint64_t)d.n_feats + (uint64_t)d.n_feats * d.row_len);
+    ModelReader rd(path);
+    if (rd.content_size() != total)
+      throw IoFail{fmt("%s: payload is %llu bytes, model expects %llu", path, (unsigned long long)rd.content_size(), (unsigned long long)total)};
+    float b = 0.f;
+    rd.read(&b, sizeof(float));
+    xfer_bias(h, 0, &b, false);
+    const int64_t chunk_rows = std::max<int64_t>(1, (int64_t)(16 << 20) / std::max<int32_t>(1, d.row_len));
+    std::vector<float> buf((size_t)chunk_rows * std::max<int32_t>(1, d.row_len));
+    for (int64_t r = 0; r < d.n_feats; r += chunk_rows) {
+      const int64_t nr = std::min<int64_t>(chunk_rows, d.n_feats - r);
+      rd.read(buf.data(), sizeof(float) * nr);
+      xfer_rows(h, 0, r, nr, buf.data(), nullptr, false);
+    }
+    if (d.row_len)
+      for (int64_t r = 0; r < d.n_feats; r += chunk_rows) {
+        const int64_t nr = std::min<int64_t>(chunk_rows, d.n_feats - r);
+        rd.read(buf.data(), sizeof(float) * nr * d.row_len);
+        xfer_rows(h, 0, r, nr, nullptr, buf.data(), false);
+      }
+    printf("loading from %s, before: %zu -> after: %zu \n", path, (size_t)rd.file_size(), (size_t)total);
+  });
+}
+
+int ftrl_save_model_text(ftrl_handle *h, const char *path) {
+  if (!h || !path) return FTRL_ERR_ARG;
+  return guarded(h, [&] {
+    const Dims &d = h->dims;
+    std::vector<float> lin((size_t)d.n_feats), vec((size_t)d.n_feats * d.row_len);
+    float b = 0.f;
+    xfer_bias(h, 0, &b, true);
+    xfer_rows(h, 0, 0, d.n_feats, lin.data(), vec.empty() ? nullptr : vec.data(), true);
+    save_text_model(path, b, lin.data(), vec.data(), d.n_feats, d.row_len);
+  });
+}
+
+int ftrl_load_model_text(ftrl_handle *h, const char *path) {
+  if (!h || !path) return FTRL_ERR_ARG;
+  return guarded(h, [&] {
+    const Dims &d = h->dims;
+    std::vector<float> lin((size_t)d.n_feats), vec((size_t)d.n_feats * d.row_len);
+    float b = 0.f;
+    load_text_model(path, &b, lin.data(), vec.data(), d.n_feats, d.row_len);
+    xfer_bias(h, 0, &b, false);
+    xfer_rows(h, 0, 0, d.n_feats, lin.data(), vec.empty() ? nullptr : vec.data(), false);
+  });
+}
+
+// ---- measurement hooks ----------------------------------------------------------------------
+int ftrl_set_stream(ftrl_handle *h, void *cuda_stream) {
+  if (!h) return FTRL_ERR_ARG;
+  return guarded(h, [&] {
+    FTRL_CUDA(cudaStreamSynchronize(h->compute));
+    if (h->own_compute && h->compute) FTRL_CUDA(cudaStreamDestroy(h->compute));
+    h->compute = static_cast<cudaStream_t>(cuda_stream);
+    h->own_compute = false;
+  });
+}
+
+int ftrl_profile_enable(ftrl_handle *h, int on) {
+  if (!h) return FTRL_ERR_ARG;
+  h->profiling = on != 0;
+  return FTRL_OK;
+}
+int ftrl_profile_reset(ftrl_handle *h) {
+  if (!h) return FTRL_ERR_ARG;
+  return guarded(h, [&] {
+    FTRL_CUDA(cudaStreamSynchronize(h->compute));
+    drain_profile(h);
+    for (auto &p : h->phases) {
+      p.ms = 0.0;
+      p.launches = 0;
+    }
+  });
+}
+int ftrl_profile_read(ftrl_handle *h, int i, const char **name, double *ms, int64_t *launches) {
+  if (!h || i < 0 || i >= PH_COUNT) return FTRL_ERR_ARG;
+  return guarded(h, [&] {
+    if (!h->pending.empty()) {
+      FTRL_CUDA(cudaStreamSynchronize(h->compute));
+      drain_profile(h);
+    }
+    if (name) *name = h->phases[i].name;
+    if (ms) *ms = h->phases[i].ms;
+    if (launches) *launches = h->phases[i].launches;
+  });
+}
+
+__global__ void k_batch_stats(int32_t nnz, uint32_t sentinel, const uint32_t *skey, const SegScan *scan,
+                              const uint8_t *occ_single, const int32_t *n_chunks, int64_t *out) {
+  // out: [0] nnz_valid, [1] n_unique, [2] n_single, [3] n_chunks
+  __shared__ unsigned long long sh[3];
+  if (threadIdx.x < 3) sh[threadIdx.x] = 0;
+  __syncthreads();
+  unsigned long long v = 0, u = 0, s1 = 0;
+  for (int32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < nnz; p += gridDim.x * blockDim.x) {
+    if (skey[p] != sentinel) {
+      v++;
+      if (scan[p].start == p) u++;
+    }
+    if (occ_single && occ_single[p]) s1++;
+  }
+  atomicAdd(&sh[0], v);
+  atomicAdd(&sh[1], u);
+  atomicAdd(&sh[2], s1);
+  __syncthreads();
+  if (threadIdx.x < 3) atomicAdd(reinterpret_cast<unsigned long long *>(out) + threadIdx.x, sh[threadIdx.x]);
+  if (blockIdx.x == 0 && threadIdx.x == 0) out[3] = *n_chunks;
+}
+
+int ftrl_last_batch_stats(ftrl_handle *h, ftrl_batch_stats *out) {
+  if (!h || !out) return FTRL_ERR_ARG;
+  return guarded(h, [&] {
+    *out = h->stats;
+    if (h->cfg.mode != FTRL_MODE_BATCH || h->nnz_cap == 0 || h->stats.n_rows == 0) return;
+    // recomputed from the workspace of the last batch (diagnostics only, not on the hot path)
+    FTRL_CUDA(cudaStreamSynchronize(h->compute));
+    DevBuf<int64_t> tmp;
+    tmp.alloc(4);
+    FTRL_CUDA(cudaMemset(tmp.p, 0, sizeof(int64_t) * 4));
+    int32_t nnz = (int32_t)h->last_nnz;
+    if (nnz > 0) {
+      const bool have_single = h->dims.model_type == FTRL_FFM && h->fuse;
+      k_batch_stats<<<256, 256, 0, h->compute>>>(nnz, (uint32_t)h->dims.n_feats, h->skey.p, h->scan.p,
+                                                 have_single ? h->occ_single.p : nullptr, h->n_chunks.p, tmp.p);
+      FTRL_CUDA(cudaGetLastError());
+    }
+    int64_t r[4] = {0, 0, 0, 0};
+    FTRL_CUDA(cudaMemcpyAsync(r, tmp.p, sizeof(r), cudaMemcpyDeviceToHost, h->compute));
+    FTRL_CUDA(cudaStreamSynchronize(h->compute));
+    out->nnz_valid = r[0];
+    out->n_unique = r[1];
+    out->n_fused_rows = r[2];
+    out->n_segmented_rows = r[1] - r[2];
+    out->n_chunks = r[3];
+  });
+}
+
+// ---- multi-GPU ------------------------------------------------------------------------------
+int ftrl_export_peer_blob(ftrl_handle *h, void *blob) {
+  if (!h || !blob) return FTRL_ERR_ARG;
+  h->err = "feature-sharded multi-GPU exchange is not built yet";
+  return FTRL_ERR_STATE;
+}
+int ftrl_attach_peers(ftrl_handle *h, const void *blobs) {
+  if (!h || !blobs) return FTRL_ERR_ARG;
+  h->err = "feature-sharded multi-GPU exchange is not built yet";
+  return FTRL_ERR_STATE;
+}
+
+}  // extern "C"

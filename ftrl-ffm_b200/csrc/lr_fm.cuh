@@ -1,0 +1,315 @@
+// lr_fm.cuh -- LR and FM minibatch kernels + the batch-level bias / loss reduction shared by all
+// three models.
+//
+// Reference functions covered: ftrl_model.cpp:44-85 (linear logit, linear/bias w and n,z updates),
+// lr.cpp:9-24, fm.cpp:21-101 (compute_fm_logit :40-67, update_vector_w :69-78,
+// update_vector_nz :80-101).  Minibatch semantics per SURVEY.md 8(a).
+#pragma once
+#include "common.cuh"
+#include "prep.cuh"
+
+namespace ftrl {
+
+// ---------------------------------------------------------------------------------------------
+// sample kernel, warp per sample.  LR: logit from lin.  FM: additionally the O(F k) sum/square
+// trick of fm.cpp:40-67; the per-factor sums S[s][f] are kept for the row kernel (the reference
+// keeps them in the member sum_vx, fm.h:24).
+// Lane mapping for FM: lane = (feature slot j, factor chunk c), C = k/VEC chunks, 32/C slots.
+// ---------------------------------------------------------------------------------------------
+template <int VEC, bool PRECISE, bool IS_FM>
+__global__ void __launch_bounds__(256)
+k_lrfm_sample(Batch b, Dims d, Hyper h, float *__restrict__ tab, float4 *__restrict__ lin,
+              const float4 *__restrict__ bias, float *__restrict__ S, float *__restrict__ g_out,
+              float *__restrict__ logit_out, double *__restrict__ loss_out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (s >= b.n_rows) return;
+  const int64_t r0 = b.row_ptr[s];
+  const int F = (int)(b.row_ptr[s + 1] - r0);
+  float acc = 0.f;
+  for (int t = lane; t < F; t += 32) {
+    const int32_t ft = b.feat[r0 + t];
+    if (ft < 0 || ft >= d.n_feats) continue;
+    const float4 e = lin[ft];
+    const float w = weight_from<PRECISE>(e.x, f_sqrt<PRECISE>(e.y), h);
+    lin[ft].z = w;
+    acc = fmaf(w, b.val[r0 + t], acc);
+  }
+  if (IS_FM) {
+    const int C = d.k / VEC;
+    const int64_t ld = d.ld, rs = 3 * ld;
+    // chunks of the factor axis are covered in rounds of 32 lanes when C > 32
+    for (int cb = 0; cb < C; cb += 32) {
+      const int Cr = min(C - cb, 32);      // chunks in this round
+      const int slots = 32 / Cr;           // features processed concurrently
+      const int j = lane / Cr, c = cb + lane % Cr;
+      const bool lane_on = j < slots;
+      Vec<VEC> sv, qv;
+#pragma unroll
+      for (int e = 0; e < VEC; e++) sv.v[e] = qv.v[e] = 0.f;
+      for (int t0 = 0; t0 < F; t0 += slots) {
+        const int t = t0 + j;
+        if (!lane_on || t >= F) continue;
+        const int32_t ft = b.feat[r0 + t];
+        if (ft < 0 || ft >= d.n_feats) continue;
+        const float x = b.val[r0 + t];
+        float *row = tab + (int64_t)ft * rs + c * VEC;
+        Vec<VEC> z, n, w;
+        z.load(row); n.load(row + ld);
+#pragma unroll
+        for (int e = 0; e < VEC; e++) {
+          w.v[e] = weight_from<PRECISE>(z.v[e], f_sqrt<PRECISE>(n.v[e]), h);
+          const float vx = w.v[e] * x;
+          sv.v[e] += vx;
+          qv.v[e] = fmaf(vx, vx, qv.v[e]);
+        }
+        w.store(row + 2 * ld);
+      }
+      // reduce over the feature slots (lanes with equal lane % Cr); Cr need not be a power of two:
+      // gather through shuffles from every slot in a fixed order.
+      Vec<VEC> st, qt;
+#pragma unroll
+      for (int e = 0; e < VEC; e++) st.v[e] = qt.v[e] = 0.f;
+      for (int jj = 0; jj < slots; jj++) {
+        const int src = jj * Cr + lane % Cr;
+#pragma unroll
+        for (int e = 0; e < VEC; e++) {
+          st.v[e] += __shfl_sync(0xffffffffu, sv.v[e], src);
+          qt.v[e] += __shfl_sync(0xffffffffu, qv.v[e], src);
+        }
+      }
+      if (lane < Cr) {
+#pragma unroll
+        for (int e = 0; e < VEC; e++) acc += 0.5f * (st.v[e] * st.v[e] - qt.v[e]);
+        st.store(S + s * (int64_t)d.k + (int64_t)(cb + lane) * VEC);
+      }
+    }
+  }
+  float logit = warp_sum(acc);
+  if (lane == 0) {
+    const float4 bz = *bias;
+    logit += weight_from<PRECISE>(bz.x, f_sqrt<PRECISE>(bz.y), h);
+    const int y = b.label[s];
+    g_out[s] = sigmoid_f(logit) - (float)y;
+    if (logit_out) logit_out[s] = logit;
+    loss_out[s] = logloss_d(y, logit);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// row kernel, warp per chunk of one feature's occurrences (sorted list).  Linear coordinate:
+// lanes stride over occurrences, fixed-order shuffle reduction.  FM latent row: lane owns
+// coordinate(s) f = lane, lane+32, ...; gv = g (x S_f - (v x) x)  (fm.cpp:89).
+// ---------------------------------------------------------------------------------------------
+constexpr int FM_MAX_REGS = 8;  // latent coordinates per lane kept in registers (k <= 256)
+
+template <bool PRECISE, bool IS_FM, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+k_lrfm_rows(Batch b, Dims d, Hyper h, float *__restrict__ tab, float4 *__restrict__ lin, int32_t ch,
+            const int32_t *__restrict__ n_chunks_p, const int32_t *__restrict__ chunk_pos,
+            const uint32_t *__restrict__ skey, const uint32_t *__restrict__ socc,
+            const SegScan *__restrict__ scan, const int32_t *__restrict__ occ_row,
+            const float *__restrict__ g_in, const float *__restrict__ S, float *__restrict__ part,
+            float2 *__restrict__ part_lin) {
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t ld = d.ld, rs = 3 * ld;
+  const int n_chunks = *n_chunks_p;
+  const int32_t nnz = (int32_t)b.nnz;
+  const uint32_t sentinel = (uint32_t)d.n_feats;
+  for (int c = blockIdx.x * WARPS + wib; c < n_chunks; c += gridDim.x * WARPS) {
+    const ChunkInfo ci = chunk_info(c, nnz, sentinel, ch, chunk_pos, skey, scan);
+    if (!ci.valid) continue;
+    const bool whole_row = ci.row_head && ci.row_last;
+    // linear coordinate
+    float sg = 0.f, sg2 = 0.f;
+    for (int p = ci.p0 + lane; p < ci.p1; p += 32) {
+      const int64_t t = socc[p];
+      const float gi = g_in[occ_row[t]] * b.val[t];
+      sg += gi;
+      sg2 = fmaf(gi, gi, sg2);
+    }
+    sg = warp_sum(sg);
+    sg2 = warp_sum(sg2);
+    // FM latent row
+    float a0[FM_MAX_REGS], a1[FM_MAX_REGS], wv[FM_MAX_REGS];
+    if (IS_FM) {
+      const float *row = tab + (int64_t)ci.key * rs;
+#pragma unroll
+      for (int r = 0; r < FM_MAX_REGS; r++) {
+        a0[r] = a1[r] = 0.f;
+        const int f = lane + 32 * r;
+        wv[r] = f < d.k ? row[2 * ld + f] : 0.f;
+      }
+      for (int p = ci.p0; p < ci.p1; p++) {
+        const int64_t t = socc[p];
+        const int32_t s = occ_row[t];
+        const float g = g_in[s], x = b.val[t];
+#pragma unroll
+        for (int r = 0; r < FM_MAX_REGS; r++) {
+          const int f = lane + 32 * r;
+          if (f < d.k) {
+            const float gv = g * (x * S[(int64_t)s * d.k + f] - (wv[r] * x) * x);
+            a0[r] += gv;
+            a1[r] = fmaf(gv, gv, a1[r]);
+          }
+        }
+      }
+    }
+    if (whole_row) {
+      if (IS_FM) {
+        float *row = tab + (int64_t)ci.key * rs;
+#pragma unroll
+        for (int r = 0; r < FM_MAX_REGS; r++) {
+          const int f = lane + 32 * r;
+          if (f < d.k) {
+            float z = row[f], n = row[ld + f];
+            ftrl_apply<PRECISE>(z, n, wv[r], a0[r], a1[r], h);
+            row[f] = z;
+            row[ld + f] = n;
+          }
+        }
+      }
+      if (lane == 0) {
+        float4 e = lin[ci.key];
+        ftrl_apply<PRECISE>(e.x, e.y, e.z, sg, sg2, h);
+        lin[ci.key] = e;
+      }
+    } else {
+      if (IS_FM) {
+        float *dst = part + (int64_t)ci.slot * 2 * ld;
+#pragma unroll
+        for (int r = 0; r < FM_MAX_REGS; r++) {
+          const int f = lane + 32 * r;
+          if (f < d.k) {
+            dst[f] = a0[r];
+            dst[ld + f] = a1[r];
+          }
+        }
+      }
+      if (lane == 0) part_lin[ci.slot] = make_float2(sg, sg2);
+    }
+  }
+}
+
+template <bool PRECISE, bool IS_FM, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+k_lrfm_combine(Dims d, Hyper h, int32_t nnz, float *__restrict__ tab, float4 *__restrict__ lin, int32_t ch,
+               const int32_t *__restrict__ n_chunks_p, const int32_t *__restrict__ chunk_pos,
+               const uint32_t *__restrict__ skey, const SegScan *__restrict__ scan,
+               const float *__restrict__ part, const float2 *__restrict__ part_lin) {
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t ld = d.ld, rs = 3 * ld;
+  const int n_chunks = *n_chunks_p;
+  const uint32_t sentinel = (uint32_t)d.n_feats;
+  for (int c = blockIdx.x * WARPS + wib; c < n_chunks; c += gridDim.x * WARPS) {
+    const ChunkInfo ci = chunk_info(c, nnz, sentinel, ch, chunk_pos, skey, scan);
+    if (!ci.valid || !ci.row_head || ci.row_last) continue;
+    int J = 1;
+    while (c + J < n_chunks && skey[chunk_pos[c + J]] == ci.key) J++;
+    if (IS_FM) {
+      float *row = tab + (int64_t)ci.key * rs;
+      const float *p0 = part + (int64_t)ci.slot * 2 * ld;
+      for (int f = lane; f < d.k; f += 32) {
+        float a0 = 0.f, a1 = 0.f;
+        for (int j = 0; j < J; j++) {
+          a0 += p0[(int64_t)j * 2 * ld + f];
+          a1 += p0[(int64_t)j * 2 * ld + ld + f];
+        }
+        float z = row[f], n = row[ld + f];
+        ftrl_apply<PRECISE>(z, n, row[2 * ld + f], a0, a1, h);
+        row[f] = z;
+        row[ld + f] = n;
+      }
+    }
+    if (lane == 0) {
+      float sg = 0.f, sg2 = 0.f;
+      for (int j = 0; j < J; j++) {
+        const float2 t = part_lin[ci.slot + j];
+        sg += t.x; sg2 += t.y;
+      }
+      float4 e = lin[ci.key];
+      ftrl_apply<PRECISE>(e.x, e.y, e.z, sg, sg2, h);
+      lin[ci.key] = e;
+    }
+  }
+}
+
+// predict (lr.cpp:20-24, fm.cpp:34-38): warp per sample, stored w only
+template <bool IS_FM>
+__global__ void __launch_bounds__(256)
+k_lrfm_predict(Batch b, Dims d, const float *__restrict__ tab, const float4 *__restrict__ lin,
+               const float4 *__restrict__ bias, int output_prob, float *__restrict__ out,
+               double *__restrict__ loss_out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (s >= b.n_rows) return;
+  const int64_t r0 = b.row_ptr[s];
+  const int F = (int)(b.row_ptr[s + 1] - r0);
+  const int64_t ld = d.ld, rs = 3 * ld;
+  float acc = 0.f;
+  for (int t = lane; t < F; t += 32) {
+    const int32_t ft = b.feat[r0 + t];
+    if (ft >= 0 && ft < d.n_feats) acc = fmaf(lin[ft].z, b.val[r0 + t], acc);
+  }
+  if (IS_FM) {
+    for (int f = lane; f < d.k; f += 32) {
+      float sv = 0.f, qv = 0.f;
+      for (int t = 0; t < F; t++) {
+        const int32_t ft = b.feat[r0 + t];
+        if (ft < 0 || ft >= d.n_feats) continue;
+        const float vx = tab[(int64_t)ft * rs + 2 * ld + f] * b.val[r0 + t];
+        sv += vx;
+        qv = fmaf(vx, vx, qv);
+      }
+      acc += 0.5f * (sv * sv - qv);
+    }
+  }
+  float logit = warp_sum(acc);
+  if (lane == 0) {
+    logit += bias->z;
+    out[s] = output_prob ? sigmoid_f(logit) : logit;
+    if (loss_out) loss_out[s] = b.label ? logloss_d(b.label[s], logit) : 0.0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// batch-level reduction (single CTA, deterministic): sum g, sum g^2 -> bias update
+// (ftrl_model.cpp:61-64, 79-85 telescoped), and the fp64 loss sum (ftrl_offline.cpp:72-82,101).
+// ---------------------------------------------------------------------------------------------
+template <bool PRECISE>
+__global__ void __launch_bounds__(1024)
+k_batch_reduce(int64_t n_rows, Hyper h, const float *__restrict__ g, const double *__restrict__ loss_s,
+               float4 *__restrict__ bias, int update_bias, double *__restrict__ loss_sum_out) {
+  __shared__ double sh[3][32];
+  double a = 0.0, q = 0.0, l = 0.0;
+  for (int64_t i = threadIdx.x; i < n_rows; i += blockDim.x) {
+    if (g) {
+      const double gi = (double)g[i];
+      a += gi;
+      q += (double)(g[i] * g[i]);
+    }
+    if (loss_s) l += loss_s[i];
+  }
+  a = warp_sum_d(a); q = warp_sum_d(q); l = warp_sum_d(l);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) { sh[0][wid] = a; sh[1][wid] = q; sh[2][wid] = l; }
+  __syncthreads();
+  if (wid == 0) {
+    const int nw = blockDim.x >> 5;
+    a = lane < nw ? sh[0][lane] : 0.0;
+    q = lane < nw ? sh[1][lane] : 0.0;
+    l = lane < nw ? sh[2][lane] : 0.0;
+    a = warp_sum_d(a); q = warp_sum_d(q); l = warp_sum_d(l);
+    if (lane == 0) {
+      if (update_bias && n_rows > 0) {
+        float4 e = *bias;
+        e.z = weight_from<PRECISE>(e.x, f_sqrt<PRECISE>(e.y), h);
+        ftrl_apply<PRECISE>(e.x, e.y, e.z, (float)a, (float)q, h);
+        *bias = e;
+      }
+      if (loss_sum_out) *loss_sum_out = l;
+    }
+  }
+}
+
+}  // namespace ftrl

@@ -1,0 +1,170 @@
+// prep.cuh -- per-batch index work that turns "contended per-feature mutexes" of the reference
+// (ftrl_model.cpp:55,68; ffm.cpp:78,99-101,125) into a sort-by-key segmented reduction:
+//   1. k_prep_rows   : validity mask (remove_out_range, ftrl_model.cpp:36-42 / ffm.cpp:30-36),
+//                      sort key per occurrence, owning sample per occurrence, per-sample flags
+//   2. radix sort    : (key = feature id, value = occurrence index)            [cub]
+//   3. segment scan  : per sorted position {row ordinal, row start}            [cub]
+//   4. chunk list    : rows cut into chunks of <= CH occurrences               [cub select]
+//   5. k_occ_class   : marks occurrences whose row occurs exactly once in the batch
+// All integer / index work, HBM-light (12-20 B per occurrence).
+#pragma once
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+namespace ftrl {
+
+// one minibatch in CSR form, all pointers in device memory
+struct Batch {
+  int64_t n_rows;
+  int64_t nnz;
+  const int64_t *row_ptr;
+  const int32_t *field;
+  const int32_t *feat;
+  const float *val;
+  const int32_t *label;
+};
+
+enum : uint8_t {
+  SF_SIMPLE = 1,   // all valid features of the sample have distinct fields
+  SF_FUSABLE = 2,  // simple and small enough for the fused per-sample finalize
+};
+
+struct SegScan {
+  int32_t cnt;    // number of row heads at or before this sorted position (1-based row ordinal)
+  int32_t start;  // sorted position of the head of this position's row
+};
+struct SegScanOp {
+  __device__ __forceinline__ SegScan operator()(const SegScan &a, const SegScan &b) const {
+    return SegScan{a.cnt + b.cnt, a.start > b.start ? a.start : b.start};
+  }
+};
+struct HeadFunctor {
+  const uint32_t *skey;
+  __device__ __forceinline__ SegScan operator()(int32_t p) const {
+    const bool head = p == 0 || skey[p] != skey[p - 1];
+    return SegScan{head ? 1 : 0, head ? p : 0};
+  }
+};
+struct ChunkHeadPred {
+  const uint32_t *skey;
+  const SegScan *scan;
+  uint32_t sentinel;
+  int32_t ch;
+  __device__ __forceinline__ bool operator()(int32_t p) const {
+    const SegScan s = scan[p];
+    if (s.start == p) return true;  // row head (also the head of the sentinel run)
+    return skey[p] != sentinel && ((p - s.start) % ch) == 0;
+  }
+};
+
+__device__ __forceinline__ bool feat_valid(const Dims &d, int32_t fld, int32_t ft) {
+  bool ok = ft >= 0 && ft < d.n_feats;
+  if (d.model_type == 2) ok = ok && fld >= 0 && fld < d.n_fields;
+  return ok;
+}
+
+// warp per sample
+__global__ void k_prep_rows(Batch b, Dims d, int32_t fuse_item_cap, int32_t vec, uint32_t *__restrict__ key,
+                            uint32_t *__restrict__ occ_idx, int32_t *__restrict__ occ_row,
+                            uint8_t *__restrict__ sflags) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (warp >= b.n_rows) return;
+  const int64_t r0 = b.row_ptr[warp], r1 = b.row_ptr[warp + 1];
+  bool simple = true;
+  int n_valid = 0;
+  uint64_t seen = 0;  // field bitmask when n_fields <= 64
+  for (int64_t base = r0; base < r1; base += 32) {
+    const int64_t t = base + lane;
+    int32_t fld = -1;
+    bool ok = false;
+    if (t < r1) {
+      fld = b.field[t];
+      const int32_t ft = b.feat[t];
+      ok = feat_valid(d, fld, ft);
+      key[t] = ok ? (uint32_t)ft : (uint32_t)d.n_feats;
+      occ_idx[t] = (uint32_t)t;
+      occ_row[t] = (int32_t)warp;
+    }
+    const unsigned okmask = __ballot_sync(0xffffffffu, ok);
+    n_valid += __popc(okmask);
+    if (d.model_type == 2) {
+      // duplicates inside this group of 32
+      const unsigned same = __match_any_sync(0xffffffffu, ok ? fld : -1 - lane);
+      if (ok && __popc(same & okmask) > 1) simple = false;
+      if (d.n_fields <= 64) {
+        const uint64_t bit = ok ? (1ull << fld) : 0ull;
+        if (bit & seen) simple = false;
+        const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)bit);
+        const unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(bit >> 32));
+        seen |= ((uint64_t)hi << 32) | lo;
+      } else if (ok) {
+        for (int64_t u = r0; u < base; u++) {  // rare: wide field spaces
+          const int32_t f2 = b.field[u];
+          if (f2 == fld && feat_valid(d, f2, b.feat[u])) simple = false;
+        }
+      }
+    }
+  }
+  simple = __all_sync(0xffffffffu, simple);
+  if (lane == 0) {
+    uint8_t f = 0;
+    if (simple) f |= SF_SIMPLE;
+    if (d.model_type == 2) {
+      const int64_t items = (int64_t)n_valid * (n_valid - 1) / 2 * ((d.k + vec - 1) / vec);
+      if (simple && items <= fuse_item_cap) f |= SF_FUSABLE;
+    } else {
+      f |= SF_FUSABLE;
+    }
+    sflags[warp] = f;
+  }
+}
+
+// chunk_pos[n_chunks] = nnz (terminator so chunk c ends at chunk_pos[c+1])
+__global__ void k_terminate(int32_t *chunk_pos, const int32_t *n_chunks, int32_t nnz) {
+  chunk_pos[*n_chunks] = nnz;
+}
+
+// occ_single[t] = 1 iff the row of occurrence t occurs exactly once in this batch
+__global__ void k_occ_class(int32_t nnz, uint32_t sentinel, const uint32_t *__restrict__ skey,
+                            const uint32_t *__restrict__ socc, uint8_t *__restrict__ occ_single) {
+  const int32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= nnz) return;
+  const uint32_t k = skey[p];
+  const bool head = p == 0 || skey[p - 1] != k;
+  const bool last = p + 1 == nnz || skey[p + 1] != k;
+  occ_single[socc[p]] = (k != sentinel && head && last) ? 1 : 0;
+}
+
+// everything a chunk-level kernel needs to know about chunk c
+struct ChunkInfo {
+  int32_t p0, p1;    // sorted-position range of this chunk
+  uint32_t key;      // feature row
+  bool valid;        // false for the sentinel run
+  bool row_head;     // first chunk of its row
+  bool row_last;     // last chunk of its row
+  int32_t j;         // chunk ordinal inside the row
+  int32_t slot;      // partial-sum slot (meaningful when the row has > 1 chunk)
+};
+
+__device__ __forceinline__ ChunkInfo chunk_info(int32_t c, int32_t nnz, uint32_t sentinel, int32_t ch,
+                                                const int32_t *__restrict__ chunk_pos,
+                                                const uint32_t *__restrict__ skey,
+                                                const SegScan *__restrict__ scan) {
+  ChunkInfo ci;
+  ci.p0 = chunk_pos[c];
+  ci.p1 = chunk_pos[c + 1];
+  ci.key = skey[ci.p0];
+  ci.valid = ci.key != sentinel;
+  const SegScan s = scan[ci.p0];
+  ci.row_head = s.start == ci.p0;
+  ci.row_last = ci.p1 >= nnz || skey[ci.p1] != ci.key;
+  ci.j = (ci.p0 - s.start) / ch;
+  // extras (non-head chunks) strictly before this row's head = (c_first + 1) - row_ordinal
+  const int32_t e0 = (c - ci.j + 1) - s.cnt;
+  ci.slot = 2 * e0 + ci.j;
+  return ci;
+}
+
+}  // namespace ftrl
