@@ -52,7 +52,7 @@ ABI_SYMBOLS = [
     "ftrl_get_rows", "ftrl_set_rows", "ftrl_row_len", "ftrl_has_zero_weights", "ftrl_save_model",
     "ftrl_load_model", "ftrl_save_model_text", "ftrl_load_model_text", "ftrl_set_stream",
     "ftrl_profile_enable", "ftrl_profile_reset", "ftrl_profile_read", "ftrl_last_batch_stats",
-    "ftrl_randomize_state",
+    "ftrl_randomize_state", "ftrl_alloc_pinned", "ftrl_free_pinned",
     "ftrl_export_peer_blob", "ftrl_attach_peers",
 ]
 
@@ -102,6 +102,10 @@ def load_library(path: str | None = None):
     lib.ftrl_profile_read.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     lib.ftrl_last_batch_stats.argtypes = [vp, C.POINTER(BatchStats)]
     lib.ftrl_randomize_state.argtypes = [vp, C.c_uint64, C.c_float, C.c_float, C.c_float]
+    lib.ftrl_alloc_pinned.argtypes = [C.c_size_t]
+    lib.ftrl_alloc_pinned.restype = vp
+    lib.ftrl_free_pinned.argtypes = [vp]
+    lib.ftrl_free_pinned.restype = None
     lib.ftrl_export_peer_blob.argtypes = [vp, vp]
     lib.ftrl_attach_peers.argtypes = [vp, vp]
     if path is None:

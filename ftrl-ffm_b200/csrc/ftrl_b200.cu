@@ -199,6 +199,7 @@ static void ensure_workspace(ftrl_handle *h, int64_t n_rows, int64_t nnz) {
   h->occ_single.ensure(nc);
   h->scan.ensure(nc);
   h->chunk_pos.ensure(nc + 2);
+  h->n_chunks.ensure(4);
   const int64_t slots = 2 * (nc / h->chunk + 2);
   if (h->dims.row_len) h->part.ensure((size_t)slots * 2 * h->dims.ld);
   h->part_lin.ensure(slots);
@@ -913,6 +914,18 @@ int ftrl_load_model_text(ftrl_handle *h, const char *path) {
     xfer_bias(h, 0, &b, false);
     xfer_rows(h, 0, 0, d.n_feats, lin.data(), vec.empty() ? nullptr : vec.data(), false);
   });
+}
+
+void *ftrl_alloc_pinned(size_t bytes) {
+  void *p = nullptr;
+  if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+void ftrl_free_pinned(void *p) {
+  if (p) cudaFreeHost(p);
 }
 
 // ---- measurement hooks ----------------------------------------------------------------------

@@ -165,6 +165,11 @@ int ftrl_load_model(ftrl_handle *h, const char *path);
 int ftrl_save_model_text(ftrl_handle *h, const char *path);
 int ftrl_load_model_text(ftrl_handle *h, const char *path);
 
+/* Page-locked host memory for the CSR staging buffers of the host program (the parser packs
+ * samples straight into these so ftrl_train_batch's copies are truly asynchronous). */
+void *ftrl_alloc_pinned(size_t bytes);
+void ftrl_free_pinned(void *p);
+
 /* ---- measurement hooks (no reference counterpart) ------------------------------ */
 /* Run all work of this handle on an existing CUDA stream (cudaStream_t passed as
  * void*), e.g. the caller's current stream, so caller-side CUDA events bracket it. */
