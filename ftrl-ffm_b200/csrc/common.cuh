@@ -67,6 +67,16 @@ __device__ __forceinline__ void ftrl_apply(float &z, float &n, float w, float sg
   n = n_new;
 }
 
+// same with sq = sqrt(n) already at hand
+template <bool PRECISE>
+__device__ __forceinline__ void ftrl_apply_sq(float &z, float &n, float sq, float w, float sg, float sg2, const Hyper &h) {
+  const float n_new = n + sg2;
+  const float d = f_sqrt<PRECISE>(n_new) - sq;
+  const float sigma = PRECISE ? f_div<true>(d, h.alpha) : d * h.inv_alpha;
+  z = (z + sg) - sigma * w;
+  n = n_new;
+}
+
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 // eval/loss.h:8-12 in fp64, no clipping

@@ -108,7 +108,7 @@ struct Phase {
   int64_t launches = 0;
 };
 
-enum PhaseId { PH_PREP = 0, PH_SORT, PH_SEGMENT, PH_SAMPLE, PH_ROWS, PH_COMBINE, PH_REDUCE, PH_EXACT, PH_PREDICT, PH_H2D, PH_COUNT };
+enum PhaseId { PH_PREP = 0, PH_SORT, PH_SEGMENT, PH_SAMPLE, PH_ROWS, PH_COMBINE, PH_REDUCE, PH_EXACT, PH_PREDICT, PH_GENERIC, PH_COUNT };
 
 struct PendingEvent {
   int phase;
@@ -139,11 +139,15 @@ struct ftrl_handle {
   int64_t rows_cap = 0, nnz_cap = 0;
   ftrl::DevBuf<uint32_t> key, occ_idx, skey, socc;
   ftrl::DevBuf<int32_t> occ_row, chunk_pos, n_chunks;
-  ftrl::DevBuf<uint8_t> sflags, occ_single, cub_tmp;
+  ftrl::DevBuf<uint8_t> sflags, fused_sorted, cub_tmp;
+  ftrl::DevBuf<int32_t> occ_pos, batch_flags;
+  ftrl::DevBuf<float> staging, staging_lin;  // per-occurrence gradient images (tile path)
   ftrl::DevBuf<ftrl::SegScan> scan;
   ftrl::DevBuf<float> g, S, part;
   ftrl::DevBuf<float2> part_lin;
-  ftrl::DevBuf<double> loss_s, loss_sum;
+  ftrl::DevBuf<float> logit_ws;
+  ftrl::DevBuf<double> red_part, loss_sum;
+  ftrl::DevBuf<unsigned int> ticket;
   ftrl::DevBuf<float> xfer;  // staging for get/set rows
   size_t cub_bytes = 0;
   int32_t chunk = 32;
@@ -164,5 +168,10 @@ struct ftrl_handle {
   // tunables (env overrides for experiments)
   int fuse = 1;
   int sample_threads = 0;
-  int precise = 1;
+  int precise = 0;  // 0: MUFU sqrt/rcp in minibatch kernels; 1: IEEE sqrt/div
+  int tile = 1;     // FFM: TMA-staged per-sample kernel for batches of distinct-field samples
+  bool tile_ok = false;
+  int tile_ctas_per_sm = 1;
+  int tile_f_cap = 0, tile_stride = 0, tile_stages = 0, tile_consumers = 0;
+  size_t tile_smem = 0;
 };

@@ -255,7 +255,7 @@ k_exact_train(Batch b, Dims d, Hyper h, float *__restrict__ tab, float4 *__restr
 __global__ void __launch_bounds__(128)
 k_exact_predict(Batch b, Dims d, const float *__restrict__ tab, const float4 *__restrict__ lin,
                 const float4 *__restrict__ bias, int output_prob, float *__restrict__ out,
-                double *__restrict__ loss_out) {
+                float *__restrict__ logit_out) {
   const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= b.n_rows) return;
   const int64_t r0 = b.row_ptr[s], r1 = b.row_ptr[s + 1];
@@ -294,7 +294,7 @@ k_exact_predict(Batch b, Dims d, const float *__restrict__ tab, const float4 *__
     }
   }
   out[s] = output_prob ? ex_sigmoid(acc) : acc;
-  if (loss_out) loss_out[s] = b.label ? logloss_d(b.label[s], acc) : 0.0;
+  if (logit_out) logit_out[s] = acc;
 }
 
 }  // namespace ftrl

@@ -1,5 +1,5 @@
-// ffm.cuh -- FFM minibatch kernels (generic LDG path): forward + fused singleton finalize,
-// segmented row update, partial combine, predict.
+// ffm.cuh -- FFM minibatch kernels (LDG path): forward + fused singleton finalize, segmented row
+// update, partial combine, predict.
 //
 // Reference functions covered (src/model/ffm.cpp): update_vector_w :72-88 (materialise w from
 // n,z), compute_ffm_logit :57-70, update_vector_nz :90-136; plus the linear/bias parts of
@@ -19,9 +19,10 @@ namespace ftrl {
 
 constexpr int FFM_CAP = 128;               // features of a sample cached in shared memory
 constexpr int PAIR_LUT_N = FFM_CAP * (FFM_CAP - 1) / 2;
+constexpr int FFM_MAX_F = 32768;           // pairs are indexed with 32 bits
 
 // flat pair index p (n-major: p = n(n-1)/2 + m, m < n) -> (m, n); independent of F
-__device__ __forceinline__ void pair_decode(int64_t p, const uint32_t *__restrict__ lut, int &m, int &n) {
+__device__ __forceinline__ void pair_decode(uint32_t p, const uint32_t *__restrict__ lut, int &m, int &n) {
   if (p < PAIR_LUT_N) {
     const uint32_t e = __ldg(lut + p);
     m = (int)(e & 0xffffu);
@@ -29,10 +30,10 @@ __device__ __forceinline__ void pair_decode(int64_t p, const uint32_t *__restric
     return;
   }
   int64_t nn = (int64_t)((1.0 + sqrt(1.0 + 8.0 * (double)p)) * 0.5);
-  while (nn * (nn - 1) / 2 > p) nn--;
-  while ((nn + 1) * nn / 2 <= p) nn++;
+  while (nn * (nn - 1) / 2 > (int64_t)p) nn--;
+  while ((nn + 1) * nn / 2 <= (int64_t)p) nn++;
   n = (int)nn;
-  m = (int)(p - nn * (nn - 1) / 2);
+  m = (int)((int64_t)p - nn * (nn - 1) / 2);
 }
 
 __global__ void k_build_pair_lut(uint32_t *lut) {
@@ -44,68 +45,96 @@ __global__ void k_build_pair_lut(uint32_t *lut) {
   lut[p] = (uint32_t)(p - n * (n - 1) / 2) | ((uint32_t)n << 16);
 }
 
+// factor-chunk decode of a flat item index: C = k / VEC chunks per pair (shift when a power of two)
+struct ItemDecode {
+  uint32_t C;
+  int shift;  // log2(C) or -1
+  __device__ __forceinline__ void operator()(uint32_t it, uint32_t &p, uint32_t &c) const {
+    if (shift >= 0) {
+      p = it >> shift;
+      c = it & (C - 1);
+    } else {
+      p = it / C;
+      c = it - p * C;
+    }
+  }
+};
+__host__ __device__ inline ItemDecode make_item_decode(int k, int vec) {
+  ItemDecode d;
+  d.C = (uint32_t)(k / vec);
+  d.shift = -1;
+  for (int s = 0; s < 16; s++)
+    if ((1u << s) == d.C) d.shift = s;
+  return d;
+}
+
 struct SampleCache {
-  int32_t fld[FFM_CAP];
-  int32_t ft[FFM_CAP];  // -1 when out of range
+  float *row[FFM_CAP];    // tab + feat * 3 ld   (nullptr when out of range)
+  int32_t fk[FFM_CAP];    // field * k
   float x[FFM_CAP];
   uint8_t fused[FFM_CAP];
 };
 
 // ---------------------------------------------------------------------------------------------
 // K1: one CTA per sample.  pass 1: gather (z,n) slices, materialise w (stored: the stale-by-one w
-// the reference keeps, ffm.cpp:72-88), logit, g, loss.  pass 2 (FUSE): rows that occur exactly once
-// in the batch, in a sample with distinct fields, are finalised here: z', n' written in place
-// (20 B per coordinate, the algorithmic minimum).  All other rows are left to k_ffm_rows.
+// the reference keeps, ffm.cpp:72-88), logit, g.  pass 2 (FUSE): rows that occur exactly once in
+// the batch, in a sample with distinct fields, are finalised here: z', n' written in place (20 B
+// per coordinate, the algorithmic minimum).  All other rows are left to k_ffm_rows.
 // ---------------------------------------------------------------------------------------------
 template <int VEC, bool PRECISE, int THREADS>
 __global__ void __launch_bounds__(THREADS)
-k_ffm_sample(Batch b, Dims d, Hyper h, float *__restrict__ tab, float4 *__restrict__ lin,
+k_ffm_sample(Batch b, Dims d, Hyper h, ItemDecode dec, float *__restrict__ tab, float4 *__restrict__ lin,
              const float4 *__restrict__ bias, const uint32_t *__restrict__ pair_lut,
-             const uint8_t *__restrict__ occ_single, const uint8_t *__restrict__ sflags, int fuse,
-             float *__restrict__ g_out, float *__restrict__ logit_out, double *__restrict__ loss_out) {
+             const int32_t *__restrict__ occ_pos, int fuse, const int32_t *__restrict__ batch_flags,
+             int skip_if_simple, float *__restrict__ g_out, float *__restrict__ logit_out) {
+  if (skip_if_simple && batch_flags[0] != 0) return;  // the tile kernels (ffm_tile.cuh) took this batch
   __shared__ SampleCache sc;
   __shared__ float red[33];
   __shared__ float s_g;
   const int tid = threadIdx.x;
   const int64_t s = blockIdx.x;
   const int64_t r0 = b.row_ptr[s];
-  const int F = (int)(b.row_ptr[s + 1] - r0);
-  const bool fusable = fuse && (sflags[s] & SF_FUSABLE);
+  int F = (int)min((int64_t)FFM_MAX_F, b.row_ptr[s + 1] - r0);
+  const bool fusable = fuse != 0;  // per occurrence: occ_pos < 0 <=> finalised here
+  const int64_t ld = d.ld, rs = 3 * ld;
   for (int t = tid; t < F && t < FFM_CAP; t += THREADS) {
     const int32_t fl = b.field[r0 + t], ft = b.feat[r0 + t];
-    sc.fld[t] = fl;
-    sc.ft[t] = feat_valid(d, fl, ft) ? ft : -1;
+    const bool ok = feat_valid(d, fl, ft);
+    sc.row[t] = ok ? tab + (int64_t)ft * rs : nullptr;
+    sc.fk[t] = fl * d.k;
     sc.x[t] = b.val[r0 + t];
-    sc.fused[t] = fusable && occ_single[r0 + t];
+    sc.fused[t] = fusable && ok && occ_pos[r0 + t] < 0;
   }
   __syncthreads();
-  auto get = [&](int m, int32_t &fl, int32_t &ft, float &x, bool &fz) {
+  auto get = [&](int m, float *&row, int32_t &fk, float &x, bool &fz) {
     if (m < FFM_CAP) {
-      fl = sc.fld[m]; ft = sc.ft[m]; x = sc.x[m]; fz = sc.fused[m];
+      row = sc.row[m]; fk = sc.fk[m]; x = sc.x[m]; fz = sc.fused[m];
     } else {
-      fl = b.field[r0 + m]; ft = b.feat[r0 + m]; x = b.val[r0 + m];
-      if (!feat_valid(d, fl, ft)) ft = -1;
-      fz = fusable && occ_single[r0 + m];
+      const int32_t fl = b.field[r0 + m], ft = b.feat[r0 + m];
+      row = feat_valid(d, fl, ft) ? tab + (int64_t)ft * rs : nullptr;
+      fk = fl * d.k;
+      x = b.val[r0 + m];
+      fz = fusable && row != nullptr && occ_pos[r0 + m] < 0;
     }
   };
-  const int C = (d.k + VEC - 1) / VEC;  // VEC divides k by construction of the dispatch
-  const int64_t n_items = (int64_t)F * (F - 1) / 2 * C;
-  const int64_t ld = d.ld, rs = 3 * ld;
+  const uint32_t n_items = (uint32_t)F * (uint32_t)(F - 1) / 2u * dec.C;
 
   // ---- pass 1 ----
   float acc = 0.f;
-  for (int64_t it = tid; it < n_items; it += THREADS) {
-    const int c = (int)(it % C);
+  for (uint32_t it = tid; it < n_items; it += THREADS) {
+    uint32_t p, c;
+    dec(it, p, c);
     int m, n;
-    pair_decode(it / C, pair_lut, m, n);
-    int32_t fm, im, fn, in;
+    pair_decode(p, pair_lut, m, n);
+    float *ra, *rb;
+    int32_t fkm, fkn;
     float xm, xn;
     bool zm, zn;
-    get(m, fm, im, xm, zm);
-    get(n, fn, in, xn, zn);
-    if (im < 0 || in < 0) continue;
-    float *pa = tab + (int64_t)im * rs + (int64_t)fn * d.k + c * VEC;
-    float *pb = tab + (int64_t)in * rs + (int64_t)fm * d.k + c * VEC;
+    get(m, ra, fkm, xm, zm);
+    get(n, rb, fkn, xn, zn);
+    if (ra == nullptr || rb == nullptr) continue;
+    float *pa = ra + fkn + c * VEC;
+    float *pb = rb + fkm + c * VEC;
     Vec<VEC> zA, nA, zB, nB, wA, wB;
     zA.load(pa); nA.load(pa + ld); zB.load(pb); nB.load(pb + ld);
     float dot = 0.f;
@@ -121,73 +150,75 @@ k_ffm_sample(Batch b, Dims d, Hyper h, float *__restrict__ tab, float4 *__restri
   }
   // linear part (ftrl_model.cpp:44-59): thread t handles feature t
   for (int t = tid; t < F; t += THREADS) {
-    int32_t fl, ft; float x; bool fz;
-    get(t, fl, ft, x, fz);
-    if (ft < 0) continue;
+    const int32_t ft = b.feat[r0 + t];
+    if (!feat_valid(d, b.field[r0 + t], ft)) continue;
     const float4 e = lin[ft];
     const float w = weight_from<PRECISE>(e.x, f_sqrt<PRECISE>(e.y), h);
     lin[ft].z = w;
-    acc = fmaf(w, x, acc);
+    acc = fmaf(w, b.val[r0 + t], acc);
   }
   float logit = block_sum(acc, red);
   if (tid == 0) {
     const float4 bz = *bias;
     logit += weight_from<PRECISE>(bz.x, f_sqrt<PRECISE>(bz.y), h);
-    const int y = b.label[s];
-    const float g = sigmoid_f(logit) - (float)y;
+    const float g = sigmoid_f(logit) - (float)b.label[s];
     s_g = g;
     g_out[s] = g;
-    if (logit_out) logit_out[s] = logit;
-    loss_out[s] = logloss_d(y, logit);
+    logit_out[s] = logit;
   }
   if (!fusable) return;
   __syncthreads();
   const float g = s_g;
 
   // ---- pass 2: finalize singleton rows (z,n re-read: L1/L2 hits) ----
-  for (int64_t it = tid; it < n_items; it += THREADS) {
-    const int c = (int)(it % C);
+  for (uint32_t it = tid; it < n_items; it += THREADS) {
+    uint32_t p, c;
+    dec(it, p, c);
     int m, n;
-    pair_decode(it / C, pair_lut, m, n);
-    int32_t fm, im, fn, in;
+    pair_decode(p, pair_lut, m, n);
+    float *ra, *rb;
+    int32_t fkm, fkn;
     float xm, xn;
     bool zm, zn;
-    get(m, fm, im, xm, zm);
-    get(n, fn, in, xn, zn);
-    if (im < 0 || in < 0 || !(zm || zn)) continue;
-    float *pa = tab + (int64_t)im * rs + (int64_t)fn * d.k + c * VEC;
-    float *pb = tab + (int64_t)in * rs + (int64_t)fm * d.k + c * VEC;
-    Vec<VEC> zA, nA, zB, nB, wA, wB;
+    get(m, ra, fkm, xm, zm);
+    get(n, rb, fkn, xn, zn);
+    if (ra == nullptr || rb == nullptr || !(zm || zn)) continue;
+    float *pa = ra + fkn + c * VEC;
+    float *pb = rb + fkm + c * VEC;
+    Vec<VEC> zA, nA, zB, nB;
     zA.load(pa); nA.load(pa + ld); zB.load(pb); nB.load(pb + ld);
     const float gx = g * (xm * xn);
+    float sqA[VEC], sqB[VEC], wA[VEC], wB[VEC];
 #pragma unroll
     for (int e = 0; e < VEC; e++) {
-      wA.v[e] = weight_from<PRECISE>(zA.v[e], f_sqrt<PRECISE>(nA.v[e]), h);
-      wB.v[e] = weight_from<PRECISE>(zB.v[e], f_sqrt<PRECISE>(nB.v[e]), h);
+      sqA[e] = f_sqrt<PRECISE>(nA.v[e]);
+      sqB[e] = f_sqrt<PRECISE>(nB.v[e]);
+      wA[e] = weight_from<PRECISE>(zA.v[e], sqA[e], h);
+      wB[e] = weight_from<PRECISE>(zB.v[e], sqB[e], h);
     }
     if (zm) {
 #pragma unroll
       for (int e = 0; e < VEC; e++) {
-        const float gv = gx * wB.v[e];
-        ftrl_apply<PRECISE>(zA.v[e], nA.v[e], wA.v[e], gv, gv * gv, h);
+        const float gv = gx * wB[e];
+        ftrl_apply_sq<PRECISE>(zA.v[e], nA.v[e], sqA[e], wA[e], gv, gv * gv, h);
       }
       zA.store(pa); nA.store(pa + ld);
     }
     if (zn) {
 #pragma unroll
       for (int e = 0; e < VEC; e++) {
-        const float gv = gx * wA.v[e];
-        ftrl_apply<PRECISE>(zB.v[e], nB.v[e], wB.v[e], gv, gv * gv, h);
+        const float gv = gx * wA[e];
+        ftrl_apply_sq<PRECISE>(zB.v[e], nB.v[e], sqB[e], wB[e], gv, gv * gv, h);
       }
       zB.store(pb); nB.store(pb + ld);
     }
   }
   for (int t = tid; t < F; t += THREADS) {
-    int32_t fl, ft; float x; bool fz;
-    get(t, fl, ft, x, fz);
-    if (ft < 0 || !fz) continue;
+    const int32_t ft = b.feat[r0 + t];
+    if (!feat_valid(d, b.field[r0 + t], ft)) continue;
+    if (!(fusable && occ_pos[r0 + t] < 0)) continue;
     float4 e = lin[ft];  // e.z = w written in pass 1 by this very thread
-    const float gi = g * x;
+    const float gi = g * b.val[r0 + t];
     ftrl_apply<PRECISE>(e.x, e.y, e.z, gi, gi * gi, h);
     lin[ft] = e;
   }
@@ -199,16 +230,22 @@ k_ffm_sample(Batch b, Dims d, Hyper h, float *__restrict__ tab, float4 *__restri
 // g_s * w[feat_n][field_m,:] * x_m x_n is accumulated into the row's (sum g, sum g^2) image in
 // shared memory; then either the closed-form update is applied (row fits one chunk) or the partial
 // image is parked for k_ffm_combine.  Rows already finalised by k_ffm_sample are skipped.
+// Latency structure: the 32 lanes first fetch the metadata of 32 occurrences in parallel (one
+// dependent chain for the whole group instead of one per occurrence); per occurrence the partner
+// gathers of up to GATHER_U warp-steps are issued together before any accumulation.
 // ---------------------------------------------------------------------------------------------
+constexpr int GATHER_U = 4;
+
 template <int VEC, bool PRECISE, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
-k_ffm_rows(Batch b, Dims d, Hyper h, float *__restrict__ tab, float4 *__restrict__ lin, int32_t ch,
+k_ffm_rows(Batch b, Dims d, Hyper h, ItemDecode dec, float *__restrict__ tab, float4 *__restrict__ lin, int32_t ch,
            const int32_t *__restrict__ n_chunks_p, const int32_t *__restrict__ chunk_pos,
            const uint32_t *__restrict__ skey, const uint32_t *__restrict__ socc,
            const SegScan *__restrict__ scan, const int32_t *__restrict__ occ_row,
-           const uint8_t *__restrict__ sflags, int fuse, const float *__restrict__ g_in,
-           float *__restrict__ part, float2 *__restrict__ part_lin) {
-  extern __shared__ float smem[];
+           const uint8_t *__restrict__ sflags, const int32_t *__restrict__ batch_flags, int skip_if_simple,
+           const float *__restrict__ g_in, float *__restrict__ part, float2 *__restrict__ part_lin) {
+  if (skip_if_simple && batch_flags[0] != 0) return;  // the tile kernels (ffm_tile.cuh) took this batch
+  extern __shared__ __align__(16) float smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t ld = d.ld, rs = 3 * ld;
   float *acc0 = smem + (int64_t)wib * 2 * ld;  // sum g
@@ -216,75 +253,102 @@ k_ffm_rows(Batch b, Dims d, Hyper h, float *__restrict__ tab, float4 *__restrict
   const int n_chunks = *n_chunks_p;
   const int32_t nnz = (int32_t)b.nnz;
   const uint32_t sentinel = (uint32_t)d.n_feats;
-  const int C = (d.k + VEC - 1) / VEC;
+  const int C = (int)dec.C;
   for (int c = blockIdx.x * WARPS + wib; c < n_chunks; c += gridDim.x * WARPS) {
-    const ChunkInfo ci = chunk_info(c, nnz, sentinel, ch, chunk_pos, skey, scan);
+    const ChunkInfo ci = chunk_info<true>(c, nnz, sentinel, ch, chunk_pos, skey, scan);
     if (!ci.valid) continue;
     const bool whole_row = ci.row_head && ci.row_last;
-    if (fuse && whole_row && ci.p1 - ci.p0 == 1) {
-      if (sflags[occ_row[socc[ci.p0]]] & SF_FUSABLE) continue;  // finalised in k_ffm_sample
-    }
     for (int64_t v = lane; v < 2 * ld; v += 32) acc0[v] = 0.f;
     __syncwarp();
-    float sg = 0.f, sg2 = 0.f;  // linear coordinate (lane 0)
-    for (int p = ci.p0; p < ci.p1; p++) {
-      const int64_t t = socc[p];
-      const int32_t s = occ_row[t];
-      const float g = g_in[s];
-      const int64_t r0 = b.row_ptr[s];
-      const int F = (int)(b.row_ptr[s + 1] - r0);
-      const int m = (int)(t - r0);
-      const float xm = b.val[t];
-      const int32_t fm = b.field[t];
-      const bool simple = sflags[s] & SF_SIMPLE;
-      const float gi = g * xm;
-      sg += gi;
-      sg2 = fmaf(gi, gi, sg2);
-      const int n_q = F * C;
-      for (int q0 = 0; q0 < n_q; q0 += 32) {
-        const int q = q0 + lane;
-        const int n = q / C, c4 = q - n * C;
-        bool act = q < n_q && n != m;
-        int32_t fn = 0, in = 0;
-        float xn = 0.f;
-        if (act) {
-          fn = b.field[r0 + n]; in = b.feat[r0 + n]; xn = b.val[r0 + n];
-          act = feat_valid(d, fn, in);
-        }
-        Vec<VEC> gv;
-        int64_t off = 0;
-        if (act) {
-          Vec<VEC> w;
-          w.load(tab + (int64_t)in * rs + 2 * ld + (int64_t)fm * d.k + c4 * VEC);
-          const float gx = g * (xm * xn);
+    float sg = 0.f, sg2 = 0.f;  // linear coordinate: lane-partial sums
+    for (int base = ci.p0; base < ci.p1; base += 32) {
+      // lane l owns occurrence base + l
+      const int my_p = base + lane;
+      int64_t my_r0 = 0;
+      int my_F = 0, my_m = 0, my_fmk = 0, my_simple = 1;
+      float my_gx = 0.f;
+      if (my_p < ci.p1) {
+        const int64_t t = socc[my_p];
+        const int32_t s = occ_row[t];
+        my_r0 = b.row_ptr[s];
+        my_F = (int)min((int64_t)FFM_MAX_F, b.row_ptr[s + 1] - my_r0);
+        my_m = (int)(t - my_r0);
+        my_fmk = b.field[t] * d.k;
+        my_simple = (sflags[s] & SF_SIMPLE) ? 1 : 0;
+        my_gx = g_in[s] * b.val[t];
+        sg += my_gx;
+        sg2 = fmaf(my_gx, my_gx, sg2);
+      }
+      const int n_here = min(32, ci.p1 - base);
+      for (int j = 0; j < n_here; j++) {
+        const int64_t r0 = __shfl_sync(0xffffffffu, my_r0, j);
+        const int F = __shfl_sync(0xffffffffu, my_F, j);
+        const int m = __shfl_sync(0xffffffffu, my_m, j);
+        const int fmk = __shfl_sync(0xffffffffu, my_fmk, j);
+        const int simple = __shfl_sync(0xffffffffu, my_simple, j);
+        const float gxm = __shfl_sync(0xffffffffu, my_gx, j);  // g_s * x_m
+        const int n_q = F * C;
+        for (int q0 = 0; q0 < n_q; q0 += 32 * GATHER_U) {
+          bool act[GATHER_U];
+          int off[GATHER_U];
+          float gx[GATHER_U];
+          const float *src[GATHER_U];
 #pragma unroll
-          for (int e = 0; e < VEC; e++) gv.v[e] = gx * w.v[e];
-          off = (int64_t)fn * d.k + c4 * VEC;
-        }
-        if (simple) {
-          if (act) {
-#pragma unroll
-            for (int e = 0; e < VEC; e++) {
-              acc0[off + e] += gv.v[e];
-              acc1[off + e] = fmaf(gv.v[e], gv.v[e], acc1[off + e]);
-            }
-          }
-        } else {
-          // partners may share a field: apply lane by lane (deterministic order)
-          for (int l = 0; l < 32; l++) {
-            if (l == lane && act) {
-#pragma unroll
-              for (int e = 0; e < VEC; e++) {
-                acc0[off + e] += gv.v[e];
-                acc1[off + e] = fmaf(gv.v[e], gv.v[e], acc1[off + e]);
+          for (int u = 0; u < GATHER_U; u++) {
+            const int q = q0 + u * 32 + lane;
+            const int n = q / C, c4 = q - n * C;
+            act[u] = q < n_q && n != m;
+            off[u] = 0;
+            gx[u] = 0.f;
+            src[u] = nullptr;
+            if (act[u]) {
+              const int32_t fn = b.field[r0 + n], in = b.feat[r0 + n];
+              const float xn = b.val[r0 + n];
+              act[u] = feat_valid(d, fn, in);
+              if (act[u]) {
+                src[u] = tab + (int64_t)in * rs + 2 * ld + fmk + c4 * VEC;
+                off[u] = fn * d.k + c4 * VEC;
+                gx[u] = gxm * xn;
               }
             }
-            __syncwarp();
+          }
+          Vec<VEC> w[GATHER_U];
+#pragma unroll
+          for (int u = 0; u < GATHER_U; u++)
+            if (act[u]) w[u].load(src[u]);
+          if (simple) {
+#pragma unroll
+            for (int u = 0; u < GATHER_U; u++)
+              if (act[u]) {
+#pragma unroll
+                for (int e = 0; e < VEC; e++) {
+                  const float gv = gx[u] * w[u].v[e];
+                  acc0[off[u] + e] += gv;
+                  acc1[off[u] + e] = fmaf(gv, gv, acc1[off[u] + e]);
+                }
+              }
+          } else {
+            // partners may share a field: apply lane by lane, step by step (deterministic order)
+#pragma unroll
+            for (int u = 0; u < GATHER_U; u++)
+              for (int l = 0; l < 32; l++) {
+                if (l == lane && act[u]) {
+#pragma unroll
+                  for (int e = 0; e < VEC; e++) {
+                    const float gv = gx[u] * w[u].v[e];
+                    acc0[off[u] + e] += gv;
+                    acc1[off[u] + e] = fmaf(gv, gv, acc1[off[u] + e]);
+                  }
+                }
+                __syncwarp();
+              }
           }
         }
+        __syncwarp();
       }
-      __syncwarp();
     }
+    sg = warp_sum(sg);
+    sg2 = warp_sum(sg2);
     if (whole_row) {
       float *row = tab + (int64_t)ci.key * rs;
       for (int64_t v = lane * VEC; v < d.row_len; v += 32 * VEC) {
@@ -314,55 +378,75 @@ k_ffm_rows(Batch b, Dims d, Hyper h, float *__restrict__ tab, float4 *__restrict
   }
 }
 
+// ---------------------------------------------------------------------------------------------
 // K3: rows spanning several chunks: sum the parked partials in chunk order, apply once.
-template <int VEC, bool PRECISE, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
+// A CTA scans THREADS consecutive chunks (one per thread) for multi-chunk row heads, then all of
+// its warps cooperate on each such row: thread -> vector of the row, loop over the partials.
+// ---------------------------------------------------------------------------------------------
+template <int VEC, bool PRECISE, int THREADS>
+__global__ void __launch_bounds__(THREADS)
 k_ffm_combine(Dims d, Hyper h, int32_t nnz, float *__restrict__ tab, float4 *__restrict__ lin, int32_t ch,
               const int32_t *__restrict__ n_chunks_p, const int32_t *__restrict__ chunk_pos,
               const uint32_t *__restrict__ skey, const SegScan *__restrict__ scan,
               const float *__restrict__ part, const float2 *__restrict__ part_lin) {
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  __shared__ int s_list[THREADS];
+  __shared__ int s_n;
+  const int tid = threadIdx.x;
   const int64_t ld = d.ld, rs = 3 * ld;
   const int n_chunks = *n_chunks_p;
   const uint32_t sentinel = (uint32_t)d.n_feats;
-  for (int c = blockIdx.x * WARPS + wib; c < n_chunks; c += gridDim.x * WARPS) {
-    const ChunkInfo ci = chunk_info(c, nnz, sentinel, ch, chunk_pos, skey, scan);
-    if (!ci.valid || !ci.row_head || ci.row_last) continue;
-    int J = 1;  // number of chunks of this row
-    while (c + J < n_chunks && skey[chunk_pos[c + J]] == ci.key) J++;
-    float *row = tab + (int64_t)ci.key * rs;
-    const float *p0 = part + (int64_t)ci.slot * 2 * ld;
-    for (int64_t v = lane * VEC; v < d.row_len; v += 32 * VEC) {
-      Vec<VEC> a0, a1;
-#pragma unroll
-      for (int e = 0; e < VEC; e++) a0.v[e] = a1.v[e] = 0.f;
-      for (int j = 0; j < J; j++) {
-        Vec<VEC> t0, t1;
-        t0.load(p0 + (int64_t)j * 2 * ld + v);
-        t1.load(p0 + (int64_t)j * 2 * ld + ld + v);
-#pragma unroll
-        for (int e = 0; e < VEC; e++) { a0.v[e] += t0.v[e]; a1.v[e] += t1.v[e]; }
-      }
-      bool any = false;
-#pragma unroll
-      for (int e = 0; e < VEC; e++) any = any || a1.v[e] != 0.f || a0.v[e] != 0.f;
-      if (!any) continue;
-      Vec<VEC> z, n, w;
-      z.load(row + v); n.load(row + ld + v); w.load(row + 2 * ld + v);
-#pragma unroll
-      for (int e = 0; e < VEC; e++) ftrl_apply<PRECISE>(z.v[e], n.v[e], w.v[e], a0.v[e], a1.v[e], h);
-      z.store(row + v); n.store(row + ld + v);
+  for (int base = blockIdx.x * THREADS; base < n_chunks; base += gridDim.x * THREADS) {
+    if (tid == 0) s_n = 0;
+    __syncthreads();
+    const int c = base + tid;
+    if (c < n_chunks) {
+      const ChunkInfo ci = chunk_head_info(c, nnz, sentinel, ch, chunk_pos, skey, scan);
+      if (ci.valid && ci.row_head && !ci.row_last) s_list[atomicAdd(&s_n, 1)] = c;
     }
-    if (lane == 0) {
-      float sg = 0.f, sg2 = 0.f;
-      for (int j = 0; j < J; j++) {
-        const float2 t = part_lin[ci.slot + j];
-        sg += t.x; sg2 += t.y;
+    __syncthreads();
+    const int n_list = s_n;
+    for (int li = 0; li < n_list; li++) {
+      // the order of s_list is arbitrary, but every row is handled exactly once and rows are independent
+      const int c0 = s_list[li];
+      const ChunkInfo ci = chunk_head_info(c0, nnz, sentinel, ch, chunk_pos, skey, scan);
+      int J = 1;  // number of chunks of this row
+      while (c0 + J < n_chunks && skey[chunk_pos[c0 + J]] == ci.key) J++;
+      float *row = tab + (int64_t)ci.key * rs;
+      const float *p0 = part + (int64_t)ci.slot * 2 * ld;
+      for (int64_t v = (int64_t)tid * VEC; v < d.row_len; v += (int64_t)THREADS * VEC) {
+        Vec<VEC> a0, a1;
+#pragma unroll
+        for (int e = 0; e < VEC; e++) a0.v[e] = a1.v[e] = 0.f;
+#pragma unroll 4
+        for (int j = 0; j < J; j++) {
+          Vec<VEC> t0, t1;
+          t0.load(p0 + (int64_t)j * 2 * ld + v);
+          t1.load(p0 + (int64_t)j * 2 * ld + ld + v);
+#pragma unroll
+          for (int e = 0; e < VEC; e++) { a0.v[e] += t0.v[e]; a1.v[e] += t1.v[e]; }
+        }
+        bool any = false;
+#pragma unroll
+        for (int e = 0; e < VEC; e++) any = any || a1.v[e] != 0.f || a0.v[e] != 0.f;
+        if (!any) continue;
+        Vec<VEC> z, n, w;
+        z.load(row + v); n.load(row + ld + v); w.load(row + 2 * ld + v);
+#pragma unroll
+        for (int e = 0; e < VEC; e++) ftrl_apply<PRECISE>(z.v[e], n.v[e], w.v[e], a0.v[e], a1.v[e], h);
+        z.store(row + v); n.store(row + ld + v);
       }
-      float4 e = lin[ci.key];
-      ftrl_apply<PRECISE>(e.x, e.y, e.z, sg, sg2, h);
-      lin[ci.key] = e;
+      if (tid == 0) {
+        float sg = 0.f, sg2 = 0.f;
+        for (int j = 0; j < J; j++) {
+          const float2 t = part_lin[ci.slot + j];
+          sg += t.x; sg2 += t.y;
+        }
+        float4 e = lin[ci.key];
+        ftrl_apply<PRECISE>(e.x, e.y, e.z, sg, sg2, h);
+        lin[ci.key] = e;
+      }
     }
+    __syncthreads();
   }
 }
 
@@ -371,22 +455,22 @@ k_ffm_combine(Dims d, Hyper h, int32_t nnz, float *__restrict__ tab, float4 *__r
 // ---------------------------------------------------------------------------------------------
 template <int VEC, int THREADS>
 __global__ void __launch_bounds__(THREADS)
-k_ffm_predict(Batch b, Dims d, const float *__restrict__ tab, const float4 *__restrict__ lin,
+k_ffm_predict(Batch b, Dims d, ItemDecode dec, const float *__restrict__ tab, const float4 *__restrict__ lin,
               const float4 *__restrict__ bias, const uint32_t *__restrict__ pair_lut, int output_prob,
-              float *__restrict__ out, double *__restrict__ loss_out) {
+              float *__restrict__ out, float *__restrict__ logit_out) {
   __shared__ float red[33];
   const int tid = threadIdx.x;
   const int64_t s = blockIdx.x;
   const int64_t r0 = b.row_ptr[s];
-  const int F = (int)(b.row_ptr[s + 1] - r0);
-  const int C = (d.k + VEC - 1) / VEC;
-  const int64_t n_items = (int64_t)F * (F - 1) / 2 * C;
+  const int F = (int)min((int64_t)FFM_MAX_F, b.row_ptr[s + 1] - r0);
+  const uint32_t n_items = (uint32_t)F * (uint32_t)(F - 1) / 2u * dec.C;
   const int64_t ld = d.ld, rs = 3 * ld;
   float acc = 0.f;
-  for (int64_t it = tid; it < n_items; it += THREADS) {
-    const int c = (int)(it % C);
+  for (uint32_t it = tid; it < n_items; it += THREADS) {
+    uint32_t p, c;
+    dec(it, p, c);
     int m, n;
-    pair_decode(it / C, pair_lut, m, n);
+    pair_decode(p, pair_lut, m, n);
     const int32_t fm = b.field[r0 + m], im = b.feat[r0 + m], fn = b.field[r0 + n], in = b.feat[r0 + n];
     if (!feat_valid(d, fm, im) || !feat_valid(d, fn, in)) continue;
     Vec<VEC> wA, wB;
@@ -405,7 +489,7 @@ k_ffm_predict(Batch b, Dims d, const float *__restrict__ tab, const float4 *__re
   if (tid == 0) {
     logit += bias->z;
     out[s] = output_prob ? sigmoid_f(logit) : logit;
-    if (loss_out) loss_out[s] = b.label ? logloss_d(b.label[s], logit) : 0.0;
+    if (logit_out) logit_out[s] = logit;
   }
 }
 

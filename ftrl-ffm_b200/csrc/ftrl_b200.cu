@@ -10,6 +10,7 @@
 #include "engine.cuh"
 #include "exact.cuh"
 #include "ffm.cuh"
+#include "ffm_tile.cuh"
 #include "lr_fm.cuh"
 #include "model_io.h"
 
@@ -169,9 +170,9 @@ static size_t cub_temp_bytes(int64_t nnz, int end_bit) {
   cub::DeviceRadixSort::SortPairs(nullptr, a, (const uint32_t *)nullptr, (uint32_t *)nullptr,
                                   (const uint32_t *)nullptr, (uint32_t *)nullptr, n, 0, end_bit);
   thrust::counting_iterator<int32_t> cnt(0);
-  auto it = thrust::make_transform_iterator(cnt, HeadFunctor{nullptr});
+  auto it = thrust::make_transform_iterator(cnt, HeadFunctor{nullptr, nullptr});
   cub::DeviceScan::InclusiveScan(nullptr, b, it, (SegScan *)nullptr, SegScanOp(), n);
-  cub::DeviceSelect::If(nullptr, c, cnt, (int32_t *)nullptr, (int32_t *)nullptr, n, ChunkHeadPred{nullptr, nullptr, 0, 1});
+  cub::DeviceSelect::If(nullptr, c, cnt, (int32_t *)nullptr, (int32_t *)nullptr, n, ChunkHeadPred{nullptr, nullptr, nullptr, 0, 1});
   return std::max(a, std::max(b, c)) + 256;
 }
 
@@ -188,7 +189,12 @@ static void ensure_workspace(ftrl_handle *h, int64_t n_rows, int64_t nnz) {
   const int64_t nc = std::max<int64_t>(h->nnz_cap, nnz + nnz / 8 + 64);
   if (nc >= (1ll << 31) - 64) throw ArgFail{"batch nnz must be < 2^31"};
   h->g.ensure(rc);
-  h->loss_s.ensure(rc);
+  h->logit_ws.ensure(rc);
+  if (!h->red_part.p) {
+    h->red_part.alloc(3 * RED_MAX_CTAS);
+    h->ticket.alloc(1);
+    FTRL_CUDA(cudaMemset(h->ticket.p, 0, sizeof(unsigned)));
+  }
   h->sflags.ensure(rc);
   if (h->dims.model_type == FTRL_FM) h->S.ensure(rc * h->dims.k);
   h->key.ensure(nc);
@@ -196,7 +202,13 @@ static void ensure_workspace(ftrl_handle *h, int64_t n_rows, int64_t nnz) {
   h->skey.ensure(nc);
   h->socc.ensure(nc);
   h->occ_row.ensure(nc);
-  h->occ_single.ensure(nc);
+  h->fused_sorted.ensure(nc);
+  h->occ_pos.ensure(nc);
+  h->batch_flags.ensure(4);
+  if (h->tile_ok) {
+    h->staging.ensure((size_t)nc * h->dims.ld);
+    h->staging_lin.ensure(nc);
+  }
   h->scan.ensure(nc);
   h->chunk_pos.ensure(nc + 2);
   h->n_chunks.ensure(4);
@@ -235,22 +247,27 @@ static int guarded(ftrl_handle *h, F &&f) {
   }
 }
 
+static int reduce_grid(int64_t n_rows) {
+  return (int)std::max<int64_t>(1, std::min<int64_t>(RED_MAX_CTAS, (n_rows + 1023) / 1024));
+}
+
 static int pick_vec(int k) { return k % 4 == 0 ? 4 : k % 2 == 0 ? 2 : 1; }
 
 // ---------------------------------------------------------------------------------------------
 // batch training, device-resident CSR
 // ---------------------------------------------------------------------------------------------
 template <int VEC, bool PRECISE>
-static void launch_ffm_sample(ftrl_handle *h, const Batch &b, float *logit_out) {
+static void launch_ffm_sample(ftrl_handle *h, const Batch &b, float *logit_out, int skip_if_simple) {
   const Dims &d = h->dims;
   const double fbar = b.n_rows ? (double)b.nnz / (double)b.n_rows : 0.0;
   const double items = fbar * (fbar - 1) * 0.5 * (d.k / VEC);
   int threads = h->sample_threads ? h->sample_threads : items <= 64 ? 64 : items <= 256 ? 128 : items <= 1024 ? 256 : 512;
   const dim3 grid((unsigned)b.n_rows);
+  const ItemDecode dec = make_item_decode(d.k, VEC);
 #define FFM_SAMPLE(T)                                                                                          \
-  k_ffm_sample<VEC, PRECISE, T><<<grid, T, 0, h->compute>>>(b, d, h->hyper, h->tab, h->lin, h->bias, h->pair_lut, \
-                                                           h->occ_single.p, h->sflags.p, h->fuse, h->g.p, logit_out, \
-                                                           h->loss_s.p)
+  k_ffm_sample<VEC, PRECISE, T><<<grid, T, 0, h->compute>>>(b, d, h->hyper, dec, h->tab, h->lin, h->bias, h->pair_lut, \
+                                                           h->occ_pos.p, h->fuse, h->batch_flags.p, skip_if_simple, \
+                                                           h->g.p, logit_out)
   if (threads <= 64) FFM_SAMPLE(64);
   else if (threads <= 128) FFM_SAMPLE(128);
   else if (threads <= 256) FFM_SAMPLE(256);
@@ -259,42 +276,73 @@ static void launch_ffm_sample(ftrl_handle *h, const Batch &b, float *logit_out) 
   FTRL_CUDA(cudaGetLastError());
 }
 
+// FFM minibatch: when every sample of the batch has distinct fields (device-side flag) the tile kernels
+// (ffm_tile.cuh) process it; otherwise the generic LDG kernels do.  Both sets are enqueued, the one that
+// does not apply returns at once -- no host round trip.
 template <int VEC, bool PRECISE>
 static void run_ffm_batch(ftrl_handle *h, const Batch &b, float *logit_out) {
   const Dims &d = h->dims;
+  const bool tile = VEC == 4 && h->tile_ok && b.nnz > 0;
+  const int grid = h->n_sms * 4;
+  const ItemDecode dec = make_item_decode(d.k, VEC);
+  if (tile) {
+    {
+      PhaseScope ps(h, PH_SAMPLE);
+      TileGeom geo;
+      geo.f_cap = h->tile_f_cap;
+      geo.stride = h->tile_stride;
+      geo.n_stage = h->tile_stages;
+      geo.consumers = h->tile_consumers;
+      geo.smem_bytes = h->tile_smem;
+      const int tgrid = (int)std::min<int64_t>(b.n_rows, (int64_t)h->n_sms * h->tile_ctas_per_sm);
+      k_ffm_tile<PRECISE><<<tgrid, geo.consumers + 32, geo.smem_bytes, h->compute>>>(
+          b, d, h->hyper, dec, geo, h->batch_flags.p, h->tab, h->lin, h->bias, h->pair_lut, h->occ_pos.p, h->staging.p,
+          h->staging_lin.p, h->g.p, logit_out);
+      FTRL_CUDA(cudaGetLastError());
+      launched(h, PH_SAMPLE);
+    }
+    {
+      PhaseScope ps(h, PH_ROWS);
+      k_ffm_staged_rows<PRECISE, 8><<<grid, 256, 0, h->compute>>>(d, h->hyper, (int32_t)b.nnz, h->batch_flags.p, h->tab,
+                                                                 h->lin, h->chunk, h->n_chunks.p, h->chunk_pos.p,
+                                                                 h->skey.p, h->scan.p, h->staging.p, h->staging_lin.p,
+                                                                 h->part.p, h->part_lin.p);
+      FTRL_CUDA(cudaGetLastError());
+      launched(h, PH_ROWS);
+    }
+  }
   {
-    PhaseScope ps(h, PH_SAMPLE);
-    launch_ffm_sample<VEC, PRECISE>(h, b, logit_out);
-    launched(h, PH_SAMPLE);
+    PhaseScope ps(h, PH_GENERIC);
+    launch_ffm_sample<VEC, PRECISE>(h, b, logit_out, tile ? 1 : 0);
+    launched(h, PH_GENERIC);
+    if (b.nnz > 0) {
+      const size_t smem8 = (size_t)8 * 2 * d.ld * sizeof(float);
+      if (smem8 <= 160 * 1024) {
+        auto kern = k_ffm_rows<VEC, PRECISE, 8>;
+        if (smem8 > 48 * 1024) FTRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
+        kern<<<grid, 256, smem8, h->compute>>>(b, d, h->hyper, dec, h->tab, h->lin, h->chunk, h->n_chunks.p, h->chunk_pos.p,
+                                               h->skey.p, h->socc.p, h->scan.p, h->occ_row.p, h->sflags.p,
+                                               h->batch_flags.p, tile ? 1 : 0, h->g.p, h->part.p, h->part_lin.p);
+      } else {
+        const size_t smem1 = (size_t)2 * d.ld * sizeof(float);
+        if (smem1 > 200 * 1024) throw ArgFail{"n_fields*n_factors too large for the row kernel"};
+        auto kern = k_ffm_rows<VEC, PRECISE, 1>;
+        FTRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+        kern<<<grid * 4, 32, smem1, h->compute>>>(b, d, h->hyper, dec, h->tab, h->lin, h->chunk, h->n_chunks.p,
+                                                  h->chunk_pos.p, h->skey.p, h->socc.p, h->scan.p, h->occ_row.p,
+                                                  h->sflags.p, h->batch_flags.p, tile ? 1 : 0, h->g.p, h->part.p,
+                                                  h->part_lin.p);
+      }
+      FTRL_CUDA(cudaGetLastError());
+      launched(h, PH_GENERIC);
+    }
   }
   if (b.nnz == 0) return;
-  const size_t smem8 = (size_t)8 * 2 * d.ld * sizeof(float);
-  const int grid = h->n_sms * 4;
-  {
-    PhaseScope ps(h, PH_ROWS);
-    if (smem8 <= 160 * 1024) {
-      auto kern = k_ffm_rows<VEC, PRECISE, 8>;
-      if (smem8 > 48 * 1024) FTRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
-      kern<<<grid, 256, smem8, h->compute>>>(b, d, h->hyper, h->tab, h->lin, h->chunk, h->n_chunks.p, h->chunk_pos.p,
-                                             h->skey.p, h->socc.p, h->scan.p, h->occ_row.p, h->sflags.p, h->fuse,
-                                             h->g.p, h->part.p, h->part_lin.p);
-    } else {
-      const size_t smem1 = (size_t)2 * d.ld * sizeof(float);
-      if (smem1 > 200 * 1024) throw ArgFail{"n_fields*n_factors too large for the row kernel"};
-      auto kern = k_ffm_rows<VEC, PRECISE, 1>;
-      FTRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-      kern<<<grid * 4, 32, smem1, h->compute>>>(b, d, h->hyper, h->tab, h->lin, h->chunk, h->n_chunks.p,
-                                                h->chunk_pos.p, h->skey.p, h->socc.p, h->scan.p, h->occ_row.p,
-                                                h->sflags.p, h->fuse, h->g.p, h->part.p, h->part_lin.p);
-    }
-    FTRL_CUDA(cudaGetLastError());
-    launched(h, PH_ROWS);
-  }
   {
     PhaseScope ps(h, PH_COMBINE);
-    k_ffm_combine<VEC, PRECISE, 8><<<grid, 256, 0, h->compute>>>(d, h->hyper, (int32_t)b.nnz, h->tab, h->lin, h->chunk,
-                                                                 h->n_chunks.p, h->chunk_pos.p, h->skey.p, h->scan.p,
-                                                                 h->part.p, h->part_lin.p);
+    k_ffm_combine<VEC, PRECISE, 256><<<grid, 256, 0, h->compute>>>(d, h->hyper, (int32_t)b.nnz, h->tab, h->lin, h->chunk,
+                                                                   h->n_chunks.p, h->chunk_pos.p, h->skey.p, h->scan.p,
+                                                                   h->part.p, h->part_lin.p);
     FTRL_CUDA(cudaGetLastError());
     launched(h, PH_COMBINE);
   }
@@ -308,7 +356,7 @@ static void run_lrfm_batch(ftrl_handle *h, const Batch &b, float *logit_out) {
     const int64_t warps = b.n_rows;
     const unsigned grid = (unsigned)((warps * 32 + 255) / 256);
     k_lrfm_sample<VEC, PRECISE, IS_FM><<<grid, 256, 0, h->compute>>>(b, d, h->hyper, h->tab, h->lin, h->bias, h->S.p,
-                                                                     h->g.p, logit_out, h->loss_s.p);
+                                                                     h->g.p, logit_out);
     FTRL_CUDA(cudaGetLastError());
     launched(h, PH_SAMPLE);
   }
@@ -338,9 +386,10 @@ static void run_prep(ftrl_handle *h, const Batch &b) {
   const uint32_t sentinel = (uint32_t)d.n_feats;
   {
     PhaseScope ps(h, PH_PREP);
+    FTRL_CUDA(cudaMemsetAsync(h->batch_flags.p, 0x01, sizeof(int32_t), h->compute));  // != 0: all samples simple
     const unsigned grid = (unsigned)((b.n_rows * 32 + 255) / 256);
-    k_prep_rows<<<grid, 256, 0, h->compute>>>(b, d, INT32_MAX, pick_vec(d.k > 0 ? d.k : 4), h->key.p, h->occ_idx.p,
-                                              h->occ_row.p, h->sflags.p);
+    k_prep_rows<<<grid, 256, 0, h->compute>>>(b, d, h->key.p, h->occ_idx.p, h->occ_row.p, h->sflags.p,
+                                              h->batch_flags.p);
     FTRL_CUDA(cudaGetLastError());
     launched(h, PH_PREP);
   }
@@ -356,19 +405,20 @@ static void run_prep(ftrl_handle *h, const Batch &b) {
   }
   {
     PhaseScope ps(h, PH_SEGMENT);
+    const int fuse = (d.model_type == FTRL_FFM && h->fuse) ? 1 : 0;
+    k_occ_class<<<(nnz + 255) / 256, 256, 0, h->compute>>>(nnz, sentinel, fuse, h->skey.p, h->socc.p, h->occ_row.p,
+                                                           h->sflags.p, h->fused_sorted.p, h->occ_pos.p);
+    launched(h, PH_SEGMENT);
     size_t bytes = h->cub_bytes;
     thrust::counting_iterator<int32_t> cnt(0);
-    auto it = thrust::make_transform_iterator(cnt, HeadFunctor{h->skey.p});
+    auto it = thrust::make_transform_iterator(cnt, HeadFunctor{h->skey.p, h->fused_sorted.p});
     FTRL_CUDA(cub::DeviceScan::InclusiveScan(h->cub_tmp.p, bytes, it, h->scan.p, SegScanOp(), nnz, h->compute));
     bytes = h->cub_bytes;
     FTRL_CUDA(cub::DeviceSelect::If(h->cub_tmp.p, bytes, cnt, h->chunk_pos.p, h->n_chunks.p, nnz,
-                                    ChunkHeadPred{h->skey.p, h->scan.p, sentinel, h->chunk}, h->compute));
+                                    ChunkHeadPred{h->skey.p, h->scan.p, h->fused_sorted.p, sentinel, h->chunk},
+                                    h->compute));
     k_terminate<<<1, 1, 0, h->compute>>>(h->chunk_pos.p, h->n_chunks.p, nnz);
     launched(h, PH_SEGMENT);
-    if (d.model_type == FTRL_FFM && h->fuse) {
-      k_occ_class<<<(nnz + 255) / 256, 256, 0, h->compute>>>(nnz, sentinel, h->skey.p, h->socc.p, h->occ_single.p);
-      launched(h, PH_SEGMENT);
-    }
     FTRL_CUDA(cudaGetLastError());
   }
 }
@@ -411,12 +461,14 @@ static void train_device(ftrl_handle *h, const Batch &b, float *logit_out, doubl
     return;
   }
   run_prep(h, b);
+  if (!logit_out) logit_out = h->logit_ws.p;
   const bool pr = h->precise != 0;
   if (pr) run_model<true>(h, b, logit_out); else run_model<false>(h, b, logit_out);
   {
     PhaseScope ps(h, PH_REDUCE);
-    if (pr) k_batch_reduce<true><<<1, 1024, 0, h->compute>>>(b.n_rows, h->hyper, h->g.p, h->loss_s.p, h->bias, 1, loss_sum_out);
-    else k_batch_reduce<false><<<1, 1024, 0, h->compute>>>(b.n_rows, h->hyper, h->g.p, h->loss_s.p, h->bias, 1, loss_sum_out);
+    const int rg = reduce_grid(b.n_rows);
+    if (pr) k_batch_reduce<true><<<rg, 256, 0, h->compute>>>(b.n_rows, h->hyper, h->g.p, logit_out, b.label, h->bias, 1, h->red_part.p, h->ticket.p, loss_sum_out);
+    else k_batch_reduce<false><<<rg, 256, 0, h->compute>>>(b.n_rows, h->hyper, h->g.p, logit_out, b.label, h->bias, 1, h->red_part.p, h->ticket.p, loss_sum_out);
     FTRL_CUDA(cudaGetLastError());
     launched(h, PH_REDUCE);
   }
@@ -430,26 +482,28 @@ static void predict_device(ftrl_handle *h, const Batch &b, int output_prob, floa
   }
   ensure_workspace(h, b.n_rows, 0);
   const Dims &d = h->dims;
-  double *loss_s = loss_sum_out ? h->loss_s.p : nullptr;
+  // the loss needs raw logits: when probabilities are requested they go to the workspace
+  float *lg = loss_sum_out ? (output_prob ? h->logit_ws.p : out) : nullptr;
+  float *lg_side = (loss_sum_out && output_prob) ? h->logit_ws.p : nullptr;
   PhaseScope ps(h, PH_PREDICT);
   if (h->cfg.mode == FTRL_MODE_SEQUENTIAL) {
     k_exact_predict<<<(unsigned)((b.n_rows + 127) / 128), 128, 0, h->compute>>>(b, d, h->tab, h->lin, h->bias, output_prob,
-                                                                               out, loss_s);
+                                                                               out, lg_side);
   } else if (d.model_type == FTRL_FFM) {
     const int vec = pick_vec(d.k);
     const dim3 grid((unsigned)b.n_rows);
-    if (vec == 4) k_ffm_predict<4, 256><<<grid, 256, 0, h->compute>>>(b, d, h->tab, h->lin, h->bias, h->pair_lut, output_prob, out, loss_s);
-    else if (vec == 2) k_ffm_predict<2, 256><<<grid, 256, 0, h->compute>>>(b, d, h->tab, h->lin, h->bias, h->pair_lut, output_prob, out, loss_s);
-    else k_ffm_predict<1, 256><<<grid, 256, 0, h->compute>>>(b, d, h->tab, h->lin, h->bias, h->pair_lut, output_prob, out, loss_s);
+    if (vec == 4) k_ffm_predict<4, 256><<<grid, 256, 0, h->compute>>>(b, d, make_item_decode(d.k, 4), h->tab, h->lin, h->bias, h->pair_lut, output_prob, out, lg_side);
+    else if (vec == 2) k_ffm_predict<2, 256><<<grid, 256, 0, h->compute>>>(b, d, make_item_decode(d.k, 2), h->tab, h->lin, h->bias, h->pair_lut, output_prob, out, lg_side);
+    else k_ffm_predict<1, 256><<<grid, 256, 0, h->compute>>>(b, d, make_item_decode(d.k, 1), h->tab, h->lin, h->bias, h->pair_lut, output_prob, out, lg_side);
   } else {
     const unsigned grid = (unsigned)((b.n_rows * 32 + 255) / 256);
-    if (d.model_type == FTRL_FM) k_lrfm_predict<true><<<grid, 256, 0, h->compute>>>(b, d, h->tab, h->lin, h->bias, output_prob, out, loss_s);
-    else k_lrfm_predict<false><<<grid, 256, 0, h->compute>>>(b, d, h->tab, h->lin, h->bias, output_prob, out, loss_s);
+    if (d.model_type == FTRL_FM) k_lrfm_predict<true><<<grid, 256, 0, h->compute>>>(b, d, h->tab, h->lin, h->bias, output_prob, out, lg_side);
+    else k_lrfm_predict<false><<<grid, 256, 0, h->compute>>>(b, d, h->tab, h->lin, h->bias, output_prob, out, lg_side);
   }
   FTRL_CUDA(cudaGetLastError());
   launched(h, PH_PREDICT);
   if (loss_sum_out) {
-    k_batch_reduce<true><<<1, 1024, 0, h->compute>>>(b.n_rows, h->hyper, nullptr, loss_s, h->bias, 0, loss_sum_out);
+    k_batch_reduce<true><<<reduce_grid(b.n_rows), 256, 0, h->compute>>>(b.n_rows, h->hyper, nullptr, lg, b.label, h->bias, 0, h->red_part.p, h->ticket.p, loss_sum_out);
     FTRL_CUDA(cudaGetLastError());
     launched(h, PH_PREDICT);
   }
@@ -595,16 +649,44 @@ int ftrl_create(const ftrl_config *cfg, ftrl_handle **out) {
     d.row_len = (int32_t)rl;
     d.ld = (int32_t)((rl + 3) / 4 * 4);
     h->hyper = Hyper{cfg->w_alpha, cfg->w_beta, cfg->w_l1, cfg->w_l2, 1.0f / cfg->w_alpha};
-    static const char *names[PH_COUNT] = {"prep_rows", "sort", "segment", "sample", "rows", "combine", "reduce", "exact", "predict", "h2d"};
+    static const char *names[PH_COUNT] = {"prep_rows", "sort", "segment", "sample", "rows", "combine", "reduce", "exact", "predict", "generic"};
     for (int i = 0; i < PH_COUNT; i++) h->phases[i].name = names[i];
     cudaDeviceProp prop;
     FTRL_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
     h->n_sms = prop.multiProcessorCount;
     h->fuse = env_int("FTRL_B200_FUSE", 1);
     h->sample_threads = env_int("FTRL_B200_SAMPLE_THREADS", 0);
-    h->precise = env_int("FTRL_B200_PRECISE", 1);
+    h->precise = env_int("FTRL_B200_PRECISE", 0);
     h->chunk = env_int("FTRL_B200_CHUNK", cfg->model_type == FTRL_FFM ? 32 : cfg->model_type == FTRL_FM ? 256 : 2048);
     if (h->chunk < 1) h->chunk = 1;
+    if (cfg->model_type == FTRL_FFM && h->chunk > 32) h->chunk = 32;  // chunk ends are found with one ballot
+    h->tile = env_int("FTRL_B200_TILE", 1);
+    if (cfg->model_type == FTRL_FFM && h->tile && h->fuse && d.k % 4 == 0 && d.n_fields <= FFM_CAP) {
+      const int stride = tile_stride(d.ld, d.k);
+      const size_t stage = tile_stage_bytes(d.n_fields, stride);
+      const size_t budget = (size_t)prop.sharedMemPerBlockOptin - 2048;  // static mbarriers / reduction scratch
+      const int64_t items = (int64_t)d.n_fields * (d.n_fields - 1) / 2 * (d.k / 4);
+      int cons = 64;
+      while (cons < 512 && cons * 3 < items) cons *= 2;
+      cons = env_int("FTRL_B200_TILE_CONSUMERS", cons);
+      if (2 * stage <= budget) {
+        int ctas = (int)std::min<size_t>(8, (size_t)prop.sharedMemPerMultiprocessor / (2 * stage + 1024));
+        ctas = std::max(1, std::min(ctas, 2048 / (cons + 32)));
+        ctas = env_int("FTRL_B200_TILE_CTAS", ctas);
+        int stages = (int)std::min<size_t>(4, ((size_t)prop.sharedMemPerMultiprocessor / ctas - 1024) / stage);
+        stages = std::max(2, std::min(stages, (int)(budget / stage)));
+        stages = env_int("FTRL_B200_TILE_STAGES", stages);
+        h->tile_ok = true;
+        h->tile_f_cap = d.n_fields;
+        h->tile_stride = stride;
+        h->tile_stages = stages;
+        h->tile_consumers = cons;
+        h->tile_ctas_per_sm = ctas;
+        h->tile_smem = stage * stages;
+        FTRL_CUDA(cudaFuncSetAttribute(k_ffm_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->tile_smem));
+        FTRL_CUDA(cudaFuncSetAttribute(k_ffm_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->tile_smem));
+      }
+    }
     FTRL_CUDA(cudaStreamCreateWithFlags(&h->compute, cudaStreamNonBlocking));
     FTRL_CUDA(cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking));
     const int64_t n = d.n_feats;
@@ -1004,7 +1086,7 @@ int ftrl_last_batch_stats(ftrl_handle *h, ftrl_batch_stats *out) {
     if (nnz > 0) {
       const bool have_single = h->dims.model_type == FTRL_FFM && h->fuse;
       k_batch_stats<<<256, 256, 0, h->compute>>>(nnz, (uint32_t)h->dims.n_feats, h->skey.p, h->scan.p,
-                                                 have_single ? h->occ_single.p : nullptr, h->n_chunks.p, tmp.p);
+                                                 have_single ? h->fused_sorted.p : nullptr, h->n_chunks.p, tmp.p);
       FTRL_CUDA(cudaGetLastError());
     }
     int64_t r[4] = {0, 0, 0, 0};

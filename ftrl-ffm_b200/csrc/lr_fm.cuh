@@ -20,7 +20,7 @@ template <int VEC, bool PRECISE, bool IS_FM>
 __global__ void __launch_bounds__(256)
 k_lrfm_sample(Batch b, Dims d, Hyper h, float *__restrict__ tab, float4 *__restrict__ lin,
               const float4 *__restrict__ bias, float *__restrict__ S, float *__restrict__ g_out,
-              float *__restrict__ logit_out, double *__restrict__ loss_out) {
+              float *__restrict__ logit_out) {
   const int lane = threadIdx.x & 31;
   const int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (s >= b.n_rows) return;
@@ -91,8 +91,7 @@ k_lrfm_sample(Batch b, Dims d, Hyper h, float *__restrict__ tab, float4 *__restr
     logit += weight_from<PRECISE>(bz.x, f_sqrt<PRECISE>(bz.y), h);
     const int y = b.label[s];
     g_out[s] = sigmoid_f(logit) - (float)y;
-    if (logit_out) logit_out[s] = logit;
-    loss_out[s] = logloss_d(y, logit);
+    logit_out[s] = logit;
   }
 }
 
@@ -117,7 +116,7 @@ k_lrfm_rows(Batch b, Dims d, Hyper h, float *__restrict__ tab, float4 *__restric
   const int32_t nnz = (int32_t)b.nnz;
   const uint32_t sentinel = (uint32_t)d.n_feats;
   for (int c = blockIdx.x * WARPS + wib; c < n_chunks; c += gridDim.x * WARPS) {
-    const ChunkInfo ci = chunk_info(c, nnz, sentinel, ch, chunk_pos, skey, scan);
+    const ChunkInfo ci = chunk_info<false>(c, nnz, sentinel, ch, chunk_pos, skey, scan);
     if (!ci.valid) continue;
     const bool whole_row = ci.row_head && ci.row_last;
     // linear coordinate
@@ -202,7 +201,7 @@ k_lrfm_combine(Dims d, Hyper h, int32_t nnz, float *__restrict__ tab, float4 *__
   const int n_chunks = *n_chunks_p;
   const uint32_t sentinel = (uint32_t)d.n_feats;
   for (int c = blockIdx.x * WARPS + wib; c < n_chunks; c += gridDim.x * WARPS) {
-    const ChunkInfo ci = chunk_info(c, nnz, sentinel, ch, chunk_pos, skey, scan);
+    const ChunkInfo ci = chunk_info<false>(c, nnz, sentinel, ch, chunk_pos, skey, scan);
     if (!ci.valid || !ci.row_head || ci.row_last) continue;
     int J = 1;
     while (c + J < n_chunks && skey[chunk_pos[c + J]] == ci.key) J++;
@@ -239,7 +238,7 @@ template <bool IS_FM>
 __global__ void __launch_bounds__(256)
 k_lrfm_predict(Batch b, Dims d, const float *__restrict__ tab, const float4 *__restrict__ lin,
                const float4 *__restrict__ bias, int output_prob, float *__restrict__ out,
-               double *__restrict__ loss_out) {
+               float *__restrict__ logit_out) {
   const int lane = threadIdx.x & 31;
   const int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (s >= b.n_rows) return;
@@ -268,47 +267,66 @@ k_lrfm_predict(Batch b, Dims d, const float *__restrict__ tab, const float4 *__r
   if (lane == 0) {
     logit += bias->z;
     out[s] = output_prob ? sigmoid_f(logit) : logit;
-    if (loss_out) loss_out[s] = b.label ? logloss_d(b.label[s], logit) : 0.0;
+    if (logit_out) logit_out[s] = logit;
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-// batch-level reduction (single CTA, deterministic): sum g, sum g^2 -> bias update
-// (ftrl_model.cpp:61-64, 79-85 telescoped), and the fp64 loss sum (ftrl_offline.cpp:72-82,101).
+// batch-level reduction, deterministic: per-CTA partial sums of g, g^2 (bias update,
+// ftrl_model.cpp:61-64, 79-85 telescoped) and of the fp64 log-loss (eval/loss.h:8-12,
+// ftrl_offline.cpp:72-82,101) computed here from the logits; the last CTA to finish adds the
+// partials in CTA order and applies the bias update.
 // ---------------------------------------------------------------------------------------------
+constexpr int RED_MAX_CTAS = 256;
+
 template <bool PRECISE>
-__global__ void __launch_bounds__(1024)
-k_batch_reduce(int64_t n_rows, Hyper h, const float *__restrict__ g, const double *__restrict__ loss_s,
-               float4 *__restrict__ bias, int update_bias, double *__restrict__ loss_sum_out) {
-  __shared__ double sh[3][32];
+__global__ void __launch_bounds__(256)
+k_batch_reduce(int64_t n_rows, Hyper h, const float *__restrict__ g, const float *__restrict__ logit,
+               const int32_t *__restrict__ label, float4 *__restrict__ bias, int update_bias,
+               double *__restrict__ partials, unsigned int *__restrict__ ticket,
+               double *__restrict__ loss_sum_out) {
+  __shared__ double sh[3][8];
+  __shared__ bool s_last;
+  const int64_t per = (n_rows + gridDim.x - 1) / gridDim.x;
+  const int64_t i0 = (int64_t)blockIdx.x * per, i1 = min(n_rows, i0 + per);
   double a = 0.0, q = 0.0, l = 0.0;
-  for (int64_t i = threadIdx.x; i < n_rows; i += blockDim.x) {
+  for (int64_t i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
     if (g) {
-      const double gi = (double)g[i];
-      a += gi;
+      a += (double)g[i];
       q += (double)(g[i] * g[i]);
     }
-    if (loss_s) l += loss_s[i];
+    if (label && logit) l += logloss_d(label[i], logit[i]);
   }
   a = warp_sum_d(a); q = warp_sum_d(q); l = warp_sum_d(l);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   if (lane == 0) { sh[0][wid] = a; sh[1][wid] = q; sh[2][wid] = l; }
   __syncthreads();
-  if (wid == 0) {
-    const int nw = blockDim.x >> 5;
-    a = lane < nw ? sh[0][lane] : 0.0;
-    q = lane < nw ? sh[1][lane] : 0.0;
-    l = lane < nw ? sh[2][lane] : 0.0;
-    a = warp_sum_d(a); q = warp_sum_d(q); l = warp_sum_d(l);
-    if (lane == 0) {
-      if (update_bias && n_rows > 0) {
-        float4 e = *bias;
-        e.z = weight_from<PRECISE>(e.x, f_sqrt<PRECISE>(e.y), h);
-        ftrl_apply<PRECISE>(e.x, e.y, e.z, (float)a, (float)q, h);
-        *bias = e;
-      }
-      if (loss_sum_out) *loss_sum_out = l;
+  if (threadIdx.x == 0) {
+    a = q = l = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) { a += sh[0][w]; q += sh[1][w]; l += sh[2][w]; }
+    partials[3 * blockIdx.x + 0] = a;
+    partials[3 * blockIdx.x + 1] = q;
+    partials[3 * blockIdx.x + 2] = l;
+    __threadfence();
+    s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    __threadfence();
+    a = q = l = 0.0;
+    for (unsigned c = 0; c < gridDim.x; c++) {
+      a += __ldcg(partials + 3 * c + 0);
+      q += __ldcg(partials + 3 * c + 1);
+      l += __ldcg(partials + 3 * c + 2);
     }
+    if (update_bias && n_rows > 0) {
+      float4 e = *bias;
+      e.z = weight_from<PRECISE>(e.x, f_sqrt<PRECISE>(e.y), h);
+      ftrl_apply<PRECISE>(e.x, e.y, e.z, (float)a, (float)q, h);
+      *bias = e;
+    }
+    if (loss_sum_out) *loss_sum_out = l;
+    *ticket = 0u;
   }
 }
 

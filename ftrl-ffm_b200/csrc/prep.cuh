@@ -1,12 +1,14 @@
 // prep.cuh -- per-batch index work that turns "contended per-feature mutexes" of the reference
 // (ftrl_model.cpp:55,68; ffm.cpp:78,99-101,125) into a sort-by-key segmented reduction:
 //   1. k_prep_rows   : validity mask (remove_out_range, ftrl_model.cpp:36-42 / ffm.cpp:30-36),
-//                      sort key per occurrence, owning sample per occurrence, per-sample flags
+//                      sort key per occurrence, owning sample per occurrence, per-sample flags,
+//                      batch flag "every sample has distinct fields"
 //   2. radix sort    : (key = feature id, value = occurrence index)            [cub]
-//   3. segment scan  : per sorted position {row ordinal, row start}            [cub]
-//   4. chunk list    : rows cut into chunks of <= CH occurrences               [cub select]
-//   5. k_occ_class   : marks occurrences whose row occurs exactly once in the batch
-// All integer / index work, HBM-light (12-20 B per occurrence).
+//   3. k_occ_class   : per occurrence: finalised inside its sample (row occurs once in the batch)
+//                      or reduced through the sorted list (its sorted position)
+//   4. segment scan  : per sorted position {ordinal among segmented rows, row start}   [cub]
+//   5. chunk list    : segmented rows cut into chunks of <= CH occurrences             [cub select]
+// All integer / index work, HBM-light (about 30 B per occurrence).
 #pragma once
 #include <cub/cub.cuh>
 
@@ -27,11 +29,11 @@ struct Batch {
 
 enum : uint8_t {
   SF_SIMPLE = 1,   // all valid features of the sample have distinct fields
-  SF_FUSABLE = 2,  // simple and small enough for the fused per-sample finalize
+  SF_FUSABLE = 2,  // rows of this sample that occur once in the batch are finalised per sample
 };
 
 struct SegScan {
-  int32_t cnt;    // number of row heads at or before this sorted position (1-based row ordinal)
+  int32_t cnt;    // number of segmented-row heads at or before this sorted position
   int32_t start;  // sorted position of the head of this position's row
 };
 struct SegScanOp {
@@ -41,17 +43,20 @@ struct SegScanOp {
 };
 struct HeadFunctor {
   const uint32_t *skey;
+  const uint8_t *fused_sorted;  // 1: row finalised per sample, not part of the segmented list
   __device__ __forceinline__ SegScan operator()(int32_t p) const {
     const bool head = p == 0 || skey[p] != skey[p - 1];
-    return SegScan{head ? 1 : 0, head ? p : 0};
+    return SegScan{(head && !fused_sorted[p]) ? 1 : 0, head ? p : 0};
   }
 };
 struct ChunkHeadPred {
   const uint32_t *skey;
   const SegScan *scan;
+  const uint8_t *fused_sorted;
   uint32_t sentinel;
   int32_t ch;
   __device__ __forceinline__ bool operator()(int32_t p) const {
+    if (fused_sorted[p]) return false;
     const SegScan s = scan[p];
     if (s.start == p) return true;  // row head (also the head of the sentinel run)
     return skey[p] != sentinel && ((p - s.start) % ch) == 0;
@@ -64,16 +69,15 @@ __device__ __forceinline__ bool feat_valid(const Dims &d, int32_t fld, int32_t f
   return ok;
 }
 
-// warp per sample
-__global__ void k_prep_rows(Batch b, Dims d, int32_t fuse_item_cap, int32_t vec, uint32_t *__restrict__ key,
-                            uint32_t *__restrict__ occ_idx, int32_t *__restrict__ occ_row,
-                            uint8_t *__restrict__ sflags) {
+// warp per sample.  batch_flags[0] is cleared to 0 when some sample repeats a field.
+__global__ void k_prep_rows(Batch b, Dims d, uint32_t *__restrict__ key, uint32_t *__restrict__ occ_idx,
+                            int32_t *__restrict__ occ_row, uint8_t *__restrict__ sflags,
+                            int32_t *__restrict__ batch_flags) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (warp >= b.n_rows) return;
   const int64_t r0 = b.row_ptr[warp], r1 = b.row_ptr[warp + 1];
   bool simple = true;
-  int n_valid = 0;
   uint64_t seen = 0;  // field bitmask when n_fields <= 64
   for (int64_t base = r0; base < r1; base += 32) {
     const int64_t t = base + lane;
@@ -88,7 +92,6 @@ __global__ void k_prep_rows(Batch b, Dims d, int32_t fuse_item_cap, int32_t vec,
       occ_row[t] = (int32_t)warp;
     }
     const unsigned okmask = __ballot_sync(0xffffffffu, ok);
-    n_valid += __popc(okmask);
     if (d.model_type == 2) {
       // duplicates inside this group of 32
       const unsigned same = __match_any_sync(0xffffffffu, ok ? fld : -1 - lane);
@@ -109,32 +112,36 @@ __global__ void k_prep_rows(Batch b, Dims d, int32_t fuse_item_cap, int32_t vec,
   }
   simple = __all_sync(0xffffffffu, simple);
   if (lane == 0) {
-    uint8_t f = 0;
-    if (simple) f |= SF_SIMPLE;
-    if (d.model_type == 2) {
-      const int64_t items = (int64_t)n_valid * (n_valid - 1) / 2 * ((d.k + vec - 1) / vec);
-      if (simple && items <= fuse_item_cap) f |= SF_FUSABLE;
-    } else {
-      f |= SF_FUSABLE;
-    }
-    sflags[warp] = f;
+    sflags[warp] = simple ? (SF_SIMPLE | SF_FUSABLE) : 0;
+    if (!simple) batch_flags[0] = 0;
   }
 }
 
-// chunk_pos[n_chunks] = nnz (terminator so chunk c ends at chunk_pos[c+1])
+// chunk_pos[n_chunks] = nnz (terminator so chunk c of the LR/FM kernels ends at chunk_pos[c+1])
 __global__ void k_terminate(int32_t *chunk_pos, const int32_t *n_chunks, int32_t nnz) {
   chunk_pos[*n_chunks] = nnz;
 }
 
-// occ_single[t] = 1 iff the row of occurrence t occurs exactly once in this batch
-__global__ void k_occ_class(int32_t nnz, uint32_t sentinel, const uint32_t *__restrict__ skey,
-                            const uint32_t *__restrict__ socc, uint8_t *__restrict__ occ_single) {
+// Classifies every occurrence from the sorted list.  A row that occurs exactly once in the batch,
+// in a sample with distinct fields, is "fused": its update is finalised by the per-sample kernel.
+//   fused_sorted[p] = 1 for such rows (p = sorted position)
+//   occ_pos[t]      = -1 when occurrence t is fused, else its sorted position p
+__global__ void k_occ_class(int32_t nnz, uint32_t sentinel, int fuse, const uint32_t *__restrict__ skey,
+                            const uint32_t *__restrict__ socc, const int32_t *__restrict__ occ_row,
+                            const uint8_t *__restrict__ sflags, uint8_t *__restrict__ fused_sorted,
+                            int32_t *__restrict__ occ_pos) {
   const int32_t p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= nnz) return;
   const uint32_t k = skey[p];
-  const bool head = p == 0 || skey[p - 1] != k;
-  const bool last = p + 1 == nnz || skey[p + 1] != k;
-  occ_single[socc[p]] = (k != sentinel && head && last) ? 1 : 0;
+  const uint32_t t = socc[p];
+  bool fused = false;
+  if (fuse && k != sentinel) {
+    const bool head = p == 0 || skey[p - 1] != k;
+    const bool last = p + 1 == nnz || skey[p + 1] != k;
+    fused = head && last && (sflags[occ_row[t]] & SF_FUSABLE);
+  }
+  fused_sorted[p] = fused ? 1 : 0;
+  occ_pos[t] = fused ? -1 : p;
 }
 
 // everything a chunk-level kernel needs to know about chunk c
@@ -148,22 +155,54 @@ struct ChunkInfo {
   int32_t slot;      // partial-sum slot (meaningful when the row has > 1 chunk)
 };
 
+// EXPLICIT_END: the chunk list skips fused rows, so the end of a chunk is found from the keys
+// (warp-cooperative, ch <= 32); otherwise the chunk ends where the next listed chunk starts.
+template <bool EXPLICIT_END>
 __device__ __forceinline__ ChunkInfo chunk_info(int32_t c, int32_t nnz, uint32_t sentinel, int32_t ch,
                                                 const int32_t *__restrict__ chunk_pos,
                                                 const uint32_t *__restrict__ skey,
                                                 const SegScan *__restrict__ scan) {
   ChunkInfo ci;
   ci.p0 = chunk_pos[c];
-  ci.p1 = chunk_pos[c + 1];
   ci.key = skey[ci.p0];
   ci.valid = ci.key != sentinel;
   const SegScan s = scan[ci.p0];
   ci.row_head = s.start == ci.p0;
-  ci.row_last = ci.p1 >= nnz || skey[ci.p1] != ci.key;
+  if (EXPLICIT_END) {
+    const int lane = threadIdx.x & 31;
+    const int32_t q = ci.p0 + lane;
+    const unsigned same = __ballot_sync(0xffffffffu, lane < ch && q < nnz && skey[q] == ci.key);
+    // keys are sorted: the run of equal keys starting at p0 is contiguous
+    const int n_occ = __ffs(~same) - 1 < 0 ? 32 : __ffs(~same) - 1;
+    ci.p1 = ci.p0 + n_occ;
+    ci.row_last = n_occ < ch || ci.p1 >= nnz || skey[ci.p1] != ci.key;
+  } else {
+    ci.p1 = chunk_pos[c + 1];
+    ci.row_last = ci.p1 >= nnz || skey[ci.p1] != ci.key;
+  }
   ci.j = (ci.p0 - s.start) / ch;
   // extras (non-head chunks) strictly before this row's head = (c_first + 1) - row_ordinal
   const int32_t e0 = (c - ci.j + 1) - s.cnt;
   ci.slot = 2 * e0 + ci.j;
+  return ci;
+}
+
+// per-thread variant for chunks that are row heads (used to find rows spanning several chunks):
+// such a row continues past its first chunk iff position p0 + ch still carries its key.
+__device__ __forceinline__ ChunkInfo chunk_head_info(int32_t c, int32_t nnz, uint32_t sentinel, int32_t ch,
+                                                     const int32_t *__restrict__ chunk_pos,
+                                                     const uint32_t *__restrict__ skey,
+                                                     const SegScan *__restrict__ scan) {
+  ChunkInfo ci;
+  ci.p0 = chunk_pos[c];
+  ci.key = skey[ci.p0];
+  ci.valid = ci.key != sentinel;
+  const SegScan s = scan[ci.p0];
+  ci.row_head = s.start == ci.p0;
+  ci.p1 = ci.p0 + ch;
+  ci.row_last = ci.p1 >= nnz || skey[ci.p1] != ci.key;
+  ci.j = (ci.p0 - s.start) / ch;
+  ci.slot = 2 * ((c - ci.j + 1) - s.cnt) + ci.j;
   return ci;
 }
 
