@@ -20,6 +20,7 @@ namespace ftrl {
 constexpr int FFM_CAP = 128;               // features of a sample cached in shared memory
 constexpr int PAIR_LUT_N = FFM_CAP * (FFM_CAP - 1) / 2;
 constexpr int FFM_MAX_F = 32768;           // pairs are indexed with 32 bits
+constexpr int FFM_SPB = 8;                 // samples walked by one CTA of the generic sample kernel
 
 // flat pair index p (n-major: p = n(n-1)/2 + m, m < n) -> (m, n); independent of F
 __device__ __forceinline__ void pair_decode(uint32_t p, const uint32_t *__restrict__ lut, int &m, int &n) {
@@ -92,7 +93,9 @@ k_ffm_sample(Batch b, Dims d, Hyper h, ItemDecode dec, float *__restrict__ tab, 
   __shared__ float red[33];
   __shared__ float s_g;
   const int tid = threadIdx.x;
-  const int64_t s = blockIdx.x;
+  // each CTA walks FFM_SPB consecutive samples (keeps the grid, hence the cost of a skipped launch, small)
+  for (int64_t s = (int64_t)blockIdx.x * FFM_SPB; s < min(b.n_rows, ((int64_t)blockIdx.x + 1) * FFM_SPB); s++) {
+  __syncthreads();  // shared sample cache / reduction scratch of the previous sample are free
   const int64_t r0 = b.row_ptr[s];
   int F = (int)min((int64_t)FFM_MAX_F, b.row_ptr[s + 1] - r0);
   const bool fusable = fuse != 0;  // per occurrence: occ_pos < 0 <=> finalised here
@@ -166,7 +169,7 @@ k_ffm_sample(Batch b, Dims d, Hyper h, ItemDecode dec, float *__restrict__ tab, 
     g_out[s] = g;
     logit_out[s] = logit;
   }
-  if (!fusable) return;
+  if (!fusable) continue;
   __syncthreads();
   const float g = s_g;
 
@@ -222,6 +225,7 @@ k_ffm_sample(Batch b, Dims d, Hyper h, ItemDecode dec, float *__restrict__ tab, 
     ftrl_apply<PRECISE>(e.x, e.y, e.z, gi, gi * gi, h);
     lin[ft] = e;
   }
+  }  // sample loop
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -78,29 +78,45 @@ __device__ __forceinline__ void named_bar_sync(int id, int n_threads) {
 }
 
 // ---- tile geometry ------------------------------------------------------------------------------
+constexpr int TILE_META_WARPS = 2;   // warps prefetching sample metadata (CSR, occurrence class, linear records)
+constexpr int TILE_MAX_STAGE = 4;    // row stages
+constexpr int TILE_MAX_META = 8;     // metadata slots
+
 struct TileGeom {
   int f_cap;        // rows per stage (= n_fields: samples with distinct fields have at most that many)
   int stride;       // floats between consecutive rows of a stage (2*ld + pad), conflict-free columns
-  int n_stage;
+  int n_stage;      // row stages (each f_cap * stride floats)
+  int n_meta;       // metadata slots (> n_stage: metadata runs ahead of the row ring)
   int consumers;    // consumer threads (multiple of 32)
   size_t smem_bytes;
 };
 
-struct StageMeta {  // per stage, per row slot (arrays of f_cap entries each, laid out by tile_smem_layout)
-  int32_t *feat;    // feature id
-  int32_t *fk;      // field * k
-  float *x;         // value
-  int32_t *pos;     // -1: row finalised here, >= 0: sorted position for the staged gradient image
-  float4 *lin;      // {z, n, w, -} of the linear coordinate, prefetched by the producer
+struct RowMeta {   // one 16-byte record per row of a sample
+  int32_t fk;      // field * k
+  float x;         // value
+  int32_t pos;     // -1: row finalised here, >= 0: sorted position for the staged gradient image
+  int32_t feat;    // feature id
+};
+struct SampleMeta {
+  RowMeta *row;     // [f_cap]
+  float4 *lin;      // [f_cap] {z, n, w, -} of the linear coordinate, prefetched
+  int32_t *hdr;     // [0] n valid rows, [1] label
   uint8_t *present; // [n_fields] 1 when some valid row of the sample carries that field
 };
 
 __host__ __device__ inline size_t tile_meta_bytes(int f_cap) {
-  // feat, fk, x, pos (4 B each) + lin (16 B) per row, + header (n valid, label) 16 B, + present[f_cap]
-  return (size_t)f_cap * (4 * 4 + 16) + 16 + (size_t)((f_cap + 15) / 16) * 16;
+  // RowMeta (16 B) + lin (16 B) per row, + header 16 B, + present[f_cap] rounded to 16
+  return (size_t)f_cap * 32 + 16 + (size_t)((f_cap + 15) / 16) * 16;
 }
 __host__ __device__ inline size_t tile_stage_bytes(int f_cap, int stride) {
-  return (size_t)f_cap * stride * sizeof(float) + ((tile_meta_bytes(f_cap) + 15) / 16) * 16;
+  return (size_t)f_cap * stride * sizeof(float);
+}
+// the pair table (m | n << 8) as uint16 for f_cap rows
+__host__ __device__ inline size_t tile_lut_bytes(int f_cap) {
+  return (((size_t)f_cap * (f_cap - 1) / 2 * 2) + 15) / 16 * 16;
+}
+__host__ __device__ inline size_t tile_smem_bytes(int f_cap, int stride, int n_stage, int n_meta) {
+  return tile_stage_bytes(f_cap, stride) * n_stage + tile_meta_bytes(f_cap) * n_meta + tile_lut_bytes(f_cap);
 }
 
 // choose stride = 2*ld + pad (floats) such that column accesses of consecutive rows by the lanes of
@@ -127,47 +143,64 @@ __host__ inline int tile_stride(int ld, int k) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_ffm_tile
+// k_ffm_tile.  IPT = items (pair, factor chunk) per consumer thread; w of pass 1 is kept in registers
+// for pass 2 (IPT * 8 floats).
 // ---------------------------------------------------------------------------------------------
 template <bool PRECISE>
-__global__ void __launch_bounds__(576, 1)
+__device__ __forceinline__ float4 weight4(const float4 &z, const float4 &n, const Hyper &h) {
+  return make_float4(weight_from<PRECISE>(z.x, f_sqrt<PRECISE>(n.x), h), weight_from<PRECISE>(z.y, f_sqrt<PRECISE>(n.y), h),
+                     weight_from<PRECISE>(z.z, f_sqrt<PRECISE>(n.z), h), weight_from<PRECISE>(z.w, f_sqrt<PRECISE>(n.w), h));
+}
+template <bool PRECISE>
+__device__ __forceinline__ void apply4(float4 &z, float4 &n, const float4 &w, const float4 &wp, float gx, const Hyper &h) {
+  float gv;
+  gv = gx * wp.x; ftrl_apply<PRECISE>(z.x, n.x, w.x, gv, gv * gv, h);
+  gv = gx * wp.y; ftrl_apply<PRECISE>(z.y, n.y, w.y, gv, gv * gv, h);
+  gv = gx * wp.z; ftrl_apply<PRECISE>(z.z, n.z, w.z, gv, gv * gv, h);
+  gv = gx * wp.w; ftrl_apply<PRECISE>(z.w, n.w, w.w, gv, gv * gv, h);
+}
+
+// Thread roles: [0, consumers) compute; warp `consumers/32` is the row producer (bulk loads / bulk
+// stores of the row ring); the next TILE_META_WARPS warps prefetch sample metadata into a deeper
+// ring so that the row producer never waits on a dependent global-load chain.
+template <bool PRECISE, int IPT>
+__global__ void __launch_bounds__(512 + 32 + 32 * TILE_META_WARPS, 1)
 k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t *__restrict__ batch_flags, float *__restrict__ tab,
            float4 *__restrict__ lin, const float4 *__restrict__ bias, const uint32_t *__restrict__ pair_lut,
            const int32_t *__restrict__ occ_pos, float *__restrict__ staging, float *__restrict__ staging_lin,
            float *__restrict__ g_out, float *__restrict__ logit_out) {
   if (batch_flags[0] == 0) return;  // some sample repeats a field: the generic kernels take this batch
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  constexpr int MAX_STAGE = 8;
-  __shared__ uint64_t bar_full[MAX_STAGE], bar_done[MAX_STAGE];
+  __shared__ uint64_t bar_full[TILE_MAX_STAGE], bar_done[TILE_MAX_STAGE];
+  __shared__ uint64_t bar_mfull[TILE_MAX_META], bar_mfree[TILE_MAX_META];
   __shared__ float s_red[40];
 
   const int tid = threadIdx.x;
   const int n_cons = geo.consumers;
   const int n_cons_warps = n_cons >> 5;
-  const bool is_producer = tid >= n_cons;  // last warp
   const int lane = tid & 31;
+  const int role = tid < n_cons ? 0 : (tid < n_cons + 32 ? 1 : 2);  // 0 consumer, 1 row producer, 2 meta
   const int ld = d.ld, k = d.k;
-  const int stride = geo.stride, f_cap = geo.f_cap, NS = geo.n_stage;
+  const int stride = geo.stride, f_cap = geo.f_cap, NS = geo.n_stage, MD = geo.n_meta;
   const size_t stage_bytes = tile_stage_bytes(f_cap, stride);
+  const size_t meta_bytes = tile_meta_bytes(f_cap);
   const int64_t rs = 3 * (int64_t)ld;
   const uint32_t row_bytes = (uint32_t)(2 * ld * sizeof(float));
+  unsigned char *meta_base = smem_raw + (size_t)NS * stage_bytes;
+  uint16_t *s_lut = reinterpret_cast<uint16_t *>(meta_base + (size_t)MD * meta_bytes);
 
   auto stage_rows = [&](int st) -> float * { return reinterpret_cast<float *>(smem_raw + (size_t)st * stage_bytes); };
-  auto stage_meta = [&](int st, StageMeta &m, int32_t *&hdr) {
-    unsigned char *p = smem_raw + (size_t)st * stage_bytes + (size_t)f_cap * stride * sizeof(float);
+  auto sample_meta = [&](int slot) {
+    SampleMeta m;
+    unsigned char *p = meta_base + (size_t)slot * meta_bytes;
+    m.row = reinterpret_cast<RowMeta *>(p);
+    p += (size_t)f_cap * 16;
     m.lin = reinterpret_cast<float4 *>(p);
     p += (size_t)f_cap * 16;
-    m.feat = reinterpret_cast<int32_t *>(p);
-    p += (size_t)f_cap * 4;
-    m.fk = reinterpret_cast<int32_t *>(p);
-    p += (size_t)f_cap * 4;
-    m.x = reinterpret_cast<float *>(p);
-    p += (size_t)f_cap * 4;
-    m.pos = reinterpret_cast<int32_t *>(p);
-    p += (size_t)f_cap * 4;
-    hdr = reinterpret_cast<int32_t *>(p);  // [0] n valid rows, [1] label
+    m.hdr = reinterpret_cast<int32_t *>(p);
     p += 16;
     m.present = p;
+    return m;
   };
 
   if (tid == 0) {
@@ -175,76 +208,103 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
       mbar_init(&bar_full[st], 1);
       mbar_init(&bar_done[st], n_cons_warps);
     }
+    for (int sl = 0; sl < MD; sl++) {
+      mbar_init(&bar_mfull[sl], 1);
+      mbar_init(&bar_mfree[sl], 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int p = tid; p < f_cap * (f_cap - 1) / 2; p += blockDim.x) {
+    const uint32_t e = pair_lut[p];
+    s_lut[p] = (uint16_t)((e & 0xffu) | ((e >> 16) << 8));
   }
   __syncthreads();
 
   const int64_t n_mine = b.n_rows > blockIdx.x ? (b.n_rows - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
-  if (is_producer) {
-    // =========================== producer warp ===========================
+  if (role == 2) {
+    // =========================== metadata warps ===========================
+    const int mw = (tid - n_cons - 32) >> 5;
+    for (int64_t it = mw; it < n_mine; it += TILE_META_WARPS) {
+      const int slot = (int)(it % MD);
+      if (it >= MD) mbar_wait(&bar_mfree[slot], (uint32_t)(((it / MD) - 1) & 1));
+      SampleMeta m = sample_meta(slot);
+      const int64_t s = blockIdx.x + it * gridDim.x;
+      const int64_t r0 = b.row_ptr[s];
+      const int F = (int)min((int64_t)1 << 20, b.row_ptr[s + 1] - r0);
+      int nv = 0;
+      for (int f = lane; f < f_cap; f += 32) m.present[f] = 0;
+      __syncwarp();
+      for (int base = 0; base < F; base += 32) {
+        const int t = base + lane;
+        int32_t fl = 0, ft = -1;
+        float x = 0.f;
+        bool ok = false;
+        if (t < F) {
+          fl = b.field[r0 + t];
+          ft = b.feat[r0 + t];
+          x = b.val[r0 + t];
+          ok = feat_valid(d, fl, ft);
+        }
+        const unsigned okm = __ballot_sync(0xffffffffu, ok);
+        const int sl = nv + __popc(okm & ((1u << lane) - 1));
+        if (ok && sl < f_cap) {
+          RowMeta rm;
+          rm.fk = fl * k;
+          rm.x = x;
+          rm.pos = occ_pos[r0 + t];
+          rm.feat = ft;
+          m.row[sl] = rm;
+          m.lin[sl] = lin[ft];
+          m.present[fl] = 1;
+        }
+        nv += __popc(okm);
+      }
+      nv = min(nv, f_cap);
+      if (lane == 0) {
+        m.hdr[0] = nv;
+        m.hdr[1] = b.label[s];
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_mfull[slot]);
+    }
+    return;
+  }
+
+  if (role == 1) {
+    // =========================== row producer warp ===========================
     for (int64_t it = 0; it < n_mine + NS; it++) {
       const int st = (int)(it % NS);
       float *rows = stage_rows(st);
-      StageMeta m;
-      int32_t *hdr;
-      stage_meta(st, m, hdr);
       if (it >= NS) {
         // retire the sample that used this stage: wait for the consumers, then store its rows
-        mbar_wait(&bar_done[st], (uint32_t)(((it / NS) - 1) & 1));
-        const int nv = hdr[0];
+        const int64_t old = it - NS;
+        const int oslot = (int)(old % MD);
+        SampleMeta m = sample_meta(oslot);
+        mbar_wait(&bar_done[st], (uint32_t)((old / NS) & 1));
+        const int nv = m.hdr[0];
         for (int r = lane; r < nv; r += 32) {
-          const int32_t pos = m.pos[r];
-          if (pos < 0) {
-            bulk_s2g(tab + (int64_t)m.feat[r] * rs, rows + (size_t)r * stride, row_bytes);
+          const RowMeta rm = m.row[r];
+          if (rm.pos < 0) {
+            bulk_s2g(tab + (int64_t)rm.feat * rs, rows + (size_t)r * stride, row_bytes);
           } else {
-            bulk_s2g(staging + (int64_t)pos * ld, rows + (size_t)r * stride, (uint32_t)(ld * sizeof(float)));
+            bulk_s2g(staging + (int64_t)rm.pos * ld, rows + (size_t)r * stride, (uint32_t)(ld * sizeof(float)));
           }
         }
         bulk_commit();
         bulk_wait_read_all();
         __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_mfree[oslot]);
       }
       if (it < n_mine) {
-        const int64_t s = blockIdx.x + it * gridDim.x;
-        const int64_t r0 = b.row_ptr[s];
-        const int F = (int)min((int64_t)1 << 20, b.row_ptr[s + 1] - r0);
-        int nv = 0;
-        for (int f = lane; f < f_cap; f += 32) m.present[f] = 0;
-        __syncwarp();
-        for (int base = 0; base < F; base += 32) {
-          const int t = base + lane;
-          int32_t fl = 0, ft = -1;
-          float x = 0.f;
-          bool ok = false;
-          if (t < F) {
-            fl = b.field[r0 + t];
-            ft = b.feat[r0 + t];
-            x = b.val[r0 + t];
-            ok = feat_valid(d, fl, ft);
-          }
-          const unsigned okm = __ballot_sync(0xffffffffu, ok);
-          const int slot = nv + __popc(okm & ((1u << lane) - 1));
-          if (ok && slot < f_cap) {
-            m.feat[slot] = ft;
-            m.fk[slot] = fl * k;
-            m.x[slot] = x;
-            m.pos[slot] = occ_pos[r0 + t];
-            m.lin[slot] = lin[ft];
-            m.present[fl] = 1;
-          }
-          nv += __popc(okm);
-        }
-        nv = min(nv, f_cap);
-        if (lane == 0) {
-          hdr[0] = nv;
-          hdr[1] = b.label[s];
-        }
-        __syncwarp();
+        const int slot = (int)(it % MD);
+        mbar_wait(&bar_mfull[slot], (uint32_t)((it / MD) & 1));
+        SampleMeta m = sample_meta(slot);
+        const int nv = m.hdr[0];
         if (lane == 0) mbar_arrive_expect_tx(&bar_full[st], (uint32_t)nv * row_bytes);
         __syncwarp();
         for (int r = lane; r < nv; r += 32)
-          bulk_g2s(rows + (size_t)r * stride, tab + (int64_t)m.feat[r] * rs, row_bytes, &bar_full[st]);
+          bulk_g2s(rows + (size_t)r * stride, tab + (int64_t)m.row[r].feat * rs, row_bytes, &bar_full[st]);
       }
     }
     bulk_wait_all();
@@ -258,51 +318,44 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
   }();
   for (int64_t it = 0; it < n_mine; it++) {
     const int st = (int)(it % NS);
+    const int slot = (int)(it % MD);
     const int64_t s = blockIdx.x + it * gridDim.x;
     float *rows = stage_rows(st);
-    StageMeta m;
-    int32_t *hdr;
-    stage_meta(st, m, hdr);
+    SampleMeta m = sample_meta(slot);
+    mbar_wait(&bar_mfull[slot], (uint32_t)((it / MD) & 1));
     mbar_wait(&bar_full[st], (uint32_t)((it / NS) & 1));
-    const int nv = hdr[0];
+    const int nv = m.hdr[0];
     const uint32_t n_items = (uint32_t)nv * (uint32_t)(nv - 1) / 2u * dec.C;
 
     // ---- pass 1: w, logit ----
     float acc = 0.f;
-    for (uint32_t item = tid; item < n_items; item += n_cons) {
-      uint32_t p, c;
-      dec(item, p, c);
-      int mi, ni;
-      pair_decode(p, pair_lut, mi, ni);
-      const int fkm = m.fk[mi], fkn = m.fk[ni];
-      float *sa = rows + (size_t)mi * stride + fkn + c * 4;  // slice A = (row m, field n)
-      float *sb = rows + (size_t)ni * stride + fkm + c * 4;  // slice B = (row n, field m)
-      const float4 zA = *reinterpret_cast<const float4 *>(sa), nA = *reinterpret_cast<const float4 *>(sa + ld);
-      const float4 zB = *reinterpret_cast<const float4 *>(sb), nB = *reinterpret_cast<const float4 *>(sb + ld);
-      float4 wA, wB;
-      wA.x = weight_from<PRECISE>(zA.x, f_sqrt<PRECISE>(nA.x), h);
-      wA.y = weight_from<PRECISE>(zA.y, f_sqrt<PRECISE>(nA.y), h);
-      wA.z = weight_from<PRECISE>(zA.z, f_sqrt<PRECISE>(nA.z), h);
-      wA.w = weight_from<PRECISE>(zA.w, f_sqrt<PRECISE>(nA.w), h);
-      wB.x = weight_from<PRECISE>(zB.x, f_sqrt<PRECISE>(nB.x), h);
-      wB.y = weight_from<PRECISE>(zB.y, f_sqrt<PRECISE>(nB.y), h);
-      wB.z = weight_from<PRECISE>(zB.z, f_sqrt<PRECISE>(nB.z), h);
-      wB.w = weight_from<PRECISE>(zB.w, f_sqrt<PRECISE>(nB.w), h);
-      const float dot = fmaf(wA.x, wB.x, fmaf(wA.y, wB.y, fmaf(wA.z, wB.z, wA.w * wB.w)));
-      acc = fmaf(dot, m.x[mi] * m.x[ni], acc);
-      // the stale-by-one w the reference keeps (ffm.cpp:72-88)
-      *reinterpret_cast<float4 *>(tab + (int64_t)m.feat[mi] * rs + 2 * ld + fkn + c * 4) = wA;
-      *reinterpret_cast<float4 *>(tab + (int64_t)m.feat[ni] * rs + 2 * ld + fkm + c * 4) = wB;
+    float4 wAc[IPT], wBc[IPT];
+#pragma unroll
+    for (int j = 0; j < IPT; j++) {
+      const uint32_t item = tid + j * n_cons;
+      if (item < n_items) {
+        uint32_t p, c;
+        dec(item, p, c);
+        const uint32_t e = s_lut[p];
+        const int mi = e & 0xff, ni = e >> 8;
+        const RowMeta rmm = m.row[mi], rmn = m.row[ni];
+        const float *sa = rows + (size_t)mi * stride + rmn.fk + c * 4;  // slice A = (row m, field n)
+        const float *sb = rows + (size_t)ni * stride + rmm.fk + c * 4;  // slice B = (row n, field m)
+        const float4 zA = *reinterpret_cast<const float4 *>(sa), nA = *reinterpret_cast<const float4 *>(sa + ld);
+        const float4 zB = *reinterpret_cast<const float4 *>(sb), nB = *reinterpret_cast<const float4 *>(sb + ld);
+        const float4 wA = weight4<PRECISE>(zA, nA, h), wB = weight4<PRECISE>(zB, nB, h);
+        wAc[j] = wA;
+        wBc[j] = wB;
+        const float dot = fmaf(wA.x, wB.x, fmaf(wA.y, wB.y, fmaf(wA.z, wB.z, wA.w * wB.w)));
+        acc = fmaf(dot, rmm.x * rmn.x, acc);
+        // the stale-by-one w the reference keeps (ffm.cpp:72-88)
+        *reinterpret_cast<float4 *>(tab + (int64_t)rmm.feat * rs + 2 * ld + rmn.fk + c * 4) = wA;
+        *reinterpret_cast<float4 *>(tab + (int64_t)rmn.feat * rs + 2 * ld + rmm.fk + c * 4) = wB;
+      }
     }
-    float lin_w = 0.f;
-    if (tid < nv) {
-      const float4 e = m.lin[tid];
-      lin_w = weight_from<PRECISE>(e.x, f_sqrt<PRECISE>(e.y), h);
-      acc = fmaf(lin_w, m.x[tid], acc);
-    }
-    for (int r = tid + n_cons; r < nv; r += n_cons) {  // f_cap > consumers (not the usual case)
+    for (int r = tid; r < nv; r += n_cons) {
       const float4 e = m.lin[r];
-      acc = fmaf(weight_from<PRECISE>(e.x, f_sqrt<PRECISE>(e.y), h), m.x[r], acc);
+      acc = fmaf(weight_from<PRECISE>(e.x, f_sqrt<PRECISE>(e.y), h), m.row[r].x, acc);
     }
     // consumer-wide sum
     acc = warp_sum(acc);
@@ -313,7 +366,7 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
       t = warp_sum(t);
       if (lane == 0) {
         const float logit = t + bias_w;
-        const float g = sigmoid_f(logit) - (float)hdr[1];
+        const float g = sigmoid_f(logit) - (float)m.hdr[1];
         s_red[32] = g;
         g_out[s] = g;
         logit_out[s] = logit;
@@ -324,67 +377,59 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
 
     // ---- pass 2: FTRL update in place (fused rows) or gradient image into the z plane (staged rows);
     //      every (row, field) slice is read and written by exactly one item (fields are distinct) ----
-    for (uint32_t item = tid; item < n_items; item += n_cons) {
-      uint32_t p, c;
-      dec(item, p, c);
-      int mi, ni;
-      pair_decode(p, pair_lut, mi, ni);
-      const int fkm = m.fk[mi], fkn = m.fk[ni];
-      float *sa = rows + (size_t)mi * stride + fkn + c * 4;
-      float *sb = rows + (size_t)ni * stride + fkm + c * 4;
-      float4 zA = *reinterpret_cast<const float4 *>(sa), nA = *reinterpret_cast<const float4 *>(sa + ld);
-      float4 zB = *reinterpret_cast<const float4 *>(sb), nB = *reinterpret_cast<const float4 *>(sb + ld);
-      const float gx = g * (m.x[mi] * m.x[ni]);
-      float sqA[4] = {f_sqrt<PRECISE>(nA.x), f_sqrt<PRECISE>(nA.y), f_sqrt<PRECISE>(nA.z), f_sqrt<PRECISE>(nA.w)};
-      float sqB[4] = {f_sqrt<PRECISE>(nB.x), f_sqrt<PRECISE>(nB.y), f_sqrt<PRECISE>(nB.z), f_sqrt<PRECISE>(nB.w)};
-      float wA[4] = {weight_from<PRECISE>(zA.x, sqA[0], h), weight_from<PRECISE>(zA.y, sqA[1], h),
-                     weight_from<PRECISE>(zA.z, sqA[2], h), weight_from<PRECISE>(zA.w, sqA[3], h)};
-      float wB[4] = {weight_from<PRECISE>(zB.x, sqB[0], h), weight_from<PRECISE>(zB.y, sqB[1], h),
-                     weight_from<PRECISE>(zB.z, sqB[2], h), weight_from<PRECISE>(zB.w, sqB[3], h)};
-      if (m.pos[mi] < 0) {
-        float gv;
-        gv = gx * wB[0]; ftrl_apply_sq<PRECISE>(zA.x, nA.x, sqA[0], wA[0], gv, gv * gv, h);
-        gv = gx * wB[1]; ftrl_apply_sq<PRECISE>(zA.y, nA.y, sqA[1], wA[1], gv, gv * gv, h);
-        gv = gx * wB[2]; ftrl_apply_sq<PRECISE>(zA.z, nA.z, sqA[2], wA[2], gv, gv * gv, h);
-        gv = gx * wB[3]; ftrl_apply_sq<PRECISE>(zA.w, nA.w, sqA[3], wA[3], gv, gv * gv, h);
-        *reinterpret_cast<float4 *>(sa) = zA;
-        *reinterpret_cast<float4 *>(sa + ld) = nA;
-      } else {
-        *reinterpret_cast<float4 *>(sa) = make_float4(gx * wB[0], gx * wB[1], gx * wB[2], gx * wB[3]);
-      }
-      if (m.pos[ni] < 0) {
-        float gv;
-        gv = gx * wA[0]; ftrl_apply_sq<PRECISE>(zB.x, nB.x, sqB[0], wB[0], gv, gv * gv, h);
-        gv = gx * wA[1]; ftrl_apply_sq<PRECISE>(zB.y, nB.y, sqB[1], wB[1], gv, gv * gv, h);
-        gv = gx * wA[2]; ftrl_apply_sq<PRECISE>(zB.z, nB.z, sqB[2], wB[2], gv, gv * gv, h);
-        gv = gx * wA[3]; ftrl_apply_sq<PRECISE>(zB.w, nB.w, sqB[3], wB[3], gv, gv * gv, h);
-        *reinterpret_cast<float4 *>(sb) = zB;
-        *reinterpret_cast<float4 *>(sb + ld) = nB;
-      } else {
-        *reinterpret_cast<float4 *>(sb) = make_float4(gx * wA[0], gx * wA[1], gx * wA[2], gx * wA[3]);
+#pragma unroll
+    for (int j = 0; j < IPT; j++) {
+      const uint32_t item = tid + j * n_cons;
+      if (item < n_items) {
+        uint32_t p, c;
+        dec(item, p, c);
+        const uint32_t e = s_lut[p];
+        const int mi = e & 0xff, ni = e >> 8;
+        const RowMeta rmm = m.row[mi], rmn = m.row[ni];
+        float *sa = rows + (size_t)mi * stride + rmn.fk + c * 4;
+        float *sb = rows + (size_t)ni * stride + rmm.fk + c * 4;
+        const float gx = g * (rmm.x * rmn.x);
+        const float4 wA = wAc[j], wB = wBc[j];
+        if (rmm.pos < 0) {
+          float4 zA = *reinterpret_cast<const float4 *>(sa), nA = *reinterpret_cast<const float4 *>(sa + ld);
+          apply4<PRECISE>(zA, nA, wA, wB, gx, h);
+          *reinterpret_cast<float4 *>(sa) = zA;
+          *reinterpret_cast<float4 *>(sa + ld) = nA;
+        } else {
+          *reinterpret_cast<float4 *>(sa) = make_float4(gx * wB.x, gx * wB.y, gx * wB.z, gx * wB.w);
+        }
+        if (rmn.pos < 0) {
+          float4 zB = *reinterpret_cast<const float4 *>(sb), nB = *reinterpret_cast<const float4 *>(sb + ld);
+          apply4<PRECISE>(zB, nB, wB, wA, gx, h);
+          *reinterpret_cast<float4 *>(sb) = zB;
+          *reinterpret_cast<float4 *>(sb + ld) = nB;
+        } else {
+          *reinterpret_cast<float4 *>(sb) = make_float4(gx * wA.x, gx * wA.y, gx * wA.z, gx * wA.w);
+        }
       }
     }
     // linear coordinate: fused -> full update; staged -> w now, gradient to staging_lin
     for (int r = tid; r < nv; r += n_cons) {
       float4 e = m.lin[r];
+      const RowMeta rm = m.row[r];
       const float w = weight_from<PRECISE>(e.x, f_sqrt<PRECISE>(e.y), h);
-      const float gi = g * m.x[r];
-      const int32_t pos = m.pos[r];
-      if (pos < 0) {
+      const float gi = g * rm.x;
+      if (rm.pos < 0) {
         e.z = w;
         ftrl_apply<PRECISE>(e.x, e.y, w, gi, gi * gi, h);
-        lin[m.feat[r]] = e;
+        lin[rm.feat] = e;
       } else {
-        lin[m.feat[r]].z = w;
-        staging_lin[pos] = gi;
+        lin[rm.feat].z = w;
+        staging_lin[rm.pos] = gi;
       }
     }
     // staged rows: slices no partner touches (own field, absent fields) must read as 0 in the image.
     // They are disjoint from the slices written above, so no barrier is needed.
     for (int q = tid; q < nv * d.n_fields; q += n_cons) {
       const int r = q / d.n_fields, f = q - r * d.n_fields;
-      if (m.pos[r] < 0) continue;
-      if (m.present[f] && f * k != m.fk[r]) continue;
+      const RowMeta rm = m.row[r];
+      if (rm.pos < 0) continue;
+      if (m.present[f] && f * k != rm.fk) continue;
       float4 *zp = reinterpret_cast<float4 *>(rows + (size_t)r * stride + f * k);
       for (int v = 0; v < (k >> 2); v++) zp[v] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
@@ -397,7 +442,7 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
 // ---------------------------------------------------------------------------------------------
 // k_ffm_staged_rows: streaming segmented reduction over the staged gradient images
 // ---------------------------------------------------------------------------------------------
-template <bool PRECISE, int WARPS>
+template <bool PRECISE, int WARPS, int R>
 __global__ void __launch_bounds__(WARPS * 32)
 k_ffm_staged_rows(Dims d, Hyper h, int32_t nnz, const int32_t *__restrict__ batch_flags, float *__restrict__ tab,
                   float4 *__restrict__ lin, int32_t ch, const int32_t *__restrict__ n_chunks_p,
@@ -405,7 +450,7 @@ k_ffm_staged_rows(Dims d, Hyper h, int32_t nnz, const int32_t *__restrict__ batc
                   const SegScan *__restrict__ scan, const float *__restrict__ staging,
                   const float *__restrict__ staging_lin, float *__restrict__ part, float2 *__restrict__ part_lin) {
   if (batch_flags[0] == 0) return;
-  constexpr int R = 4;  // float4 accumulators per lane and pass: covers 512 floats of the row per pass
+  // R float4 accumulators per lane and pass: one pass covers 128*R floats of the row
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t ld = d.ld, rs = 3 * ld;
   const int n_chunks = *n_chunks_p;

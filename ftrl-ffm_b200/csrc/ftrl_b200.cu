@@ -262,7 +262,7 @@ static void launch_ffm_sample(ftrl_handle *h, const Batch &b, float *logit_out, 
   const double fbar = b.n_rows ? (double)b.nnz / (double)b.n_rows : 0.0;
   const double items = fbar * (fbar - 1) * 0.5 * (d.k / VEC);
   int threads = h->sample_threads ? h->sample_threads : items <= 64 ? 64 : items <= 256 ? 128 : items <= 1024 ? 256 : 512;
-  const dim3 grid((unsigned)b.n_rows);
+  const dim3 grid((unsigned)((b.n_rows + FFM_SPB - 1) / FFM_SPB));
   const ItemDecode dec = make_item_decode(d.k, VEC);
 #define FFM_SAMPLE(T)                                                                                          \
   k_ffm_sample<VEC, PRECISE, T><<<grid, T, 0, h->compute>>>(b, d, h->hyper, dec, h->tab, h->lin, h->bias, h->pair_lut, \
@@ -292,21 +292,35 @@ static void run_ffm_batch(ftrl_handle *h, const Batch &b, float *logit_out) {
       geo.f_cap = h->tile_f_cap;
       geo.stride = h->tile_stride;
       geo.n_stage = h->tile_stages;
+      geo.n_meta = h->tile_meta;
       geo.consumers = h->tile_consumers;
       geo.smem_bytes = h->tile_smem;
       const int tgrid = (int)std::min<int64_t>(b.n_rows, (int64_t)h->n_sms * h->tile_ctas_per_sm);
-      k_ffm_tile<PRECISE><<<tgrid, geo.consumers + 32, geo.smem_bytes, h->compute>>>(
-          b, d, h->hyper, dec, geo, h->batch_flags.p, h->tab, h->lin, h->bias, h->pair_lut, h->occ_pos.p, h->staging.p,
-          h->staging_lin.p, h->g.p, logit_out);
+#define FFM_TILE(I)                                                                                              \
+  k_ffm_tile<PRECISE, I><<<tgrid, geo.consumers + 32 + 32 * TILE_META_WARPS, geo.smem_bytes, h->compute>>>(                                \
+      b, d, h->hyper, dec, geo, h->batch_flags.p, h->tab, h->lin, h->bias, h->pair_lut, h->occ_pos.p, h->staging.p, \
+      h->staging_lin.p, h->g.p, logit_out)
+      if (h->tile_ipt <= 1) FFM_TILE(1);
+      else if (h->tile_ipt == 2) FFM_TILE(2);
+      else if (h->tile_ipt == 3) FFM_TILE(3);
+      else FFM_TILE(4);
+#undef FFM_TILE
       FTRL_CUDA(cudaGetLastError());
       launched(h, PH_SAMPLE);
     }
     {
       PhaseScope ps(h, PH_ROWS);
-      k_ffm_staged_rows<PRECISE, 8><<<grid, 256, 0, h->compute>>>(d, h->hyper, (int32_t)b.nnz, h->batch_flags.p, h->tab,
-                                                                 h->lin, h->chunk, h->n_chunks.p, h->chunk_pos.p,
-                                                                 h->skey.p, h->scan.p, h->staging.p, h->staging_lin.p,
-                                                                 h->part.p, h->part_lin.p);
+      const int nvec = d.ld / 4;
+#define FFM_STAGED(RR)                                                                                             \
+  k_ffm_staged_rows<PRECISE, 8, RR><<<grid * 2, 256, 0, h->compute>>>(d, h->hyper, (int32_t)b.nnz, h->batch_flags.p, h->tab, \
+                                                                     h->lin, h->chunk, h->n_chunks.p, h->chunk_pos.p, \
+                                                                     h->skey.p, h->scan.p, h->staging.p,           \
+                                                                     h->staging_lin.p, h->part.p, h->part_lin.p)
+      if (nvec <= 32) FFM_STAGED(1);
+      else if (nvec <= 64) FFM_STAGED(2);
+      else if (nvec <= 96) FFM_STAGED(3);
+      else FFM_STAGED(4);
+#undef FFM_STAGED
       FTRL_CUDA(cudaGetLastError());
       launched(h, PH_ROWS);
     }
@@ -669,22 +683,36 @@ int ftrl_create(const ftrl_config *cfg, ftrl_handle **out) {
       int cons = 64;
       while (cons < 512 && cons * 3 < items) cons *= 2;
       cons = env_int("FTRL_B200_TILE_CONSUMERS", cons);
-      if (2 * stage <= budget) {
-        int ctas = (int)std::min<size_t>(8, (size_t)prop.sharedMemPerMultiprocessor / (2 * stage + 1024));
-        ctas = std::max(1, std::min(ctas, 2048 / (cons + 32)));
+      const int ipt = (int)((items + cons - 1) / cons);
+      const size_t lut = tile_lut_bytes(d.n_fields) + 4 * tile_meta_bytes(d.n_fields);  // + minimal meta ring
+      if (2 * stage + lut <= budget && ipt <= 4) {
+        int ctas = (int)std::min<size_t>(8, (size_t)prop.sharedMemPerMultiprocessor / (2 * stage + lut + 2048));
+        ctas = std::max(1, std::min(ctas, 2048 / (cons + 32 + 32 * TILE_META_WARPS)));
         ctas = env_int("FTRL_B200_TILE_CTAS", ctas);
-        int stages = (int)std::min<size_t>(4, ((size_t)prop.sharedMemPerMultiprocessor / ctas - 1024) / stage);
-        stages = std::max(2, std::min(stages, (int)(budget / stage)));
+        int stages = (int)std::min<size_t>(TILE_MAX_STAGE, ((size_t)prop.sharedMemPerMultiprocessor / ctas - 2048 - lut) / stage);
+        stages = std::max(2, std::min(stages, (int)((budget - lut) / stage)));
         stages = env_int("FTRL_B200_TILE_STAGES", stages);
+        int metas = std::min(TILE_MAX_META, stages + 4);
+        while (metas > stages + 1 && tile_smem_bytes(d.n_fields, stride, stages, metas) > budget) metas--;
+        metas = env_int("FTRL_B200_TILE_META", metas);
+        h->tile_meta = metas;
         h->tile_ok = true;
         h->tile_f_cap = d.n_fields;
         h->tile_stride = stride;
         h->tile_stages = stages;
         h->tile_consumers = cons;
+        h->tile_ipt = std::max(1, ipt);
         h->tile_ctas_per_sm = ctas;
-        h->tile_smem = stage * stages;
-        FTRL_CUDA(cudaFuncSetAttribute(k_ffm_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->tile_smem));
-        FTRL_CUDA(cudaFuncSetAttribute(k_ffm_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->tile_smem));
+        h->tile_smem = tile_smem_bytes(d.n_fields, stride, stages, metas);
+        const int sm = (int)h->tile_smem;
+        FTRL_CUDA(cudaFuncSetAttribute(k_ffm_tile<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+        FTRL_CUDA(cudaFuncSetAttribute(k_ffm_tile<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+        FTRL_CUDA(cudaFuncSetAttribute(k_ffm_tile<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+        FTRL_CUDA(cudaFuncSetAttribute(k_ffm_tile<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+        FTRL_CUDA(cudaFuncSetAttribute(k_ffm_tile<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+        FTRL_CUDA(cudaFuncSetAttribute(k_ffm_tile<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+        FTRL_CUDA(cudaFuncSetAttribute(k_ffm_tile<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+        FTRL_CUDA(cudaFuncSetAttribute(k_ffm_tile<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
       }
     }
     FTRL_CUDA(cudaStreamCreateWithFlags(&h->compute, cudaStreamNonBlocking));
