@@ -229,7 +229,7 @@ class FtrlModel:
         return b, lin, vec
 
     def get_state(self) -> dict:
-        """{bias: [w, n, z], lin_w, lin_n, lin_z, vec_w, vec_n, vec_z} -- same keys as oracle.cpu_model"""
+        """{bias: [w, n, z], lin_w, lin_n, lin_z, vec_w, vec_n, vec_z} (planes in the reference layout)"""
         st = {}
         bias = np.zeros(3, np.float32)
         for which, nm in ((0, "w"), (1, "n"), (2, "z")):

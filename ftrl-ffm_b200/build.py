@@ -11,6 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 HOST = os.path.join(HERE, "host")
 LIB = os.path.join(HERE, "libftrl_b200.so")
 MAIN = os.path.join(HERE, "main")
+PARSER_LIB = os.path.join(HERE, "libftrl_host_parser.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -60,10 +61,13 @@ def build_host(force: bool = False) -> str | None:
     if not force and _newer(MAIN, srcs + [LIB]):
         return MAIN
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else (shutil.which("g++") or "g++")
-    cmd = [cxx, "-O3", "-std=c++17", "-pthread", "-I", os.path.join(os.path.dirname(HERE), "include"),
-           "-o", MAIN] + [s for s in _sources(HOST) if s.endswith(".cpp")] + \
-          ["-L", HERE, "-l:libftrl_b200.so", "-Wl,-rpath,$ORIGIN"]
+    inc = ["-I", os.path.join(os.path.dirname(HERE), "include")]
+    cmd = [cxx, "-O3", "-std=c++17", "-pthread"] + inc + ["-o", MAIN, os.path.join(HOST, "main.cpp"),
+                                                          "-L", HERE, "-l:libftrl_b200.so", "-Wl,-rpath,$ORIGIN"]
     subprocess.run(cmd, check=True, cwd=HOST)
+    # the parser alone as a tiny C library: lets the CPU test-suite check it against the reference's Parser
+    subprocess.run([cxx, "-O3", "-std=c++17", "-pthread", "-fPIC", "-shared"] + inc +
+                   ["-o", PARSER_LIB, os.path.join(HOST, "parser_capi.cpp")], check=True, cwd=HOST)
     return MAIN
 
 

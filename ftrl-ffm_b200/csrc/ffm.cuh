@@ -383,20 +383,28 @@ k_ffm_rows(Batch b, Dims d, Hyper h, ItemDecode dec, float *__restrict__ tab, fl
 }
 
 // ---------------------------------------------------------------------------------------------
-// K3: rows spanning several chunks: sum the parked partials in chunk order, apply once.
-// A CTA scans THREADS consecutive chunks (one per thread) for multi-chunk row heads, then all of
-// its warps cooperate on each such row: thread -> vector of the row, loop over the partials.
+// K3: rows spanning several chunks: sum the parked partials, apply once.
+// A CTA scans THREADS consecutive chunks (one per thread) for multi-chunk row heads, then all of its
+// warps cooperate on each such row: warp w sums the partials j = w, w+WARPS, ... (lanes over the
+// row's float4 vectors, both planes), the per-warp sums are combined in warp order through shared
+// memory (fixed order => deterministic), and one thread per vector applies the closed form.
 // ---------------------------------------------------------------------------------------------
-template <int VEC, bool PRECISE, int THREADS>
+constexpr int COMB_VPL = 3;  // float4 vectors per lane and plane per block of the row (96 vectors = 384 floats)
+
+template <bool PRECISE, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 k_ffm_combine(Dims d, Hyper h, int32_t nnz, float *__restrict__ tab, float4 *__restrict__ lin, int32_t ch,
               const int32_t *__restrict__ n_chunks_p, const int32_t *__restrict__ chunk_pos,
               const uint32_t *__restrict__ skey, const SegScan *__restrict__ scan,
               const float *__restrict__ part, const float2 *__restrict__ part_lin) {
+  constexpr int WARPS = THREADS / 32;
+  constexpr int VB = 32 * COMB_VPL;  // vectors per block
   __shared__ int s_list[THREADS];
   __shared__ int s_n;
-  const int tid = threadIdx.x;
+  __shared__ float4 s_acc[WARPS][2][VB];
+  const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
   const int64_t ld = d.ld, rs = 3 * ld;
+  const int nvec = (int)(ld >> 2);
   const int n_chunks = *n_chunks_p;
   const uint32_t sentinel = (uint32_t)d.n_feats;
   for (int base = blockIdx.x * THREADS; base < n_chunks; base += gridDim.x * THREADS) {
@@ -416,38 +424,66 @@ k_ffm_combine(Dims d, Hyper h, int32_t nnz, float *__restrict__ tab, float4 *__r
       int J = 1;  // number of chunks of this row
       while (c0 + J < n_chunks && skey[chunk_pos[c0 + J]] == ci.key) J++;
       float *row = tab + (int64_t)ci.key * rs;
-      const float *p0 = part + (int64_t)ci.slot * 2 * ld;
-      for (int64_t v = (int64_t)tid * VEC; v < d.row_len; v += (int64_t)THREADS * VEC) {
-        Vec<VEC> a0, a1;
+      const float4 *p0 = reinterpret_cast<const float4 *>(part + (int64_t)ci.slot * 2 * ld);
+      for (int vb = 0; vb < nvec; vb += VB) {
+        float4 a0[COMB_VPL], a1[COMB_VPL];
 #pragma unroll
-        for (int e = 0; e < VEC; e++) a0.v[e] = a1.v[e] = 0.f;
-#pragma unroll 4
-        for (int j = 0; j < J; j++) {
-          Vec<VEC> t0, t1;
-          t0.load(p0 + (int64_t)j * 2 * ld + v);
-          t1.load(p0 + (int64_t)j * 2 * ld + ld + v);
+        for (int r = 0; r < COMB_VPL; r++) a0[r] = a1[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 2
+        for (int j = wib; j < J; j += WARPS) {
+          const float4 *pj = p0 + (int64_t)j * 2 * nvec;
 #pragma unroll
-          for (int e = 0; e < VEC; e++) { a0.v[e] += t0.v[e]; a1.v[e] += t1.v[e]; }
+          for (int r = 0; r < COMB_VPL; r++) {
+            const int v = vb + r * 32 + lane;
+            if (v < nvec) {
+              const float4 t0 = __ldcs(pj + v), t1 = __ldcs(pj + nvec + v);
+              a0[r].x += t0.x; a0[r].y += t0.y; a0[r].z += t0.z; a0[r].w += t0.w;
+              a1[r].x += t1.x; a1[r].y += t1.y; a1[r].z += t1.z; a1[r].w += t1.w;
+            }
+          }
         }
-        bool any = false;
 #pragma unroll
-        for (int e = 0; e < VEC; e++) any = any || a1.v[e] != 0.f || a0.v[e] != 0.f;
-        if (!any) continue;
-        Vec<VEC> z, n, w;
-        z.load(row + v); n.load(row + ld + v); w.load(row + 2 * ld + v);
-#pragma unroll
-        for (int e = 0; e < VEC; e++) ftrl_apply<PRECISE>(z.v[e], n.v[e], w.v[e], a0.v[e], a1.v[e], h);
-        z.store(row + v); n.store(row + ld + v);
+        for (int r = 0; r < COMB_VPL; r++) {
+          s_acc[wib][0][r * 32 + lane] = a0[r];
+          s_acc[wib][1][r * 32 + lane] = a1[r];
+        }
+        __syncthreads();
+        if (tid < VB && vb + tid < nvec) {
+          const int v = vb + tid;
+          float4 s0 = s_acc[0][0][tid], s1 = s_acc[0][1][tid];
+          for (int w = 1; w < WARPS; w++) {
+            const float4 t0 = s_acc[w][0][tid], t1 = s_acc[w][1][tid];
+            s0.x += t0.x; s0.y += t0.y; s0.z += t0.z; s0.w += t0.w;
+            s1.x += t1.x; s1.y += t1.y; s1.z += t1.z; s1.w += t1.w;
+          }
+          const bool any = s0.x != 0.f || s0.y != 0.f || s0.z != 0.f || s0.w != 0.f || s1.x != 0.f || s1.y != 0.f ||
+                           s1.z != 0.f || s1.w != 0.f;
+          if (any) {
+            float4 z = reinterpret_cast<float4 *>(row)[v], n = reinterpret_cast<float4 *>(row + ld)[v];
+            const float4 w = reinterpret_cast<float4 *>(row + 2 * ld)[v];
+            ftrl_apply<PRECISE>(z.x, n.x, w.x, s0.x, s1.x, h);
+            ftrl_apply<PRECISE>(z.y, n.y, w.y, s0.y, s1.y, h);
+            ftrl_apply<PRECISE>(z.z, n.z, w.z, s0.z, s1.z, h);
+            ftrl_apply<PRECISE>(z.w, n.w, w.w, s0.w, s1.w, h);
+            reinterpret_cast<float4 *>(row)[v] = z;
+            reinterpret_cast<float4 *>(row + ld)[v] = n;
+          }
+        }
+        __syncthreads();
       }
-      if (tid == 0) {
+      if (wib == 0) {
         float sg = 0.f, sg2 = 0.f;
-        for (int j = 0; j < J; j++) {
+        for (int j = lane; j < J; j += 32) {
           const float2 t = part_lin[ci.slot + j];
           sg += t.x; sg2 += t.y;
         }
-        float4 e = lin[ci.key];
-        ftrl_apply<PRECISE>(e.x, e.y, e.z, sg, sg2, h);
-        lin[ci.key] = e;
+        sg = warp_sum(sg);
+        sg2 = warp_sum(sg2);
+        if (lane == 0) {
+          float4 e = lin[ci.key];
+          ftrl_apply<PRECISE>(e.x, e.y, e.z, sg, sg2, h);
+          lin[ci.key] = e;
+        }
       }
     }
     __syncthreads();

@@ -354,7 +354,7 @@ static void run_ffm_batch(ftrl_handle *h, const Batch &b, float *logit_out) {
   if (b.nnz == 0) return;
   {
     PhaseScope ps(h, PH_COMBINE);
-    k_ffm_combine<VEC, PRECISE, 256><<<grid, 256, 0, h->compute>>>(d, h->hyper, (int32_t)b.nnz, h->tab, h->lin, h->chunk,
+    k_ffm_combine<PRECISE, 256><<<grid, 256, 0, h->compute>>>(d, h->hyper, (int32_t)b.nnz, h->tab, h->lin, h->chunk,
                                                                    h->n_chunks.p, h->chunk_pos.p, h->skey.p, h->scan.p,
                                                                    h->part.p, h->part_lin.p);
     FTRL_CUDA(cudaGetLastError());

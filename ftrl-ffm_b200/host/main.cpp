@@ -1,0 +1,300 @@
+// main.cpp -- drop-in for the reference's `main` (src/main.cpp) on top of the C ABI (ftrl_b200.h).
+// C++17, no CUDA headers: everything device-side goes through libftrl_b200.so.
+//
+//   offline (--online false): src/task/ftrl_offline.cpp -- load the whole file, shuffle the sample
+//            order every epoch (:67-71), train, print `epoch %d train time ...`, evaluate (:56-61)
+//   online  (--online true, the default): src/task/ftrl_online.cpp -- stream the file in order every
+//            epoch (producer/consumer of src/concurrent/pc_task.cpp -> chunked read + parser threads),
+//            evaluate through the streaming Evaluator (src/eval/evaluate.cpp)
+// The reference's per-sample worker loop (ftrl_offline.cpp:74-83) becomes: pack `batch_size` samples
+// into a pinned CSR buffer, ftrl_train_batch (asynchronous: the copy of batch i+1 and the parsing of
+// the next chunk overlap the kernels of batch i), sum the fp64 losses at the epoch barrier (ftrl_sync,
+// the ThreadPool::synchronize of thread_pool.h:82-88).
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+#include <random>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "ftrl_b200.h"
+#include "options.hpp"
+#include "parser.hpp"
+
+namespace {
+
+using clk = std::chrono::steady_clock;
+double since(clk::time_point t0) { return std::chrono::duration<double>(clk::now() - t0).count(); }
+
+[[noreturn]] void die(ftrl_handle *h, const char *what) {
+  fprintf(stderr, "%s: %s\n", what, ftrl_last_error(h));
+  exit(EXIT_FAILURE);
+}
+
+// pinned CSR staging buffers; a buffer handed to call i is reusable once call i+3 has returned
+struct PinnedCsr {
+  int64_t *row_ptr = nullptr;
+  int32_t *field = nullptr, *feat = nullptr, *label = nullptr;
+  float *val = nullptr;
+  size_t cap_rows = 0, cap_nnz = 0;
+  void ensure(size_t rows, size_t nnz) {
+    if (rows > cap_rows) {
+      ftrl_free_pinned(row_ptr);
+      ftrl_free_pinned(label);
+      cap_rows = rows + rows / 4 + 16;
+      row_ptr = (int64_t *)ftrl_alloc_pinned(sizeof(int64_t) * (cap_rows + 1));
+      label = (int32_t *)ftrl_alloc_pinned(sizeof(int32_t) * cap_rows);
+    }
+    if (nnz > cap_nnz) {
+      ftrl_free_pinned(field);
+      ftrl_free_pinned(feat);
+      ftrl_free_pinned(val);
+      cap_nnz = nnz + nnz / 4 + 64;
+      field = (int32_t *)ftrl_alloc_pinned(sizeof(int32_t) * cap_nnz);
+      feat = (int32_t *)ftrl_alloc_pinned(sizeof(int32_t) * cap_nnz);
+      val = (float *)ftrl_alloc_pinned(sizeof(float) * cap_nnz);
+    }
+    if (!row_ptr || !label || (cap_nnz && (!field || !feat || !val))) {
+      fprintf(stderr, "pinned host allocation failed\n");
+      exit(EXIT_FAILURE);
+    }
+  }
+};
+
+class Trainer {
+ public:
+  Trainer(const host::Options &o) : opt_(o) {
+    ftrl_config c;
+    ftrl_config_default(&c);
+    if (o.model_type == "LR") c.model_type = FTRL_LR;
+    else if (o.model_type == "FM") c.model_type = FTRL_FM;
+    else if (o.model_type == "FFM") c.model_type = FTRL_FFM;
+    else {
+      // ftrl_offline.cpp:29-32
+      fprintf(stderr, "Invalid model_type: %s, expect `LR`, `FM` or `FFM`.\n", o.model_type.c_str());
+      throw std::invalid_argument("invalid model_type");
+    }
+    c.n_feats = o.n_feats;
+    c.n_fields = o.n_fields;
+    c.n_factors = o.n_factors;
+    c.init_mean = o.init_mean;
+    c.init_stddev = o.init_stddev;
+    c.w_alpha = o.w_alpha;
+    c.w_beta = o.w_beta;
+    c.w_l1 = o.w_l1;
+    c.w_l2 = o.w_l2;
+    c.device = o.device;
+    c.mode = o.batch_size == 1 ? FTRL_MODE_SEQUENTIAL : FTRL_MODE_BATCH;
+    c.seed = o.seed ? o.seed : std::random_device{}();
+    if (ftrl_create(&c, &h_) != FTRL_OK) die(nullptr, "ftrl_create");
+    // sequential mode walks the samples of a call in order on the device: hand over large blocks
+    block_ = o.batch_size == 1 ? 8192 : (size_t)o.batch_size;
+  }
+  ~Trainer() { ftrl_destroy(h_); }
+
+  // trains (or scores) samples idx[begin..end) of `data`; losses are appended to loss_parts_
+  void submit(const host::Csr &data, const int32_t *order, size_t begin, size_t end, bool train) {
+    PinnedCsr &p = pin_[next_pin_];
+    next_pin_ = (next_pin_ + 1) % kPins;
+    const size_t rows = end - begin;
+    size_t nnz = 0;
+    for (size_t i = begin; i < end; i++) {
+      const size_t r = order ? (size_t)order[i] : i;
+      nnz += (size_t)(data.row_ptr[r + 1] - data.row_ptr[r]);
+    }
+    p.ensure(rows, nnz);
+    size_t w = 0;
+    p.row_ptr[0] = 0;
+    for (size_t i = begin; i < end; i++) {
+      const size_t r = order ? (size_t)order[i] : i;
+      const size_t a = (size_t)data.row_ptr[r], n = (size_t)data.row_ptr[r + 1] - a;
+      memcpy(p.field + w, data.field.data() + a, n * sizeof(int32_t));
+      memcpy(p.feat + w, data.feat.data() + a, n * sizeof(int32_t));
+      memcpy(p.val + w, data.val.data() + a, n * sizeof(float));
+      w += n;
+      p.row_ptr[i - begin + 1] = (int64_t)w;
+      p.label[i - begin] = data.label[r];
+    }
+    // the library writes through these pointers at ftrl_sync: never reallocate with calls in flight
+    if (loss_parts_.size() + 1 >= loss_parts_.capacity()) sync();
+    loss_parts_.push_back(0.0);
+    double *slot = &loss_parts_.back();
+    int rc;
+    if (train)
+      rc = ftrl_train_batch(h_, (int64_t)rows, p.row_ptr, p.field, p.feat, p.val, p.label, nullptr, slot);
+    else {
+      rc = ftrl_predict_batch(h_, (int64_t)rows, p.row_ptr, p.field, p.feat, p.val, p.label, 0, score_sink(rows), slot);
+    }
+    if (rc != FTRL_OK) die(h_, train ? "ftrl_train_batch" : "ftrl_predict_batch");
+    n_submitted_ += rows;
+  }
+
+  void run_block(const host::Csr &data, const int32_t *order, size_t n, bool train) {
+    for (size_t b = 0; b < n; b += block_) submit(data, order, b, std::min(n, b + block_), train);
+  }
+
+  void sync() {
+    if (ftrl_sync(h_) != FTRL_OK) die(h_, "ftrl_sync");
+    for (double v : loss_parts_) loss_total_ += v;
+    loss_parts_.clear();
+  }
+
+  // mean loss since the last call (ftrl_offline.cpp:101-102, ftrl_online.cpp:82-94)
+  double take_loss() {
+    sync();
+    const double r = n_submitted_ ? loss_total_ / (double)n_submitted_ : 0.0;
+    loss_total_ = 0.0;
+    n_submitted_ = 0;
+    return r;
+  }
+
+  void begin_epoch(size_t expected_calls) { loss_parts_.reserve(std::max<size_t>(expected_calls + 8, 4096)); }
+  ftrl_handle *handle() { return h_; }
+
+ private:
+  float *score_sink(size_t rows) {
+    // predictions themselves are not needed by the driver (only the loss); fixed-size sink per slot
+    // (rows <= block_), never reallocated while calls are in flight
+    if (sink_[next_pin_].size() < block_) sink_[next_pin_].resize(block_);
+    (void)rows;
+    return sink_[next_pin_].data();
+  }
+  static constexpr int kPins = 4;
+  host::Options opt_;
+  ftrl_handle *h_ = nullptr;
+  size_t block_ = 1024;
+  PinnedCsr pin_[kPins];
+  std::vector<float> sink_[kPins];
+  int next_pin_ = 0;
+  std::vector<double> loss_parts_;
+  double loss_total_ = 0.0;
+  size_t n_submitted_ = 0;
+};
+
+// Reader::load_from_file (src/data/reader.cpp:50-91)
+void load_file(const std::string &path, bool libffm, int n_threads, host::Csr &out) {
+  printf("Loading data from file: %s\n", path.c_str());
+  const auto t0 = clk::now();
+  std::vector<char> buf;
+  if (!host::read_file(path, buf)) {
+    fprintf(stderr, "fail to open %s\n", path.c_str());
+    exit(EXIT_FAILURE);
+  }
+  host::parse_buffer(buf.data(), buf.size(), libffm, n_threads, out);
+  printf("Total number of samples loaded: %zu\n", out.rows());
+  printf("parsing data time: %.4lfs\n", since(t0));
+}
+
+// FtrlOffline::train / evaluate / one_epoch (src/task/ftrl_offline.cpp:44-103)
+void run_offline(const host::Options &o) {
+  Trainer tr(o);
+  const bool libffm = o.file_type == "libffm";
+  host::Csr train, eval;
+  load_file(o.train_path, libffm, o.thread_num, train);
+  if (!o.eval_path.empty()) load_file(o.eval_path, libffm, o.thread_num, eval);
+  std::mt19937 gen(o.seed ? (uint32_t)o.seed : std::random_device{}());
+  std::vector<int32_t> order(train.rows());
+  for (int ep = 1; ep <= o.epoch; ep++) {
+    const auto t0 = clk::now();
+    std::iota(order.begin(), order.end(), 0);
+    std::shuffle(order.begin(), order.end(), gen);  // ftrl_offline.cpp:69-71
+    tr.begin_epoch(train.rows() / std::max<long>(1, o.batch_size) + 1);
+    tr.run_block(train, order.data(), train.rows(), true);
+    const double loss = tr.take_loss();
+    printf("epoch %d train time: %.4lfs, train loss: %.4lf\n", ep, since(t0), loss);
+    if (!o.eval_path.empty()) {
+      const auto t1 = clk::now();
+      tr.run_block(eval, nullptr, eval.rows(), false);
+      const double el = tr.take_loss();
+      printf("epoch %d eval time: %.4lfs, eval loss: %.4lf\n", ep, since(t1), el);
+    }
+  }
+  if (!o.model_path.empty() && ftrl_save_model(tr.handle(), o.model_path.c_str(), 10) != FTRL_OK)
+    die(tr.handle(), "ftrl_save_model");
+}
+
+// one streaming pass over a file in file order: PcTask::run (src/concurrent/pc_task.cpp:22-80) with
+// FtrlOnline::run_task (ftrl_online.cpp:70-80) / Evaluator::run_task (evaluate.cpp:23-33) as consumer
+double stream_file(Trainer &tr, const std::string &path, bool libffm, int n_threads, bool train) {
+  FILE *f = fopen(path.c_str(), "rb");
+  if (!f) {
+    fprintf(stderr, "open file <%s> error. \n", path.c_str());  // pc_task.cpp:8
+    exit(EXIT_FAILURE);
+  }
+  std::vector<char> buf(32u << 20);
+  size_t have = 0;
+  bool eof = false;
+  long lines = 0, next_log = 1000000;
+  host::Csr csr;
+  tr.begin_epoch(1u << 16);
+  while (!eof || have) {
+    if (!eof) {
+      const size_t got = fread(buf.data() + have, 1, buf.size() - have, f);
+      have += got;
+      if (got == 0) eof = true;
+    }
+    size_t use = have;
+    if (!eof) {  // cut at the last complete line
+      while (use > 0 && buf[use - 1] != '\n') use--;
+      if (use == 0) {
+        if (have == buf.size()) buf.resize(buf.size() * 2);
+        continue;
+      }
+    }
+    if (use == 0) break;
+    csr.clear();
+    host::parse_buffer(buf.data(), use, libffm, n_threads, csr);
+    tr.run_block(csr, nullptr, csr.rows(), train);  // copies into pinned staging: csr/buf are free again
+    lines += (long)csr.rows();
+    while (lines >= next_log) {  // pc_task.cpp:47-49
+      printf("%ld lines finished...\n", next_log);
+      next_log += 1000000;
+    }
+    memmove(buf.data(), buf.data() + use, have - use);
+    have -= use;
+  }
+  fclose(f);
+  return tr.take_loss();
+}
+
+// FtrlOnline::train / evaluate (src/task/ftrl_online.cpp:42-68)
+void run_online(const host::Options &o) {
+  Trainer tr(o);
+  const bool libffm = o.file_type == "libffm";
+  if (o.cmd) return;  // `// todo: online learning` in the reference (ftrl_online.cpp:55-57)
+  for (int ep = 1; ep <= o.epoch; ep++) {
+    const auto t0 = clk::now();
+    const double loss = stream_file(tr, o.train_path, libffm, o.thread_num, true);
+    printf("epoch %d train time: %.4lfs, train loss: %.4lf\n", ep, since(t0), loss);
+    if (!o.eval_path.empty()) {
+      const auto t1 = clk::now();
+      const double el = stream_file(tr, o.eval_path, libffm, o.thread_num, false);
+      printf("epoch %d eval time: %.4lfs, eval loss: %.4lf\n", ep, since(t1), el);
+    }
+  }
+  if (!o.model_path.empty() && ftrl_save_model(tr.handle(), o.model_path.c_str(), 10) != FTRL_OK)
+    die(tr.handle(), "ftrl_save_model");
+}
+
+}  // namespace
+
+int main(int argc, char *argv[]) {
+  host::Options opt;
+  try {
+    host::parse_options(argc, argv, opt);
+  } catch (const std::invalid_argument &e) {  // src/main.cpp:18-24
+    fprintf(stderr, "invalid argument: %s\n", e.what());
+    fputs(host::kHelp, stdout);
+    exit(EXIT_FAILURE);
+  }
+  try {
+    if (opt.online) run_online(opt); else run_offline(opt);
+  } catch (const std::invalid_argument &e) {
+    fprintf(stderr, "%s\n", e.what());
+    return EXIT_FAILURE;
+  }
+  return 0;
+}

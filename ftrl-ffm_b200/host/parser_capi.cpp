@@ -1,0 +1,26 @@
+// parser_capi.cpp -- C entry points around host/parser.hpp so the parser can be tested without a GPU
+// (tests/test_host_parser.py compares it with the reference's Parser through oracle/_ref).
+#include <cstring>
+
+#include "parser.hpp"
+
+extern "C" {
+
+// parses `len` bytes of libsvm/libffm text with n_threads workers.  Returns the number of rows; the
+// arrays are owned by the library until the next call (single-threaded use).
+static host::Csr g_csr;
+
+int64_t host_parse_text(const char *buf, int64_t len, int libffm, int n_threads) {
+  g_csr.clear();
+  host::parse_buffer(buf, (size_t)len, libffm != 0, n_threads, g_csr);
+  return (int64_t)g_csr.rows();
+}
+int64_t host_parse_nnz() { return (int64_t)g_csr.feat.size(); }
+void host_parse_fetch(int64_t *row_ptr, int32_t *field, int32_t *feat, float *val, int32_t *label) {
+  memcpy(row_ptr, g_csr.row_ptr.data(), sizeof(int64_t) * g_csr.row_ptr.size());
+  memcpy(field, g_csr.field.data(), sizeof(int32_t) * g_csr.field.size());
+  memcpy(feat, g_csr.feat.data(), sizeof(int32_t) * g_csr.feat.size());
+  memcpy(val, g_csr.val.data(), sizeof(float) * g_csr.val.size());
+  memcpy(label, g_csr.label.data(), sizeof(int32_t) * g_csr.label.size());
+}
+}

@@ -19,6 +19,10 @@
 #include <mutex>
 #include <numeric>
 #include <random>
+#include <regex>
+#include <fstream>
+#include <iostream>
+#include <sstream>
 #include <shared_mutex>
 #include <string>
 #include <string_view>
@@ -28,6 +32,7 @@
 
 #define private public
 #define protected public
+#include "data/parser.h"
 #include "data/sample.h"
 #include "eval/loss.h"
 #include "model/ffm.h"
@@ -267,6 +272,35 @@ double ftrl_ref_train_staged(void *h, int n_threads, int shuffle, uint32_t seed,
       std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   if (loss_out) *loss_out = total_num ? total / static_cast<double>(total_num) : 0.0;
   return secs;
+}
+
+// The reference's own line parsers (src/data/parser.cpp:11-41 libsvm, :62-103 libffm).
+// Returns the number of kept features, or -1 if the reference throws on this line.
+int ftrl_ref_parse_line(int libffm, const char *line, int cap, int32_t *field, int32_t *feat, float *val,
+                        int *label) {
+  Sample s;
+  try {
+    if (libffm) {
+      ftrl::FFMParser p;
+      p.parse(line, s);
+    } else {
+      ftrl::LibsvmParser p;
+      p.parse(line, s);
+    }
+  } catch (...) {
+    return -1;
+  }
+  int n = 0;
+  for (auto &[f, i, v] : s.x) {
+    if (n < cap) {
+      field[n] = f;
+      feat[n] = i;
+      val[n] = v;
+    }
+    n++;
+  }
+  *label = s.y;
+  return n;
 }
 
 // scalar helpers of the reference

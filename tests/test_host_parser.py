@@ -1,0 +1,118 @@
+"""CPU tests of the C++ host parser (ftrl-ffm_b200/host/parser.hpp) against the reference's own
+Parser classes (through oracle/_ref when present) and the reference's unit test tests/test_data.cpp."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import ftrl_ffm_b200 as pkg
+from ftrl_ffm_b200.build import PARSER_LIB, build_host
+from oracle.cpu_model import REF_SO, have_ref
+
+# tests/common.h:12-24 of the reference
+REF_TEST_SAMPLES = (
+    "0 0:1:1 1:13:1 2:21:1 3:31:1\n"
+    "1 0:4:1 1:11:1 2:23:1 3:32:1\n"
+    "1 0:2:1 1:13:1 2:25:1 3:34:1\n"
+    "0 0:1:1 1:14:1 2:21:1 3:32:1\n"
+    "0 0:2:1 1:15:1 2:22:1 3:34:1\n"
+    "1 0:4:1 1:11:1 2:21:1 3:35:1\n"
+    "1 0:5:1 1:12:1 2:23:1 3:31:1\n"
+    "1 0:5:1 1:12:1 2:25:1 3:38:1\n"
+    "0 0:2:1 1:11:1 2:24:1 3:37:1\n"
+    "1 0:1:1 1:15:1 2:22:1 3:35:1")
+
+
+def parser_lib():
+    if not os.path.exists(PARSER_LIB):
+        build_host()
+    lib = C.CDLL(PARSER_LIB)
+    lib.host_parse_text.restype = C.c_int64
+    lib.host_parse_text.argtypes = [C.c_char_p, C.c_int64, C.c_int, C.c_int]
+    lib.host_parse_nnz.restype = C.c_int64
+    lib.host_parse_fetch.argtypes = [C.c_void_p] * 5
+    return lib
+
+
+def parse(text, libffm, n_threads=1):
+    lib = parser_lib()
+    raw = text.encode()
+    n = lib.host_parse_text(raw, len(raw), int(libffm), n_threads)
+    nnz = lib.host_parse_nnz()
+    rp = np.zeros(n + 1, np.int64)
+    fi, fe, va, la = np.zeros(nnz, np.int32), np.zeros(nnz, np.int32), np.zeros(nnz, np.float32), np.zeros(n, np.int32)
+    lib.host_parse_fetch(*(a.ctypes.data_as(C.c_void_p) for a in (rp, fi, fe, va, la)))
+    return {"row_ptr": rp, "field": fi, "feat": fe, "val": va, "label": la}
+
+
+def test_reference_test_data_cpp():
+    """tests/test_data.cpp:9-18: 10 samples, data[0].y == 0, x[0] == (0,1,1), x[3] == (3,31,1); partitioned
+    multi-threaded loading keeps file order"""
+    for nt in (1, 4):
+        d = parse(REF_TEST_SAMPLES, True, nt)
+        assert len(d["label"]) == 10 and d["label"][0] == 0
+        assert (d["field"][0], d["feat"][0], d["val"][0]) == (0, 1, 1.0)
+        assert (d["field"][3], d["feat"][3], d["val"][3]) == (3, 31, 1.0)
+        assert list(d["label"]) == [0, 1, 1, 0, 0, 1, 1, 1, 0, 1]
+
+
+def test_parsing_rules():
+    # label > 0 -> 1 else 0; value 0 dropped; libsvm field forced to 0; '+', exponents, trailing blanks, CRLF
+    d = parse("3 5:0.5 7:0 9:1e-2 \r\n-1 2:+2.5\n0 4:1\n\n", False)
+    assert list(d["label"]) == [1, 0, 0]
+    assert list(d["row_ptr"]) == [0, 2, 3, 4]
+    assert list(d["feat"]) == [5, 9, 2, 4] and list(d["field"]) == [0, 0, 0, 0]
+    np.testing.assert_array_equal(d["val"], np.array([0.5, 1e-2, 2.5, 1.0], np.float32))
+    d = parse("1 0:3:1.5 12:400:-2\n", True)
+    assert list(d["field"]) == [0, 12] and list(d["feat"]) == [3, 400] and list(d["val"]) == [1.5, -2.0]
+
+
+def test_threads_give_identical_csr():
+    rng = np.random.default_rng(0)
+    b = pkg.synth.random_csr(rng, 5000, 1000, 9, max_nnz=9, oob_frac=0.0)
+    import tempfile
+    with tempfile.NamedTemporaryFile("w", suffix=".ffm", delete=False) as f:
+        path = f.name
+    try:
+        pkg.synth.write_text(b, path, "libffm")
+        text = open(path).read()
+    finally:
+        os.remove(path)
+    one, many = parse(text, True, 1), parse(text, True, 7)
+    for k in one:
+        np.testing.assert_array_equal(one[k], many[k])
+    keep = b["val"] != 0
+    np.testing.assert_array_equal(one["feat"], b["feat"][keep])
+    np.testing.assert_array_equal(one["field"], b["field"][keep])
+    np.testing.assert_array_equal(one["val"], b["val"][keep])
+    np.testing.assert_array_equal(one["label"], b["label"])
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built")
+def test_against_reference_parser_line_by_line():
+    ref = C.CDLL(REF_SO)
+    ref.ftrl_ref_parse_line.argtypes = [C.c_int, C.c_char_p, C.c_int] + [C.c_void_p] * 3 + [C.POINTER(C.c_int)]
+    rng = np.random.default_rng(1)
+    for libffm in (True, False):
+        lines = []
+        for _ in range(300):
+            toks = [str(int(rng.integers(-2, 3)))]
+            for _ in range(int(rng.integers(0, 7))):
+                v = rng.choice(["1", "0", "0.25", "-3.5", "1e-3", "12.", ".5", "0.0", "7e2"])
+                ft = int(rng.integers(0, 100000))
+                toks.append(f"{int(rng.integers(0, 40))}:{ft}:{v}" if libffm else f"{ft}:{v}")
+            lines.append(" ".join(toks))
+        got = parse("\n".join(lines) + "\n", libffm, 3)
+        assert len(got["label"]) == len(lines)
+        fi, fe, va = np.zeros(64, np.int32), np.zeros(64, np.int32), np.zeros(64, np.float32)
+        for r, line in enumerate(lines):
+            lab = C.c_int(0)
+            n = ref.ftrl_ref_parse_line(int(libffm), line.encode(), 64, fi.ctypes.data, fe.ctypes.data,
+                                        va.ctypes.data, C.byref(lab))
+            a, e = got["row_ptr"][r], got["row_ptr"][r + 1]
+            assert n == e - a, line
+            assert lab.value == got["label"][r]
+            np.testing.assert_array_equal(got["field"][a:e], fi[:n])
+            np.testing.assert_array_equal(got["feat"][a:e], fe[:n])
+            np.testing.assert_array_equal(got["val"][a:e], va[:n])
