@@ -9,6 +9,6 @@
 Import through the alias module at the repo root: `import ftrl_ffm_b200`.
 """
 from .binding import (ABI_SYMBOLS, LIB_PATH, MODE_BATCH, MODE_SEQUENTIAL, BatchStats, Config, FtrlError,  # noqa: F401
-                      FtrlModel, load_library)
+                      FtrlModel, LogicalShards, load_library, merge_states, shard_state)
 from .build import build_host, build_library  # noqa: F401
 from . import synth  # noqa: F401

@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(HERE, "libftrl_b200.so")
 
 MODEL_TYPES = {"LR": 0, "FM": 1, "FFM": 2}
 MODE_BATCH, MODE_SEQUENTIAL = 0, 1
-PEER_BLOB_BYTES = 512
+PEER_BLOB_BYTES = 1024
 
 
 class FtrlError(RuntimeError):
@@ -220,8 +220,8 @@ class FtrlModel:
     # -- state ------------------------------------------------------------------------
     def _get(self, which):
         b = np.zeros(1, np.float32)
-        lin = np.zeros(self.n_feats, np.float32)
-        vec = np.zeros((self.n_feats, self.row_len), np.float32) if self.row_len else None
+        lin = np.zeros(self.n_local, np.float32)
+        vec = np.zeros((self.n_local, self.row_len), np.float32) if self.row_len else None
         if which == 0:
             self._check(self.lib.ftrl_get_weights(self.h, _np_ptr(b), _np_ptr(lin), _np_ptr(vec)))
         else:
@@ -247,7 +247,7 @@ class FtrlModel:
             lin = np.ascontiguousarray(st["lin_" + nm], np.float32) if "lin_" + nm in st else None
             vec = None
             if self.row_len and "vec_" + nm in st:
-                vec = np.ascontiguousarray(st["vec_" + nm], np.float32).reshape(self.n_feats, self.row_len)
+                vec = np.ascontiguousarray(st["vec_" + nm], np.float32).reshape(self.n_local, self.row_len)
             if which == 0:
                 self._check(self.lib.ftrl_set_weights(self.h, _np_ptr(b), _np_ptr(lin), _np_ptr(vec)))
             else:
@@ -307,7 +307,79 @@ class FtrlModel:
     def randomize_state(self, seed=1, z_scale=300.0, n_lo=0.5, n_hi=3.0):
         self._check(self.lib.ftrl_randomize_state(self.h, int(seed), z_scale, n_lo, n_hi))
 
+    # -- multi-GPU (feature-sharded tables) ------------------------------------------------
+    def export_peer_blob(self) -> bytes:
+        buf = C.create_string_buffer(PEER_BLOB_BYTES)
+        self._check(self.lib.ftrl_export_peer_blob(self.h, buf))
+        return buf.raw
+
+    def attach_peers(self, blobs) -> None:
+        """blobs: the PEER_BLOB_BYTES-sized blobs of ranks 0..world_size-1, in rank order"""
+        raw = b"".join(bytes(b) for b in blobs)
+        assert len(raw) == PEER_BLOB_BYTES * self.cfg.world_size
+        self._check(self.lib.ftrl_attach_peers(self.h, raw))
+
+    @property
+    def n_local(self) -> int:
+        """rows of lin / vec held by this rank (all of them on a single GPU)"""
+        g, r = max(1, self.cfg.world_size), self.cfg.rank
+        return (self.cfg.n_feats - r + g - 1) // g if g > 1 else self.cfg.n_feats
+
     def last_batch_stats(self) -> dict:
         s = BatchStats()
         self._check(self.lib.ftrl_last_batch_stats(self.h, C.byref(s)))
         return {n: getattr(s, n) for n, _ in BatchStats._fields_ if n != "reserved"}
+
+
+# ---- feature-sharded helpers -----------------------------------------------------------------------
+def shard_state(st: dict, world: int, rank: int) -> dict:
+    """the rows rank, rank + world, ... of a full model state (bias is replicated)"""
+    return {k: (v if k == "bias" else np.ascontiguousarray(v[rank::world])) for k, v in st.items()}
+
+
+def merge_states(shards: list) -> dict:
+    """inverse of shard_state"""
+    world = len(shards)
+    out = {"bias": shards[0]["bias"]}
+    for k in shards[0]:
+        if k == "bias":
+            continue
+        n = sum(len(s[k]) for s in shards)
+        full = np.zeros((n,) + shards[0][k].shape[1:], shards[0][k].dtype)
+        for r, s in enumerate(shards):
+            full[r::world] = s[k]
+        out[k] = full
+    return out
+
+
+class LogicalShards:
+    """`world` feature shards inside ONE process (one handle per shard, on the given devices -- by default
+    all on device 0).  Used by the tests to check that the sharded exchange is invariant to the number of
+    shards without needing several GPUs; real multi-GPU runs use one process per GPU (see bench.py)."""
+
+    def __init__(self, world, devices=None, **kw):
+        devices = devices or [0] * world
+        self.world = world
+        self.models = [FtrlModel(rank=r, world_size=world, device=devices[r], **kw) for r in range(world)]
+        blobs = [m.export_peer_blob() for m in self.models]
+        for m in self.models:
+            m.attach_peers(blobs)
+
+    def set_state(self, st):
+        for r, m in enumerate(self.models):
+            m.set_state(shard_state(st, self.world, r))
+
+    def get_state(self):
+        return merge_states([m.get_state() for m in self.models])
+
+    def train(self, batches):
+        """batches[r]: the CSR dict of rank r's share of the global minibatch.  All ranks are enqueued
+        before any is synchronised (the device-side barriers need every rank in flight)."""
+        pend = [m.train(**b, sync=False) for m, b in zip(self.models, batches)]
+        for m in self.models:
+            m.sync()
+        return [(lg, float(ls[0])) for lg, ls in pend]
+
+    def close(self):
+        for m in self.models:
+            m.close()

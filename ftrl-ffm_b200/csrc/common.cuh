@@ -28,6 +28,30 @@ struct Dims {
 
 enum : int { PLANE_Z = 0, PLANE_N = 1, PLANE_W = 2 };
 
+// ---- feature-sharded tables -------------------------------------------------------------------
+// Row `feat` lives on shard feat mod G at local row feat div G (G a power of two, G = 1: one GPU).
+// Peer shards are mapped into this process (CUDA IPC) and reached over NVLink with the same
+// instructions: bulk copies, 128-bit stores.
+constexpr int MAX_SHARDS = 8;
+struct Shards {
+  int G, log2G, rank, pad;
+  float *tab[MAX_SHARDS];
+  float4 *lin[MAX_SHARDS];
+  float *staging[MAX_SHARDS];
+  float *staging_lin[MAX_SHARDS];
+  __device__ __forceinline__ float *row(int32_t feat, int64_t rs) const {
+    return tab[feat & (G - 1)] + (int64_t)(feat >> log2G) * rs;
+  }
+  __device__ __forceinline__ float4 *linp(int32_t feat) const { return lin[feat & (G - 1)] + (feat >> log2G); }
+  __device__ __forceinline__ float *stage(int32_t feat, int32_t pos, int64_t ld) const {
+    return staging[feat & (G - 1)] + (int64_t)pos * ld;
+  }
+  __device__ __forceinline__ float *stage_lin(int32_t feat, int32_t pos) const {
+    return staging_lin[feat & (G - 1)] + pos;
+  }
+};
+
+
 constexpr int32_t KEY_INVALID_BITS = 0;  // invalid occurrences get key == n_feats (sorts last)
 
 // ---------------------------------------------------------------------------------------------

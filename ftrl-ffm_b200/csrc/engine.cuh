@@ -13,6 +13,7 @@
 #include "../../include/ftrl_b200.h"
 #include "common.cuh"
 #include "prep.cuh"
+#include "shard.cuh"
 
 namespace ftrl {
 
@@ -164,6 +165,20 @@ struct ftrl_handle {
   ftrl_batch_stats stats{};
   int64_t launches_this_call = 0;
   int64_t last_nnz = 0;
+
+  // feature-sharded multi-GPU (shard.cuh): this rank holds rows feat with feat % G == rank
+  int G = 1, log2G = 0, rank = 0;
+  int64_t n_local = 0;          // rows of lin / tab held here
+  ftrl::Shards shards{};        // per-owner table / staging pointers (self when G == 1)
+  ftrl::Peers peers{};
+  ftrl::SyncArea *sync = nullptr;
+  uint32_t epoch = 0;
+  bool attached = false;
+  int64_t ow_cap = 0;           // owner-side capacity: occurrences this rank may own per step
+  ftrl::DevBuf<uint32_t> okey, osrc;
+  ftrl::DevBuf<int32_t> sel, n_sel;
+  ftrl::DevBuf<double> red4;
+  std::vector<void *> ipc_opened;
 
   // tunables (env overrides for experiments)
   int fuse = 1;

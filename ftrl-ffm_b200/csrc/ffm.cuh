@@ -495,7 +495,7 @@ k_ffm_combine(Dims d, Hyper h, int32_t nnz, float *__restrict__ tab, float4 *__r
 // ---------------------------------------------------------------------------------------------
 template <int VEC, int THREADS>
 __global__ void __launch_bounds__(THREADS)
-k_ffm_predict(Batch b, Dims d, ItemDecode dec, const float *__restrict__ tab, const float4 *__restrict__ lin,
+k_ffm_predict(Batch b, Dims d, ItemDecode dec, const __grid_constant__ Shards sh,
               const float4 *__restrict__ bias, const uint32_t *__restrict__ pair_lut, int output_prob,
               float *__restrict__ out, float *__restrict__ logit_out) {
   __shared__ float red[33];
@@ -514,8 +514,8 @@ k_ffm_predict(Batch b, Dims d, ItemDecode dec, const float *__restrict__ tab, co
     const int32_t fm = b.field[r0 + m], im = b.feat[r0 + m], fn = b.field[r0 + n], in = b.feat[r0 + n];
     if (!feat_valid(d, fm, im) || !feat_valid(d, fn, in)) continue;
     Vec<VEC> wA, wB;
-    wA.load(tab + (int64_t)im * rs + 2 * ld + (int64_t)fn * d.k + c * VEC);
-    wB.load(tab + (int64_t)in * rs + 2 * ld + (int64_t)fm * d.k + c * VEC);
+    wA.load(sh.row(im, rs) + 2 * ld + (int64_t)fn * d.k + c * VEC);
+    wB.load(sh.row(in, rs) + 2 * ld + (int64_t)fm * d.k + c * VEC);
     float dot = 0.f;
 #pragma unroll
     for (int e = 0; e < VEC; e++) dot = fmaf(wA.v[e], wB.v[e], dot);
@@ -523,7 +523,7 @@ k_ffm_predict(Batch b, Dims d, ItemDecode dec, const float *__restrict__ tab, co
   }
   for (int t = tid; t < F; t += THREADS) {
     const int32_t fl = b.field[r0 + t], ft = b.feat[r0 + t];
-    if (feat_valid(d, fl, ft)) acc = fmaf(lin[ft].z, b.val[r0 + t], acc);
+    if (feat_valid(d, fl, ft)) acc = fmaf(sh.linp(ft)->z, b.val[r0 + t], acc);
   }
   float logit = block_sum(acc, red);
   if (tid == 0) {

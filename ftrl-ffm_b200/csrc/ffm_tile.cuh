@@ -165,10 +165,9 @@ __device__ __forceinline__ void apply4(float4 &z, float4 &n, const float4 &w, co
 // ring so that the row producer never waits on a dependent global-load chain.
 template <bool PRECISE, int IPT>
 __global__ void __launch_bounds__(512 + 32 + 32 * TILE_META_WARPS, 1)
-k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t *__restrict__ batch_flags, float *__restrict__ tab,
-           float4 *__restrict__ lin, const float4 *__restrict__ bias, const uint32_t *__restrict__ pair_lut,
-           const int32_t *__restrict__ occ_pos, float *__restrict__ staging, float *__restrict__ staging_lin,
-           float *__restrict__ g_out, float *__restrict__ logit_out) {
+k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t *__restrict__ batch_flags,
+           const __grid_constant__ Shards sh, const float4 *__restrict__ bias, const uint32_t *__restrict__ pair_lut,
+           const int32_t *__restrict__ occ_pos, float *__restrict__ g_out, float *__restrict__ logit_out) {
   if (batch_flags[0] == 0) return;  // some sample repeats a field: the generic kernels take this batch
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint64_t bar_full[TILE_MAX_STAGE], bar_done[TILE_MAX_STAGE];
@@ -255,7 +254,7 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
           rm.pos = occ_pos[r0 + t];
           rm.feat = ft;
           m.row[sl] = rm;
-          m.lin[sl] = lin[ft];
+          m.lin[sl] = *sh.linp(ft);
           m.present[fl] = 1;
         }
         nv += __popc(okm);
@@ -286,9 +285,9 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
         for (int r = lane; r < nv; r += 32) {
           const RowMeta rm = m.row[r];
           if (rm.pos < 0) {
-            bulk_s2g(tab + (int64_t)rm.feat * rs, rows + (size_t)r * stride, row_bytes);
+            bulk_s2g(sh.row(rm.feat, rs), rows + (size_t)r * stride, row_bytes);
           } else {
-            bulk_s2g(staging + (int64_t)rm.pos * ld, rows + (size_t)r * stride, (uint32_t)(ld * sizeof(float)));
+            bulk_s2g(sh.stage(rm.feat, rm.pos, ld), rows + (size_t)r * stride, (uint32_t)(ld * sizeof(float)));
           }
         }
         bulk_commit();
@@ -304,7 +303,7 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
         if (lane == 0) mbar_arrive_expect_tx(&bar_full[st], (uint32_t)nv * row_bytes);
         __syncwarp();
         for (int r = lane; r < nv; r += 32)
-          bulk_g2s(rows + (size_t)r * stride, tab + (int64_t)m.row[r].feat * rs, row_bytes, &bar_full[st]);
+          bulk_g2s(rows + (size_t)r * stride, sh.row(m.row[r].feat, rs), row_bytes, &bar_full[st]);
       }
     }
     bulk_wait_all();
@@ -349,8 +348,8 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
         const float dot = fmaf(wA.x, wB.x, fmaf(wA.y, wB.y, fmaf(wA.z, wB.z, wA.w * wB.w)));
         acc = fmaf(dot, rmm.x * rmn.x, acc);
         // the stale-by-one w the reference keeps (ffm.cpp:72-88)
-        *reinterpret_cast<float4 *>(tab + (int64_t)rmm.feat * rs + 2 * ld + rmn.fk + c * 4) = wA;
-        *reinterpret_cast<float4 *>(tab + (int64_t)rmn.feat * rs + 2 * ld + rmm.fk + c * 4) = wB;
+        *reinterpret_cast<float4 *>(sh.row(rmm.feat, rs) + 2 * ld + rmn.fk + c * 4) = wA;
+        *reinterpret_cast<float4 *>(sh.row(rmn.feat, rs) + 2 * ld + rmm.fk + c * 4) = wB;
       }
     }
     for (int r = tid; r < nv; r += n_cons) {
@@ -417,10 +416,10 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
       if (rm.pos < 0) {
         e.z = w;
         ftrl_apply<PRECISE>(e.x, e.y, w, gi, gi * gi, h);
-        lin[rm.feat] = e;
+        *sh.linp(rm.feat) = e;
       } else {
-        lin[rm.feat].z = w;
-        staging_lin[rm.pos] = gi;
+        sh.linp(rm.feat)->z = w;
+        *sh.stage_lin(rm.feat, rm.pos) = gi;
       }
     }
     // staged rows: slices no partner touches (own field, absent fields) must read as 0 in the image.

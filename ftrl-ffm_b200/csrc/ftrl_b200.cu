@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <unistd.h>
 
 #include <thrust/iterator/counting_iterator.h>
 #include <thrust/iterator/transform_iterator.h>
@@ -21,8 +22,10 @@ static thread_local std::string g_create_error;
 // ---------------------------------------------------------------------------------------------
 // small kernels: init, layout conversion, zero scan
 // ---------------------------------------------------------------------------------------------
+// (G, rank): this shard holds global rows rank, rank + G, ...; random streams are indexed by GLOBAL row so
+// the initial model does not depend on the number of shards
 __global__ void k_init_tab(float *tab, int64_t n_rows, int32_t row_len, int32_t ld, float mean, float stddev,
-                           uint64_t seed) {
+                           uint64_t seed, int G, int rank) {
   // one thread per 4 consecutive floats of the w plane of one row
   const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t per_row = ld / 4;
@@ -30,7 +33,7 @@ __global__ void k_init_tab(float *tab, int64_t n_rows, int32_t row_len, int32_t 
   const int64_t row = q / per_row;
   const int v = (int)(q % per_row) * 4;
   float *base = tab + row * 3 * (int64_t)ld;
-  const float4 gz = gaussian4((uint64_t)q, seed, 1u);
+  const float4 gz = gaussian4((uint64_t)((row * G + rank) * per_row + v / 4), seed, 1u);
   const float r[4] = {gz.x, gz.y, gz.z, gz.w};
   for (int e = 0; e < 4; e++) {
     base[v + e] = 0.f;
@@ -39,25 +42,25 @@ __global__ void k_init_tab(float *tab, int64_t n_rows, int32_t row_len, int32_t 
   }
 }
 
-__global__ void k_init_lin(float4 *lin, int64_t n, float mean, float stddev, uint64_t seed) {
-  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t i0 = q * 4;
-  if (i0 >= n) return;
-  const float4 gz = gaussian4((uint64_t)q, seed, 2u);
-  const float r[4] = {gz.x, gz.y, gz.z, gz.w};
-  for (int e = 0; e < 4 && i0 + e < n; e++) lin[i0 + e] = make_float4(0.f, 0.f, fmaf(stddev, r[e], mean), 0.f);
+__global__ void k_init_lin(float4 *lin, int64_t n, float mean, float stddev, uint64_t seed, int G, int rank) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 gz = gaussian4((uint64_t)(i * G + rank), seed, 2u);
+  lin[i] = make_float4(0.f, 0.f, fmaf(stddev, gz.x, mean), 0.f);
 }
 
 __global__ void k_randomize(float *tab, float4 *lin, float4 *bias, int64_t n_rows, int32_t row_len, int32_t ld,
-                            uint64_t seed, float z_scale, float n_lo, float n_hi) {
+                            uint64_t seed, float z_scale, float n_lo, float n_hi, int G, int rank) {
   // one thread per 4 consecutive coordinates; slot 0 of each row additionally handles the linear record
   const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t per_row = ld > 0 ? ld / 4 : 1;
   if (q >= n_rows * per_row) return;
   const int64_t row = q / per_row;
   const int v = (int)(q % per_row) * 4;
-  const float4 gz = gaussian4((uint64_t)q, seed, 11u);
-  const uint4 u = philox4x32_10(make_uint4((uint32_t)q, (uint32_t)(q >> 32), 12u, 0u),
+  const int64_t grow = row * G + rank;           // global row
+  const int64_t gq = grow * per_row + v / 4;     // global counter: independent of the sharding
+  const float4 gz = gaussian4((uint64_t)gq, seed, 11u);
+  const uint4 u = philox4x32_10(make_uint4((uint32_t)gq, (uint32_t)(gq >> 32), 12u, 0u),
                                 make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
   const float kk = 2.3283064365386963e-10f;
   const float zr[4] = {gz.x, gz.y, gz.z, gz.w};
@@ -71,12 +74,15 @@ __global__ void k_randomize(float *tab, float4 *lin, float4 *bias, int64_t n_row
       }
   }
   if (v == 0) {
-    const float4 g2 = gaussian4((uint64_t)row, seed, 13u);
+    const float4 g2 = gaussian4((uint64_t)grow, seed, 13u);
     float4 e = lin[row];
     e.x = z_scale * g2.x;
     e.y = n_lo + (n_hi - n_lo) * fabsf(g2.y) * 0.25f;
     lin[row] = e;
-    if (row == 0) *bias = make_float4(z_scale * 0.01f * g2.z, 0.5f * (n_lo + n_hi), 0.f, 0.f);
+    if (row == 0) {  // replicated bias: the same value on every shard
+      const float4 g0 = gaussian4(0ull, seed, 13u);
+      *bias = make_float4(z_scale * 0.01f * g0.z, 0.5f * (n_lo + n_hi), 0.f, 0.f);
+    }
   }
 }
 
@@ -182,6 +188,19 @@ static int key_bits(int32_t n_feats) {
   return bits;
 }
 
+// single-GPU handles: the one shard is this handle itself (staging buffers may have been reallocated)
+static void refresh_shards(ftrl_handle *h) {
+  if (h->G > 1 && h->attached) return;
+  Shards &sh = h->shards;
+  sh.G = 1;
+  sh.log2G = 0;
+  sh.rank = 0;
+  sh.tab[0] = h->tab;
+  sh.lin[0] = h->lin;
+  sh.staging[0] = h->staging.p;
+  sh.staging_lin[0] = h->staging_lin.p;
+}
+
 static void ensure_workspace(ftrl_handle *h, int64_t n_rows, int64_t nnz) {
   if (n_rows <= h->rows_cap && nnz <= h->nnz_cap) return;
   FTRL_CUDA(cudaStreamSynchronize(h->compute));
@@ -202,23 +221,37 @@ static void ensure_workspace(ftrl_handle *h, int64_t n_rows, int64_t nnz) {
   h->skey.ensure(nc);
   h->socc.ensure(nc);
   h->occ_row.ensure(nc);
-  h->fused_sorted.ensure(nc);
+  // owner side of a sharded run: this rank may own up to 2x its own share of the occurrences
+  const int64_t oc = h->G > 1 ? 2 * nc + 1024 : nc;
+  if (h->G > 1 && h->attached) throw ArgFail{"batch exceeds max_batch_rows / max_batch_nnz of a multi-GPU handle"};
+  h->ow_cap = oc;
+  if (h->G > 1) {
+    h->okey.ensure(oc);
+    h->osrc.ensure(oc);
+    h->sel.ensure(oc);
+    h->n_sel.ensure(4);
+    h->red4.ensure(4);
+    h->skey.ensure(oc);
+    h->socc.ensure(oc);
+  }
+  h->fused_sorted.ensure(oc);
   h->occ_pos.ensure(nc);
   h->batch_flags.ensure(4);
   if (h->tile_ok) {
-    h->staging.ensure((size_t)nc * h->dims.ld);
-    h->staging_lin.ensure(nc);
+    h->staging.ensure((size_t)oc * h->dims.ld);
+    h->staging_lin.ensure(oc);
   }
-  h->scan.ensure(nc);
-  h->chunk_pos.ensure(nc + 2);
+  h->scan.ensure(oc);
+  h->chunk_pos.ensure(oc + 2);
   h->n_chunks.ensure(4);
-  const int64_t slots = 2 * (nc / h->chunk + 2);
+  const int64_t slots = 2 * (oc / h->chunk + 2);
   if (h->dims.row_len) h->part.ensure((size_t)slots * 2 * h->dims.ld);
   h->part_lin.ensure(slots);
-  h->cub_bytes = cub_temp_bytes(nc, key_bits(h->dims.n_feats));
+  h->cub_bytes = cub_temp_bytes(h->G > 1 ? (int64_t)h->G * nc : nc, key_bits(h->dims.n_feats));
   h->cub_tmp.ensure(h->cub_bytes);
   h->rows_cap = rc;
   h->nnz_cap = nc;
+  refresh_shards(h);
 }
 
 template <typename F>
@@ -298,8 +331,7 @@ static void run_ffm_batch(ftrl_handle *h, const Batch &b, float *logit_out) {
       const int tgrid = (int)std::min<int64_t>(b.n_rows, (int64_t)h->n_sms * h->tile_ctas_per_sm);
 #define FFM_TILE(I)                                                                                              \
   k_ffm_tile<PRECISE, I><<<tgrid, geo.consumers + 32 + 32 * TILE_META_WARPS, geo.smem_bytes, h->compute>>>(                                \
-      b, d, h->hyper, dec, geo, h->batch_flags.p, h->tab, h->lin, h->bias, h->pair_lut, h->occ_pos.p, h->staging.p, \
-      h->staging_lin.p, h->g.p, logit_out)
+      b, d, h->hyper, dec, geo, h->batch_flags.p, h->shards, h->bias, h->pair_lut, h->occ_pos.p, h->g.p, logit_out)
       if (h->tile_ipt <= 1) FFM_TILE(1);
       else if (h->tile_ipt == 2) FFM_TILE(2);
       else if (h->tile_ipt == 3) FFM_TILE(3);
@@ -454,13 +486,21 @@ static void run_model(ftrl_handle *h, const Batch &b, float *logit_out) {
   }
 }
 
+template <bool PRECISE>
+static void train_device_sharded(ftrl_handle *h, const Batch &b, float *logit_out, double *loss_sum_out);
+
 static void train_device(ftrl_handle *h, const Batch &b, float *logit_out, double *loss_sum_out) {
   h->launches_this_call = 0;
   h->stats = ftrl_batch_stats{};
   h->stats.n_rows = b.n_rows;
   h->last_nnz = b.nnz;
-  if (b.n_rows <= 0) {
+  if (b.n_rows <= 0 && h->G == 1) {
     if (loss_sum_out) FTRL_CUDA(cudaMemsetAsync(loss_sum_out, 0, sizeof(double), h->compute));
+    return;
+  }
+  if (h->G > 1) {
+    if (h->precise) train_device_sharded<true>(h, b, logit_out, loss_sum_out);
+    else train_device_sharded<false>(h, b, logit_out, loss_sum_out);
     return;
   }
   ensure_workspace(h, b.n_rows, b.nnz);
@@ -481,8 +521,8 @@ static void train_device(ftrl_handle *h, const Batch &b, float *logit_out, doubl
   {
     PhaseScope ps(h, PH_REDUCE);
     const int rg = reduce_grid(b.n_rows);
-    if (pr) k_batch_reduce<true><<<rg, 256, 0, h->compute>>>(b.n_rows, h->hyper, h->g.p, logit_out, b.label, h->bias, 1, h->red_part.p, h->ticket.p, loss_sum_out);
-    else k_batch_reduce<false><<<rg, 256, 0, h->compute>>>(b.n_rows, h->hyper, h->g.p, logit_out, b.label, h->bias, 1, h->red_part.p, h->ticket.p, loss_sum_out);
+    if (pr) k_batch_reduce<true><<<rg, 256, 0, h->compute>>>(b.n_rows, h->hyper, h->g.p, logit_out, b.label, h->bias, 1, h->red_part.p, h->ticket.p, loss_sum_out, nullptr);
+    else k_batch_reduce<false><<<rg, 256, 0, h->compute>>>(b.n_rows, h->hyper, h->g.p, logit_out, b.label, h->bias, 1, h->red_part.p, h->ticket.p, loss_sum_out, nullptr);
     FTRL_CUDA(cudaGetLastError());
     launched(h, PH_REDUCE);
   }
@@ -506,9 +546,9 @@ static void predict_device(ftrl_handle *h, const Batch &b, int output_prob, floa
   } else if (d.model_type == FTRL_FFM) {
     const int vec = pick_vec(d.k);
     const dim3 grid((unsigned)b.n_rows);
-    if (vec == 4) k_ffm_predict<4, 256><<<grid, 256, 0, h->compute>>>(b, d, make_item_decode(d.k, 4), h->tab, h->lin, h->bias, h->pair_lut, output_prob, out, lg_side);
-    else if (vec == 2) k_ffm_predict<2, 256><<<grid, 256, 0, h->compute>>>(b, d, make_item_decode(d.k, 2), h->tab, h->lin, h->bias, h->pair_lut, output_prob, out, lg_side);
-    else k_ffm_predict<1, 256><<<grid, 256, 0, h->compute>>>(b, d, make_item_decode(d.k, 1), h->tab, h->lin, h->bias, h->pair_lut, output_prob, out, lg_side);
+    if (vec == 4) k_ffm_predict<4, 256><<<grid, 256, 0, h->compute>>>(b, d, make_item_decode(d.k, 4), h->shards, h->bias, h->pair_lut, output_prob, out, lg_side);
+    else if (vec == 2) k_ffm_predict<2, 256><<<grid, 256, 0, h->compute>>>(b, d, make_item_decode(d.k, 2), h->shards, h->bias, h->pair_lut, output_prob, out, lg_side);
+    else k_ffm_predict<1, 256><<<grid, 256, 0, h->compute>>>(b, d, make_item_decode(d.k, 1), h->shards, h->bias, h->pair_lut, output_prob, out, lg_side);
   } else {
     const unsigned grid = (unsigned)((b.n_rows * 32 + 255) / 256);
     if (d.model_type == FTRL_FM) k_lrfm_predict<true><<<grid, 256, 0, h->compute>>>(b, d, h->tab, h->lin, h->bias, output_prob, out, lg_side);
@@ -517,7 +557,7 @@ static void predict_device(ftrl_handle *h, const Batch &b, int output_prob, floa
   FTRL_CUDA(cudaGetLastError());
   launched(h, PH_PREDICT);
   if (loss_sum_out) {
-    k_batch_reduce<true><<<reduce_grid(b.n_rows), 256, 0, h->compute>>>(b.n_rows, h->hyper, nullptr, lg, b.label, h->bias, 0, h->red_part.p, h->ticket.p, loss_sum_out);
+    k_batch_reduce<true><<<reduce_grid(b.n_rows), 256, 0, h->compute>>>(b.n_rows, h->hyper, nullptr, lg, b.label, h->bias, 0, h->red_part.p, h->ticket.p, loss_sum_out, nullptr);
     FTRL_CUDA(cudaGetLastError());
     launched(h, PH_PREDICT);
   }
@@ -605,6 +645,141 @@ static void check_device_err(ftrl_handle *h) {
 // ---------------------------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------
+// feature-sharded multi-GPU step (shard.cuh)
+// ---------------------------------------------------------------------------------------------
+static void peer_barrier(ftrl_handle *h) {
+  h->epoch++;
+  k_peer_barrier<<<1, 32, 0, h->compute>>>(h->peers, h->epoch);
+  FTRL_CUDA(cudaGetLastError());
+}
+
+template <bool PRECISE>
+static void train_device_sharded(ftrl_handle *h, const Batch &b, float *logit_out, double *loss_sum_out) {
+  if (!h->attached) throw StateFail{"multi-GPU handle: call ftrl_attach_peers before training"};
+  const Dims &d = h->dims;
+  if (b.n_rows > h->rows_cap || b.nnz > h->nnz_cap) throw ArgFail{"batch exceeds max_batch_rows / max_batch_nnz of a multi-GPU handle"};
+  const int32_t nnz = (int32_t)b.nnz;
+  const int32_t nnz_max = (int32_t)h->cfg.max_batch_nnz;
+  const uint32_t sentinel = (uint32_t)d.n_feats;
+  const uint32_t lsent = (uint32_t)h->n_local;  // sentinel in local-row space (n_local may differ by 1 across ranks)
+  const int32_t oc = (int32_t)h->ow_cap;
+  if (!logit_out) logit_out = h->logit_ws.p;
+  {
+    PhaseScope ps(h, PH_PREP);
+    FTRL_CUDA(cudaMemsetAsync(h->batch_flags.p, 0x01, sizeof(int32_t), h->compute));
+    if (b.n_rows > 0) {
+      const unsigned grid = (unsigned)((b.n_rows * 32 + 255) / 256);
+      k_prep_rows<<<grid, 256, 0, h->compute>>>(b, d, h->key.p, h->occ_idx.p, h->occ_row.p, h->sflags.p, h->batch_flags.p);
+    }
+    k_publish<<<1, 32, 0, h->compute>>>(h->peers, nnz, h->batch_flags.p);
+    FTRL_CUDA(cudaGetLastError());
+    launched(h, PH_PREP, 2);
+    peer_barrier(h);  // 1: every rank's keys / nnz are published
+  }
+  {
+    PhaseScope ps(h, PH_SORT);
+    k_merge_flags<<<1, 1, 0, h->compute>>>(h->peers, h->batch_flags.p, h->d_err);
+    size_t bytes = h->cub_bytes;
+    thrust::counting_iterator<int32_t> cnt(0);
+    FTRL_CUDA(cub::DeviceSelect::If(h->cub_tmp.p, bytes, cnt, h->sel.p, h->n_sel.p, h->G * nnz_max,
+                                    OwnedPred{h->peers, nnz_max, sentinel}, h->compute));
+    k_fill_owned<<<(oc + 255) / 256, 256, 0, h->compute>>>(h->peers, nnz_max, oc, lsent, h->sel.p, h->n_sel.p, h->okey.p,
+                                                          h->osrc.p, h->d_err);
+    bytes = h->cub_bytes;
+    FTRL_CUDA(cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, bytes, h->okey.p, h->skey.p, h->osrc.p, h->socc.p, oc, 0,
+                                              key_bits((int32_t)h->n_local), h->compute));
+    FTRL_CUDA(cudaGetLastError());
+    launched(h, PH_SORT, 2);
+  }
+  {
+    PhaseScope ps(h, PH_SEGMENT);
+    k_occ_class_sharded<<<(oc + 255) / 256, 256, 0, h->compute>>>(h->peers, oc, lsent, h->skey.p, h->socc.p, h->fused_sorted.p);
+    size_t bytes = h->cub_bytes;
+    thrust::counting_iterator<int32_t> cnt(0);
+    auto it = thrust::make_transform_iterator(cnt, HeadFunctor{h->skey.p, h->fused_sorted.p});
+    FTRL_CUDA(cub::DeviceScan::InclusiveScan(h->cub_tmp.p, bytes, it, h->scan.p, SegScanOp(), oc, h->compute));
+    bytes = h->cub_bytes;
+    FTRL_CUDA(cub::DeviceSelect::If(h->cub_tmp.p, bytes, cnt, h->chunk_pos.p, h->n_chunks.p, oc,
+                                    ChunkHeadPred{h->skey.p, h->scan.p, h->fused_sorted.p, lsent, h->chunk}, h->compute));
+    k_terminate<<<1, 1, 0, h->compute>>>(h->chunk_pos.p, h->n_chunks.p, oc);
+    FTRL_CUDA(cudaGetLastError());
+    launched(h, PH_SEGMENT, 2);
+    peer_barrier(h);  // 2: every occurrence knows its class / staging position
+  }
+  const ItemDecode dec = make_item_decode(d.k, 4);
+  const int grid = h->n_sms * 4;
+  {
+    PhaseScope ps(h, PH_SAMPLE);
+    if (b.n_rows > 0) {
+      TileGeom geo;
+      geo.f_cap = h->tile_f_cap;
+      geo.stride = h->tile_stride;
+      geo.n_stage = h->tile_stages;
+      geo.n_meta = h->tile_meta;
+      geo.consumers = h->tile_consumers;
+      geo.smem_bytes = h->tile_smem;
+      const int tgrid = (int)std::min<int64_t>(b.n_rows, (int64_t)h->n_sms * h->tile_ctas_per_sm);
+#define FFM_TILE(I)                                                                                              \
+  k_ffm_tile<PRECISE, I><<<tgrid, geo.consumers + 32 + 32 * TILE_META_WARPS, geo.smem_bytes, h->compute>>>(        \
+      b, d, h->hyper, dec, geo, h->batch_flags.p, h->shards, h->bias, h->pair_lut, h->occ_pos.p, h->g.p, logit_out)
+      if (h->tile_ipt <= 1) FFM_TILE(1);
+      else if (h->tile_ipt == 2) FFM_TILE(2);
+      else if (h->tile_ipt == 3) FFM_TILE(3);
+      else FFM_TILE(4);
+#undef FFM_TILE
+      FTRL_CUDA(cudaGetLastError());
+      launched(h, PH_SAMPLE);
+    }
+  }
+  {
+    PhaseScope ps(h, PH_REDUCE);
+    k_batch_reduce<PRECISE><<<reduce_grid(std::max<int64_t>(1, b.n_rows)), 256, 0, h->compute>>>(
+        b.n_rows, h->hyper, h->g.p, logit_out, b.label, h->bias, 0, h->red_part.p, h->ticket.p, loss_sum_out, h->red4.p);
+    k_publish_red<<<1, 32, 0, h->compute>>>(h->peers, h->red4.p);
+    FTRL_CUDA(cudaGetLastError());
+    launched(h, PH_REDUCE, 2);
+    peer_barrier(h);  // 3: all gradient images are staged at their owners, all partials are exchanged
+    k_bias_apply<PRECISE><<<1, 1, 0, h->compute>>>(h->peers, h->hyper, h->bias);
+    launched(h, PH_REDUCE);
+  }
+  {
+    PhaseScope ps(h, PH_ROWS);
+    const int nvec = d.ld / 4;
+#define FFM_STAGED(RR)                                                                                             \
+  k_ffm_staged_rows<PRECISE, 8, RR><<<grid * 2, 256, 0, h->compute>>>(d, h->hyper, oc, h->batch_flags.p, h->tab, h->lin, \
+                                                                     h->chunk, h->n_chunks.p, h->chunk_pos.p, h->skey.p, \
+                                                                     h->scan.p, h->staging.p, h->staging_lin.p,      \
+                                                                     h->part.p, h->part_lin.p)
+    if (nvec <= 32) FFM_STAGED(1);
+    else if (nvec <= 64) FFM_STAGED(2);
+    else if (nvec <= 96) FFM_STAGED(3);
+    else FFM_STAGED(4);
+#undef FFM_STAGED
+    FTRL_CUDA(cudaGetLastError());
+    launched(h, PH_ROWS);
+  }
+  {
+    PhaseScope ps(h, PH_COMBINE);
+    k_ffm_combine<PRECISE, 256><<<grid, 256, 0, h->compute>>>(d, h->hyper, oc, h->tab, h->lin, h->chunk, h->n_chunks.p,
+                                                              h->chunk_pos.p, h->skey.p, h->scan.p, h->part.p, h->part_lin.p);
+    FTRL_CUDA(cudaGetLastError());
+    launched(h, PH_COMBINE);
+  }
+  h->stats.kernel_launches = h->launches_this_call;
+}
+
+struct PeerBlob {  // FTRL_PEER_BLOB_BYTES
+  uint32_t magic;
+  int32_t rank, world, device;
+  int64_t pid;
+  int64_t nnz_cap, ow_cap;
+  void *raw[7];                // same-process attach
+  cudaIpcMemHandle_t ipc[7];   // tab, lin, staging, staging_lin, key, occ_pos, sync
+};
+static_assert(sizeof(PeerBlob) <= FTRL_PEER_BLOB_BYTES, "peer blob too large");
+
+
 extern "C" {
 
 int ftrl_abi_version(void) { return FTRL_B200_ABI_VERSION; }
@@ -663,6 +838,19 @@ int ftrl_create(const ftrl_config *cfg, ftrl_handle **out) {
     d.row_len = (int32_t)rl;
     d.ld = (int32_t)((rl + 3) / 4 * 4);
     h->hyper = Hyper{cfg->w_alpha, cfg->w_beta, cfg->w_l1, cfg->w_l2, 1.0f / cfg->w_alpha};
+    h->G = h->cfg.world_size;
+    h->rank = h->cfg.rank;
+    if (h->G > 1) {
+      if (h->G > MAX_SHARDS || (h->G & (h->G - 1))) throw ArgFail{"world_size must be 1, 2, 4 or 8"};
+      if (h->rank < 0 || h->rank >= h->G) throw ArgFail{"rank out of range"};
+      if (cfg->model_type != FTRL_FFM || cfg->mode != FTRL_MODE_BATCH)
+        throw ArgFail{"feature-sharded multi-GPU runs support FFM in minibatch mode only"};
+      if (cfg->max_batch_rows <= 0 || cfg->max_batch_nnz <= 0)
+        throw ArgFail{"multi-GPU runs need max_batch_rows / max_batch_nnz (buffers are mapped by peers, they cannot grow)"};
+      if (cfg->max_batch_nnz >= (1ll << SRC_SHIFT)) throw ArgFail{"max_batch_nnz must be < 2^28 in multi-GPU runs"};
+      while ((1 << h->log2G) < h->G) h->log2G++;
+    }
+    h->n_local = h->G > 1 ? ((int64_t)cfg->n_feats - h->rank + h->G - 1) / h->G : cfg->n_feats;
     static const char *names[PH_COUNT] = {"prep_rows", "sort", "segment", "sample", "rows", "combine", "reduce", "exact", "predict", "generic"};
     for (int i = 0; i < PH_COUNT; i++) h->phases[i].name = names[i];
     cudaDeviceProp prop;
@@ -717,7 +905,8 @@ int ftrl_create(const ftrl_config *cfg, ftrl_handle **out) {
     }
     FTRL_CUDA(cudaStreamCreateWithFlags(&h->compute, cudaStreamNonBlocking));
     FTRL_CUDA(cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking));
-    const int64_t n = d.n_feats;
+    if (h->G > 1 && !h->tile_ok) throw ArgFail{"multi-GPU runs need the tile path (n_factors % 4 == 0, sample tile must fit shared memory)"};
+    const int64_t n = std::max<int64_t>(1, h->n_local);
     FTRL_CUDA(cudaMalloc(&h->lin, sizeof(float4) * n));
     FTRL_CUDA(cudaMalloc(&h->bias, sizeof(float4)));
     FTRL_CUDA(cudaMemsetAsync(h->bias, 0, sizeof(float4), h->compute));
@@ -725,14 +914,19 @@ int ftrl_create(const ftrl_config *cfg, ftrl_handle **out) {
     FTRL_CUDA(cudaMemsetAsync(h->d_err, 0, sizeof(int32_t), h->compute));
     FTRL_CUDA(cudaMalloc(&h->pair_lut, sizeof(uint32_t) * PAIR_LUT_N));
     k_build_pair_lut<<<(PAIR_LUT_N + 255) / 256, 256, 0, h->compute>>>(h->pair_lut);
-    k_init_lin<<<(unsigned)(((n + 3) / 4 + 255) / 256), 256, 0, h->compute>>>(h->lin, n, cfg->init_mean, cfg->init_stddev, cfg->seed);
+    k_init_lin<<<(unsigned)((n + 255) / 256), 256, 0, h->compute>>>(h->lin, n, cfg->init_mean, cfg->init_stddev, cfg->seed, h->G, h->rank);
     if (d.row_len) {
       FTRL_CUDA(cudaMalloc(&h->tab, sizeof(float) * 3 * (size_t)d.ld * (size_t)n));
       const int64_t q = n * (d.ld / 4);
-      k_init_tab<<<(unsigned)((q + 255) / 256), 256, 0, h->compute>>>(h->tab, n, d.row_len, d.ld, cfg->init_mean, cfg->init_stddev, cfg->seed);
+      k_init_tab<<<(unsigned)((q + 255) / 256), 256, 0, h->compute>>>(h->tab, n, d.row_len, d.ld, cfg->init_mean, cfg->init_stddev, cfg->seed, h->G, h->rank);
     }
     FTRL_CUDA(cudaGetLastError());
     if (cfg->max_batch_rows > 0) ensure_workspace(h, cfg->max_batch_rows, std::max<int64_t>(cfg->max_batch_nnz, 0));
+    if (h->G > 1) {
+      FTRL_CUDA(cudaMalloc(&h->sync, sizeof(SyncArea)));
+      FTRL_CUDA(cudaMemsetAsync(h->sync, 0, sizeof(SyncArea), h->compute));
+    }
+    refresh_shards(h);
     FTRL_CUDA(cudaStreamSynchronize(h->compute));
   });
   if (rc != FTRL_OK) {
@@ -756,6 +950,8 @@ void ftrl_destroy(ftrl_handle *h) {
     cudaEventDestroy(pe.b);
   }
   for (auto e : h->event_pool) cudaEventDestroy(e);
+  for (void *p : h->ipc_opened) cudaIpcCloseMemHandle(p);
+  if (h->sync) cudaFree(h->sync);
   if (h->tab) cudaFree(h->tab);
   if (h->lin) cudaFree(h->lin);
   if (h->bias) cudaFree(h->bias);
@@ -833,7 +1029,7 @@ int ftrl_sync(ftrl_handle *h) {
 static void xfer_rows(ftrl_handle *h, int which, int64_t row0, int64_t n_rows, float *lin, float *vec, bool get) {
   const Dims &d = h->dims;
   if (which < 0 || which > 2) throw ArgFail{"which must be 0 (w), 1 (n) or 2 (z)"};
-  if (row0 < 0 || n_rows < 0 || row0 + n_rows > d.n_feats) throw ArgFail{"row range out of bounds"};
+  if (row0 < 0 || n_rows < 0 || row0 + n_rows > h->n_local) throw ArgFail{"row range out of bounds"};
   const int plane = plane_of(which);
   FTRL_CUDA(cudaStreamSynchronize(h->compute));
   const int64_t chunk_rows = std::max<int64_t>(1, (int64_t)(16 << 20) / std::max<int32_t>(1, d.row_len));
@@ -887,14 +1083,14 @@ int ftrl_get_weights(ftrl_handle *h, float *bias, float *lin_w, float *vec_w) {
   if (!h) return FTRL_ERR_ARG;
   return guarded(h, [&] {
     xfer_bias(h, 0, bias, true);
-    xfer_rows(h, 0, 0, h->dims.n_feats, lin_w, vec_w, true);
+    xfer_rows(h, 0, 0, h->n_local, lin_w, vec_w, true);
   });
 }
 int ftrl_set_weights(ftrl_handle *h, const float *bias, const float *lin_w, const float *vec_w) {
   if (!h) return FTRL_ERR_ARG;
   return guarded(h, [&] {
     xfer_bias(h, 0, const_cast<float *>(bias), false);
-    xfer_rows(h, 0, 0, h->dims.n_feats, const_cast<float *>(lin_w), const_cast<float *>(vec_w), false);
+    xfer_rows(h, 0, 0, h->n_local, const_cast<float *>(lin_w), const_cast<float *>(vec_w), false);
   });
 }
 int ftrl_get_state(ftrl_handle *h, int which, float *bias_s, float *lin_s, float *vec_s) {
@@ -902,7 +1098,7 @@ int ftrl_get_state(ftrl_handle *h, int which, float *bias_s, float *lin_s, float
   return guarded(h, [&] {
     if (which != 1 && which != 2) throw ArgFail{"which must be 1 (n) or 2 (z)"};
     xfer_bias(h, which, bias_s, true);
-    xfer_rows(h, which, 0, h->dims.n_feats, lin_s, vec_s, true);
+    xfer_rows(h, which, 0, h->n_local, lin_s, vec_s, true);
   });
 }
 int ftrl_set_state(ftrl_handle *h, int which, const float *bias_s, const float *lin_s, const float *vec_s) {
@@ -910,7 +1106,7 @@ int ftrl_set_state(ftrl_handle *h, int which, const float *bias_s, const float *
   return guarded(h, [&] {
     if (which != 1 && which != 2) throw ArgFail{"which must be 1 (n) or 2 (z)"};
     xfer_bias(h, which, const_cast<float *>(bias_s), false);
-    xfer_rows(h, which, 0, h->dims.n_feats, const_cast<float *>(lin_s), const_cast<float *>(vec_s), false);
+    xfer_rows(h, which, 0, h->n_local, const_cast<float *>(lin_s), const_cast<float *>(vec_s), false);
   });
 }
 
@@ -919,8 +1115,8 @@ int ftrl_has_zero_weights(ftrl_handle *h, int *out) {
   return guarded(h, [&] {
     const Dims &d = h->dims;
     FTRL_CUDA(cudaMemsetAsync(h->d_err, 0, sizeof(int32_t), h->compute));
-    const int64_t q = (int64_t)d.n_feats * (d.row_len + 1);
-    k_has_zero<<<(unsigned)((q + 255) / 256), 256, 0, h->compute>>>(h->tab, h->lin, d.n_feats, d.row_len, d.ld, h->d_err);
+    const int64_t q = h->n_local * (d.row_len + 1);
+    k_has_zero<<<(unsigned)((q + 255) / 256), 256, 0, h->compute>>>(h->tab, h->lin, h->n_local, d.row_len, d.ld, h->d_err);
     FTRL_CUDA(cudaGetLastError());
     int32_t f = 0;
     FTRL_CUDA(cudaMemcpyAsync(&f, h->d_err, sizeof(f), cudaMemcpyDeviceToHost, h->compute));
@@ -938,9 +1134,9 @@ int ftrl_randomize_state(ftrl_handle *h, uint64_t seed, float z_scale, float n_l
     if (!(n_lo >= 0.f) || !(n_hi >= n_lo)) throw ArgFail{"need 0 <= n_lo <= n_hi"};
     const Dims &d = h->dims;
     const int64_t per_row = d.ld > 0 ? d.ld / 4 : 1;
-    const int64_t q = (int64_t)d.n_feats * per_row;
-    k_randomize<<<(unsigned)((q + 255) / 256), 256, 0, h->compute>>>(h->tab, h->lin, h->bias, d.n_feats, d.row_len, d.ld,
-                                                                    seed, z_scale, n_lo, n_hi);
+    const int64_t q = h->n_local * per_row;
+    k_randomize<<<(unsigned)((q + 255) / 256), 256, 0, h->compute>>>(h->tab, h->lin, h->bias, h->n_local, d.row_len, d.ld,
+                                                                    seed, z_scale, n_lo, n_hi, h->G, h->rank);
     FTRL_CUDA(cudaGetLastError());
     FTRL_CUDA(cudaStreamSynchronize(h->compute));
   });
@@ -950,6 +1146,7 @@ int ftrl_randomize_state(ftrl_handle *h, uint64_t seed, float z_scale, float n_l
 int ftrl_save_model(ftrl_handle *h, const char *path, int compress_level) {
   if (!h || !path) return FTRL_ERR_ARG;
   return guarded(h, [&] {
+    if (h->G > 1) throw StateFail{"model files of a feature-sharded run are not supported yet: save per shard with ftrl_get_rows"};
     const Dims &d = h->dims;
     const uint64_t total = sizeof(float) * (1ull + (uint64_t)d.n_feats + (uint64_t)d.n_feats * d.row_len);
     ModelWriter w(path, compress_level, total);
@@ -977,6 +1174,7 @@ int ftrl_save_model(ftrl_handle *h, const char *path, int compress_level) {
 int ftrl_load_model(ftrl_handle *h, const char *path) {
   if (!h || !path) return FTRL_ERR_ARG;
   return guarded(h, [&] {
+    if (h->G > 1) throw StateFail{"model files of a feature-sharded run are not supported yet: save per shard with ftrl_get_rows"};
     const Dims &d = h->dims;
     const uint64_t total = sizeof(float) * (1ull + (uint64_t)d.n_feats + (uint64_t)d.n_feats * d.row_len);
     ModelReader rd(path);
@@ -1005,6 +1203,7 @@ int ftrl_load_model(ftrl_handle *h, const char *path) {
 int ftrl_save_model_text(ftrl_handle *h, const char *path) {
   if (!h || !path) return FTRL_ERR_ARG;
   return guarded(h, [&] {
+    if (h->G > 1) throw StateFail{"model files of a feature-sharded run are not supported yet: save per shard with ftrl_get_rows"};
     const Dims &d = h->dims;
     std::vector<float> lin((size_t)d.n_feats), vec((size_t)d.n_feats * d.row_len);
     float b = 0.f;
@@ -1017,6 +1216,7 @@ int ftrl_save_model_text(ftrl_handle *h, const char *path) {
 int ftrl_load_model_text(ftrl_handle *h, const char *path) {
   if (!h || !path) return FTRL_ERR_ARG;
   return guarded(h, [&] {
+    if (h->G > 1) throw StateFail{"model files of a feature-sharded run are not supported yet: save per shard with ftrl_get_rows"};
     const Dims &d = h->dims;
     std::vector<float> lin((size_t)d.n_feats), vec((size_t)d.n_feats * d.row_len);
     float b = 0.f;
@@ -1110,10 +1310,11 @@ int ftrl_last_batch_stats(ftrl_handle *h, ftrl_batch_stats *out) {
     DevBuf<int64_t> tmp;
     tmp.alloc(4);
     FTRL_CUDA(cudaMemset(tmp.p, 0, sizeof(int64_t) * 4));
-    int32_t nnz = (int32_t)h->last_nnz;
+    // sharded runs: the sorted list is the owner-side list (rows this rank owns, from all ranks' samples)
+    int32_t nnz = h->G > 1 ? (int32_t)h->ow_cap : (int32_t)h->last_nnz;
     if (nnz > 0) {
       const bool have_single = h->dims.model_type == FTRL_FFM && h->fuse;
-      k_batch_stats<<<256, 256, 0, h->compute>>>(nnz, (uint32_t)h->dims.n_feats, h->skey.p, h->scan.p,
+      k_batch_stats<<<256, 256, 0, h->compute>>>(nnz, h->G > 1 ? (uint32_t)h->n_local : (uint32_t)h->dims.n_feats, h->skey.p, h->scan.p,
                                                  have_single ? h->fused_sorted.p : nullptr, h->n_chunks.p, tmp.p);
       FTRL_CUDA(cudaGetLastError());
     }
@@ -1131,13 +1332,76 @@ int ftrl_last_batch_stats(ftrl_handle *h, ftrl_batch_stats *out) {
 // ---- multi-GPU ------------------------------------------------------------------------------
 int ftrl_export_peer_blob(ftrl_handle *h, void *blob) {
   if (!h || !blob) return FTRL_ERR_ARG;
-  h->err = "feature-sharded multi-GPU exchange is not built yet";
-  return FTRL_ERR_STATE;
+  return guarded(h, [&] {
+    if (h->G <= 1) throw StateFail{"not a multi-GPU handle (world_size <= 1)"};
+    PeerBlob pb;
+    memset(&pb, 0, sizeof(pb));
+    pb.magic = 0xF7B20001u;
+    pb.rank = h->rank;
+    pb.world = h->G;
+    pb.device = h->cfg.device;
+    pb.pid = (int64_t)getpid();
+    pb.nnz_cap = h->nnz_cap;
+    pb.ow_cap = h->ow_cap;
+    void *ptrs[7] = {h->tab, h->lin, h->staging.p, h->staging_lin.p, h->key.p, h->occ_pos.p, h->sync};
+    for (int i = 0; i < 7; i++) {
+      pb.raw[i] = ptrs[i];
+      if (!ptrs[i]) throw StateFail{"multi-GPU buffers are not allocated"};
+      FTRL_CUDA(cudaIpcGetMemHandle(&pb.ipc[i], ptrs[i]));
+    }
+    memset(blob, 0, FTRL_PEER_BLOB_BYTES);
+    memcpy(blob, &pb, sizeof(pb));
+  });
 }
+
 int ftrl_attach_peers(ftrl_handle *h, const void *blobs) {
   if (!h || !blobs) return FTRL_ERR_ARG;
-  h->err = "feature-sharded multi-GPU exchange is not built yet";
-  return FTRL_ERR_STATE;
+  return guarded(h, [&] {
+    if (h->G <= 1) throw StateFail{"not a multi-GPU handle (world_size <= 1)"};
+    if (h->attached) throw StateFail{"peers already attached"};
+    Shards sh{};
+    Peers pr{};
+    sh.G = pr.G = h->G;
+    sh.log2G = pr.log2G = h->log2G;
+    sh.rank = pr.rank = h->rank;
+    for (int q = 0; q < h->G; q++) {
+      PeerBlob pb;
+      memcpy(&pb, static_cast<const char *>(blobs) + (size_t)q * FTRL_PEER_BLOB_BYTES, sizeof(pb));
+      if (pb.magic != 0xF7B20001u || pb.rank != q || pb.world != h->G) throw ArgFail{fmt("peer blob %d is not from rank %d of %d", q, q, h->G)};
+      if (pb.nnz_cap != h->nnz_cap) throw ArgFail{"all ranks must use the same max_batch_nnz"};
+      void *ptr[7];
+      if (q == h->rank) {
+        void *mine[7] = {h->tab, h->lin, h->staging.p, h->staging_lin.p, h->key.p, h->occ_pos.p, h->sync};
+        memcpy(ptr, mine, sizeof(ptr));
+      } else if (pb.pid == (int64_t)getpid()) {
+        // same process (several handles in one process): plain pointers, peer access if another device
+        if (pb.device != h->cfg.device) {
+          int can = 0;
+          FTRL_CUDA(cudaDeviceCanAccessPeer(&can, h->cfg.device, pb.device));
+          if (!can) throw StateFail{fmt("device %d cannot access device %d", h->cfg.device, pb.device)};
+          cudaError_t e = cudaDeviceEnablePeerAccess(pb.device, 0);
+          if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) FTRL_CUDA(e);
+          cudaGetLastError();
+        }
+        memcpy(ptr, pb.raw, sizeof(ptr));
+      } else {
+        for (int i = 0; i < 7; i++) {
+          FTRL_CUDA(cudaIpcOpenMemHandle(&ptr[i], pb.ipc[i], cudaIpcMemLazyEnablePeerAccess));
+          h->ipc_opened.push_back(ptr[i]);
+        }
+      }
+      sh.tab[q] = static_cast<float *>(ptr[0]);
+      sh.lin[q] = static_cast<float4 *>(ptr[1]);
+      sh.staging[q] = static_cast<float *>(ptr[2]);
+      sh.staging_lin[q] = static_cast<float *>(ptr[3]);
+      pr.key[q] = static_cast<const uint32_t *>(ptr[4]);
+      pr.occ_pos[q] = static_cast<int32_t *>(ptr[5]);
+      pr.sync[q] = static_cast<SyncArea *>(ptr[6]);
+    }
+    h->shards = sh;
+    h->peers = pr;
+    h->attached = true;
+  });
 }
 
 }  // extern "C"

@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(256)
 k_batch_reduce(int64_t n_rows, Hyper h, const float *__restrict__ g, const float *__restrict__ logit,
                const int32_t *__restrict__ label, float4 *__restrict__ bias, int update_bias,
                double *__restrict__ partials, unsigned int *__restrict__ ticket,
-               double *__restrict__ loss_sum_out) {
+               double *__restrict__ loss_sum_out, double *__restrict__ publish4) {
   __shared__ double sh[3][8];
   __shared__ bool s_last;
   const int64_t per = (n_rows + gridDim.x - 1) / gridDim.x;
@@ -319,7 +319,9 @@ k_batch_reduce(int64_t n_rows, Hyper h, const float *__restrict__ g, const float
       q += __ldcg(partials + 3 * c + 1);
       l += __ldcg(partials + 3 * c + 2);
     }
-    if (update_bias && n_rows > 0) {
+    if (publish4) {  // sharded run: the bias update happens after the partials of all ranks are exchanged
+      publish4[0] = a; publish4[1] = q; publish4[2] = l; publish4[3] = (double)n_rows;
+    } else if (update_bias && n_rows > 0) {
       float4 e = *bias;
       e.z = weight_from<PRECISE>(e.x, f_sqrt<PRECISE>(e.y), h);
       ftrl_apply<PRECISE>(e.x, e.y, e.z, (float)a, (float)q, h);

@@ -199,7 +199,7 @@ int ftrl_randomize_state(ftrl_handle *h, uint64_t seed, float z_scale, float n_l
 /* Opaque, fixed-size descriptor of this rank's device tables that peers can map
  * (cudaIpcMemHandle-based).  Exchange the blobs out of band (e.g. an all-gather over
  * torch.distributed / MPI), then hand all world_size blobs to ftrl_attach_peers. */
-#define FTRL_PEER_BLOB_BYTES 512
+#define FTRL_PEER_BLOB_BYTES 1024
 int ftrl_export_peer_blob(ftrl_handle *h, void *blob /* FTRL_PEER_BLOB_BYTES */);
 int ftrl_attach_peers(ftrl_handle *h, const void *blobs /* world_size * FTRL_PEER_BLOB_BYTES */);
 

@@ -1,6 +1,9 @@
 import os
 import sys
 
+# several logical shards in one process need their streams on distinct hardware queues
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 import numpy as np
 import pytest
 

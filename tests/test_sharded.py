@@ -1,0 +1,101 @@
+"""Feature-sharded multi-GPU path.
+
+CPU part (gloo, world_size 2): the host-side plumbing a launcher needs -- exchanging fixed-size peer blobs
+with an all-gather and the shard <-> full-table index mapping.
+GPU part: G logical shards inside one process on one GPU must give the same model as a single GPU
+(shard-count invariance)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from conftest import assert_close, assert_state_close
+import ftrl_ffm_b200 as pkg
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # what bench.py does with the blobs of ftrl_export_peer_blob
+    blob = torch.full((pkg.binding.PEER_BLOB_BYTES,), rank + 1, dtype=torch.uint8)
+    out = [torch.zeros_like(blob) for _ in range(world)]
+    dist.all_gather(out, blob)
+    ok = all(int(o[0]) == r + 1 and int(o[-1]) == r + 1 for r, o in enumerate(out))
+    # per-rank share of a global batch + shard mapping
+    rng = np.random.default_rng(0)
+    st = pkg.synth.random_state(rng, 37, 6)
+    mine = pkg.shard_state(st, world, rank)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, {k: v.tolist() for k, v in mine.items()})
+    merged = pkg.merge_states([{k: np.asarray(v, np.float32) for k, v in g.items()} for g in gathered])
+    ok = ok and all(np.array_equal(merged[k], st[k]) for k in st)
+    t = torch.tensor([1.0 + rank])
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ok = ok and float(t) == float(world)
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_blob_exchange_and_shard_mapping():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]
+
+
+def test_shard_state_round_trip():
+    rng = np.random.default_rng(1)
+    st = pkg.synth.random_state(rng, 41, 8)
+    for g in (1, 2, 4, 8):
+        parts = [pkg.shard_state(st, g, r) for r in range(g)]
+        assert sum(len(p["lin_w"]) for p in parts) == 41
+        merged = pkg.merge_states(parts)
+        for k in st:
+            assert np.array_equal(merged[k], st[k])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 4])
+def test_shard_count_invariance_on_one_gpu(world):
+    rng = np.random.default_rng(5)
+    nf, nfl, k, B = 3000, 13, 8, 512
+    kw = dict(model_type="FFM", n_feats=nf, n_fields=nfl, n_factors=k)
+    single = pkg.FtrlModel(**kw)
+    sharded = pkg.LogicalShards(world, max_batch_rows=B, max_batch_nnz=B * nfl, **kw)
+    st = pkg.synth.random_state(rng, nf, nfl * k)
+    single.set_state(st)
+    sharded.set_state(st)
+    for step in range(3):
+        parts = [pkg.synth.criteo_batch(B, nfl, nf, seed=100 * step + r, dist="zipf" if step % 2 else "uniform")
+                 for r in range(world)]
+        # the single GPU sees the concatenation of all ranks' samples as ONE minibatch
+        glob = {"row_ptr": np.concatenate([[0]] + [p["row_ptr"][1:] + i * B * nfl for i, p in enumerate(parts)]),
+                "field": np.concatenate([p["field"] for p in parts]), "feat": np.concatenate([p["feat"] for p in parts]),
+                "val": np.concatenate([p["val"] for p in parts]), "label": np.concatenate([p["label"] for p in parts])}
+        lg1, loss1 = single.train(**glob)
+        outs = sharded.train(parts)
+        lgG = np.concatenate([o[0] for o in outs])
+        assert_close(lgG, lg1, 1e-5, 2e-6, f"logits step {step}")
+        assert abs(sum(o[1] for o in outs) - loss1) <= 1e-6 * max(1.0, abs(loss1))
+        assert_state_close(sharded.get_state(), single.get_state(), rtol=2e-5, atol=2e-6, atol_z=2e-4,
+                           name=f"G={world} step {step}")
+    sharded.close()
