@@ -376,8 +376,14 @@ class LogicalShards:
         """batches[r]: the CSR dict of rank r's share of the global minibatch.  All ranks are enqueued
         before any is synchronised (the device-side barriers need every rank in flight)."""
         pend = [m.train(**b, sync=False) for m, b in zip(self.models, batches)]
+        err = None
         for m in self.models:
-            m.sync()
+            try:
+                m.sync()
+            except FtrlError as e:  # keep draining the other ranks, then report
+                err = e
+        if err:
+            raise err
         return [(lg, float(ls[0])) for lg, ls in pend]
 
     def close(self):

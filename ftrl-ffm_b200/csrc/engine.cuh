@@ -173,6 +173,7 @@ struct ftrl_handle {
   ftrl::Peers peers{};
   ftrl::SyncArea *sync = nullptr;
   uint32_t epoch = 0;
+  long long barrier_timeout_cycles = 40000000000ll;
   bool attached = false;
   int64_t ow_cap = 0;           // owner-side capacity: occurrences this rank may own per step
   ftrl::DevBuf<uint32_t> okey, osrc;

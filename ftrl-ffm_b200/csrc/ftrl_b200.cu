@@ -247,7 +247,7 @@ static void ensure_workspace(ftrl_handle *h, int64_t n_rows, int64_t nnz) {
   const int64_t slots = 2 * (oc / h->chunk + 2);
   if (h->dims.row_len) h->part.ensure((size_t)slots * 2 * h->dims.ld);
   h->part_lin.ensure(slots);
-  h->cub_bytes = cub_temp_bytes(h->G > 1 ? (int64_t)h->G * nc : nc, key_bits(h->dims.n_feats));
+  h->cub_bytes = cub_temp_bytes(h->G > 1 ? std::max<int64_t>((int64_t)h->G * nc, oc) : nc, key_bits(h->dims.n_feats));
   h->cub_tmp.ensure(h->cub_bytes);
   h->rows_cap = rc;
   h->nnz_cap = nc;
@@ -638,6 +638,9 @@ static void check_device_err(ftrl_handle *h) {
   FTRL_CUDA(cudaMemcpy(&e, h->d_err, sizeof(e), cudaMemcpyDeviceToHost));
   if (e) {
     FTRL_CUDA(cudaMemset(h->d_err, 0, sizeof(e)));
+    if (e == 2) throw ArgFail{"multi-GPU run: a sample repeats a field (the sharded path needs distinct fields per sample)"};
+    if (e == 3) throw ArgFail{"multi-GPU run: the rows owned by this rank exceed the workspace (extreme id skew)"};
+    if (e == 4) throw StateFail{"multi-GPU run: a peer did not reach the device barrier in time"};
     throw ArgFail{"sequential mode: a sample exceeds the supported size (more than 96 valid features, or FM n_factors > 1024)"};
   }
 }
@@ -650,7 +653,7 @@ static void check_device_err(ftrl_handle *h) {
 // ---------------------------------------------------------------------------------------------
 static void peer_barrier(ftrl_handle *h) {
   h->epoch++;
-  k_peer_barrier<<<1, 32, 0, h->compute>>>(h->peers, h->epoch);
+  k_peer_barrier<<<1, 32, 0, h->compute>>>(h->peers, h->epoch, h->barrier_timeout_cycles, h->d_err);
   FTRL_CUDA(cudaGetLastError());
 }
 
@@ -859,6 +862,7 @@ int ftrl_create(const ftrl_config *cfg, ftrl_handle **out) {
     h->fuse = env_int("FTRL_B200_FUSE", 1);
     h->sample_threads = env_int("FTRL_B200_SAMPLE_THREADS", 0);
     h->precise = env_int("FTRL_B200_PRECISE", 0);
+    h->barrier_timeout_cycles = (long long)env_int("FTRL_B200_BARRIER_TIMEOUT_S", 20) * 2000000000ll;
     h->chunk = env_int("FTRL_B200_CHUNK", cfg->model_type == FTRL_FFM ? 32 : cfg->model_type == FTRL_FM ? 256 : 2048);
     if (h->chunk < 1) h->chunk = 1;
     if (cfg->model_type == FTRL_FFM && h->chunk > 32) h->chunk = 32;  // chunk ends are found with one ballot
@@ -921,7 +925,24 @@ int ftrl_create(const ftrl_config *cfg, ftrl_handle **out) {
       k_init_tab<<<(unsigned)((q + 255) / 256), 256, 0, h->compute>>>(h->tab, n, d.row_len, d.ld, cfg->init_mean, cfg->init_stddev, cfg->seed, h->G, h->rank);
     }
     FTRL_CUDA(cudaGetLastError());
-    if (cfg->max_batch_rows > 0) ensure_workspace(h, cfg->max_batch_rows, std::max<int64_t>(cfg->max_batch_nnz, 0));
+    if (cfg->max_batch_rows > 0) {
+      // no allocation on the hot path: workspace and the CSR staging slots are sized up front
+      const int64_t mr = cfg->max_batch_rows, mn = std::max<int64_t>(cfg->max_batch_nnz, 0);
+      ensure_workspace(h, mr, mn);
+      for (auto &sl : h->slots) {
+        sl.row_ptr.ensure(mr + 1);
+        sl.label.ensure(mr);
+        sl.out.ensure(mr);
+        sl.loss.ensure(1);
+        sl.h_out.ensure(mr);
+        sl.h_loss.ensure(1);
+        sl.field.ensure(mn);
+        sl.feat.ensure(mn);
+        sl.val.ensure(mn);
+        FTRL_CUDA(cudaEventCreateWithFlags(&sl.copied, cudaEventDisableTiming));
+        FTRL_CUDA(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+      }
+    }
     if (h->G > 1) {
       FTRL_CUDA(cudaMalloc(&h->sync, sizeof(SyncArea)));
       FTRL_CUDA(cudaMemsetAsync(h->sync, 0, sizeof(SyncArea), h->compute));
@@ -1021,7 +1042,7 @@ int ftrl_sync(ftrl_handle *h) {
     FTRL_CUDA(cudaStreamSynchronize(h->copy));
     FTRL_CUDA(cudaStreamSynchronize(h->compute));
     for (auto &s : h->slots) retire_slot(h, s);
-    if (h->cfg.mode == FTRL_MODE_SEQUENTIAL) check_device_err(h);
+    if (h->cfg.mode == FTRL_MODE_SEQUENTIAL || h->G > 1) check_device_err(h);
   });
 }
 
@@ -1397,6 +1418,53 @@ int ftrl_attach_peers(ftrl_handle *h, const void *blobs) {
       pr.key[q] = static_cast<const uint32_t *>(ptr[4]);
       pr.occ_pos[q] = static_cast<int32_t *>(ptr[5]);
       pr.sync[q] = static_cast<SyncArea *>(ptr[6]);
+    }
+    // Dry run of one complete sharded step against this rank alone (one sample whose features are all out
+    // of range: no row is touched; the bias is restored afterwards).  CUDA loads kernels lazily and defers
+    // a first-time load while another kernel is running -- with spinning device barriers that turns into a
+    // stall, so every kernel of the step is loaded here, before the first real step.
+    {
+      Shards self{};
+      self.G = 1;
+      self.tab[0] = h->tab;
+      self.lin[0] = h->lin;
+      self.staging[0] = h->staging.p;
+      self.staging_lin[0] = h->staging_lin.p;
+      Peers me{};
+      me.G = 1;
+      me.sync[0] = h->sync;
+      me.key[0] = h->key.p;
+      me.occ_pos[0] = h->occ_pos.p;
+      const int G = h->G, log2G = h->log2G, rank = h->rank;
+      const int64_t n_local = h->n_local;
+      h->shards = self;
+      h->peers = me;
+      h->attached = true;
+      Slot &ws = h->slots[0];
+      const int64_t rp[2] = {0, 2};
+      const int32_t bad[2] = {-1, -1}, lab = 0;
+      const float one[2] = {1.f, 1.f};
+      float4 bias_save;
+      FTRL_CUDA(cudaMemcpy(&bias_save, h->bias, sizeof(float4), cudaMemcpyDeviceToHost));
+      FTRL_CUDA(cudaMemcpy(ws.row_ptr.p, rp, sizeof(rp), cudaMemcpyHostToDevice));
+      FTRL_CUDA(cudaMemcpy(ws.field.p, bad, sizeof(bad), cudaMemcpyHostToDevice));
+      FTRL_CUDA(cudaMemcpy(ws.feat.p, bad, sizeof(bad), cudaMemcpyHostToDevice));
+      FTRL_CUDA(cudaMemcpy(ws.val.p, one, sizeof(one), cudaMemcpyHostToDevice));
+      FTRL_CUDA(cudaMemcpy(ws.label.p, &lab, sizeof(lab), cudaMemcpyHostToDevice));
+      Batch wb{1, 2, ws.row_ptr.p, ws.field.p, ws.feat.p, ws.val.p, ws.label.p};
+      // the dry run is a 1-shard run over the local rows
+      h->G = 1; h->log2G = 0; h->rank = 0;
+      const int64_t save_max = h->cfg.max_batch_nnz;
+      h->cfg.max_batch_nnz = std::min<int64_t>(save_max, 64);
+      h->G = 2;  // keep the sharded code path (G > 1 checks) but with self-only peers (peers.G == 1)
+      if (h->precise) train_device_sharded<true>(h, wb, nullptr, ws.loss.p); else train_device_sharded<false>(h, wb, nullptr, ws.loss.p);
+      FTRL_CUDA(cudaStreamSynchronize(h->compute));
+      h->cfg.max_batch_nnz = save_max;
+      h->G = G; h->log2G = log2G; h->rank = rank; h->n_local = n_local;
+      FTRL_CUDA(cudaMemcpy(h->bias, &bias_save, sizeof(float4), cudaMemcpyHostToDevice));
+      FTRL_CUDA(cudaMemset(h->d_err, 0, sizeof(int32_t)));
+      FTRL_CUDA(cudaMemset(h->sync, 0, sizeof(SyncArea)));
+      h->epoch = 0;
     }
     h->shards = sh;
     h->peers = pr;

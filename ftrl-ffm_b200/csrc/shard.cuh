@@ -49,14 +49,20 @@ __global__ void k_publish(Peers pr, int32_t nnz, const int32_t *batch_flags) {
   pr.sync[q]->simple[pr.rank] = batch_flags[0];
 }
 
-// all ranks arrive; returns when every rank has reached `epoch`
-__global__ void k_peer_barrier(Peers pr, uint32_t epoch) {
+// all ranks arrive; returns when every rank has reached `epoch`.  A peer that never arrives (crashed
+// process, failed call) must not hang the GPU: after `timeout_cycles` the wait gives up and raises err = 4.
+__global__ void k_peer_barrier(Peers pr, uint32_t epoch, long long timeout_cycles, int32_t *err) {
   const int q = threadIdx.x;
   if (q < pr.G) {
     __threadfence_system();
     *reinterpret_cast<volatile uint32_t *>(&pr.sync[q]->flag[pr.rank]) = epoch;
     const volatile uint32_t *mine = reinterpret_cast<const volatile uint32_t *>(&pr.sync[pr.rank]->flag[q]);
+    const long long t0 = clock64();
     while ((int32_t)(*mine - epoch) < 0) {
+      if (clock64() - t0 > timeout_cycles) {
+        *err = 4;
+        break;
+      }
     }
     __threadfence_system();
   }
