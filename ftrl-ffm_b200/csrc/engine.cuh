@@ -142,6 +142,9 @@ struct ftrl_handle {
   ftrl::DevBuf<int32_t> occ_row, chunk_pos, n_chunks;
   ftrl::DevBuf<uint8_t> sflags, fused_sorted, cub_tmp;
   ftrl::DevBuf<int32_t> occ_pos, batch_flags;
+  ftrl::DevBuf<uint64_t> pmask;                 // per occurrence: fields of the other features of its sample
+  ftrl::DevBuf<unsigned long long> rowmask;     // per segmented row: fields touched in this batch
+  ftrl::PmaskSrc pmask_src{};
   ftrl::DevBuf<float> staging, staging_lin;  // per-occurrence gradient images (tile path)
   ftrl::DevBuf<ftrl::SegScan> scan;
   ftrl::DevBuf<float> g, S, part;
@@ -188,6 +191,6 @@ struct ftrl_handle {
   int tile = 1;     // FFM: TMA-staged per-sample kernel for batches of distinct-field samples
   bool tile_ok = false;
   int tile_ctas_per_sm = 1;
-  int tile_f_cap = 0, tile_stride = 0, tile_stages = 0, tile_consumers = 0, tile_ipt = 1, tile_meta = 4;
+  int tile_f_cap = 0, tile_stride = 0, tile_stages = 0, tile_consumers = 0, tile_ipt = 1, tile_meta = 4, tile_dbg = 0;
   size_t tile_smem = 0;
 };

@@ -36,6 +36,9 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -79,6 +82,15 @@ __device__ __forceinline__ void named_bar_sync(int id, int n_threads) {
 
 // ---- tile geometry ------------------------------------------------------------------------------
 constexpr int TILE_META_WARPS = 2;   // warps prefetching sample metadata (CSR, occurrence class, linear records)
+// warps moving rows: single GPU 1 loader + 1 storer (TMA bulk copies only); sharded runs add warps that move
+// REMOTE rows with 128-bit loads/stores through registers (bulk copies to peer memory over NVLink are
+// latency-bound per operation, plain loads/stores pipeline deeply)
+constexpr int TILE_LOADERS_SHARDED = 4, TILE_STORERS_SHARDED = 2;
+__host__ __device__ constexpr int tile_loaders(bool sharded) { return sharded ? TILE_LOADERS_SHARDED : 1; }
+__host__ __device__ constexpr int tile_storers(bool sharded) { return sharded ? TILE_STORERS_SHARDED : 1; }
+__host__ __device__ constexpr int tile_threads(int consumers, bool sharded) {
+  return consumers + 32 * (tile_loaders(sharded) + tile_storers(sharded) + TILE_META_WARPS);
+}
 constexpr int TILE_MAX_STAGE = 4;    // row stages
 constexpr int TILE_MAX_META = 8;     // metadata slots
 
@@ -88,6 +100,7 @@ struct TileGeom {
   int n_stage;      // row stages (each f_cap * stride floats)
   int n_meta;       // metadata slots (> n_stage: metadata runs ahead of the row ring)
   int consumers;    // consumer threads (multiple of 32)
+  int dbg;          // experiment switches (FTRL_B200_TILE_DBG): 1 skip w stores, 2 skip row/image stores, 4 local lin only
   size_t smem_bytes;
 };
 
@@ -100,13 +113,14 @@ struct RowMeta {   // one 16-byte record per row of a sample
 struct SampleMeta {
   RowMeta *row;     // [f_cap]
   float4 *lin;      // [f_cap] {z, n, w, -} of the linear coordinate, prefetched
-  int32_t *hdr;     // [0] n valid rows, [1] label
+  int32_t *hdr;     // [0] n valid rows, [1] label, [2] n remote rows
+  uint8_t *remote;  // [f_cap] row slots whose feature lives on another shard
   uint8_t *present; // [n_fields] 1 when some valid row of the sample carries that field
 };
 
 __host__ __device__ inline size_t tile_meta_bytes(int f_cap) {
   // RowMeta (16 B) + lin (16 B) per row, + header 16 B, + present[f_cap] rounded to 16
-  return (size_t)f_cap * 32 + 16 + (size_t)((f_cap + 15) / 16) * 16;
+  return (size_t)f_cap * 32 + 16 + 2 * (size_t)((f_cap + 15) / 16) * 16;
 }
 __host__ __device__ inline size_t tile_stage_bytes(int f_cap, int stride) {
   return (size_t)f_cap * stride * sizeof(float);
@@ -163,14 +177,14 @@ __device__ __forceinline__ void apply4(float4 &z, float4 &n, const float4 &w, co
 // Thread roles: [0, consumers) compute; warp `consumers/32` is the row producer (bulk loads / bulk
 // stores of the row ring); the next TILE_META_WARPS warps prefetch sample metadata into a deeper
 // ring so that the row producer never waits on a dependent global-load chain.
-template <bool PRECISE, int IPT>
-__global__ void __launch_bounds__(512 + 32 + 32 * TILE_META_WARPS, 1)
+template <bool PRECISE, int IPT, bool SHARDED>
+__global__ void __launch_bounds__(SHARDED ? tile_threads(384, true) : tile_threads(512, false), 1)
 k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t *__restrict__ batch_flags,
            const __grid_constant__ Shards sh, const float4 *__restrict__ bias, const uint32_t *__restrict__ pair_lut,
            const int32_t *__restrict__ occ_pos, float *__restrict__ g_out, float *__restrict__ logit_out) {
   if (batch_flags[0] == 0) return;  // some sample repeats a field: the generic kernels take this batch
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ uint64_t bar_full[TILE_MAX_STAGE], bar_done[TILE_MAX_STAGE];
+  __shared__ uint64_t bar_full[TILE_MAX_STAGE], bar_done[TILE_MAX_STAGE], bar_free[TILE_MAX_STAGE];
   __shared__ uint64_t bar_mfull[TILE_MAX_META], bar_mfree[TILE_MAX_META];
   __shared__ float s_red[40];
 
@@ -178,7 +192,9 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
   const int n_cons = geo.consumers;
   const int n_cons_warps = n_cons >> 5;
   const int lane = tid & 31;
-  const int role = tid < n_cons ? 0 : (tid < n_cons + 32 ? 1 : 2);  // 0 consumer, 1 row producer, 2 meta
+  // 0 consumer, 1 row loader, 3 row storer, 2 metadata
+  constexpr int NL = tile_loaders(SHARDED), NSW = tile_storers(SHARDED);
+  const int role = tid < n_cons ? 0 : (tid < n_cons + 32 * NL ? 1 : (tid < n_cons + 32 * (NL + NSW) ? 3 : 2));
   const int ld = d.ld, k = d.k;
   const int stride = geo.stride, f_cap = geo.f_cap, NS = geo.n_stage, MD = geo.n_meta;
   const size_t stage_bytes = tile_stage_bytes(f_cap, stride);
@@ -199,17 +215,20 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
     m.hdr = reinterpret_cast<int32_t *>(p);
     p += 16;
     m.present = p;
+    p += (size_t)((f_cap + 15) / 16) * 16;
+    m.remote = p;
     return m;
   };
 
   if (tid == 0) {
     for (int st = 0; st < NS; st++) {
-      mbar_init(&bar_full[st], 1);
+      mbar_init(&bar_full[st], NL);
       mbar_init(&bar_done[st], n_cons_warps);
+      mbar_init(&bar_free[st], NSW);
     }
     for (int sl = 0; sl < MD; sl++) {
       mbar_init(&bar_mfull[sl], 1);
-      mbar_init(&bar_mfree[sl], 1);
+      mbar_init(&bar_mfree[sl], NSW);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -223,7 +242,7 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
 
   if (role == 2) {
     // =========================== metadata warps ===========================
-    const int mw = (tid - n_cons - 32) >> 5;
+    const int mw = (tid - n_cons - 32 * (NL + NSW)) >> 5;
     for (int64_t it = mw; it < n_mine; it += TILE_META_WARPS) {
       const int slot = (int)(it % MD);
       if (it >= MD) mbar_wait(&bar_mfree[slot], (uint32_t)(((it / MD) - 1) & 1));
@@ -260,9 +279,21 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
         nv += __popc(okm);
       }
       nv = min(nv, f_cap);
+      __syncwarp();
+      int n_remote = 0;
+      if (SHARDED) {
+        for (int base = 0; base < nv; base += 32) {
+          const int r = base + lane;
+          const bool rem = r < nv && (m.row[r].feat & (sh.G - 1)) != sh.rank;
+          const unsigned rmask = __ballot_sync(0xffffffffu, rem);
+          if (rem) m.remote[n_remote + __popc(rmask & ((1u << lane) - 1))] = (uint8_t)r;
+          n_remote += __popc(rmask);
+        }
+      }
       if (lane == 0) {
         m.hdr[0] = nv;
         m.hdr[1] = b.label[s];
+        m.hdr[2] = n_remote;
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_mfull[slot]);
@@ -270,20 +301,90 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
     return;
   }
 
+  const int nvec = ld >> 2;  // float4 vectors per plane
+  auto is_remote = [&](int32_t feat) { return SHARDED && (feat & (sh.G - 1)) != sh.rank; };
+
   if (role == 1) {
-    // =========================== row producer warp ===========================
-    for (int64_t it = 0; it < n_mine + NS; it++) {
+    // =========================== row loader warps ===========================
+    const int lw = (tid - n_cons) >> 5;  // loader warp index
+    for (int64_t it = 0; it < n_mine; it++) {
       const int st = (int)(it % NS);
       float *rows = stage_rows(st);
-      if (it >= NS) {
-        // retire the sample that used this stage: wait for the consumers, then store its rows
-        const int64_t old = it - NS;
-        const int oslot = (int)(old % MD);
-        SampleMeta m = sample_meta(oslot);
-        mbar_wait(&bar_done[st], (uint32_t)((old / NS) & 1));
-        const int nv = m.hdr[0];
+      if (it >= NS) mbar_wait(&bar_free[st], (uint32_t)(((it / NS) - 1) & 1));  // previous occupant stored
+      const int slot = (int)(it % MD);
+      mbar_wait(&bar_mfull[slot], (uint32_t)((it / MD) & 1));
+      SampleMeta m = sample_meta(slot);
+      const int nv = m.hdr[0];
+      if (lw == 0) {
+        // local rows: TMA bulk copies.  Fused rows bring z and n (they are updated here); staged rows bring
+        // only the w plane their owner materialised (k_row_materialise), into the z-plane slot of the stage
+        int bytes = 0;
         for (int r = lane; r < nv; r += 32) {
           const RowMeta rm = m.row[r];
+          if (!is_remote(rm.feat)) bytes += rm.pos < 0 ? (int)row_bytes : (int)(row_bytes / 2);
+        }
+        bytes = (int)warp_sum((float)bytes);
+        if (lane == 0) mbar_expect_tx(&bar_full[st], (uint32_t)bytes);
+        __syncwarp();
+        for (int r = lane; r < nv; r += 32) {
+          const RowMeta rm = m.row[r];
+          if (is_remote(rm.feat)) continue;
+          if (rm.pos < 0) bulk_g2s(rows + (size_t)r * stride, sh.row(rm.feat, rs), row_bytes, &bar_full[st]);
+          else bulk_g2s(rows + (size_t)r * stride, sh.row(rm.feat, rs) + 2 * ld, row_bytes / 2, &bar_full[st]);
+        }
+      }
+      if (SHARDED) {
+        // remote rows (always staged: w plane only): all loader warps, 128-bit loads over NVLink.  The
+        // (remote row, vector) items are spread over the loader threads so that every lane issues all of
+        // its loads back to back: one NVLink round trip per sample instead of one per row.
+        constexpr int LU = 14;
+        const int lt = tid - n_cons;  // lane among the loader threads
+        const int n_remote = m.hdr[2];
+        const int n_items = n_remote * nvec;
+        for (int i0 = 0; i0 < n_items; i0 += LU * NL * 32) {
+          float4 buf[LU];
+#pragma unroll
+          for (int u = 0; u < LU; u++) {
+            const int i = i0 + u * NL * 32 + lt;
+            if (i < n_items) {
+              const int ri = i / nvec, v = i - ri * nvec;
+              const RowMeta rm = m.row[m.remote[ri]];
+              buf[u] = __ldcs(reinterpret_cast<const float4 *>(sh.row(rm.feat, rs) + 2 * ld) + v);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < LU; u++) {
+            const int i = i0 + u * NL * 32 + lt;
+            if (i < n_items) {
+              const int ri = i / nvec, v = i - ri * nvec;
+              reinterpret_cast<float4 *>(rows + (size_t)m.remote[ri] * stride)[v] = buf[u];
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_full[st]);
+    }
+    return;
+  }
+
+  if (role == 3) {
+    // =========================== row storer warps ===========================
+    // retire samples in order: wait for the consumers, store the rows / gradient images (local: bulk
+    // stores; remote: 128-bit stores), then hand the stage back to the loaders and the metadata slot back
+    // to the metadata warps
+    const int sw = (tid - n_cons - 32 * NL) >> 5;
+    for (int64_t it = 0; it < n_mine; it++) {
+      const int st = (int)(it % NS);
+      const int slot = (int)(it % MD);
+      float *rows = stage_rows(st);
+      SampleMeta m = sample_meta(slot);
+      mbar_wait(&bar_done[st], (uint32_t)((it / NS) & 1));
+      const int nv = m.hdr[0];
+      if (sw == 0) {
+        for (int r = lane; r < nv && !(geo.dbg & 2); r += 32) {
+          const RowMeta rm = m.row[r];
+          if (is_remote(rm.feat)) continue;
           if (rm.pos < 0) {
             bulk_s2g(sh.row(rm.feat, rs), rows + (size_t)r * stride, row_bytes);
           } else {
@@ -291,22 +392,25 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
           }
         }
         bulk_commit();
-        bulk_wait_read_all();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_mfree[oslot]);
       }
-      if (it < n_mine) {
-        const int slot = (int)(it % MD);
-        mbar_wait(&bar_mfull[slot], (uint32_t)((it / MD) & 1));
-        SampleMeta m = sample_meta(slot);
-        const int nv = m.hdr[0];
-        if (lane == 0) mbar_arrive_expect_tx(&bar_full[st], (uint32_t)nv * row_bytes);
-        __syncwarp();
-        for (int r = lane; r < nv; r += 32)
-          bulk_g2s(rows + (size_t)r * stride, sh.row(m.row[r].feat, rs), row_bytes, &bar_full[st]);
+      if (SHARDED && !(geo.dbg & 2)) {
+        const int stt = tid - n_cons - 32 * NL;  // lane among the storer threads
+        for (int r = 0; r < nv; r++) {
+          const RowMeta rm = m.row[r];
+          if (!is_remote(rm.feat)) continue;
+          float4 *dst = reinterpret_cast<float4 *>(sh.stage(rm.feat, rm.pos, ld));
+          const float4 *src = reinterpret_cast<const float4 *>(rows + (size_t)r * stride);
+          for (int v = stt; v < nvec; v += NSW * 32) __stcs(dst + v, src[v]);
+        }
+      }
+      if (sw == 0) bulk_wait_read_all();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&bar_free[st]);
+        mbar_arrive(&bar_mfree[slot]);
       }
     }
-    bulk_wait_all();
+    if (sw == 0) bulk_wait_all();
     return;
   }
 
@@ -340,21 +444,28 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
         const RowMeta rmm = m.row[mi], rmn = m.row[ni];
         const float *sa = rows + (size_t)mi * stride + rmn.fk + c * 4;  // slice A = (row m, field n)
         const float *sb = rows + (size_t)ni * stride + rmm.fk + c * 4;  // slice B = (row n, field m)
-        const float4 zA = *reinterpret_cast<const float4 *>(sa), nA = *reinterpret_cast<const float4 *>(sa + ld);
-        const float4 zB = *reinterpret_cast<const float4 *>(sb), nB = *reinterpret_cast<const float4 *>(sb + ld);
-        const float4 wA = weight4<PRECISE>(zA, nA, h), wB = weight4<PRECISE>(zB, nB, h);
+        // staged rows hold w itself in the z-plane slot; fused rows hold (z, n): w = W(n, z), stored as the
+        // stale-by-one w the reference keeps (ffm.cpp:72-88)
+        float4 wA = *reinterpret_cast<const float4 *>(sa), wB = *reinterpret_cast<const float4 *>(sb);
+        if (rmm.pos < 0) {
+          wA = weight4<PRECISE>(wA, *reinterpret_cast<const float4 *>(sa + ld), h);
+          *reinterpret_cast<float4 *>(sh.row(rmm.feat, rs) + 2 * ld + rmn.fk + c * 4) = wA;
+        }
+        if (rmn.pos < 0) {
+          wB = weight4<PRECISE>(wB, *reinterpret_cast<const float4 *>(sb + ld), h);
+          *reinterpret_cast<float4 *>(sh.row(rmn.feat, rs) + 2 * ld + rmm.fk + c * 4) = wB;
+        }
         wAc[j] = wA;
         wBc[j] = wB;
         const float dot = fmaf(wA.x, wB.x, fmaf(wA.y, wB.y, fmaf(wA.z, wB.z, wA.w * wB.w)));
         acc = fmaf(dot, rmm.x * rmn.x, acc);
-        // the stale-by-one w the reference keeps (ffm.cpp:72-88)
-        *reinterpret_cast<float4 *>(sh.row(rmm.feat, rs) + 2 * ld + rmn.fk + c * 4) = wA;
-        *reinterpret_cast<float4 *>(sh.row(rmn.feat, rs) + 2 * ld + rmm.fk + c * 4) = wB;
       }
     }
     for (int r = tid; r < nv; r += n_cons) {
       const float4 e = m.lin[r];
-      acc = fmaf(weight_from<PRECISE>(e.x, f_sqrt<PRECISE>(e.y), h), m.row[r].x, acc);
+      const RowMeta rm = m.row[r];
+      const float w = rm.pos < 0 ? weight_from<PRECISE>(e.x, f_sqrt<PRECISE>(e.y), h) : e.z;
+      acc = fmaf(w, rm.x, acc);
     }
     // consumer-wide sum
     acc = warp_sum(acc);
@@ -411,15 +522,14 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
     for (int r = tid; r < nv; r += n_cons) {
       float4 e = m.lin[r];
       const RowMeta rm = m.row[r];
-      const float w = weight_from<PRECISE>(e.x, f_sqrt<PRECISE>(e.y), h);
       const float gi = g * rm.x;
       if (rm.pos < 0) {
+        const float w = weight_from<PRECISE>(e.x, f_sqrt<PRECISE>(e.y), h);
         e.z = w;
         ftrl_apply<PRECISE>(e.x, e.y, w, gi, gi * gi, h);
         *sh.linp(rm.feat) = e;
       } else {
-        sh.linp(rm.feat)->z = w;
-        *sh.stage_lin(rm.feat, rm.pos) = gi;
+        *sh.stage_lin(rm.feat, rm.pos) = gi;  // w of staged rows was materialised by their owner
       }
     }
     // staged rows: slices no partner touches (own field, absent fields) must read as 0 in the image.
@@ -435,6 +545,58 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
     fence_async_smem();
     __syncwarp();
     if (lane == 0) mbar_arrive(&bar_done[st]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// owner-side pre-pass for the segmented ("staged") rows: materialise w = W(n,z) (ffm.cpp:72-88,
+// ftrl_model.cpp:52-59) for exactly the slices the batch touches, BEFORE the sample kernels run, so
+// that those only need the row's w plane (4 B per coordinate instead of z,n = 8 B) and never store w.
+//   k_row_touch       : rowmask[row] = OR over the row's occurrences of "fields of the other features
+//                       of that sample" (chunk-parallel, atomicOr)
+//   k_row_materialise : one warp per row head: w for the slices in rowmask, and the linear w
+// ---------------------------------------------------------------------------------------------
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+k_row_touch(int32_t nnz, uint32_t sentinel, int32_t ch, const int32_t *__restrict__ batch_flags,
+            const int32_t *__restrict__ n_chunks_p, const int32_t *__restrict__ chunk_pos,
+            const uint32_t *__restrict__ skey, const uint32_t *__restrict__ socc, const SegScan *__restrict__ scan,
+            PmaskSrc pm, unsigned long long *__restrict__ rowmask) {
+  if (batch_flags[0] == 0) return;
+  const int wib = threadIdx.x >> 5;
+  const int n_chunks = *n_chunks_p;
+  for (int c = blockIdx.x * WARPS + wib; c < n_chunks; c += gridDim.x * WARPS) {
+    const ChunkInfo ci = chunk_info<true>(c, nnz, sentinel, ch, chunk_pos, skey, scan);
+    if (!ci.valid) continue;
+    row_touch_chunk(c, ci, ch, socc, pm, rowmask);
+  }
+}
+
+template <bool PRECISE, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+k_row_materialise(Dims d, Hyper h, int32_t nnz, uint32_t sentinel, int32_t ch, const int32_t *__restrict__ batch_flags,
+                  const int32_t *__restrict__ n_chunks_p, const int32_t *__restrict__ chunk_pos,
+                  const uint32_t *__restrict__ skey, const SegScan *__restrict__ scan,
+                  const unsigned long long *__restrict__ rowmask, float *__restrict__ tab, float4 *__restrict__ lin) {
+  if (batch_flags[0] == 0) return;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t ld = d.ld, rs = 3 * ld;
+  const int n_chunks = *n_chunks_p;
+  const int vpf = d.k >> 2;  // float4 vectors per field slice
+  for (int c = blockIdx.x * WARPS + wib; c < n_chunks; c += gridDim.x * WARPS) {
+    const ChunkInfo ci = chunk_head_info(c, nnz, sentinel, ch, chunk_pos, skey, scan);
+    if (!ci.valid || !ci.row_head) continue;
+    const unsigned long long mask = rowmask[c];
+    float *row = tab + (int64_t)ci.key * rs;
+    for (int v = lane; v < d.n_fields * vpf; v += 32) {
+      if (!((mask >> (v / vpf)) & 1ull)) continue;
+      const float4 z = reinterpret_cast<const float4 *>(row)[v], n = reinterpret_cast<const float4 *>(row + ld)[v];
+      reinterpret_cast<float4 *>(row + 2 * ld)[v] = weight4<PRECISE>(z, n, h);
+    }
+    if (lane == 0) {
+      const float4 e = lin[ci.key];
+      lin[ci.key].z = weight_from<PRECISE>(e.x, f_sqrt<PRECISE>(e.y), h);
+    }
   }
 }
 

@@ -199,6 +199,7 @@ static void refresh_shards(ftrl_handle *h) {
   sh.lin[0] = h->lin;
   sh.staging[0] = h->staging.p;
   sh.staging_lin[0] = h->staging_lin.p;
+  h->pmask_src.p[0] = h->pmask.p;
 }
 
 static void ensure_workspace(ftrl_handle *h, int64_t n_rows, int64_t nnz) {
@@ -237,6 +238,10 @@ static void ensure_workspace(ftrl_handle *h, int64_t n_rows, int64_t nnz) {
   h->fused_sorted.ensure(oc);
   h->occ_pos.ensure(nc);
   h->batch_flags.ensure(4);
+  if (h->tile_ok) {
+    h->pmask.ensure(nc);
+    h->rowmask.ensure(oc + 2);
+  }
   if (h->tile_ok) {
     h->staging.ensure((size_t)oc * h->dims.ld);
     h->staging_lin.ensure(oc);
@@ -327,10 +332,11 @@ static void run_ffm_batch(ftrl_handle *h, const Batch &b, float *logit_out) {
       geo.n_stage = h->tile_stages;
       geo.n_meta = h->tile_meta;
       geo.consumers = h->tile_consumers;
+      geo.dbg = h->tile_dbg;
       geo.smem_bytes = h->tile_smem;
       const int tgrid = (int)std::min<int64_t>(b.n_rows, (int64_t)h->n_sms * h->tile_ctas_per_sm);
 #define FFM_TILE(I)                                                                                              \
-  k_ffm_tile<PRECISE, I><<<tgrid, geo.consumers + 32 + 32 * TILE_META_WARPS, geo.smem_bytes, h->compute>>>(                                \
+  k_ffm_tile<PRECISE, I, false><<<tgrid, tile_threads(geo.consumers, false), geo.smem_bytes, h->compute>>>(                                \
       b, d, h->hyper, dec, geo, h->batch_flags.p, h->shards, h->bias, h->pair_lut, h->occ_pos.p, h->g.p, logit_out)
       if (h->tile_ipt <= 1) FFM_TILE(1);
       else if (h->tile_ipt == 2) FFM_TILE(2);
@@ -426,6 +432,25 @@ static void run_lrfm_batch(ftrl_handle *h, const Batch &b, float *logit_out) {
   }
 }
 
+// owner-side pre-pass of the tile path: materialise w of the segmented rows (ffm_tile.cuh)
+static void run_row_prepass(ftrl_handle *h, int32_t n_sorted, uint32_t sentinel) {
+  const Dims &d = h->dims;
+  const int grid = h->n_sms * 4;
+  FTRL_CUDA(cudaMemsetAsync(h->rowmask.p, 0, sizeof(unsigned long long) * (size_t)(n_sorted + 2), h->compute));
+  k_row_touch<8><<<grid, 256, 0, h->compute>>>(n_sorted, sentinel, h->chunk, h->batch_flags.p, h->n_chunks.p, h->chunk_pos.p,
+                                               h->skey.p, h->socc.p, h->scan.p, h->pmask_src, h->rowmask.p);
+  if (h->precise)
+    k_row_materialise<true, 8><<<grid, 256, 0, h->compute>>>(d, h->hyper, n_sorted, sentinel, h->chunk, h->batch_flags.p,
+                                                             h->n_chunks.p, h->chunk_pos.p, h->skey.p, h->scan.p,
+                                                             h->rowmask.p, h->tab, h->lin);
+  else
+    k_row_materialise<false, 8><<<grid, 256, 0, h->compute>>>(d, h->hyper, n_sorted, sentinel, h->chunk, h->batch_flags.p,
+                                                              h->n_chunks.p, h->chunk_pos.p, h->skey.p, h->scan.p,
+                                                              h->rowmask.p, h->tab, h->lin);
+  FTRL_CUDA(cudaGetLastError());
+  launched(h, PH_SEGMENT, 2);
+}
+
 static void run_prep(ftrl_handle *h, const Batch &b) {
   const Dims &d = h->dims;
   const int32_t nnz = (int32_t)b.nnz;
@@ -435,7 +460,7 @@ static void run_prep(ftrl_handle *h, const Batch &b) {
     FTRL_CUDA(cudaMemsetAsync(h->batch_flags.p, 0x01, sizeof(int32_t), h->compute));  // != 0: all samples simple
     const unsigned grid = (unsigned)((b.n_rows * 32 + 255) / 256);
     k_prep_rows<<<grid, 256, 0, h->compute>>>(b, d, h->key.p, h->occ_idx.p, h->occ_row.p, h->sflags.p,
-                                              h->batch_flags.p);
+                                              h->batch_flags.p, h->tile_ok ? h->pmask.p : nullptr);
     FTRL_CUDA(cudaGetLastError());
     launched(h, PH_PREP);
   }
@@ -465,6 +490,7 @@ static void run_prep(ftrl_handle *h, const Batch &b) {
                                     h->compute));
     k_terminate<<<1, 1, 0, h->compute>>>(h->chunk_pos.p, h->n_chunks.p, nnz);
     launched(h, PH_SEGMENT);
+    if (d.model_type == FTRL_FFM && h->tile_ok) run_row_prepass(h, nnz, sentinel);
     FTRL_CUDA(cudaGetLastError());
   }
 }
@@ -673,7 +699,8 @@ static void train_device_sharded(ftrl_handle *h, const Batch &b, float *logit_ou
     FTRL_CUDA(cudaMemsetAsync(h->batch_flags.p, 0x01, sizeof(int32_t), h->compute));
     if (b.n_rows > 0) {
       const unsigned grid = (unsigned)((b.n_rows * 32 + 255) / 256);
-      k_prep_rows<<<grid, 256, 0, h->compute>>>(b, d, h->key.p, h->occ_idx.p, h->occ_row.p, h->sflags.p, h->batch_flags.p);
+      k_prep_rows<<<grid, 256, 0, h->compute>>>(b, d, h->key.p, h->occ_idx.p, h->occ_row.p, h->sflags.p, h->batch_flags.p,
+                                                h->pmask.p);
     }
     k_publish<<<1, 32, 0, h->compute>>>(h->peers, nnz, h->batch_flags.p);
     FTRL_CUDA(cudaGetLastError());
@@ -708,7 +735,8 @@ static void train_device_sharded(ftrl_handle *h, const Batch &b, float *logit_ou
     k_terminate<<<1, 1, 0, h->compute>>>(h->chunk_pos.p, h->n_chunks.p, oc);
     FTRL_CUDA(cudaGetLastError());
     launched(h, PH_SEGMENT, 2);
-    peer_barrier(h);  // 2: every occurrence knows its class / staging position
+    run_row_prepass(h, oc, lsent);
+    peer_barrier(h);  // 2: every occurrence knows its class / staging position, w of staged rows is materialised
   }
   const ItemDecode dec = make_item_decode(d.k, 4);
   const int grid = h->n_sms * 4;
@@ -721,10 +749,11 @@ static void train_device_sharded(ftrl_handle *h, const Batch &b, float *logit_ou
       geo.n_stage = h->tile_stages;
       geo.n_meta = h->tile_meta;
       geo.consumers = h->tile_consumers;
+      geo.dbg = h->tile_dbg;
       geo.smem_bytes = h->tile_smem;
       const int tgrid = (int)std::min<int64_t>(b.n_rows, (int64_t)h->n_sms * h->tile_ctas_per_sm);
 #define FFM_TILE(I)                                                                                              \
-  k_ffm_tile<PRECISE, I><<<tgrid, geo.consumers + 32 + 32 * TILE_META_WARPS, geo.smem_bytes, h->compute>>>(        \
+  k_ffm_tile<PRECISE, I, true><<<tgrid, tile_threads(geo.consumers, true), geo.smem_bytes, h->compute>>>(        \
       b, d, h->hyper, dec, geo, h->batch_flags.p, h->shards, h->bias, h->pair_lut, h->occ_pos.p, h->g.p, logit_out)
       if (h->tile_ipt <= 1) FFM_TILE(1);
       else if (h->tile_ipt == 2) FFM_TILE(2);
@@ -777,8 +806,8 @@ struct PeerBlob {  // FTRL_PEER_BLOB_BYTES
   int32_t rank, world, device;
   int64_t pid;
   int64_t nnz_cap, ow_cap;
-  void *raw[7];                // same-process attach
-  cudaIpcMemHandle_t ipc[7];   // tab, lin, staging, staging_lin, key, occ_pos, sync
+  void *raw[8];                // same-process attach
+  cudaIpcMemHandle_t ipc[8];   // tab, lin, staging, staging_lin, key, occ_pos, sync, pmask
 };
 static_assert(sizeof(PeerBlob) <= FTRL_PEER_BLOB_BYTES, "peer blob too large");
 
@@ -867,19 +896,21 @@ int ftrl_create(const ftrl_config *cfg, ftrl_handle **out) {
     if (h->chunk < 1) h->chunk = 1;
     if (cfg->model_type == FTRL_FFM && h->chunk > 32) h->chunk = 32;  // chunk ends are found with one ballot
     h->tile = env_int("FTRL_B200_TILE", 1);
-    if (cfg->model_type == FTRL_FFM && h->tile && h->fuse && d.k % 4 == 0 && d.n_fields <= FFM_CAP) {
+    h->tile_dbg = env_int("FTRL_B200_TILE_DBG", 0);
+    if (cfg->model_type == FTRL_FFM && h->tile && h->fuse && d.k % 4 == 0 && d.n_fields <= 64) {
       const int stride = tile_stride(d.ld, d.k);
       const size_t stage = tile_stage_bytes(d.n_fields, stride);
       const size_t budget = (size_t)prop.sharedMemPerBlockOptin - 2048;  // static mbarriers / reduction scratch
       const int64_t items = (int64_t)d.n_fields * (d.n_fields - 1) / 2 * (d.k / 4);
       int cons = 64;
       while (cons < 512 && cons * 3 < items) cons *= 2;
+      if (h->G > 1) cons = std::min(cons, 384);  // sharded runs spend threads on the warps that move remote rows
       cons = env_int("FTRL_B200_TILE_CONSUMERS", cons);
       const int ipt = (int)((items + cons - 1) / cons);
       const size_t lut = tile_lut_bytes(d.n_fields) + 4 * tile_meta_bytes(d.n_fields);  // + minimal meta ring
       if (2 * stage + lut <= budget && ipt <= 4) {
         int ctas = (int)std::min<size_t>(8, (size_t)prop.sharedMemPerMultiprocessor / (2 * stage + lut + 2048));
-        ctas = std::max(1, std::min(ctas, 2048 / (cons + 32 + 32 * TILE_META_WARPS)));
+        ctas = std::max(1, std::min(ctas, 2048 / tile_threads(cons, h->G > 1)));
         ctas = env_int("FTRL_B200_TILE_CTAS", ctas);
         int stages = (int)std::min<size_t>(TILE_MAX_STAGE, ((size_t)prop.sharedMemPerMultiprocessor / ctas - 2048 - lut) / stage);
         stages = std::max(2, std::min(stages, (int)((budget - lut) / stage)));
@@ -897,14 +928,12 @@ int ftrl_create(const ftrl_config *cfg, ftrl_handle **out) {
         h->tile_ctas_per_sm = ctas;
         h->tile_smem = tile_smem_bytes(d.n_fields, stride, stages, metas);
         const int sm = (int)h->tile_smem;
-        FTRL_CUDA(cudaFuncSetAttribute(k_ffm_tile<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-        FTRL_CUDA(cudaFuncSetAttribute(k_ffm_tile<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-        FTRL_CUDA(cudaFuncSetAttribute(k_ffm_tile<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-        FTRL_CUDA(cudaFuncSetAttribute(k_ffm_tile<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-        FTRL_CUDA(cudaFuncSetAttribute(k_ffm_tile<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-        FTRL_CUDA(cudaFuncSetAttribute(k_ffm_tile<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-        FTRL_CUDA(cudaFuncSetAttribute(k_ffm_tile<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-        FTRL_CUDA(cudaFuncSetAttribute(k_ffm_tile<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+#define TILE_ATTR(P, I, S) FTRL_CUDA(cudaFuncSetAttribute(k_ffm_tile<P, I, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm))
+        TILE_ATTR(false, 1, false); TILE_ATTR(false, 2, false); TILE_ATTR(false, 3, false); TILE_ATTR(false, 4, false);
+        TILE_ATTR(true, 1, false); TILE_ATTR(true, 2, false); TILE_ATTR(true, 3, false); TILE_ATTR(true, 4, false);
+        TILE_ATTR(false, 1, true); TILE_ATTR(false, 2, true); TILE_ATTR(false, 3, true); TILE_ATTR(false, 4, true);
+        TILE_ATTR(true, 1, true); TILE_ATTR(true, 2, true); TILE_ATTR(true, 3, true); TILE_ATTR(true, 4, true);
+#undef TILE_ATTR
       }
     }
     FTRL_CUDA(cudaStreamCreateWithFlags(&h->compute, cudaStreamNonBlocking));
@@ -1364,8 +1393,8 @@ int ftrl_export_peer_blob(ftrl_handle *h, void *blob) {
     pb.pid = (int64_t)getpid();
     pb.nnz_cap = h->nnz_cap;
     pb.ow_cap = h->ow_cap;
-    void *ptrs[7] = {h->tab, h->lin, h->staging.p, h->staging_lin.p, h->key.p, h->occ_pos.p, h->sync};
-    for (int i = 0; i < 7; i++) {
+    void *ptrs[8] = {h->tab, h->lin, h->staging.p, h->staging_lin.p, h->key.p, h->occ_pos.p, h->sync, h->pmask.p};
+    for (int i = 0; i < 8; i++) {
       pb.raw[i] = ptrs[i];
       if (!ptrs[i]) throw StateFail{"multi-GPU buffers are not allocated"};
       FTRL_CUDA(cudaIpcGetMemHandle(&pb.ipc[i], ptrs[i]));
@@ -1382,6 +1411,7 @@ int ftrl_attach_peers(ftrl_handle *h, const void *blobs) {
     if (h->attached) throw StateFail{"peers already attached"};
     Shards sh{};
     Peers pr{};
+    PmaskSrc pms{};
     sh.G = pr.G = h->G;
     sh.log2G = pr.log2G = h->log2G;
     sh.rank = pr.rank = h->rank;
@@ -1390,9 +1420,9 @@ int ftrl_attach_peers(ftrl_handle *h, const void *blobs) {
       memcpy(&pb, static_cast<const char *>(blobs) + (size_t)q * FTRL_PEER_BLOB_BYTES, sizeof(pb));
       if (pb.magic != 0xF7B20001u || pb.rank != q || pb.world != h->G) throw ArgFail{fmt("peer blob %d is not from rank %d of %d", q, q, h->G)};
       if (pb.nnz_cap != h->nnz_cap) throw ArgFail{"all ranks must use the same max_batch_nnz"};
-      void *ptr[7];
+      void *ptr[8];
       if (q == h->rank) {
-        void *mine[7] = {h->tab, h->lin, h->staging.p, h->staging_lin.p, h->key.p, h->occ_pos.p, h->sync};
+        void *mine[8] = {h->tab, h->lin, h->staging.p, h->staging_lin.p, h->key.p, h->occ_pos.p, h->sync, h->pmask.p};
         memcpy(ptr, mine, sizeof(ptr));
       } else if (pb.pid == (int64_t)getpid()) {
         // same process (several handles in one process): plain pointers, peer access if another device
@@ -1406,7 +1436,7 @@ int ftrl_attach_peers(ftrl_handle *h, const void *blobs) {
         }
         memcpy(ptr, pb.raw, sizeof(ptr));
       } else {
-        for (int i = 0; i < 7; i++) {
+        for (int i = 0; i < 8; i++) {
           FTRL_CUDA(cudaIpcOpenMemHandle(&ptr[i], pb.ipc[i], cudaIpcMemLazyEnablePeerAccess));
           h->ipc_opened.push_back(ptr[i]);
         }
@@ -1418,6 +1448,7 @@ int ftrl_attach_peers(ftrl_handle *h, const void *blobs) {
       pr.key[q] = static_cast<const uint32_t *>(ptr[4]);
       pr.occ_pos[q] = static_cast<int32_t *>(ptr[5]);
       pr.sync[q] = static_cast<SyncArea *>(ptr[6]);
+      pms.p[q] = static_cast<const uint64_t *>(ptr[7]);
     }
     // Dry run of one complete sharded step against this rank alone (one sample whose features are all out
     // of range: no row is touched; the bias is restored afterwards).  CUDA loads kernels lazily and defers
@@ -1439,6 +1470,8 @@ int ftrl_attach_peers(ftrl_handle *h, const void *blobs) {
       const int64_t n_local = h->n_local;
       h->shards = self;
       h->peers = me;
+      h->pmask_src = PmaskSrc{};
+      h->pmask_src.p[0] = h->pmask.p;
       h->attached = true;
       Slot &ws = h->slots[0];
       const int64_t rp[2] = {0, 2};
@@ -1468,6 +1501,7 @@ int ftrl_attach_peers(ftrl_handle *h, const void *blobs) {
     }
     h->shards = sh;
     h->peers = pr;
+    h->pmask_src = pms;
     h->attached = true;
   });
 }

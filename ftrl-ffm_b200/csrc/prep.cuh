@@ -70,9 +70,11 @@ __device__ __forceinline__ bool feat_valid(const Dims &d, int32_t fld, int32_t f
 }
 
 // warp per sample.  batch_flags[0] is cleared to 0 when some sample repeats a field.
+// pmask[t] (FFM, n_fields <= 64): bit f set iff some OTHER valid feature of t's sample carries field f,
+// i.e. the slices of t's row this sample touches (ffm.cpp:72-88 touches (feat_m, field_n) for n != m).
 __global__ void k_prep_rows(Batch b, Dims d, uint32_t *__restrict__ key, uint32_t *__restrict__ occ_idx,
                             int32_t *__restrict__ occ_row, uint8_t *__restrict__ sflags,
-                            int32_t *__restrict__ batch_flags) {
+                            int32_t *__restrict__ batch_flags, uint64_t *__restrict__ pmask) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (warp >= b.n_rows) return;
@@ -114,6 +116,15 @@ __global__ void k_prep_rows(Batch b, Dims d, uint32_t *__restrict__ key, uint32_
   if (lane == 0) {
     sflags[warp] = simple ? (SF_SIMPLE | SF_FUSABLE) : 0;
     if (!simple) batch_flags[0] = 0;
+  }
+  if (pmask && d.model_type == 2 && d.n_fields <= 64) {
+    // `seen` now holds the field set of the whole sample (identical on all lanes)
+    for (int64_t t = r0 + lane; t < r1; t += 32) {
+      const int32_t fld = b.field[t];
+      const bool ok = feat_valid(d, fld, b.feat[t]);
+      // with distinct fields the own field is carried by this feature only
+      pmask[t] = ok ? (seen & ~(1ull << fld)) : 0ull;
+    }
   }
 }
 
@@ -185,6 +196,31 @@ __device__ __forceinline__ ChunkInfo chunk_info(int32_t c, int32_t nnz, uint32_t
   const int32_t e0 = (c - ci.j + 1) - s.cnt;
   ci.slot = 2 * e0 + ci.j;
   return ci;
+}
+
+constexpr int SRC_SHIFT = 28;  // source = (rank << 28) | occurrence index  (nnz per rank < 2^28)
+constexpr uint32_t SRC_MASK = (1u << SRC_SHIFT) - 1;
+
+// where the per-occurrence masks of every rank live (single GPU: p[0] only)
+struct PmaskSrc {
+  const uint64_t *p[MAX_SHARDS];
+  __device__ __forceinline__ unsigned long long operator()(uint32_t src) const {
+    return p[src >> SRC_SHIFT][src & SRC_MASK];
+  }
+};
+
+// Row-level field masks of the segmented rows: rowmask[head chunk] |= OR of pmask over the chunk's
+// occurrences (integer OR: order-independent, so the atomic keeps the result deterministic).
+// `src` decoding: occurrence src lives on rank src >> 28 at index src & (2^28-1) (single GPU: rank 0).
+template <typename PmaskOf>
+__device__ __forceinline__ void row_touch_chunk(int c, const ChunkInfo &ci, int ch, const uint32_t *__restrict__ socc,
+                                                PmaskOf pmask_of, unsigned long long *__restrict__ rowmask) {
+  const int lane = threadIdx.x & 31;
+  unsigned long long m = 0ull;
+  for (int p = ci.p0 + lane; p < ci.p1; p += 32) m |= pmask_of(socc[p]);
+  const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)m);
+  const unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(m >> 32));
+  if (lane == 0) atomicOr(&rowmask[c - ci.j], ((unsigned long long)hi << 32) | lo);
 }
 
 // per-thread variant for chunks that are row heads (used to find rows spanning several chunks):

@@ -24,9 +24,6 @@
 
 namespace ftrl {
 
-constexpr int SRC_SHIFT = 28;  // source = (rank << 28) | occurrence index  (nnz per rank < 2^28)
-constexpr uint32_t SRC_MASK = (1u << SRC_SHIFT) - 1;
-
 // lives in device memory of every rank, mapped by all peers
 struct SyncArea {
   uint32_t flag[MAX_SHARDS];      // flag[q] = last barrier epoch rank q has reached (written by q)
@@ -120,7 +117,9 @@ __global__ void k_occ_class_sharded(Peers pr, int32_t n, uint32_t sentinel, cons
   const uint32_t src = socc[p];
   const bool head = p == 0 || skey[p - 1] != k;
   const bool last = p + 1 == n || skey[p + 1] != k;
-  const bool fused = head && last;
+  // finalised inside the sample only when the sample lives on the owner: remote rows always go through
+  // the owner (w in, gradient image out: 8 B per coordinate over NVLink instead of 20 B)
+  const bool fused = head && last && (int)(src >> SRC_SHIFT) == pr.rank;
   fused_sorted[p] = fused ? 1 : 0;
   pr.occ_pos[src >> SRC_SHIFT][src & SRC_MASK] = fused ? -1 : p;
 }
