@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--cpu-samples", type=int, default=0, help="samples of the bounded CPU-baseline run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the extra uniform-id roofline measurement")
     return ap.parse_args()
 
 
@@ -301,8 +302,8 @@ def main():
     torch.cuda.synchronize()
     prof = m.profile()
     m.profile_enable(False)
-    hot = ["sample", "rows", "combine"]
-    hot_ms = sum(prof[p]["ms"] for p in hot) / args.steps
+    hot = ["materialise", "sample", "rows", "combine", "generic"]  # forward + FTRL update kernels
+    hot_ms = sum(prof[p]["ms"] for p in hot if p in prof) / args.steps
     Ubar = float(np.mean([U[i % len(U)] for i in range(args.steps)]))
     bytes_alg = alg_bytes(model, n_fields, k, Ubar, nnz * world, B * world) / world  # per GPU
     peak, peak_src = peaks()
@@ -316,11 +317,47 @@ def main():
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src,
-                "kernels": "k_ffm_sample + k_ffm_rows + k_ffm_combine (forward + FTRL update)" if model == "FFM"
+                "kernels": "k_row_touch + k_row_materialise + k_ffm_tile + k_ffm_staged_rows + k_ffm_combine "
+                           "(forward + FTRL update)" if model == "FFM"
                 else "k_lrfm_sample + k_lrfm_rows + k_lrfm_combine",
                 "alg_bytes_per_step": bytes_alg, "kernel_ms_per_step": hot_ms,
                 "phase_ms_per_step": {p: v["ms"] / args.steps for p, v in prof.items() if v["ms"] > 0},
                 "U_over_nnz": Ubar / nnz}
+
+    # ---- the cache-hostile case SURVEY.md 8(d) asks to report next to it: uniform ids (U ~ nnz) ----
+    roofline_uniform = None
+    if args.dist == "zipf" and not args.no_secondary and world == 1:
+        ub = [pkg.synth.criteo_batch(B, n_fields, n_feats, seed=4242 + i, dist="uniform") for i in range(3)]
+        udev = [{key: torch.from_numpy(np.ascontiguousarray(v)).cuda() for key, v in b_.items()} for b_ in ub]
+
+        def step_u(i):
+            d = udev[i % len(udev)]
+            m.train_device(B, nnz, d["row_ptr"].data_ptr(), d["field"].data_ptr(), d["feat"].data_ptr(),
+                           d["val"].data_ptr(), d["label"].data_ptr(), 0, d_loss.data_ptr())
+        Uu = []
+        for i in range(len(udev)):
+            step_u(i)
+            Uu.append(m.last_batch_stats()["n_unique"])
+        nsteps_u = 6
+        m.profile_enable(True)
+        m.profile_reset()
+        torch.cuda.synchronize()
+        u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        u0.record(stream)
+        for i in range(nsteps_u):
+            step_u(i)
+        u1.record(stream)
+        torch.cuda.synchronize()
+        uprof = m.profile()
+        m.profile_enable(False)
+        u_hot = sum(uprof[p]["ms"] for p in hot if p in uprof) / nsteps_u
+        u_bytes = alg_bytes(model, n_fields, k, float(np.mean([Uu[i % len(Uu)] for i in range(nsteps_u)])), nnz, B)
+        u_ach = u_bytes / (u_hot / 1e3) / 1e9
+        roofline_uniform = {"achieved": u_ach, "peak": peak, "unit": "GB/s", "frac": u_ach / peak,
+                            "value_samples_per_s": B * nsteps_u / (u0.elapsed_time(u1) / 1e3),
+                            "kernel_ms_per_step": u_hot, "alg_bytes_per_step": u_bytes,
+                            "U_over_nnz": float(np.mean(Uu)) / nnz}
+        del udev
 
     # ---- end to end through the host-pointer C ABI: pinned host CSR, H2D + D2H inside the timed region ----
     e2e = None
@@ -386,7 +423,7 @@ def main():
                        f"rows pulled/pushed over NVLink peer memory inside the kernels, global batch {B * world}",
                        "distinct_batches": len(batches), "fused_rows_per_step": fused_rows},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_per_step) * args.steps,
-            "roofline": roofline, "cpu_baseline": cpu,
+            "roofline": roofline, "roofline_uniform_ids": roofline_uniform, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -109,7 +109,7 @@ struct Phase {
   int64_t launches = 0;
 };
 
-enum PhaseId { PH_PREP = 0, PH_SORT, PH_SEGMENT, PH_SAMPLE, PH_ROWS, PH_COMBINE, PH_REDUCE, PH_EXACT, PH_PREDICT, PH_GENERIC, PH_COUNT };
+enum PhaseId { PH_PREP = 0, PH_SORT, PH_SEGMENT, PH_SAMPLE, PH_ROWS, PH_COMBINE, PH_REDUCE, PH_EXACT, PH_PREDICT, PH_GENERIC, PH_MATERIALISE, PH_COUNT };
 
 struct PendingEvent {
   int phase;

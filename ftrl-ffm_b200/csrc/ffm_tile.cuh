@@ -273,7 +273,7 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
           rm.pos = occ_pos[r0 + t];
           rm.feat = ft;
           m.row[sl] = rm;
-          m.lin[sl] = *sh.linp(ft);
+          m.lin[sl] = (geo.dbg & 4) && (ft & (sh.G - 1)) != sh.rank ? make_float4(0.f, 1.f, 0.01f, 0.f) : *sh.linp(ft);
           m.present[fl] = 1;
         }
         nv += __popc(okm);
@@ -339,7 +339,7 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
         // its loads back to back: one NVLink round trip per sample instead of one per row.
         constexpr int LU = 14;
         const int lt = tid - n_cons;  // lane among the loader threads
-        const int n_remote = m.hdr[2];
+        const int n_remote = (geo.dbg & 16) ? 0 : m.hdr[2];
         const int n_items = n_remote * nvec;
         for (int i0 = 0; i0 < n_items; i0 += LU * NL * 32) {
           float4 buf[LU];
@@ -529,7 +529,7 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
         ftrl_apply<PRECISE>(e.x, e.y, w, gi, gi * gi, h);
         *sh.linp(rm.feat) = e;
       } else {
-        *sh.stage_lin(rm.feat, rm.pos) = gi;  // w of staged rows was materialised by their owner
+        if (!((geo.dbg & 8) && is_remote(rm.feat))) *sh.stage_lin(rm.feat, rm.pos) = gi;  // w of staged rows: materialised by their owner
       }
     }
     // staged rows: slices no partner touches (own field, absent fields) must read as 0 in the image.

@@ -434,6 +434,7 @@ static void run_lrfm_batch(ftrl_handle *h, const Batch &b, float *logit_out) {
 
 // owner-side pre-pass of the tile path: materialise w of the segmented rows (ffm_tile.cuh)
 static void run_row_prepass(ftrl_handle *h, int32_t n_sorted, uint32_t sentinel) {
+  PhaseScope ps(h, PH_MATERIALISE);
   const Dims &d = h->dims;
   const int grid = h->n_sms * 4;
   FTRL_CUDA(cudaMemsetAsync(h->rowmask.p, 0, sizeof(unsigned long long) * (size_t)(n_sorted + 2), h->compute));
@@ -448,7 +449,7 @@ static void run_row_prepass(ftrl_handle *h, int32_t n_sorted, uint32_t sentinel)
                                                               h->n_chunks.p, h->chunk_pos.p, h->skey.p, h->scan.p,
                                                               h->rowmask.p, h->tab, h->lin);
   FTRL_CUDA(cudaGetLastError());
-  launched(h, PH_SEGMENT, 2);
+  launched(h, PH_MATERIALISE, 2);
 }
 
 static void run_prep(ftrl_handle *h, const Batch &b) {
@@ -490,9 +491,9 @@ static void run_prep(ftrl_handle *h, const Batch &b) {
                                     h->compute));
     k_terminate<<<1, 1, 0, h->compute>>>(h->chunk_pos.p, h->n_chunks.p, nnz);
     launched(h, PH_SEGMENT);
-    if (d.model_type == FTRL_FFM && h->tile_ok) run_row_prepass(h, nnz, sentinel);
     FTRL_CUDA(cudaGetLastError());
   }
+  if (d.model_type == FTRL_FFM && h->tile_ok) run_row_prepass(h, nnz, sentinel);
 }
 
 template <bool PRECISE>
@@ -735,9 +736,9 @@ static void train_device_sharded(ftrl_handle *h, const Batch &b, float *logit_ou
     k_terminate<<<1, 1, 0, h->compute>>>(h->chunk_pos.p, h->n_chunks.p, oc);
     FTRL_CUDA(cudaGetLastError());
     launched(h, PH_SEGMENT, 2);
-    run_row_prepass(h, oc, lsent);
-    peer_barrier(h);  // 2: every occurrence knows its class / staging position, w of staged rows is materialised
   }
+  run_row_prepass(h, oc, lsent);
+  peer_barrier(h);  // 2: every occurrence knows its class / staging position, w of staged rows is materialised
   const ItemDecode dec = make_item_decode(d.k, 4);
   const int grid = h->n_sms * 4;
   {
@@ -883,7 +884,7 @@ int ftrl_create(const ftrl_config *cfg, ftrl_handle **out) {
       while ((1 << h->log2G) < h->G) h->log2G++;
     }
     h->n_local = h->G > 1 ? ((int64_t)cfg->n_feats - h->rank + h->G - 1) / h->G : cfg->n_feats;
-    static const char *names[PH_COUNT] = {"prep_rows", "sort", "segment", "sample", "rows", "combine", "reduce", "exact", "predict", "generic"};
+    static const char *names[PH_COUNT] = {"prep_rows", "sort", "segment", "sample", "rows", "combine", "reduce", "exact", "predict", "generic", "materialise"};
     for (int i = 0; i < PH_COUNT; i++) h->phases[i].name = names[i];
     cudaDeviceProp prop;
     FTRL_CUDA(cudaGetDeviceProperties(&prop, cfg->device));

@@ -15,6 +15,26 @@ __global__ void rd(const float4 *src, float4 *sink, size_t n_chunks, int vpc, in
   }
   if (acc.x == 12345.f) sink[0] = acc;
 }
+
+// limited-concurrency probe: 148 CTAs x 128 threads, every lane keeps LU scattered 16-byte loads in flight (like the
+// loader warps of k_ffm_tile); effective latency = bytes in flight / bandwidth
+__global__ void rd_lowconc(const float4 *src, float4 *sink, size_t n_chunks, int vpc, int iters) {
+  constexpr int LU = 14;
+  const int t = threadIdx.x;
+  float4 acc = make_float4(0, 0, 0, 0);
+  for (int it = 0; it < iters; it++) {
+    float4 buf[LU];
+#pragma unroll
+    for (int u = 0; u < LU; u++) {
+      const size_t item = ((size_t)it * gridDim.x + blockIdx.x) * (LU * 128) + u * 128 + t;
+      const size_t c = ((item / vpc) * 2654435761ull) % n_chunks;
+      buf[u] = __ldcs(src + c * vpc + item % vpc);
+    }
+#pragma unroll
+    for (int u = 0; u < LU; u++) { acc.x += buf[u].x; acc.y += buf[u].y; }
+  }
+  if (acc.x == 12345.f) sink[0] = acc;
+}
 __global__ void wr(float4 *dst, size_t n_chunks, int vpc, int scatter) {
   const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((size_t)gridDim.x * blockDim.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -40,6 +60,12 @@ int main() {
     }
     float ms; cudaEventElapsedTime(&ms, a, b);
     printf("%s %s %s blocks=%d: %.1f GB/s\n", tgt ? "REMOTE" : "local ", scatter ? "scattered-1248B" : "contiguous     ", w ? "write" : "read ", blocks, bytes / ms / 1e6);
+  }
+  for (int tgt = 0; tgt < 2; tgt++) for (int rep = 0; rep < 2; rep++) {
+    cudaEventRecord(a); rd_lowconc<<<148, 128>>>(tgt ? remote : local, sink, n_chunks, vpc, 400); cudaEventRecord(b); CK(cudaEventSynchronize(b));
+    float ms; cudaEventElapsedTime(&ms, a, b);
+    const double by = 148.0 * 128 * 14 * 16 * 400;
+    printf("%s same-process low-concurrency scattered read: %.1f GB/s -> effective latency %.2f us\n", tgt ? "REMOTE" : "local ", by / ms / 1e6, 148.0 * 128 * 14 * 16 / (by / ms / 1e3) * 1e-3 * 1e3);
   }
   return 0;
 }
