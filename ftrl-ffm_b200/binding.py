@@ -253,6 +253,13 @@ class FtrlModel:
             else:
                 self._check(self.lib.ftrl_set_state(self.h, which, _np_ptr(b), _np_ptr(lin), _np_ptr(vec)))
 
+    def get_rows(self, which, row0, n_rows):
+        """(lin, vec) of local rows [row0, row0 + n_rows); which: 0 = w, 1 = n, 2 = z (ftrl_get_rows)"""
+        lin = np.zeros(n_rows, np.float32)
+        vec = np.zeros((n_rows, self.row_len), np.float32) if self.row_len else None
+        self._check(self.lib.ftrl_get_rows(self.h, int(which), int(row0), int(n_rows), _np_ptr(lin), _np_ptr(vec)))
+        return lin, vec
+
     @property
     def bias(self):
         return float(self._get(0)[0][0])
