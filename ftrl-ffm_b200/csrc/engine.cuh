@@ -49,13 +49,22 @@ inline std::string fmt(const char *f, ...) {
   return buf;
 }
 
+// Device allocations are sized in whole 2 MiB pages.  Measured on B200 (tools/exp/ipc2.cu): a cudaMalloc
+// block whose size is NOT a multiple of 2 MiB is imported by cudaIpcOpenMemHandle with small pages, and
+// scattered peer reads of it over NVLink drop from ~635 GB/s to ~75 GB/s (TLB misses); every buffer a
+// peer rank may map therefore has to be a whole number of 2 MiB pages.
+inline size_t page_round(size_t bytes) {
+  constexpr size_t PAGE = size_t(2) << 20;
+  return (bytes + PAGE - 1) / PAGE * PAGE;
+}
+
 template <typename T>
 struct DevBuf {
   T *p = nullptr;
   size_t n = 0;
   void alloc(size_t count) {
     release();
-    if (count) FTRL_CUDA(cudaMalloc(&p, count * sizeof(T)));
+    if (count) FTRL_CUDA(cudaMalloc(&p, page_round(count * sizeof(T))));
     n = count;
   }
   void ensure(size_t count) {

@@ -601,9 +601,12 @@ k_row_materialise(Dims d, Hyper h, int32_t nnz, uint32_t sentinel, int32_t ch, c
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_ffm_staged_rows: streaming segmented reduction over the staged gradient images
+// k_ffm_staged_rows: streaming segmented reduction over the staged gradient images.
+// Work item = (chunk of <= 32 occurrences of one row, part of 32 float4 vectors of the row): one warp,
+// one 512-byte coalesced load per occurrence, all loads of the chunk independent (unrolled by 8), so a
+// row of 78 vectors is reduced by three warps in parallel.  Part 0 also reduces the linear coordinate.
 // ---------------------------------------------------------------------------------------------
-template <bool PRECISE, int WARPS, int R>
+template <bool PRECISE, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
 k_ffm_staged_rows(Dims d, Hyper h, int32_t nnz, const int32_t *__restrict__ batch_flags, float *__restrict__ tab,
                   float4 *__restrict__ lin, int32_t ch, const int32_t *__restrict__ n_chunks_p,
@@ -611,74 +614,80 @@ k_ffm_staged_rows(Dims d, Hyper h, int32_t nnz, const int32_t *__restrict__ batc
                   const SegScan *__restrict__ scan, const float *__restrict__ staging,
                   const float *__restrict__ staging_lin, float *__restrict__ part, float2 *__restrict__ part_lin) {
   if (batch_flags[0] == 0) return;
-  // R float4 accumulators per lane and pass: one pass covers 128*R floats of the row
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t ld = d.ld, rs = 3 * ld;
   const int n_chunks = *n_chunks_p;
   const uint32_t sentinel = (uint32_t)d.n_feats;
   const int nvec = (int)(ld >> 2);
-  for (int c = blockIdx.x * WARPS + wib; c < n_chunks; c += gridDim.x * WARPS) {
+  const int parts = (nvec + 31) >> 5;
+  const int64_t n_items = (int64_t)n_chunks * parts;
+  for (int64_t item = (int64_t)blockIdx.x * WARPS + wib; item < n_items; item += (int64_t)gridDim.x * WARPS) {
+    const int c = (int)(item / parts), part_i = (int)(item - (int64_t)c * parts);
     const ChunkInfo ci = chunk_info<true>(c, nnz, sentinel, ch, chunk_pos, skey, scan);
     if (!ci.valid) continue;
     const bool whole_row = ci.row_head && ci.row_last;
-    // linear coordinate
-    float sg = 0.f, sg2 = 0.f;
-    for (int p = ci.p0 + lane; p < ci.p1; p += 32) {
-      const float gi = staging_lin[p];
-      sg += gi;
-      sg2 = fmaf(gi, gi, sg2);
-    }
-    sg = warp_sum(sg);
-    sg2 = warp_sum(sg2);
-    float *row = tab + (int64_t)ci.key * rs;
-    float *pdst = part + (int64_t)ci.slot * 2 * ld;
-    for (int vb = 0; vb < nvec; vb += 32 * R) {
-      float4 a0[R], a1[R];
+    const int v = part_i * 32 + lane;
+    const bool on = v < nvec;
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+    const float4 *src = reinterpret_cast<const float4 *>(staging + (int64_t)ci.p0 * ld) + (on ? v : 0);
+    const int n_occ = ci.p1 - ci.p0;
+    int p = 0;
+    for (; p + 8 <= n_occ; p += 8) {
+      float4 gq[8];
 #pragma unroll
-      for (int r = 0; r < R; r++) a0[r] = a1[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-      for (int p = ci.p0; p < ci.p1; p++) {
-        const float4 *src = reinterpret_cast<const float4 *>(staging + (int64_t)p * ld);
+      for (int u = 0; u < 8; u++) gq[u] = on ? __ldcs(src + (int64_t)(p + u) * nvec) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int r = 0; r < R; r++) {
-          const int v = vb + r * 32 + lane;
-          if (v < nvec) {
-            const float4 gq = __ldcs(src + v);
-            a0[r].x += gq.x; a0[r].y += gq.y; a0[r].z += gq.z; a0[r].w += gq.w;
-            a1[r].x = fmaf(gq.x, gq.x, a1[r].x); a1[r].y = fmaf(gq.y, gq.y, a1[r].y);
-            a1[r].z = fmaf(gq.z, gq.z, a1[r].z); a1[r].w = fmaf(gq.w, gq.w, a1[r].w);
-          }
-        }
+      for (int u = 0; u < 8; u++) {
+        a0.x += gq[u].x; a0.y += gq[u].y; a0.z += gq[u].z; a0.w += gq[u].w;
+        a1.x = fmaf(gq[u].x, gq[u].x, a1.x); a1.y = fmaf(gq[u].y, gq[u].y, a1.y);
+        a1.z = fmaf(gq[u].z, gq[u].z, a1.z); a1.w = fmaf(gq[u].w, gq[u].w, a1.w);
       }
-#pragma unroll
-      for (int r = 0; r < R; r++) {
-        const int v = vb + r * 32 + lane;
-        if (v >= nvec) continue;
-        if (whole_row) {
-          const bool any = a1[r].x != 0.f || a1[r].y != 0.f || a1[r].z != 0.f || a1[r].w != 0.f ||
-                           a0[r].x != 0.f || a0[r].y != 0.f || a0[r].z != 0.f || a0[r].w != 0.f;
-          if (!any) continue;
+    }
+    for (; p < n_occ; p++) {
+      const float4 gq = on ? __ldcs(src + (int64_t)p * nvec) : make_float4(0.f, 0.f, 0.f, 0.f);
+      a0.x += gq.x; a0.y += gq.y; a0.z += gq.z; a0.w += gq.w;
+      a1.x = fmaf(gq.x, gq.x, a1.x); a1.y = fmaf(gq.y, gq.y, a1.y);
+      a1.z = fmaf(gq.z, gq.z, a1.z); a1.w = fmaf(gq.w, gq.w, a1.w);
+    }
+    float *row = tab + (int64_t)ci.key * rs;
+    if (on) {
+      if (whole_row) {
+        const bool any = a1.x != 0.f || a1.y != 0.f || a1.z != 0.f || a1.w != 0.f || a0.x != 0.f || a0.y != 0.f ||
+                         a0.z != 0.f || a0.w != 0.f;
+        if (any) {
           float4 z = reinterpret_cast<float4 *>(row)[v], n = reinterpret_cast<float4 *>(row + ld)[v];
           const float4 w = reinterpret_cast<float4 *>(row + 2 * ld)[v];
-          ftrl_apply<PRECISE>(z.x, n.x, w.x, a0[r].x, a1[r].x, h);
-          ftrl_apply<PRECISE>(z.y, n.y, w.y, a0[r].y, a1[r].y, h);
-          ftrl_apply<PRECISE>(z.z, n.z, w.z, a0[r].z, a1[r].z, h);
-          ftrl_apply<PRECISE>(z.w, n.w, w.w, a0[r].w, a1[r].w, h);
+          ftrl_apply<PRECISE>(z.x, n.x, w.x, a0.x, a1.x, h);
+          ftrl_apply<PRECISE>(z.y, n.y, w.y, a0.y, a1.y, h);
+          ftrl_apply<PRECISE>(z.z, n.z, w.z, a0.z, a1.z, h);
+          ftrl_apply<PRECISE>(z.w, n.w, w.w, a0.w, a1.w, h);
           reinterpret_cast<float4 *>(row)[v] = z;
           reinterpret_cast<float4 *>(row + ld)[v] = n;
-        } else {
-          reinterpret_cast<float4 *>(pdst)[v] = a0[r];
-          reinterpret_cast<float4 *>(pdst + ld)[v] = a1[r];
         }
+      } else {
+        float *pdst = part + (int64_t)ci.slot * 2 * ld;
+        reinterpret_cast<float4 *>(pdst)[v] = a0;
+        reinterpret_cast<float4 *>(pdst + ld)[v] = a1;
       }
     }
-    if (lane == 0) {
-      if (whole_row) {
-        float4 e = lin[ci.key];
-        ftrl_apply<PRECISE>(e.x, e.y, e.z, sg, sg2, h);
-        lin[ci.key] = e;
-      } else {
-        part_lin[ci.slot] = make_float2(sg, sg2);
+    if (part_i == 0) {
+      // linear coordinate
+      float sg = 0.f, sg2 = 0.f;
+      for (int q = ci.p0 + lane; q < ci.p1; q += 32) {
+        const float gi = staging_lin[q];
+        sg += gi;
+        sg2 = fmaf(gi, gi, sg2);
+      }
+      sg = warp_sum(sg);
+      sg2 = warp_sum(sg2);
+      if (lane == 0) {
+        if (whole_row) {
+          float4 e = lin[ci.key];
+          ftrl_apply<PRECISE>(e.x, e.y, e.z, sg, sg2, h);
+          lin[ci.key] = e;
+        } else {
+          part_lin[ci.slot] = make_float2(sg, sg2);
+        }
       }
     }
   }

@@ -348,17 +348,16 @@ static void run_ffm_batch(ftrl_handle *h, const Batch &b, float *logit_out) {
     }
     {
       PhaseScope ps(h, PH_ROWS);
-      const int nvec = d.ld / 4;
-#define FFM_STAGED(RR)                                                                                             \
-  k_ffm_staged_rows<PRECISE, 8, RR><<<grid * 2, 256, 0, h->compute>>>(d, h->hyper, (int32_t)b.nnz, h->batch_flags.p, h->tab, \
-                                                                     h->lin, h->chunk, h->n_chunks.p, h->chunk_pos.p, \
-                                                                     h->skey.p, h->scan.p, h->staging.p,           \
-                                                                     h->staging_lin.p, h->part.p, h->part_lin.p)
-      if (nvec <= 32) FFM_STAGED(1);
-      else if (nvec <= 64) FFM_STAGED(2);
-      else if (nvec <= 96) FFM_STAGED(3);
-      else FFM_STAGED(4);
-#undef FFM_STAGED
+      if (h->precise)
+        k_ffm_staged_rows<true, 8><<<grid * 4, 256, 0, h->compute>>>(d, h->hyper, (int32_t)b.nnz, h->batch_flags.p, h->tab, h->lin,
+                                                                    h->chunk, h->n_chunks.p, h->chunk_pos.p, h->skey.p,
+                                                                    h->scan.p, h->staging.p, h->staging_lin.p, h->part.p,
+                                                                    h->part_lin.p);
+      else
+        k_ffm_staged_rows<false, 8><<<grid * 4, 256, 0, h->compute>>>(d, h->hyper, (int32_t)b.nnz, h->batch_flags.p, h->tab, h->lin,
+                                                                     h->chunk, h->n_chunks.p, h->chunk_pos.p, h->skey.p,
+                                                                     h->scan.p, h->staging.p, h->staging_lin.p, h->part.p,
+                                                                     h->part_lin.p);
       FTRL_CUDA(cudaGetLastError());
       launched(h, PH_ROWS);
     }
@@ -778,17 +777,9 @@ static void train_device_sharded(ftrl_handle *h, const Batch &b, float *logit_ou
   }
   {
     PhaseScope ps(h, PH_ROWS);
-    const int nvec = d.ld / 4;
-#define FFM_STAGED(RR)                                                                                             \
-  k_ffm_staged_rows<PRECISE, 8, RR><<<grid * 2, 256, 0, h->compute>>>(d, h->hyper, oc, h->batch_flags.p, h->tab, h->lin, \
-                                                                     h->chunk, h->n_chunks.p, h->chunk_pos.p, h->skey.p, \
-                                                                     h->scan.p, h->staging.p, h->staging_lin.p,      \
-                                                                     h->part.p, h->part_lin.p)
-    if (nvec <= 32) FFM_STAGED(1);
-    else if (nvec <= 64) FFM_STAGED(2);
-    else if (nvec <= 96) FFM_STAGED(3);
-    else FFM_STAGED(4);
-#undef FFM_STAGED
+    k_ffm_staged_rows<PRECISE, 8><<<grid * 4, 256, 0, h->compute>>>(d, h->hyper, oc, h->batch_flags.p, h->tab, h->lin, h->chunk,
+                                                                   h->n_chunks.p, h->chunk_pos.p, h->skey.p, h->scan.p,
+                                                                   h->staging.p, h->staging_lin.p, h->part.p, h->part_lin.p);
     FTRL_CUDA(cudaGetLastError());
     launched(h, PH_ROWS);
   }
@@ -941,7 +932,7 @@ int ftrl_create(const ftrl_config *cfg, ftrl_handle **out) {
     FTRL_CUDA(cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking));
     if (h->G > 1 && !h->tile_ok) throw ArgFail{"multi-GPU runs need the tile path (n_factors % 4 == 0, sample tile must fit shared memory)"};
     const int64_t n = std::max<int64_t>(1, h->n_local);
-    FTRL_CUDA(cudaMalloc(&h->lin, sizeof(float4) * n));
+    FTRL_CUDA(cudaMalloc(&h->lin, page_round(sizeof(float4) * n)));
     FTRL_CUDA(cudaMalloc(&h->bias, sizeof(float4)));
     FTRL_CUDA(cudaMemsetAsync(h->bias, 0, sizeof(float4), h->compute));
     FTRL_CUDA(cudaMalloc(&h->d_err, sizeof(int32_t)));
@@ -950,7 +941,7 @@ int ftrl_create(const ftrl_config *cfg, ftrl_handle **out) {
     k_build_pair_lut<<<(PAIR_LUT_N + 255) / 256, 256, 0, h->compute>>>(h->pair_lut);
     k_init_lin<<<(unsigned)((n + 255) / 256), 256, 0, h->compute>>>(h->lin, n, cfg->init_mean, cfg->init_stddev, cfg->seed, h->G, h->rank);
     if (d.row_len) {
-      FTRL_CUDA(cudaMalloc(&h->tab, sizeof(float) * 3 * (size_t)d.ld * (size_t)n));
+      FTRL_CUDA(cudaMalloc(&h->tab, page_round(sizeof(float) * 3 * (size_t)d.ld * (size_t)n)));
       const int64_t q = n * (d.ld / 4);
       k_init_tab<<<(unsigned)((q + 255) / 256), 256, 0, h->compute>>>(h->tab, n, d.row_len, d.ld, cfg->init_mean, cfg->init_stddev, cfg->seed, h->G, h->rank);
     }
@@ -974,7 +965,7 @@ int ftrl_create(const ftrl_config *cfg, ftrl_handle **out) {
       }
     }
     if (h->G > 1) {
-      FTRL_CUDA(cudaMalloc(&h->sync, sizeof(SyncArea)));
+      FTRL_CUDA(cudaMalloc(&h->sync, page_round(sizeof(SyncArea))));
       FTRL_CUDA(cudaMemsetAsync(h->sync, 0, sizeof(SyncArea), h->compute));
     }
     refresh_shards(h);
@@ -1508,3 +1499,52 @@ int ftrl_attach_peers(ftrl_handle *h, const void *blobs) {
 }
 
 }  // extern "C"
+
+// ---- debug probe (tools/ only, not part of the ABI): scattered row traffic against one shard ----
+namespace ftrl {
+__global__ void k_dbg_peer_traffic(Shards sh, int q, int64_t n_local, int64_t ld, int32_t n_rows, int flags, float *sink) {
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int lane = threadIdx.x & 31, nvec = (int)(ld >> 2);
+  float acc = 0.f;
+  for (int64_t i = warp; i < n_rows; i += nw) {
+    const int64_t row = (int64_t)(((uint64_t)i * 2654435761ull) % (uint64_t)n_local);
+    if (flags & 1) {
+      const float4 *p = reinterpret_cast<const float4 *>(sh.tab[q] + row * 3 * ld + 2 * ld);
+      for (int v = lane; v < nvec; v += 32) acc += __ldcs(p + v).x;
+    }
+    if (flags & 2) {
+      float4 *p = reinterpret_cast<float4 *>(sh.staging[q] + i * ld);
+      for (int v = lane; v < nvec; v += 32) __stcs(p + v, make_float4(0.f, 0.f, 0.f, 0.f));
+    }
+    if (flags & 4) {
+      const float4 *p = reinterpret_cast<const float4 *>(sh.staging[q] + (row % n_rows) * ld);
+      for (int v = lane; v < nvec; v += 32) acc += __ldcs(p + v).x;
+    }
+    if (flags & 8) {  // destroys the w plane: probe only
+      float4 *p = reinterpret_cast<float4 *>(sh.tab[q] + row * 3 * ld + 2 * ld);
+      for (int v = lane; v < nvec; v += 32) __stcs(p + v, make_float4(0.f, 0.f, 0.f, 0.f));
+    }
+    if (flags & 16) {  // sequential rows instead of hashed
+      const float4 *p = reinterpret_cast<const float4 *>(sh.tab[q] + (i % n_local) * 3 * ld + 2 * ld);
+      for (int v = lane; v < nvec; v += 32) acc += __ldcs(p + v).x;
+    }
+  }
+  if (acc == 12345.f) sink[0] = acc;
+}
+}  // namespace ftrl
+extern "C" int ftrl_dbg_peer_traffic(ftrl_handle *h, int q, int flags, int n_rows, int grid, int reps, float *ms_out) {
+  return guarded(h, [&] {
+    cudaEvent_t a, b;
+    FTRL_CUDA(cudaEventCreate(&a));
+    FTRL_CUDA(cudaEventCreate(&b));
+    FTRL_CUDA(cudaEventRecord(a, h->compute));
+    for (int r = 0; r < reps; r++)
+      ftrl::k_dbg_peer_traffic<<<grid, 256, 0, h->compute>>>(h->shards, q, h->n_local, h->dims.ld, n_rows, flags, h->logit_ws.p);
+    FTRL_CUDA(cudaEventRecord(b, h->compute));
+    FTRL_CUDA(cudaEventSynchronize(b));
+    FTRL_CUDA(cudaEventElapsedTime(ms_out, a, b));
+    *ms_out /= reps;
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+  });
+}

@@ -7,12 +7,12 @@ import numpy as np
 import ftrl_ffm_b200 as pkg
 
 G = int(sys.argv[1]) if len(sys.argv) > 1 else 2
-nfl, nf, k, B = 39, 10_000_000, 8, 65536
+nfl, nf, k, B = 39, int(os.environ.get('NF', 10_000_000)), 8, 65536
 sh = pkg.LogicalShards(G, devices=list(range(G)), model_type="FFM", n_feats=nf, n_fields=nfl, n_factors=k,
                        max_batch_rows=B, max_batch_nnz=B * nfl)
 for m in sh.models:
     m.randomize_state(seed=7)
-batches = [[pkg.synth.criteo_batch(B, nfl, nf, seed=42 + 1000 * r + i) for r in range(G)] for i in range(3)]
+batches = [[pkg.synth.criteo_batch(B, nfl, nf, seed=42 + 1000 * r + i, dist=os.environ.get('DIST','zipf')) for r in range(G)] for i in range(3)]
 for m in sh.models:
     m.profile_enable(True)
 for i in range(2):

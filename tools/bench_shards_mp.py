@@ -8,14 +8,14 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 def worker(rank, G, q_out, q_in, q_res):
     import numpy as np
     import ftrl_ffm_b200 as pkg
-    nfl, nf, k, B = 39, 10_000_000, 8, 65536
+    nfl, nf, k, B = 39, int(os.environ.get('NF', 10_000_000)), 8, 65536
     m = pkg.FtrlModel("FFM", n_feats=nf, n_fields=nfl, n_factors=k, device=rank, rank=rank, world_size=G,
                       max_batch_rows=B, max_batch_nnz=B * nfl)
     q_out.put((rank, m.export_peer_blob()))
     blobs = q_in.get()
     m.attach_peers(blobs)
     m.randomize_state(seed=7)
-    batches = [pkg.synth.criteo_batch(B, nfl, nf, seed=42 + 1000 * rank + i) for i in range(3)]
+    batches = [pkg.synth.criteo_batch(B, nfl, nf, seed=42 + 1000 * rank + i, dist=os.environ.get('DIST','zipf')) for i in range(3)]
     q_out.put((rank, "ready")); q_in.get()
     m.profile_enable(True)
     for i in range(2):
