@@ -30,27 +30,40 @@ enum : int { PLANE_Z = 0, PLANE_N = 1, PLANE_W = 2 };
 
 // ---- feature-sharded tables -------------------------------------------------------------------
 // Row `feat` lives on shard feat mod G at local row feat div G (G a power of two, G = 1: one GPU).
-// Peer shards are mapped into this process (CUDA IPC) and reached over NVLink with the same
-// instructions: bulk copies, 128-bit stores.
+// Peer shards are mapped into this process (CUDA IPC) and reached over NVLink with ordinary loads / stores.
 constexpr int MAX_SHARDS = 8;
-struct Shards {
+struct Shards {   // every shard's tables (predict reads rows where they live)
   int G, log2G, rank, pad;
   float *tab[MAX_SHARDS];
   float4 *lin[MAX_SHARDS];
-  float *staging[MAX_SHARDS];
-  float *staging_lin[MAX_SHARDS];
   __device__ __forceinline__ float *row(int32_t feat, int64_t rs) const {
     return tab[feat & (G - 1)] + (int64_t)(feat >> log2G) * rs;
   }
   __device__ __forceinline__ float4 *linp(int32_t feat) const { return lin[feat & (G - 1)] + (feat >> log2G); }
-  __device__ __forceinline__ float *stage(int32_t feat, int32_t pos, int64_t ld) const {
-    return staging[feat & (G - 1)] + (int64_t)pos * ld;
-  }
-  __device__ __forceinline__ float *stage_lin(int32_t feat, int32_t pos) const {
-    return staging_lin[feat & (G - 1)] + pos;
-  }
 };
 
+// What the per-sample training kernel sees: the local shard, the per-step cache of remote rows (their w
+// plane, pulled once per distinct row: shard.cuh) and the local staging area of gradient images.
+// A row is named by a locator: >= 0 local row index; < 0: -1 - (sorted head position of the remote row).
+struct RowSpace {
+  float *tab;            // [n_local][3][ld]
+  float4 *lin;           // [n_local]
+  float *staging;        // [sorted position][ld]
+  float *staging_lin;    // [sorted position]
+  const float *rc_w;     // [sorted head position][ld]   (null when G == 1)
+  const float *rc_lin;   // [sorted head position]
+  int log2G, rank, Gm1, pad;
+};
+
+// Where the reduced (sum g, sum g^2) of a row goes (k_ffm_staged_rows / k_ffm_combine).  Single GPU: applied
+// in place.  Sharded: dst_at[sorted head position] = -2 apply here (this rank owns the row and is its only
+// contributor), >= 0: slot in the owner's inbox.
+struct Export {
+  int on, log2G, Gm1, pad;
+  const int32_t *dst_at;
+  float *inbox[MAX_SHARDS];        // [slot][2][ld]
+  float2 *inbox_lin[MAX_SHARDS];   // [slot]
+};
 
 constexpr int32_t KEY_INVALID_BITS = 0;  // invalid occurrences get key == n_feats (sorts last)
 

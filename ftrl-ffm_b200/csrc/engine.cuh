@@ -118,7 +118,7 @@ struct Phase {
   int64_t launches = 0;
 };
 
-enum PhaseId { PH_PREP = 0, PH_SORT, PH_SEGMENT, PH_SAMPLE, PH_ROWS, PH_COMBINE, PH_REDUCE, PH_EXACT, PH_PREDICT, PH_GENERIC, PH_MATERIALISE, PH_COUNT };
+enum PhaseId { PH_PREP = 0, PH_SORT, PH_SEGMENT, PH_SAMPLE, PH_ROWS, PH_COMBINE, PH_REDUCE, PH_EXACT, PH_PREDICT, PH_GENERIC, PH_MATERIALISE, PH_EXCHANGE, PH_PULL, PH_APPLY, PH_COUNT };
 
 struct PendingEvent {
   int phase;
@@ -181,15 +181,25 @@ struct ftrl_handle {
   // feature-sharded multi-GPU (shard.cuh): this rank holds rows feat with feat % G == rank
   int G = 1, log2G = 0, rank = 0;
   int64_t n_local = 0;          // rows of lin / tab held here
-  ftrl::Shards shards{};        // per-owner table / staging pointers (self when G == 1)
+  ftrl::Shards shards{};        // every shard's tables (predict)
+  ftrl::RowSpace rowspace{};    // what the per-sample training kernel addresses
+  ftrl::Export exportd{};       // where reduced row sums go (single GPU: applied in place)
   ftrl::Peers peers{};
   ftrl::SyncArea *sync = nullptr;
   uint32_t epoch = 0;
   long long barrier_timeout_cycles = 40000000000ll;
   bool attached = false;
-  int64_t ow_cap = 0;           // owner-side capacity: occurrences this rank may own per step
-  ftrl::DevBuf<uint32_t> okey, osrc;
+  int64_t ow_cap = 0;           // owner-side capacity: (row, rank) contributions this rank may own per step
+  ftrl::DevBuf<uint32_t> okey, osrc, ckey, csrc;   // owned contributions, unsorted / sorted by local row
+  ftrl::DevBuf<uint8_t> cflag;
   ftrl::DevBuf<int32_t> sel, n_sel;
+  ftrl::DevBuf<ftrl::MaskScan> mscan;              // segmented OR-scan of the field masks over the sorted list
+  ftrl::DevBuf<int32_t> uhead, n_uall, dst_at;     // distinct rows of the local batch (sorted head positions)
+  ftrl::DevBuf<uint32_t> ukey, uinfo;
+  ftrl::DevBuf<unsigned long long> umask;
+  ftrl::DevBuf<float> rc_w, rc_lin;                // cache of remote rows (w plane), by sorted head position
+  ftrl::DevBuf<float> inbox;                       // [contribution][2][ld] (sum g, sum g^2) from the contributing ranks
+  ftrl::DevBuf<float2> inbox_lin;
   ftrl::DevBuf<double> red4;
   std::vector<void *> ipc_opened;
 

@@ -396,7 +396,7 @@ __global__ void __launch_bounds__(THREADS)
 k_ffm_combine(Dims d, Hyper h, int32_t nnz, float *__restrict__ tab, float4 *__restrict__ lin, int32_t ch,
               const int32_t *__restrict__ n_chunks_p, const int32_t *__restrict__ chunk_pos,
               const uint32_t *__restrict__ skey, const SegScan *__restrict__ scan,
-              const float *__restrict__ part, const float2 *__restrict__ part_lin) {
+              const float *__restrict__ part, const float2 *__restrict__ part_lin, const __grid_constant__ Export ex) {
   constexpr int WARPS = THREADS / 32;
   constexpr int VB = 32 * COMB_VPL;  // vectors per block
   __shared__ int s_list[THREADS];
@@ -423,7 +423,10 @@ k_ffm_combine(Dims d, Hyper h, int32_t nnz, float *__restrict__ tab, float4 *__r
       const ChunkInfo ci = chunk_head_info(c0, nnz, sentinel, ch, chunk_pos, skey, scan);
       int J = 1;  // number of chunks of this row
       while (c0 + J < n_chunks && skey[chunk_pos[c0 + J]] == ci.key) J++;
-      float *row = tab + (int64_t)ci.key * rs;
+      const int32_t dst = ex.on ? ex.dst_at[ci.p0] : -2;  // sharded: >= 0 -> the sum goes to the owner's inbox
+      const int64_t lrow = (int64_t)(ci.key >> ex.log2G);
+      float *row = tab + lrow * rs;
+      float *o = dst >= 0 ? ex.inbox[ci.key & ex.Gm1] + (int64_t)dst * 2 * ld : nullptr;
       const float4 *p0 = reinterpret_cast<const float4 *>(part + (int64_t)ci.slot * 2 * ld);
       for (int vb = 0; vb < nvec; vb += VB) {
         float4 a0[COMB_VPL], a1[COMB_VPL];
@@ -458,7 +461,10 @@ k_ffm_combine(Dims d, Hyper h, int32_t nnz, float *__restrict__ tab, float4 *__r
           }
           const bool any = s0.x != 0.f || s0.y != 0.f || s0.z != 0.f || s0.w != 0.f || s1.x != 0.f || s1.y != 0.f ||
                            s1.z != 0.f || s1.w != 0.f;
-          if (any) {
+          if (o) {
+            reinterpret_cast<float4 *>(o)[v] = s0;
+            reinterpret_cast<float4 *>(o + ld)[v] = s1;
+          } else if (any) {
             float4 z = reinterpret_cast<float4 *>(row)[v], n = reinterpret_cast<float4 *>(row + ld)[v];
             const float4 w = reinterpret_cast<float4 *>(row + 2 * ld)[v];
             ftrl_apply<PRECISE>(z.x, n.x, w.x, s0.x, s1.x, h);
@@ -480,9 +486,13 @@ k_ffm_combine(Dims d, Hyper h, int32_t nnz, float *__restrict__ tab, float4 *__r
         sg = warp_sum(sg);
         sg2 = warp_sum(sg2);
         if (lane == 0) {
-          float4 e = lin[ci.key];
-          ftrl_apply<PRECISE>(e.x, e.y, e.z, sg, sg2, h);
-          lin[ci.key] = e;
+          if (dst >= 0) {
+            ex.inbox_lin[ci.key & ex.Gm1][dst] = make_float2(sg, sg2);
+          } else {
+            float4 e = lin[lrow];
+            ftrl_apply<PRECISE>(e.x, e.y, e.z, sg, sg2, h);
+            lin[lrow] = e;
+          }
         }
       }
     }

@@ -82,15 +82,8 @@ __device__ __forceinline__ void named_bar_sync(int id, int n_threads) {
 
 // ---- tile geometry ------------------------------------------------------------------------------
 constexpr int TILE_META_WARPS = 2;   // warps prefetching sample metadata (CSR, occurrence class, linear records)
-// warps moving rows: single GPU 1 loader + 1 storer (TMA bulk copies only); sharded runs add warps that move
-// REMOTE rows with 128-bit loads/stores through registers (bulk copies to peer memory over NVLink are
-// latency-bound per operation, plain loads/stores pipeline deeply)
-constexpr int TILE_LOADERS_SHARDED = 4, TILE_STORERS_SHARDED = 2;
-__host__ __device__ constexpr int tile_loaders(bool sharded) { return sharded ? TILE_LOADERS_SHARDED : 1; }
-__host__ __device__ constexpr int tile_storers(bool sharded) { return sharded ? TILE_STORERS_SHARDED : 1; }
-__host__ __device__ constexpr int tile_threads(int consumers, bool sharded) {
-  return consumers + 32 * (tile_loaders(sharded) + tile_storers(sharded) + TILE_META_WARPS);
-}
+// + one row-loader warp and one row-storer warp (TMA bulk copies)
+__host__ __device__ constexpr int tile_threads(int consumers) { return consumers + 32 * (2 + TILE_META_WARPS); }
 constexpr int TILE_MAX_STAGE = 4;    // row stages
 constexpr int TILE_MAX_META = 8;     // metadata slots
 
@@ -108,13 +101,12 @@ struct RowMeta {   // one 16-byte record per row of a sample
   int32_t fk;      // field * k
   float x;         // value
   int32_t pos;     // -1: row finalised here, >= 0: sorted position for the staged gradient image
-  int32_t feat;    // feature id
+  int32_t loc;     // row locator (RowSpace): >= 0 local row, < 0: -1 - head position in the remote-row cache
 };
 struct SampleMeta {
   RowMeta *row;     // [f_cap]
   float4 *lin;      // [f_cap] {z, n, w, -} of the linear coordinate, prefetched
-  int32_t *hdr;     // [0] n valid rows, [1] label, [2] n remote rows
-  uint8_t *remote;  // [f_cap] row slots whose feature lives on another shard
+  int32_t *hdr;     // [0] n valid rows, [1] label
   uint8_t *present; // [n_fields] 1 when some valid row of the sample carries that field
 };
 
@@ -177,11 +169,12 @@ __device__ __forceinline__ void apply4(float4 &z, float4 &n, const float4 &w, co
 // Thread roles: [0, consumers) compute; warp `consumers/32` is the row producer (bulk loads / bulk
 // stores of the row ring); the next TILE_META_WARPS warps prefetch sample metadata into a deeper
 // ring so that the row producer never waits on a dependent global-load chain.
-template <bool PRECISE, int IPT, bool SHARDED>
-__global__ void __launch_bounds__(SHARDED ? tile_threads(384, true) : tile_threads(512, false), 1)
+template <bool PRECISE, int IPT>
+__global__ void __launch_bounds__(tile_threads(512), 1)
 k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t *__restrict__ batch_flags,
-           const __grid_constant__ Shards sh, const float4 *__restrict__ bias, const uint32_t *__restrict__ pair_lut,
-           const int32_t *__restrict__ occ_pos, float *__restrict__ g_out, float *__restrict__ logit_out) {
+           const __grid_constant__ RowSpace rsp, const float4 *__restrict__ bias, const uint32_t *__restrict__ pair_lut,
+           const int32_t *__restrict__ occ_pos, const SegScan *__restrict__ scan, float *__restrict__ g_out,
+           float *__restrict__ logit_out) {
   if (batch_flags[0] == 0) return;  // some sample repeats a field: the generic kernels take this batch
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint64_t bar_full[TILE_MAX_STAGE], bar_done[TILE_MAX_STAGE], bar_free[TILE_MAX_STAGE];
@@ -193,7 +186,7 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
   const int n_cons_warps = n_cons >> 5;
   const int lane = tid & 31;
   // 0 consumer, 1 row loader, 3 row storer, 2 metadata
-  constexpr int NL = tile_loaders(SHARDED), NSW = tile_storers(SHARDED);
+  constexpr int NL = 1, NSW = 1;
   const int role = tid < n_cons ? 0 : (tid < n_cons + 32 * NL ? 1 : (tid < n_cons + 32 * (NL + NSW) ? 3 : 2));
   const int ld = d.ld, k = d.k;
   const int stride = geo.stride, f_cap = geo.f_cap, NS = geo.n_stage, MD = geo.n_meta;
@@ -215,8 +208,6 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
     m.hdr = reinterpret_cast<int32_t *>(p);
     p += 16;
     m.present = p;
-    p += (size_t)((f_cap + 15) / 16) * 16;
-    m.remote = p;
     return m;
   };
 
@@ -271,29 +262,24 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
           rm.fk = fl * k;
           rm.x = x;
           rm.pos = occ_pos[r0 + t];
-          rm.feat = ft;
+          if ((ft & rsp.Gm1) == rsp.rank) {
+            rm.loc = ft >> rsp.log2G;
+            m.lin[sl] = rsp.lin[rm.loc];
+          } else {  // remote rows are never fused: pos >= 0, the row's cache slot is its sorted head position
+            const int32_t head = scan[rm.pos].start;
+            rm.loc = -1 - head;
+            m.lin[sl] = make_float4(0.f, 0.f, rsp.rc_lin[head], 0.f);
+          }
           m.row[sl] = rm;
-          m.lin[sl] = (geo.dbg & 4) && (ft & (sh.G - 1)) != sh.rank ? make_float4(0.f, 1.f, 0.01f, 0.f) : *sh.linp(ft);
           m.present[fl] = 1;
         }
         nv += __popc(okm);
       }
       nv = min(nv, f_cap);
       __syncwarp();
-      int n_remote = 0;
-      if (SHARDED) {
-        for (int base = 0; base < nv; base += 32) {
-          const int r = base + lane;
-          const bool rem = r < nv && (m.row[r].feat & (sh.G - 1)) != sh.rank;
-          const unsigned rmask = __ballot_sync(0xffffffffu, rem);
-          if (rem) m.remote[n_remote + __popc(rmask & ((1u << lane) - 1))] = (uint8_t)r;
-          n_remote += __popc(rmask);
-        }
-      }
       if (lane == 0) {
         m.hdr[0] = nv;
         m.hdr[1] = b.label[s];
-        m.hdr[2] = n_remote;
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_mfull[slot]);
@@ -301,12 +287,13 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
     return;
   }
 
-  const int nvec = ld >> 2;  // float4 vectors per plane
-  auto is_remote = [&](int32_t feat) { return SHARDED && (feat & (sh.G - 1)) != sh.rank; };
+  // w plane of a staged row: the local table, or the cache of remote rows
+  auto w_plane = [&](int32_t loc) -> const float * {
+    return loc >= 0 ? rsp.tab + (int64_t)loc * rs + 2 * ld : rsp.rc_w + (int64_t)(-1 - loc) * ld;
+  };
 
   if (role == 1) {
     // =========================== row loader warps ===========================
-    const int lw = (tid - n_cons) >> 5;  // loader warp index
     for (int64_t it = 0; it < n_mine; it++) {
       const int st = (int)(it % NS);
       float *rows = stage_rows(st);
@@ -315,51 +302,18 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
       mbar_wait(&bar_mfull[slot], (uint32_t)((it / MD) & 1));
       SampleMeta m = sample_meta(slot);
       const int nv = m.hdr[0];
-      if (lw == 0) {
-        // local rows: TMA bulk copies.  Fused rows bring z and n (they are updated here); staged rows bring
-        // only the w plane their owner materialised (k_row_materialise), into the z-plane slot of the stage
+      {
+        // TMA bulk copies.  Fused rows bring z and n (they are updated here); staged rows bring only the w
+        // plane their owner materialised, into the z-plane slot of the stage
         int bytes = 0;
-        for (int r = lane; r < nv; r += 32) {
-          const RowMeta rm = m.row[r];
-          if (!is_remote(rm.feat)) bytes += rm.pos < 0 ? (int)row_bytes : (int)(row_bytes / 2);
-        }
+        for (int r = lane; r < nv; r += 32) bytes += m.row[r].pos < 0 ? (int)row_bytes : (int)(row_bytes / 2);
         bytes = (int)warp_sum((float)bytes);
         if (lane == 0) mbar_expect_tx(&bar_full[st], (uint32_t)bytes);
         __syncwarp();
         for (int r = lane; r < nv; r += 32) {
           const RowMeta rm = m.row[r];
-          if (is_remote(rm.feat)) continue;
-          if (rm.pos < 0) bulk_g2s(rows + (size_t)r * stride, sh.row(rm.feat, rs), row_bytes, &bar_full[st]);
-          else bulk_g2s(rows + (size_t)r * stride, sh.row(rm.feat, rs) + 2 * ld, row_bytes / 2, &bar_full[st]);
-        }
-      }
-      if (SHARDED) {
-        // remote rows (always staged: w plane only): all loader warps, 128-bit loads over NVLink.  The
-        // (remote row, vector) items are spread over the loader threads so that every lane issues all of
-        // its loads back to back: one NVLink round trip per sample instead of one per row.
-        constexpr int LU = 14;
-        const int lt = tid - n_cons;  // lane among the loader threads
-        const int n_remote = (geo.dbg & 16) ? 0 : m.hdr[2];
-        const int n_items = n_remote * nvec;
-        for (int i0 = 0; i0 < n_items; i0 += LU * NL * 32) {
-          float4 buf[LU];
-#pragma unroll
-          for (int u = 0; u < LU; u++) {
-            const int i = i0 + u * NL * 32 + lt;
-            if (i < n_items) {
-              const int ri = i / nvec, v = i - ri * nvec;
-              const RowMeta rm = m.row[m.remote[ri]];
-              buf[u] = __ldcs(reinterpret_cast<const float4 *>(sh.row(rm.feat, rs) + 2 * ld) + v);
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < LU; u++) {
-            const int i = i0 + u * NL * 32 + lt;
-            if (i < n_items) {
-              const int ri = i / nvec, v = i - ri * nvec;
-              reinterpret_cast<float4 *>(rows + (size_t)m.remote[ri] * stride)[v] = buf[u];
-            }
-          }
+          if (rm.pos < 0) bulk_g2s(rows + (size_t)r * stride, rsp.tab + (int64_t)rm.loc * rs, row_bytes, &bar_full[st]);
+          else bulk_g2s(rows + (size_t)r * stride, w_plane(rm.loc), row_bytes / 2, &bar_full[st]);
         }
       }
       __syncwarp();
@@ -370,10 +324,8 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
 
   if (role == 3) {
     // =========================== row storer warps ===========================
-    // retire samples in order: wait for the consumers, store the rows / gradient images (local: bulk
-    // stores; remote: 128-bit stores), then hand the stage back to the loaders and the metadata slot back
-    // to the metadata warps
-    const int sw = (tid - n_cons - 32 * NL) >> 5;
+    // retire samples in order: wait for the consumers, bulk-store the rows / gradient images, then hand the
+    // stage back to the loader and the metadata slot back to the metadata warps
     for (int64_t it = 0; it < n_mine; it++) {
       const int st = (int)(it % NS);
       const int slot = (int)(it % MD);
@@ -381,36 +333,20 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
       SampleMeta m = sample_meta(slot);
       mbar_wait(&bar_done[st], (uint32_t)((it / NS) & 1));
       const int nv = m.hdr[0];
-      if (sw == 0) {
-        for (int r = lane; r < nv && !(geo.dbg & 2); r += 32) {
-          const RowMeta rm = m.row[r];
-          if (is_remote(rm.feat)) continue;
-          if (rm.pos < 0) {
-            bulk_s2g(sh.row(rm.feat, rs), rows + (size_t)r * stride, row_bytes);
-          } else {
-            bulk_s2g(sh.stage(rm.feat, rm.pos, ld), rows + (size_t)r * stride, (uint32_t)(ld * sizeof(float)));
-          }
-        }
-        bulk_commit();
+      for (int r = lane; r < nv && !(geo.dbg & 2); r += 32) {
+        const RowMeta rm = m.row[r];
+        if (rm.pos < 0) bulk_s2g(rsp.tab + (int64_t)rm.loc * rs, rows + (size_t)r * stride, row_bytes);
+        else bulk_s2g(rsp.staging + (int64_t)rm.pos * ld, rows + (size_t)r * stride, (uint32_t)(ld * sizeof(float)));
       }
-      if (SHARDED && !(geo.dbg & 2)) {
-        const int stt = tid - n_cons - 32 * NL;  // lane among the storer threads
-        for (int r = 0; r < nv; r++) {
-          const RowMeta rm = m.row[r];
-          if (!is_remote(rm.feat)) continue;
-          float4 *dst = reinterpret_cast<float4 *>(sh.stage(rm.feat, rm.pos, ld));
-          const float4 *src = reinterpret_cast<const float4 *>(rows + (size_t)r * stride);
-          for (int v = stt; v < nvec; v += NSW * 32) __stcs(dst + v, src[v]);
-        }
-      }
-      if (sw == 0) bulk_wait_read_all();
+      bulk_commit();
+      bulk_wait_read_all();
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(&bar_free[st]);
         mbar_arrive(&bar_mfree[slot]);
       }
     }
-    if (sw == 0) bulk_wait_all();
+    bulk_wait_all();
     return;
   }
 
@@ -449,11 +385,11 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
         float4 wA = *reinterpret_cast<const float4 *>(sa), wB = *reinterpret_cast<const float4 *>(sb);
         if (rmm.pos < 0) {
           wA = weight4<PRECISE>(wA, *reinterpret_cast<const float4 *>(sa + ld), h);
-          *reinterpret_cast<float4 *>(sh.row(rmm.feat, rs) + 2 * ld + rmn.fk + c * 4) = wA;
+          *reinterpret_cast<float4 *>(rsp.tab + (int64_t)rmm.loc * rs + 2 * ld + rmn.fk + c * 4) = wA;
         }
         if (rmn.pos < 0) {
           wB = weight4<PRECISE>(wB, *reinterpret_cast<const float4 *>(sb + ld), h);
-          *reinterpret_cast<float4 *>(sh.row(rmn.feat, rs) + 2 * ld + rmm.fk + c * 4) = wB;
+          *reinterpret_cast<float4 *>(rsp.tab + (int64_t)rmn.loc * rs + 2 * ld + rmm.fk + c * 4) = wB;
         }
         wAc[j] = wA;
         wBc[j] = wB;
@@ -527,9 +463,9 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
         const float w = weight_from<PRECISE>(e.x, f_sqrt<PRECISE>(e.y), h);
         e.z = w;
         ftrl_apply<PRECISE>(e.x, e.y, w, gi, gi * gi, h);
-        *sh.linp(rm.feat) = e;
+        rsp.lin[rm.loc] = e;
       } else {
-        if (!((geo.dbg & 8) && is_remote(rm.feat))) *sh.stage_lin(rm.feat, rm.pos) = gi;  // w of staged rows: materialised by their owner
+        rsp.staging_lin[rm.pos] = gi;  // w of staged rows: materialised by their owner
       }
     }
     // staged rows: slices no partner touches (own field, absent fields) must read as 0 in the image.
@@ -612,7 +548,8 @@ k_ffm_staged_rows(Dims d, Hyper h, int32_t nnz, const int32_t *__restrict__ batc
                   float4 *__restrict__ lin, int32_t ch, const int32_t *__restrict__ n_chunks_p,
                   const int32_t *__restrict__ chunk_pos, const uint32_t *__restrict__ skey,
                   const SegScan *__restrict__ scan, const float *__restrict__ staging,
-                  const float *__restrict__ staging_lin, float *__restrict__ part, float2 *__restrict__ part_lin) {
+                  const float *__restrict__ staging_lin, float *__restrict__ part, float2 *__restrict__ part_lin,
+                  const __grid_constant__ Export ex) {
   if (batch_flags[0] == 0) return;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t ld = d.ld, rs = 3 * ld;
@@ -649,9 +586,17 @@ k_ffm_staged_rows(Dims d, Hyper h, int32_t nnz, const int32_t *__restrict__ batc
       a1.x = fmaf(gq.x, gq.x, a1.x); a1.y = fmaf(gq.y, gq.y, a1.y);
       a1.z = fmaf(gq.z, gq.z, a1.z); a1.w = fmaf(gq.w, gq.w, a1.w);
     }
-    float *row = tab + (int64_t)ci.key * rs;
+    // sharded runs: the sum goes to the row's owner unless this rank owns the row and is its only contributor
+    const int32_t dst = (ex.on && whole_row) ? ex.dst_at[ci.p0] : -2;
+    const int64_t lrow = (int64_t)(ci.key >> ex.log2G);
+    float *row = tab + lrow * rs;
     if (on) {
-      if (whole_row) {
+      if (whole_row && dst >= 0) {
+        // one occurrence: sum g^2 = g^2, the owner squares it (half the bytes over NVLink)
+        float *o = ex.inbox[ci.key & ex.Gm1] + (int64_t)dst * 2 * ld;
+        reinterpret_cast<float4 *>(o)[v] = a0;
+        if (n_occ > 1) reinterpret_cast<float4 *>(o + ld)[v] = a1;
+      } else if (whole_row) {
         const bool any = a1.x != 0.f || a1.y != 0.f || a1.z != 0.f || a1.w != 0.f || a0.x != 0.f || a0.y != 0.f ||
                          a0.z != 0.f || a0.w != 0.f;
         if (any) {
@@ -681,10 +626,12 @@ k_ffm_staged_rows(Dims d, Hyper h, int32_t nnz, const int32_t *__restrict__ batc
       sg = warp_sum(sg);
       sg2 = warp_sum(sg2);
       if (lane == 0) {
-        if (whole_row) {
-          float4 e = lin[ci.key];
+        if (whole_row && dst >= 0) {
+          ex.inbox_lin[ci.key & ex.Gm1][dst] = make_float2(sg, sg2);
+        } else if (whole_row) {
+          float4 e = lin[lrow];
           ftrl_apply<PRECISE>(e.x, e.y, e.z, sg, sg2, h);
-          lin[ci.key] = e;
+          lin[lrow] = e;
         } else {
           part_lin[ci.slot] = make_float2(sg, sg2);
         }

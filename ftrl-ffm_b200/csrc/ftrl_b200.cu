@@ -178,6 +178,10 @@ static size_t cub_temp_bytes(int64_t nnz, int end_bit) {
   thrust::counting_iterator<int32_t> cnt(0);
   auto it = thrust::make_transform_iterator(cnt, HeadFunctor{nullptr, nullptr});
   cub::DeviceScan::InclusiveScan(nullptr, b, it, (SegScan *)nullptr, SegScanOp(), n);
+  size_t b2 = 0;
+  auto mit = thrust::make_transform_iterator(cnt, MaskIn{nullptr, nullptr, nullptr});
+  cub::DeviceScan::InclusiveScan(nullptr, b2, mit, (MaskScan *)nullptr, MaskScanOp(), n);
+  b = std::max(b, b2);
   cub::DeviceSelect::If(nullptr, c, cnt, (int32_t *)nullptr, (int32_t *)nullptr, n, ChunkHeadPred{nullptr, nullptr, nullptr, 0, 1});
   return std::max(a, std::max(b, c)) + 256;
 }
@@ -197,9 +201,14 @@ static void refresh_shards(ftrl_handle *h) {
   sh.rank = 0;
   sh.tab[0] = h->tab;
   sh.lin[0] = h->lin;
-  sh.staging[0] = h->staging.p;
-  sh.staging_lin[0] = h->staging_lin.p;
   h->pmask_src.p[0] = h->pmask.p;
+  RowSpace &rsp = h->rowspace;
+  rsp = RowSpace{};
+  rsp.tab = h->tab;
+  rsp.lin = h->lin;
+  rsp.staging = h->staging.p;
+  rsp.staging_lin = h->staging_lin.p;
+  h->exportd = Export{};
 }
 
 static void ensure_workspace(ftrl_handle *h, int64_t n_rows, int64_t nnz) {
@@ -222,34 +231,47 @@ static void ensure_workspace(ftrl_handle *h, int64_t n_rows, int64_t nnz) {
   h->skey.ensure(nc);
   h->socc.ensure(nc);
   h->occ_row.ensure(nc);
-  // owner side of a sharded run: this rank may own up to 2x its own share of the occurrences
+  // owner side of a sharded run: the (row, rank) contributions this rank may own per step -- up to 2x the
+  // distinct rows of its own batch (err 3 beyond that: extreme id skew)
   const int64_t oc = h->G > 1 ? 2 * nc + 1024 : nc;
   if (h->G > 1 && h->attached) throw ArgFail{"batch exceeds max_batch_rows / max_batch_nnz of a multi-GPU handle"};
   h->ow_cap = oc;
   if (h->G > 1) {
     h->okey.ensure(oc);
     h->osrc.ensure(oc);
+    h->ckey.ensure(oc);
+    h->csrc.ensure(oc);
+    h->cflag.ensure(oc);
     h->sel.ensure(oc);
     h->n_sel.ensure(4);
     h->red4.ensure(4);
-    h->skey.ensure(oc);
-    h->socc.ensure(oc);
+    h->mscan.ensure(nc);
+    h->uhead.ensure(nc + 1);
+    h->n_uall.ensure(4);
+    h->dst_at.ensure(nc);
+    h->ukey.ensure(nc);
+    h->uinfo.ensure(nc);
+    h->umask.ensure(nc);
+    h->rc_w.ensure((size_t)nc * h->dims.ld);
+    h->rc_lin.ensure(nc);
+    h->inbox.ensure((size_t)oc * 2 * h->dims.ld);
+    h->inbox_lin.ensure(oc);
   }
-  h->fused_sorted.ensure(oc);
+  h->fused_sorted.ensure(nc);
   h->occ_pos.ensure(nc);
   h->batch_flags.ensure(4);
   if (h->tile_ok) {
     h->pmask.ensure(nc);
-    h->rowmask.ensure(oc + 2);
+    h->rowmask.ensure(nc + 2);
   }
   if (h->tile_ok) {
-    h->staging.ensure((size_t)oc * h->dims.ld);
-    h->staging_lin.ensure(oc);
+    h->staging.ensure((size_t)nc * h->dims.ld);
+    h->staging_lin.ensure(nc);
   }
-  h->scan.ensure(oc);
-  h->chunk_pos.ensure(oc + 2);
+  h->scan.ensure(nc);
+  h->chunk_pos.ensure(nc + 2);
   h->n_chunks.ensure(4);
-  const int64_t slots = 2 * (oc / h->chunk + 2);
+  const int64_t slots = 2 * (nc / h->chunk + 2);
   if (h->dims.row_len) h->part.ensure((size_t)slots * 2 * h->dims.ld);
   h->part_lin.ensure(slots);
   h->cub_bytes = cub_temp_bytes(h->G > 1 ? std::max<int64_t>((int64_t)h->G * nc, oc) : nc, key_bits(h->dims.n_feats));
@@ -336,8 +358,8 @@ static void run_ffm_batch(ftrl_handle *h, const Batch &b, float *logit_out) {
       geo.smem_bytes = h->tile_smem;
       const int tgrid = (int)std::min<int64_t>(b.n_rows, (int64_t)h->n_sms * h->tile_ctas_per_sm);
 #define FFM_TILE(I)                                                                                              \
-  k_ffm_tile<PRECISE, I, false><<<tgrid, tile_threads(geo.consumers, false), geo.smem_bytes, h->compute>>>(                                \
-      b, d, h->hyper, dec, geo, h->batch_flags.p, h->shards, h->bias, h->pair_lut, h->occ_pos.p, h->g.p, logit_out)
+  k_ffm_tile<PRECISE, I><<<tgrid, tile_threads(geo.consumers), geo.smem_bytes, h->compute>>>(                   \
+      b, d, h->hyper, dec, geo, h->batch_flags.p, h->rowspace, h->bias, h->pair_lut, h->occ_pos.p, h->scan.p, h->g.p, logit_out)
       if (h->tile_ipt <= 1) FFM_TILE(1);
       else if (h->tile_ipt == 2) FFM_TILE(2);
       else if (h->tile_ipt == 3) FFM_TILE(3);
@@ -352,12 +374,12 @@ static void run_ffm_batch(ftrl_handle *h, const Batch &b, float *logit_out) {
         k_ffm_staged_rows<true, 8><<<grid * 4, 256, 0, h->compute>>>(d, h->hyper, (int32_t)b.nnz, h->batch_flags.p, h->tab, h->lin,
                                                                     h->chunk, h->n_chunks.p, h->chunk_pos.p, h->skey.p,
                                                                     h->scan.p, h->staging.p, h->staging_lin.p, h->part.p,
-                                                                    h->part_lin.p);
+                                                                    h->part_lin.p, h->exportd);
       else
         k_ffm_staged_rows<false, 8><<<grid * 4, 256, 0, h->compute>>>(d, h->hyper, (int32_t)b.nnz, h->batch_flags.p, h->tab, h->lin,
                                                                      h->chunk, h->n_chunks.p, h->chunk_pos.p, h->skey.p,
                                                                      h->scan.p, h->staging.p, h->staging_lin.p, h->part.p,
-                                                                     h->part_lin.p);
+                                                                     h->part_lin.p, h->exportd);
       FTRL_CUDA(cudaGetLastError());
       launched(h, PH_ROWS);
     }
@@ -393,7 +415,7 @@ static void run_ffm_batch(ftrl_handle *h, const Batch &b, float *logit_out) {
     PhaseScope ps(h, PH_COMBINE);
     k_ffm_combine<PRECISE, 256><<<grid, 256, 0, h->compute>>>(d, h->hyper, (int32_t)b.nnz, h->tab, h->lin, h->chunk,
                                                                    h->n_chunks.p, h->chunk_pos.p, h->skey.p, h->scan.p,
-                                                                   h->part.p, h->part_lin.p);
+                                                                   h->part.p, h->part_lin.p, h->exportd);
     FTRL_CUDA(cudaGetLastError());
     launched(h, PH_COMBINE);
   }
@@ -690,56 +712,96 @@ static void train_device_sharded(ftrl_handle *h, const Batch &b, float *logit_ou
   if (b.n_rows > h->rows_cap || b.nnz > h->nnz_cap) throw ArgFail{"batch exceeds max_batch_rows / max_batch_nnz of a multi-GPU handle"};
   const int32_t nnz = (int32_t)b.nnz;
   const int32_t nnz_max = (int32_t)h->cfg.max_batch_nnz;
+  const int32_t ucap = (int32_t)h->nnz_cap;
   const uint32_t sentinel = (uint32_t)d.n_feats;
   const uint32_t lsent = (uint32_t)h->n_local;  // sentinel in local-row space (n_local may differ by 1 across ranks)
   const int32_t oc = (int32_t)h->ow_cap;
+  const int grid = h->n_sms * 4;
+  thrust::counting_iterator<int32_t> cnt(0);
   if (!logit_out) logit_out = h->logit_ws.p;
   {
     PhaseScope ps(h, PH_PREP);
     FTRL_CUDA(cudaMemsetAsync(h->batch_flags.p, 0x01, sizeof(int32_t), h->compute));
     if (b.n_rows > 0) {
-      const unsigned grid = (unsigned)((b.n_rows * 32 + 255) / 256);
-      k_prep_rows<<<grid, 256, 0, h->compute>>>(b, d, h->key.p, h->occ_idx.p, h->occ_row.p, h->sflags.p, h->batch_flags.p,
-                                                h->pmask.p);
+      const unsigned pg = (unsigned)((b.n_rows * 32 + 255) / 256);
+      k_prep_rows<<<pg, 256, 0, h->compute>>>(b, d, h->key.p, h->occ_idx.p, h->occ_row.p, h->sflags.p, h->batch_flags.p,
+                                              h->pmask.p);
+      launched(h, PH_PREP);
     }
-    k_publish<<<1, 32, 0, h->compute>>>(h->peers, nnz, h->batch_flags.p);
     FTRL_CUDA(cudaGetLastError());
-    launched(h, PH_PREP, 2);
-    peer_barrier(h);  // 1: every rank's keys / nnz are published
   }
   {
     PhaseScope ps(h, PH_SORT);
+    if (nnz > 0) {
+      size_t bytes = h->cub_bytes;
+      FTRL_CUDA(cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, bytes, h->key.p, h->skey.p, h->occ_idx.p, h->socc.p, nnz, 0,
+                                                key_bits(d.n_feats), h->compute));
+    }
+  }
+  {
+    // distinct rows of the local batch, their field masks; tell the peers
+    PhaseScope ps(h, PH_SEGMENT);
+    if (nnz > 0) {
+      k_occ_class<<<(nnz + 255) / 256, 256, 0, h->compute>>>(nnz, sentinel, 0, h->skey.p, h->socc.p, h->occ_row.p, h->sflags.p,
+                                                             h->fused_sorted.p, h->occ_pos.p);
+      size_t bytes = h->cub_bytes;
+      auto mit = thrust::make_transform_iterator(cnt, MaskIn{h->skey.p, h->socc.p, h->pmask.p});
+      FTRL_CUDA(cub::DeviceScan::InclusiveScan(h->cub_tmp.p, bytes, mit, h->mscan.p, MaskScanOp(), nnz, h->compute));
+      bytes = h->cub_bytes;
+      FTRL_CUDA(cub::DeviceSelect::If(h->cub_tmp.p, bytes, cnt, h->uhead.p, h->n_uall.p, nnz, RowHeadPred{h->skey.p}, h->compute));
+    }
+    k_publish_unique<<<(std::max(nnz, 1) + 255) / 256, 256, 0, h->compute>>>(h->peers, nnz, sentinel, ucap, h->uhead.p, h->n_uall.p,
+                                                                             h->skey.p, h->mscan.p, h->batch_flags.p, h->ukey.p,
+                                                                             h->uinfo.p, h->umask.p);
+    FTRL_CUDA(cudaGetLastError());
+    launched(h, PH_SEGMENT, 2);
+    peer_barrier(h);  // 1: every rank's distinct-row list is published
+  }
+  {
+    // owner side: contributions (row, rank) of the rows this rank owns
+    PhaseScope ps(h, PH_EXCHANGE);
     k_merge_flags<<<1, 1, 0, h->compute>>>(h->peers, h->batch_flags.p, h->d_err);
     size_t bytes = h->cub_bytes;
-    thrust::counting_iterator<int32_t> cnt(0);
     FTRL_CUDA(cub::DeviceSelect::If(h->cub_tmp.p, bytes, cnt, h->sel.p, h->n_sel.p, h->G * nnz_max,
-                                    OwnedPred{h->peers, nnz_max, sentinel}, h->compute));
+                                    OwnedPred{h->peers, nnz_max}, h->compute));
     k_fill_owned<<<(oc + 255) / 256, 256, 0, h->compute>>>(h->peers, nnz_max, oc, lsent, h->sel.p, h->n_sel.p, h->okey.p,
                                                           h->osrc.p, h->d_err);
     bytes = h->cub_bytes;
-    FTRL_CUDA(cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, bytes, h->okey.p, h->skey.p, h->osrc.p, h->socc.p, oc, 0,
+    FTRL_CUDA(cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, bytes, h->okey.p, h->ckey.p, h->osrc.p, h->csrc.p, oc, 0,
                                               key_bits((int32_t)h->n_local), h->compute));
+    k_contrib_class<<<(oc + 255) / 256, 256, 0, h->compute>>>(h->peers, oc, h->n_sel.p, lsent, h->ckey.p, h->csrc.p, h->socc.p,
+                                                             h->cflag.p, h->fused_sorted.p, h->occ_pos.p);
+    k_owner_materialise<PRECISE, 256><<<grid, 256, 0, h->compute>>>(h->peers, d, h->hyper, oc, h->n_sel.p, h->batch_flags.p,
+                                                                    h->ckey.p, h->csrc.p, h->cflag.p, h->tab, h->lin);
     FTRL_CUDA(cudaGetLastError());
-    launched(h, PH_SORT, 2);
+    launched(h, PH_EXCHANGE, 4);
   }
   {
+    // local chunk list of the rows that are not finalised inside a sample
     PhaseScope ps(h, PH_SEGMENT);
-    k_occ_class_sharded<<<(oc + 255) / 256, 256, 0, h->compute>>>(h->peers, oc, lsent, h->skey.p, h->socc.p, h->fused_sorted.p);
-    size_t bytes = h->cub_bytes;
-    thrust::counting_iterator<int32_t> cnt(0);
-    auto it = thrust::make_transform_iterator(cnt, HeadFunctor{h->skey.p, h->fused_sorted.p});
-    FTRL_CUDA(cub::DeviceScan::InclusiveScan(h->cub_tmp.p, bytes, it, h->scan.p, SegScanOp(), oc, h->compute));
-    bytes = h->cub_bytes;
-    FTRL_CUDA(cub::DeviceSelect::If(h->cub_tmp.p, bytes, cnt, h->chunk_pos.p, h->n_chunks.p, oc,
-                                    ChunkHeadPred{h->skey.p, h->scan.p, h->fused_sorted.p, lsent, h->chunk}, h->compute));
-    k_terminate<<<1, 1, 0, h->compute>>>(h->chunk_pos.p, h->n_chunks.p, oc);
+    if (nnz > 0) {
+      size_t bytes = h->cub_bytes;
+      auto it = thrust::make_transform_iterator(cnt, HeadFunctor{h->skey.p, h->fused_sorted.p});
+      FTRL_CUDA(cub::DeviceScan::InclusiveScan(h->cub_tmp.p, bytes, it, h->scan.p, SegScanOp(), nnz, h->compute));
+      bytes = h->cub_bytes;
+      FTRL_CUDA(cub::DeviceSelect::If(h->cub_tmp.p, bytes, cnt, h->chunk_pos.p, h->n_chunks.p, nnz,
+                                      ChunkHeadPred{h->skey.p, h->scan.p, h->fused_sorted.p, sentinel, h->chunk}, h->compute));
+      k_terminate<<<1, 1, 0, h->compute>>>(h->chunk_pos.p, h->n_chunks.p, nnz);
+    } else {
+      FTRL_CUDA(cudaMemsetAsync(h->n_chunks.p, 0, sizeof(int32_t), h->compute));
+    }
     FTRL_CUDA(cudaGetLastError());
-    launched(h, PH_SEGMENT, 2);
+    launched(h, PH_SEGMENT);
+    peer_barrier(h);  // 2: classes / inbox slots are known everywhere, w of the touched slices is materialised
   }
-  run_row_prepass(h, oc, lsent);
-  peer_barrier(h);  // 2: every occurrence knows its class / staging position, w of staged rows is materialised
+  {
+    PhaseScope ps(h, PH_PULL);
+    k_pull<8><<<grid, 256, 0, h->compute>>>(h->peers, d, nnz, sentinel, h->batch_flags.p, h->uhead.p, h->n_uall.p, h->skey.p,
+                                            h->rc_w.p, h->rc_lin.p);
+    FTRL_CUDA(cudaGetLastError());
+    launched(h, PH_PULL);
+  }
   const ItemDecode dec = make_item_decode(d.k, 4);
-  const int grid = h->n_sms * 4;
   {
     PhaseScope ps(h, PH_SAMPLE);
     if (b.n_rows > 0) {
@@ -752,9 +814,9 @@ static void train_device_sharded(ftrl_handle *h, const Batch &b, float *logit_ou
       geo.dbg = h->tile_dbg;
       geo.smem_bytes = h->tile_smem;
       const int tgrid = (int)std::min<int64_t>(b.n_rows, (int64_t)h->n_sms * h->tile_ctas_per_sm);
-#define FFM_TILE(I)                                                                                              \
-  k_ffm_tile<PRECISE, I, true><<<tgrid, tile_threads(geo.consumers, true), geo.smem_bytes, h->compute>>>(        \
-      b, d, h->hyper, dec, geo, h->batch_flags.p, h->shards, h->bias, h->pair_lut, h->occ_pos.p, h->g.p, logit_out)
+#define FFM_TILE(I)                                                                                            \
+  k_ffm_tile<PRECISE, I><<<tgrid, tile_threads(geo.consumers), geo.smem_bytes, h->compute>>>(                  \
+      b, d, h->hyper, dec, geo, h->batch_flags.p, h->rowspace, h->bias, h->pair_lut, h->occ_pos.p, h->scan.p, h->g.p, logit_out)
       if (h->tile_ipt <= 1) FFM_TILE(1);
       else if (h->tile_ipt == 2) FFM_TILE(2);
       else if (h->tile_ipt == 3) FFM_TILE(3);
@@ -771,35 +833,45 @@ static void train_device_sharded(ftrl_handle *h, const Batch &b, float *logit_ou
     k_publish_red<<<1, 32, 0, h->compute>>>(h->peers, h->red4.p);
     FTRL_CUDA(cudaGetLastError());
     launched(h, PH_REDUCE, 2);
-    peer_barrier(h);  // 3: all gradient images are staged at their owners, all partials are exchanged
-    k_bias_apply<PRECISE><<<1, 1, 0, h->compute>>>(h->peers, h->hyper, h->bias);
-    launched(h, PH_REDUCE);
   }
   {
+    // local duplicates are reduced here; each row's sum goes to its owner's inbox (or is applied here)
     PhaseScope ps(h, PH_ROWS);
-    k_ffm_staged_rows<PRECISE, 8><<<grid * 4, 256, 0, h->compute>>>(d, h->hyper, oc, h->batch_flags.p, h->tab, h->lin, h->chunk,
+    k_ffm_staged_rows<PRECISE, 8><<<grid * 4, 256, 0, h->compute>>>(d, h->hyper, nnz, h->batch_flags.p, h->tab, h->lin, h->chunk,
                                                                    h->n_chunks.p, h->chunk_pos.p, h->skey.p, h->scan.p,
-                                                                   h->staging.p, h->staging_lin.p, h->part.p, h->part_lin.p);
+                                                                   h->staging.p, h->staging_lin.p, h->part.p, h->part_lin.p,
+                                                                   h->exportd);
     FTRL_CUDA(cudaGetLastError());
     launched(h, PH_ROWS);
   }
   {
     PhaseScope ps(h, PH_COMBINE);
-    k_ffm_combine<PRECISE, 256><<<grid, 256, 0, h->compute>>>(d, h->hyper, oc, h->tab, h->lin, h->chunk, h->n_chunks.p,
-                                                              h->chunk_pos.p, h->skey.p, h->scan.p, h->part.p, h->part_lin.p);
+    k_ffm_combine<PRECISE, 256><<<grid, 256, 0, h->compute>>>(d, h->hyper, nnz, h->tab, h->lin, h->chunk, h->n_chunks.p,
+                                                              h->chunk_pos.p, h->skey.p, h->scan.p, h->part.p, h->part_lin.p,
+                                                              h->exportd);
     FTRL_CUDA(cudaGetLastError());
     launched(h, PH_COMBINE);
+    peer_barrier(h);  // 3: every contribution is in its owner's inbox, the bias partials are exchanged
+  }
+  {
+    PhaseScope ps(h, PH_APPLY);
+    k_owner_apply<PRECISE, 256><<<grid, 256, 0, h->compute>>>(h->peers, d, h->hyper, oc, h->n_sel.p, h->batch_flags.p, h->ckey.p,
+                                                              h->cflag.p, h->inbox.p, h->inbox_lin.p, h->tab, h->lin);
+    k_bias_apply<PRECISE><<<1, 1, 0, h->compute>>>(h->peers, h->hyper, h->bias);
+    FTRL_CUDA(cudaGetLastError());
+    launched(h, PH_APPLY, 2);
   }
   h->stats.kernel_launches = h->launches_this_call;
 }
 
+constexpr int PEER_BUFS = 9;
 struct PeerBlob {  // FTRL_PEER_BLOB_BYTES
   uint32_t magic;
   int32_t rank, world, device;
   int64_t pid;
   int64_t nnz_cap, ow_cap;
-  void *raw[8];                // same-process attach
-  cudaIpcMemHandle_t ipc[8];   // tab, lin, staging, staging_lin, key, occ_pos, sync, pmask
+  void *raw[PEER_BUFS];                // same-process attach
+  cudaIpcMemHandle_t ipc[PEER_BUFS];   // tab, lin, ukey, uinfo, umask, dst_at, inbox, inbox_lin, sync
 };
 static_assert(sizeof(PeerBlob) <= FTRL_PEER_BLOB_BYTES, "peer blob too large");
 
@@ -875,7 +947,7 @@ int ftrl_create(const ftrl_config *cfg, ftrl_handle **out) {
       while ((1 << h->log2G) < h->G) h->log2G++;
     }
     h->n_local = h->G > 1 ? ((int64_t)cfg->n_feats - h->rank + h->G - 1) / h->G : cfg->n_feats;
-    static const char *names[PH_COUNT] = {"prep_rows", "sort", "segment", "sample", "rows", "combine", "reduce", "exact", "predict", "generic", "materialise"};
+    static const char *names[PH_COUNT] = {"prep_rows", "sort", "segment", "sample", "rows", "combine", "reduce", "exact", "predict", "generic", "materialise", "exchange", "pull", "apply"};
     for (int i = 0; i < PH_COUNT; i++) h->phases[i].name = names[i];
     cudaDeviceProp prop;
     FTRL_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
@@ -896,13 +968,12 @@ int ftrl_create(const ftrl_config *cfg, ftrl_handle **out) {
       const int64_t items = (int64_t)d.n_fields * (d.n_fields - 1) / 2 * (d.k / 4);
       int cons = 64;
       while (cons < 512 && cons * 3 < items) cons *= 2;
-      if (h->G > 1) cons = std::min(cons, 384);  // sharded runs spend threads on the warps that move remote rows
       cons = env_int("FTRL_B200_TILE_CONSUMERS", cons);
       const int ipt = (int)((items + cons - 1) / cons);
       const size_t lut = tile_lut_bytes(d.n_fields) + 4 * tile_meta_bytes(d.n_fields);  // + minimal meta ring
       if (2 * stage + lut <= budget && ipt <= 4) {
         int ctas = (int)std::min<size_t>(8, (size_t)prop.sharedMemPerMultiprocessor / (2 * stage + lut + 2048));
-        ctas = std::max(1, std::min(ctas, 2048 / tile_threads(cons, h->G > 1)));
+        ctas = std::max(1, std::min(ctas, 2048 / tile_threads(cons)));
         ctas = env_int("FTRL_B200_TILE_CTAS", ctas);
         int stages = (int)std::min<size_t>(TILE_MAX_STAGE, ((size_t)prop.sharedMemPerMultiprocessor / ctas - 2048 - lut) / stage);
         stages = std::max(2, std::min(stages, (int)((budget - lut) / stage)));
@@ -920,11 +991,9 @@ int ftrl_create(const ftrl_config *cfg, ftrl_handle **out) {
         h->tile_ctas_per_sm = ctas;
         h->tile_smem = tile_smem_bytes(d.n_fields, stride, stages, metas);
         const int sm = (int)h->tile_smem;
-#define TILE_ATTR(P, I, S) FTRL_CUDA(cudaFuncSetAttribute(k_ffm_tile<P, I, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm))
-        TILE_ATTR(false, 1, false); TILE_ATTR(false, 2, false); TILE_ATTR(false, 3, false); TILE_ATTR(false, 4, false);
-        TILE_ATTR(true, 1, false); TILE_ATTR(true, 2, false); TILE_ATTR(true, 3, false); TILE_ATTR(true, 4, false);
-        TILE_ATTR(false, 1, true); TILE_ATTR(false, 2, true); TILE_ATTR(false, 3, true); TILE_ATTR(false, 4, true);
-        TILE_ATTR(true, 1, true); TILE_ATTR(true, 2, true); TILE_ATTR(true, 3, true); TILE_ATTR(true, 4, true);
+#define TILE_ATTR(P, I) FTRL_CUDA(cudaFuncSetAttribute(k_ffm_tile<P, I>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm))
+        TILE_ATTR(false, 1); TILE_ATTR(false, 2); TILE_ATTR(false, 3); TILE_ATTR(false, 4);
+        TILE_ATTR(true, 1); TILE_ATTR(true, 2); TILE_ATTR(true, 3); TILE_ATTR(true, 4);
 #undef TILE_ATTR
       }
     }
@@ -1372,21 +1441,27 @@ int ftrl_last_batch_stats(ftrl_handle *h, ftrl_batch_stats *out) {
 }
 
 // ---- multi-GPU ------------------------------------------------------------------------------
+static void peer_buffers(ftrl_handle *h, void **ptrs) {
+  void *mine[PEER_BUFS] = {h->tab, h->lin, h->ukey.p, h->uinfo.p, h->umask.p, h->dst_at.p, h->inbox.p, h->inbox_lin.p, h->sync};
+  memcpy(ptrs, mine, sizeof(mine));
+}
+
 int ftrl_export_peer_blob(ftrl_handle *h, void *blob) {
   if (!h || !blob) return FTRL_ERR_ARG;
   return guarded(h, [&] {
     if (h->G <= 1) throw StateFail{"not a multi-GPU handle (world_size <= 1)"};
     PeerBlob pb;
     memset(&pb, 0, sizeof(pb));
-    pb.magic = 0xF7B20001u;
+    pb.magic = 0xF7B20002u;
     pb.rank = h->rank;
     pb.world = h->G;
     pb.device = h->cfg.device;
     pb.pid = (int64_t)getpid();
     pb.nnz_cap = h->nnz_cap;
     pb.ow_cap = h->ow_cap;
-    void *ptrs[8] = {h->tab, h->lin, h->staging.p, h->staging_lin.p, h->key.p, h->occ_pos.p, h->sync, h->pmask.p};
-    for (int i = 0; i < 8; i++) {
+    void *ptrs[PEER_BUFS];
+    peer_buffers(h, ptrs);
+    for (int i = 0; i < PEER_BUFS; i++) {
       pb.raw[i] = ptrs[i];
       if (!ptrs[i]) throw StateFail{"multi-GPU buffers are not allocated"};
       FTRL_CUDA(cudaIpcGetMemHandle(&pb.ipc[i], ptrs[i]));
@@ -1396,6 +1471,34 @@ int ftrl_export_peer_blob(ftrl_handle *h, void *blob) {
   });
 }
 
+static void wire_peer(ftrl_handle *, Shards &sh, Peers &pr, Export &ex, int q, void *const *ptr) {
+  sh.tab[q] = static_cast<float *>(ptr[0]);
+  sh.lin[q] = static_cast<float4 *>(ptr[1]);
+  pr.tab[q] = static_cast<const float *>(ptr[0]);
+  pr.lin[q] = static_cast<const float4 *>(ptr[1]);
+  pr.ukey[q] = static_cast<const uint32_t *>(ptr[2]);
+  pr.uinfo[q] = static_cast<const uint32_t *>(ptr[3]);
+  pr.umask[q] = static_cast<const unsigned long long *>(ptr[4]);
+  pr.dst_at[q] = static_cast<int32_t *>(ptr[5]);
+  ex.inbox[q] = static_cast<float *>(ptr[6]);
+  ex.inbox_lin[q] = static_cast<float2 *>(ptr[7]);
+  pr.sync[q] = static_cast<SyncArea *>(ptr[8]);
+}
+
+static void set_rowspace(ftrl_handle *h, int log2G, int rank, int G) {
+  RowSpace &rsp = h->rowspace;
+  rsp = RowSpace{};
+  rsp.tab = h->tab;
+  rsp.lin = h->lin;
+  rsp.staging = h->staging.p;
+  rsp.staging_lin = h->staging_lin.p;
+  rsp.rc_w = h->rc_w.p;
+  rsp.rc_lin = h->rc_lin.p;
+  rsp.log2G = log2G;
+  rsp.rank = rank;
+  rsp.Gm1 = G - 1;
+}
+
 int ftrl_attach_peers(ftrl_handle *h, const void *blobs) {
   if (!h || !blobs) return FTRL_ERR_ARG;
   return guarded(h, [&] {
@@ -1403,19 +1506,22 @@ int ftrl_attach_peers(ftrl_handle *h, const void *blobs) {
     if (h->attached) throw StateFail{"peers already attached"};
     Shards sh{};
     Peers pr{};
-    PmaskSrc pms{};
+    Export ex{};
     sh.G = pr.G = h->G;
     sh.log2G = pr.log2G = h->log2G;
     sh.rank = pr.rank = h->rank;
+    ex.on = 1;
+    ex.log2G = h->log2G;
+    ex.Gm1 = h->G - 1;
+    ex.dst_at = h->dst_at.p;
     for (int q = 0; q < h->G; q++) {
       PeerBlob pb;
       memcpy(&pb, static_cast<const char *>(blobs) + (size_t)q * FTRL_PEER_BLOB_BYTES, sizeof(pb));
-      if (pb.magic != 0xF7B20001u || pb.rank != q || pb.world != h->G) throw ArgFail{fmt("peer blob %d is not from rank %d of %d", q, q, h->G)};
+      if (pb.magic != 0xF7B20002u || pb.rank != q || pb.world != h->G) throw ArgFail{fmt("peer blob %d is not from rank %d of %d", q, q, h->G)};
       if (pb.nnz_cap != h->nnz_cap) throw ArgFail{"all ranks must use the same max_batch_nnz"};
-      void *ptr[8];
+      void *ptr[PEER_BUFS];
       if (q == h->rank) {
-        void *mine[8] = {h->tab, h->lin, h->staging.p, h->staging_lin.p, h->key.p, h->occ_pos.p, h->sync, h->pmask.p};
-        memcpy(ptr, mine, sizeof(ptr));
+        peer_buffers(h, ptr);
       } else if (pb.pid == (int64_t)getpid()) {
         // same process (several handles in one process): plain pointers, peer access if another device
         if (pb.device != h->cfg.device) {
@@ -1428,42 +1534,32 @@ int ftrl_attach_peers(ftrl_handle *h, const void *blobs) {
         }
         memcpy(ptr, pb.raw, sizeof(ptr));
       } else {
-        for (int i = 0; i < 8; i++) {
+        for (int i = 0; i < PEER_BUFS; i++) {
           FTRL_CUDA(cudaIpcOpenMemHandle(&ptr[i], pb.ipc[i], cudaIpcMemLazyEnablePeerAccess));
           h->ipc_opened.push_back(ptr[i]);
         }
       }
-      sh.tab[q] = static_cast<float *>(ptr[0]);
-      sh.lin[q] = static_cast<float4 *>(ptr[1]);
-      sh.staging[q] = static_cast<float *>(ptr[2]);
-      sh.staging_lin[q] = static_cast<float *>(ptr[3]);
-      pr.key[q] = static_cast<const uint32_t *>(ptr[4]);
-      pr.occ_pos[q] = static_cast<int32_t *>(ptr[5]);
-      pr.sync[q] = static_cast<SyncArea *>(ptr[6]);
-      pms.p[q] = static_cast<const uint64_t *>(ptr[7]);
+      wire_peer(h, sh, pr, ex, q, ptr);
     }
     // Dry run of one complete sharded step against this rank alone (one sample whose features are all out
     // of range: no row is touched; the bias is restored afterwards).  CUDA loads kernels lazily and defers
     // a first-time load while another kernel is running -- with spinning device barriers that turns into a
     // stall, so every kernel of the step is loaded here, before the first real step.
     {
-      Shards self{};
-      self.G = 1;
-      self.tab[0] = h->tab;
-      self.lin[0] = h->lin;
-      self.staging[0] = h->staging.p;
-      self.staging_lin[0] = h->staging_lin.p;
+      Shards self_sh{};
       Peers me{};
-      me.G = 1;
-      me.sync[0] = h->sync;
-      me.key[0] = h->key.p;
-      me.occ_pos[0] = h->occ_pos.p;
+      Export self_ex{};
+      self_sh.G = me.G = 1;
+      self_ex.on = 1;
+      self_ex.dst_at = h->dst_at.p;
+      void *mine[PEER_BUFS];
+      peer_buffers(h, mine);
+      wire_peer(h, self_sh, me, self_ex, 0, mine);
       const int G = h->G, log2G = h->log2G, rank = h->rank;
-      const int64_t n_local = h->n_local;
-      h->shards = self;
+      h->shards = self_sh;
       h->peers = me;
-      h->pmask_src = PmaskSrc{};
-      h->pmask_src.p[0] = h->pmask.p;
+      h->exportd = self_ex;
+      set_rowspace(h, 0, 0, 1);
       h->attached = true;
       Slot &ws = h->slots[0];
       const int64_t rp[2] = {0, 2};
@@ -1477,15 +1573,13 @@ int ftrl_attach_peers(ftrl_handle *h, const void *blobs) {
       FTRL_CUDA(cudaMemcpy(ws.val.p, one, sizeof(one), cudaMemcpyHostToDevice));
       FTRL_CUDA(cudaMemcpy(ws.label.p, &lab, sizeof(lab), cudaMemcpyHostToDevice));
       Batch wb{1, 2, ws.row_ptr.p, ws.field.p, ws.feat.p, ws.val.p, ws.label.p};
-      // the dry run is a 1-shard run over the local rows
-      h->G = 1; h->log2G = 0; h->rank = 0;
       const int64_t save_max = h->cfg.max_batch_nnz;
       h->cfg.max_batch_nnz = std::min<int64_t>(save_max, 64);
-      h->G = 2;  // keep the sharded code path (G > 1 checks) but with self-only peers (peers.G == 1)
+      h->G = 1;  // the owner-side select scans G * max_batch_nnz candidates: one shard here
       if (h->precise) train_device_sharded<true>(h, wb, nullptr, ws.loss.p); else train_device_sharded<false>(h, wb, nullptr, ws.loss.p);
       FTRL_CUDA(cudaStreamSynchronize(h->compute));
       h->cfg.max_batch_nnz = save_max;
-      h->G = G; h->log2G = log2G; h->rank = rank; h->n_local = n_local;
+      h->G = G; h->log2G = log2G; h->rank = rank;
       FTRL_CUDA(cudaMemcpy(h->bias, &bias_save, sizeof(float4), cudaMemcpyHostToDevice));
       FTRL_CUDA(cudaMemset(h->d_err, 0, sizeof(int32_t)));
       FTRL_CUDA(cudaMemset(h->sync, 0, sizeof(SyncArea)));
@@ -1493,7 +1587,8 @@ int ftrl_attach_peers(ftrl_handle *h, const void *blobs) {
     }
     h->shards = sh;
     h->peers = pr;
-    h->pmask_src = pms;
+    h->exportd = ex;
+    set_rowspace(h, h->log2G, h->rank, h->G);
     h->attached = true;
   });
 }
@@ -1502,7 +1597,7 @@ int ftrl_attach_peers(ftrl_handle *h, const void *blobs) {
 
 // ---- debug probe (tools/ only, not part of the ABI): scattered row traffic against one shard ----
 namespace ftrl {
-__global__ void k_dbg_peer_traffic(Shards sh, int q, int64_t n_local, int64_t ld, int32_t n_rows, int flags, float *sink) {
+__global__ void k_dbg_peer_traffic(Shards sh, Export ex, int q, int64_t n_local, int64_t ld, int32_t n_rows, int flags, float *sink) {
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int lane = threadIdx.x & 31, nvec = (int)(ld >> 2);
   float acc = 0.f;
@@ -1513,11 +1608,11 @@ __global__ void k_dbg_peer_traffic(Shards sh, int q, int64_t n_local, int64_t ld
       for (int v = lane; v < nvec; v += 32) acc += __ldcs(p + v).x;
     }
     if (flags & 2) {
-      float4 *p = reinterpret_cast<float4 *>(sh.staging[q] + i * ld);
+      float4 *p = reinterpret_cast<float4 *>(ex.inbox[q] + i * ld);
       for (int v = lane; v < nvec; v += 32) __stcs(p + v, make_float4(0.f, 0.f, 0.f, 0.f));
     }
     if (flags & 4) {
-      const float4 *p = reinterpret_cast<const float4 *>(sh.staging[q] + (row % n_rows) * ld);
+      const float4 *p = reinterpret_cast<const float4 *>(ex.inbox[q] + (row % n_rows) * ld);
       for (int v = lane; v < nvec; v += 32) acc += __ldcs(p + v).x;
     }
     if (flags & 8) {  // destroys the w plane: probe only
@@ -1539,7 +1634,7 @@ extern "C" int ftrl_dbg_peer_traffic(ftrl_handle *h, int q, int flags, int n_row
     FTRL_CUDA(cudaEventCreate(&b));
     FTRL_CUDA(cudaEventRecord(a, h->compute));
     for (int r = 0; r < reps; r++)
-      ftrl::k_dbg_peer_traffic<<<grid, 256, 0, h->compute>>>(h->shards, q, h->n_local, h->dims.ld, n_rows, flags, h->logit_ws.p);
+      ftrl::k_dbg_peer_traffic<<<grid, 256, 0, h->compute>>>(h->shards, h->exportd, q, h->n_local, h->dims.ld, n_rows, flags, h->logit_ws.p);
     FTRL_CUDA(cudaEventRecord(b, h->compute));
     FTRL_CUDA(cudaEventSynchronize(b));
     FTRL_CUDA(cudaEventElapsedTime(ms_out, a, b));

@@ -1,22 +1,31 @@
 // shard.cuh -- multi-GPU: feature-sharded tables, one process per GPU, peers mapped over NVLink.
 //
-// Row `feat` of lin / tab lives on rank feat mod G at local row feat div G; the samples
-// of a global minibatch are split across ranks.  Per step, on every rank r (all on its stream):
-//   S1  k_prep_rows over the local samples; k_publish tells every peer the local nnz / batch flag
+// Row `feat` of lin / tab lives on rank feat mod G at local row feat div G; the samples of a
+// global minibatch are split across ranks.  Every rank runs the single-GPU pipeline on its own samples; what
+// crosses NVLink is one w plane IN and one gradient sum OUT per DISTINCT (row, rank) pair -- not per
+// occurrence -- because duplicates are reduced where the samples live.  Per step, on every rank (all on its
+// stream):
+//   S1  k_prep_rows, radix sort by feature id, segmented OR-scan of the field masks, list of the distinct
+//       rows of the local batch (k_publish_unique: feature id, sorted head position, "single occurrence",
+//       field mask); the count goes to every peer
 //   --  barrier 1 (device-side, flags in peer memory)
-//   S2  owner side: DeviceSelect over ALL ranks' key buffers (read over NVLink) keeps the occurrences
-//       whose row this rank owns, in (rank, occurrence) order -> deterministic; k_fill_owned turns them
-//       into (local row, source) pairs; radix sort; k_occ_class_sharded classifies every occurrence and
-//       writes its class / staging position straight into the SAMPLE-side rank's occ_pos buffer
+//   S2  owner side: DeviceSelect over ALL ranks' distinct-row lists (read over NVLink) keeps the rows this
+//       rank owns, in (rank, row) order -> deterministic; radix sort by local row = the contribution list;
+//       k_contrib_class: a row touched once, by its owner only, is finalised inside that sample ("fused");
+//       a row touched by its owner only is reduced and applied there; every other contribution gets a slot
+//       of the owner's inbox (written into the contributing rank's dst_at); k_owner_materialise writes
+//       w = W(n,z) for the slices the global batch touches
 //   --  barrier 2
-//   S3  k_ffm_tile over the local samples: bulk copies pull the rows from their owners, updated rows
-//       and gradient images are bulk-stored back to the owners (Shards in ffm_tile.cuh); the local
-//       (sum g, sum g^2) goes to every peer (k_batch_reduce with peers)
+//   S3  k_pull: w plane of every distinct remote row -> local row cache (one NVLink read per distinct row);
+//       k_ffm_tile over the local samples (all addresses local: shard rows, row cache, staging);
+//       k_ffm_staged_rows / k_ffm_combine reduce the local duplicates and store each row's (sum g, sum g^2)
+//       into the owner's inbox (Export); the local (sum g, sum g^2, loss) of the bias goes to every peer
 //   --  barrier 3
-//   S4  owner side: k_ffm_staged_rows + k_ffm_combine on the local shard; k_bias_apply sums the G
-//       partials in rank order, so the replicated bias stays bit-identical on all ranks
-// The exchange is therefore not a separate all-to-all: the kernels that need remote rows load and
-// store them in place through peer pointers, tile by tile.
+//   S4  owner side: k_owner_apply sums the <= G inbox entries of a row in rank order and applies the
+//       closed-form FTRL update; k_bias_apply sums the G bias partials in rank order, so the replicated
+//       bias stays bit-identical on all ranks
+// The exchange is not a separate all-to-all: the kernels that need remote data load / store it in place
+// through peer pointers.
 #pragma once
 #include "common.cuh"
 #include "ffm_tile.cuh"
@@ -27,23 +36,77 @@ namespace ftrl {
 // lives in device memory of every rank, mapped by all peers
 struct SyncArea {
   uint32_t flag[MAX_SHARDS];      // flag[q] = last barrier epoch rank q has reached (written by q)
-  int32_t nnz[MAX_SHARDS];        // nnz[q]  = occurrences of rank q's current batch (written by q)
+  int32_t n_uniq[MAX_SHARDS];     // n_uniq[q] = distinct rows of rank q's current batch (written by q)
   int32_t simple[MAX_SHARDS];     // simple[q] != 0: every sample of rank q's batch has distinct fields
   double red[MAX_SHARDS][4];      // red[q] = {sum g, sum g^2, sum loss, n_rows} of rank q's batch
 };
 
+constexpr uint32_t UINFO_SINGLE = 1u << 30;  // uinfo = sorted head position | UINFO_SINGLE
+constexpr uint32_t UINFO_POS = UINFO_SINGLE - 1;
+
 struct Peers {
   int G, log2G, rank, pad;
   SyncArea *sync[MAX_SHARDS];
-  const uint32_t *key[MAX_SHARDS];
-  int32_t *occ_pos[MAX_SHARDS];
+  const uint32_t *ukey[MAX_SHARDS];              // [u] feature id of the u-th distinct row of that rank's batch
+  const uint32_t *uinfo[MAX_SHARDS];             // [u] sorted head position | single-occurrence flag
+  const unsigned long long *umask[MAX_SHARDS];   // [u] fields of the row the rank's batch touches
+  int32_t *dst_at[MAX_SHARDS];                   // [sorted head position] inbox slot, written by the owner
+  const float *tab[MAX_SHARDS];
+  const float4 *lin[MAX_SHARDS];
 };
 
-__global__ void k_publish(Peers pr, int32_t nnz, const int32_t *batch_flags) {
-  const int q = threadIdx.x;
-  if (q >= pr.G) return;
-  pr.sync[q]->nnz[pr.rank] = nnz;
-  pr.sync[q]->simple[pr.rank] = batch_flags[0];
+// ---- S1: distinct rows of the local batch --------------------------------------------------------
+struct MaskScan {
+  int32_t start;  // sorted position of the row head at or before this position (0 when none in the range)
+  int32_t pad;
+  unsigned long long mask;
+};
+struct MaskScanOp {  // segmented OR: a range that contains a row head restarts the mask
+  __device__ __forceinline__ MaskScan operator()(const MaskScan &a, const MaskScan &b) const {
+    MaskScan r;
+    r.start = a.start > b.start ? a.start : b.start;
+    r.pad = 0;
+    r.mask = b.start > 0 ? b.mask : (a.mask | b.mask);
+    return r;
+  }
+};
+struct MaskIn {
+  const uint32_t *skey, *socc;
+  const uint64_t *pmask;
+  __device__ __forceinline__ MaskScan operator()(int32_t p) const {
+    const bool head = p == 0 || skey[p] != skey[p - 1];
+    return MaskScan{head ? p : 0, 0, (unsigned long long)pmask[socc[p]]};
+  }
+};
+struct RowHeadPred {
+  const uint32_t *skey;
+  __device__ __forceinline__ bool operator()(int32_t p) const { return p == 0 || skey[p] != skey[p - 1]; }
+};
+
+// one thread per listed row head; thread 0 also tells every peer how many distinct rows this rank has
+__global__ void k_publish_unique(Peers pr, int32_t nnz, uint32_t sentinel, int32_t cap, const int32_t *__restrict__ uhead,
+                                 const int32_t *__restrict__ n_uall_p, const uint32_t *__restrict__ skey,
+                                 const MaskScan *__restrict__ mscan, const int32_t *__restrict__ batch_flags,
+                                 uint32_t *__restrict__ ukey, uint32_t *__restrict__ uinfo,
+                                 unsigned long long *__restrict__ umask) {
+  const int32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+  const int32_t n_uall = nnz > 0 ? *n_uall_p : 0;
+  if (u == 0) {
+    int32_t n = n_uall;
+    if (n > 0 && skey[uhead[n - 1]] == sentinel) n--;  // the run of invalid occurrences sorts last
+    for (int q = 0; q < pr.G; q++) {
+      pr.sync[q]->n_uniq[pr.rank] = n;
+      pr.sync[q]->simple[pr.rank] = batch_flags[0];
+    }
+  }
+  if (u >= n_uall || u >= cap) return;
+  const int32_t p = uhead[u];
+  const uint32_t key = skey[p];
+  if (key == sentinel) return;
+  const int32_t next = u + 1 < n_uall ? uhead[u + 1] : nnz;
+  ukey[u] = key;
+  uinfo[u] = (uint32_t)p | (next - p == 1 ? UINFO_SINGLE : 0u);
+  umask[u] = mscan[next - 1].mask;
 }
 
 // all ranks arrive; returns when every rank has reached `epoch`.  A peer that never arrives (crashed
@@ -73,55 +136,227 @@ __global__ void k_merge_flags(Peers pr, int32_t *batch_flags, int32_t *err) {
   if (!all) *err = 2;  // sharded mode has no generic fallback yet
 }
 
+// ---- S2: owner side ---------------------------------------------------------------------------------
 struct OwnedPred {
   Peers pr;
   int32_t nnz_max;
-  uint32_t sentinel;
   __device__ __forceinline__ bool operator()(int32_t idx) const {
-    const int q = idx / nnz_max, t = idx - q * nnz_max;
-    if (t >= pr.sync[pr.rank]->nnz[q]) return false;
-    const uint32_t key = pr.key[q][t];
-    return key != sentinel && (int)(key & (uint32_t)(pr.G - 1)) == pr.rank;
+    const int q = idx / nnz_max, u = idx - q * nnz_max;
+    if (u >= pr.sync[pr.rank]->n_uniq[q]) return false;
+    return (int)(pr.ukey[q][u] & (uint32_t)(pr.G - 1)) == pr.rank;
   }
 };
 
-// (local row, source) pairs of the owned occurrences; the tail up to `cap` is padded with the sentinel
+// (local row, source) pairs of the owned contributions; the tail up to `cap` is padded with the sentinel
 __global__ void k_fill_owned(Peers pr, int32_t nnz_max, int32_t cap, uint32_t local_sentinel,
                              const int32_t *__restrict__ sel, const int32_t *__restrict__ n_sel,
                              uint32_t *__restrict__ okey, uint32_t *__restrict__ osrc, int32_t *__restrict__ err) {
   const int32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= cap) return;
   const int32_t n = *n_sel;
-  if (j == 0 && n > cap) *err = 3;  // owned occurrences exceed the workspace (extreme skew)
+  if (j == 0 && n > cap) *err = 3;  // owned contributions exceed the workspace (extreme skew)
   if (j < n) {
     const int32_t idx = sel[j];
-    const int q = idx / nnz_max, t = idx - q * nnz_max;
-    okey[j] = pr.key[q][t] >> pr.log2G;
-    osrc[j] = ((uint32_t)q << SRC_SHIFT) | (uint32_t)t;
+    const int q = idx / nnz_max, u = idx - q * nnz_max;
+    okey[j] = pr.ukey[q][u] >> pr.log2G;
+    osrc[j] = ((uint32_t)q << SRC_SHIFT) | (uint32_t)u;
   } else {
     okey[j] = local_sentinel;
     osrc[j] = 0;
   }
 }
 
-// sharded twin of k_occ_class: the class / staging position goes to the rank that holds the sample
-__global__ void k_occ_class_sharded(Peers pr, int32_t n, uint32_t sentinel, const uint32_t *__restrict__ skey,
-                                    const uint32_t *__restrict__ socc, uint8_t *__restrict__ fused_sorted) {
-  const int32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n) return;
-  const uint32_t k = skey[p];
-  if (k == sentinel) {
-    fused_sorted[p] = 0;
+enum : uint8_t {
+  CF_SINGLE = 1,  // the contribution is one occurrence: only the gradient plane is in the inbox
+  CF_APPLY = 2,   // head of a run of contributions that k_owner_apply reduces
+  CF_MAT = 4,     // head of a run whose w must be materialised before the samples run
+};
+
+// one thread per sorted contribution c (ckey sorted, contributions of one row in rank order)
+__global__ void k_contrib_class(Peers pr, int32_t cap, const int32_t *__restrict__ n_sel, uint32_t lsent,
+                                const uint32_t *__restrict__ ckey, const uint32_t *__restrict__ csrc,
+                                const uint32_t *__restrict__ socc, uint8_t *__restrict__ cflag,
+                                uint8_t *__restrict__ fused_sorted, int32_t *__restrict__ occ_pos) {
+  const int32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int32_t n = min(*n_sel, cap);
+  if (c >= n) return;
+  const uint32_t k = ckey[c];
+  if (k == lsent) {
+    cflag[c] = 0;
     return;
   }
-  const uint32_t src = socc[p];
-  const bool head = p == 0 || skey[p - 1] != k;
-  const bool last = p + 1 == n || skey[p + 1] != k;
-  // finalised inside the sample only when the sample lives on the owner: remote rows always go through
-  // the owner (w in, gradient image out: 8 B per coordinate over NVLink instead of 20 B)
-  const bool fused = head && last && (int)(src >> SRC_SHIFT) == pr.rank;
-  fused_sorted[p] = fused ? 1 : 0;
-  pr.occ_pos[src >> SRC_SHIFT][src & SRC_MASK] = fused ? -1 : p;
+  const bool head = c == 0 || ckey[c - 1] != k;
+  const bool last = c + 1 >= n || ckey[c + 1] != k;
+  const uint32_t src = csrc[c];
+  const int q = (int)(src >> SRC_SHIFT);
+  const uint32_t info = pr.uinfo[q][src & SRC_MASK];
+  const int32_t p_head = (int32_t)(info & UINFO_POS);
+  const bool single = (info & UINFO_SINGLE) != 0;
+  if (head && last && q == pr.rank) {
+    if (single) {  // finalised inside its sample by k_ffm_tile
+      fused_sorted[p_head] = 1;
+      occ_pos[socc[p_head]] = -1;
+      cflag[c] = 0;
+    } else {       // reduced and applied by this rank's own row kernels
+      pr.dst_at[q][p_head] = -2;
+      cflag[c] = CF_MAT;
+    }
+    return;
+  }
+  pr.dst_at[q][p_head] = c;
+  cflag[c] = (uint8_t)((single ? CF_SINGLE : 0) | (head ? (CF_APPLY | CF_MAT) : 0));
+}
+
+// w = W(n,z) (ffm.cpp:72-88, ftrl_model.cpp:52-59) for exactly the slices the global batch touches, and the
+// linear w: run heads are compacted per block, then one warp per row
+template <bool PRECISE, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+k_owner_materialise(Peers pr, Dims d, Hyper h, int32_t cap, const int32_t *__restrict__ n_sel,
+                    const int32_t *__restrict__ batch_flags, const uint32_t *__restrict__ ckey,
+                    const uint32_t *__restrict__ csrc, const uint8_t *__restrict__ cflag, float *__restrict__ tab,
+                    float4 *__restrict__ lin) {
+  if (batch_flags[0] == 0) return;
+  constexpr int WARPS = THREADS / 32;
+  __shared__ int s_list[THREADS];
+  __shared__ int s_n;
+  const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+  const int32_t n = min(*n_sel, cap);
+  const int64_t ld = d.ld, rs = 3 * ld;
+  const int vpf = d.k >> 2;
+  for (int base = blockIdx.x * THREADS; base < n; base += gridDim.x * THREADS) {
+    if (tid == 0) s_n = 0;
+    __syncthreads();
+    const int c = base + tid;
+    if (c < n && (cflag[c] & CF_MAT)) s_list[atomicAdd(&s_n, 1)] = c;
+    __syncthreads();
+    const int n_list = s_n;
+    for (int li = wib; li < n_list; li += WARPS) {
+      const int c0 = s_list[li];
+      const uint32_t k = ckey[c0];
+      unsigned long long m = 0ull;
+      if (lane < pr.G && c0 + lane < n && ckey[c0 + lane] == k) {
+        const uint32_t src = csrc[c0 + lane];
+        m = pr.umask[src >> SRC_SHIFT][src & SRC_MASK];
+      }
+      const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)m);
+      const unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(m >> 32));
+      const unsigned long long mask = ((unsigned long long)hi << 32) | lo;
+      float *row = tab + (int64_t)k * rs;
+      for (int v = lane; v < d.n_fields * vpf; v += 32) {
+        if (!((mask >> (v / vpf)) & 1ull)) continue;
+        const float4 z = reinterpret_cast<const float4 *>(row)[v], nn = reinterpret_cast<const float4 *>(row + ld)[v];
+        reinterpret_cast<float4 *>(row + 2 * ld)[v] = weight4<PRECISE>(z, nn, h);
+      }
+      if (lane == 0) {
+        const float4 e = lin[k];
+        lin[k].z = weight_from<PRECISE>(e.x, f_sqrt<PRECISE>(e.y), h);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---- S3: pull the w plane of every distinct remote row into the local row cache ----------------------
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+k_pull(Peers pr, Dims d, int32_t nnz, uint32_t sentinel, const int32_t *__restrict__ batch_flags,
+       const int32_t *__restrict__ uhead, const int32_t *__restrict__ n_uall_p, const uint32_t *__restrict__ skey,
+       float *__restrict__ rc_w, float *__restrict__ rc_lin) {
+  if (batch_flags[0] == 0) return;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int32_t n_uall = nnz > 0 ? *n_uall_p : 0;
+  const int64_t ld = d.ld, rs = 3 * ld;
+  const int nvec = (int)(ld >> 2);
+  for (int32_t u = blockIdx.x * WARPS + wib; u < n_uall; u += gridDim.x * WARPS) {
+    const int32_t p = uhead[u];
+    const uint32_t key = skey[p];
+    if (key == sentinel) continue;
+    const int q = (int)(key & (uint32_t)(pr.G - 1));
+    if (q == pr.rank) continue;
+    const int64_t lrow = (int64_t)(key >> pr.log2G);
+    const float4 *src = reinterpret_cast<const float4 *>(pr.tab[q] + lrow * rs + 2 * ld);
+    float4 *dst = reinterpret_cast<float4 *>(rc_w + (int64_t)p * ld);
+    float4 buf[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+      if (lane + 32 * i < nvec) buf[i] = __ldcs(src + lane + 32 * i);
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+      if (lane + 32 * i < nvec) dst[lane + 32 * i] = buf[i];
+    for (int v = lane + 128; v < nvec; v += 32) dst[v] = __ldcs(src + v);
+    if (lane == 0) rc_lin[p] = pr.lin[q][lrow].z;
+  }
+}
+
+// ---- S4: owner side: sum the inbox entries of a row in rank order, closed-form FTRL update -------------
+// work item = (run of contributions of one row, part of 32 float4 vectors); part 0 also does the linear term
+template <bool PRECISE, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+k_owner_apply(Peers pr, Dims d, Hyper h, int32_t cap, const int32_t *__restrict__ n_sel,
+              const int32_t *__restrict__ batch_flags, const uint32_t *__restrict__ ckey,
+              const uint8_t *__restrict__ cflag, const float *__restrict__ inbox, const float2 *__restrict__ inbox_lin,
+              float *__restrict__ tab, float4 *__restrict__ lin) {
+  if (batch_flags[0] == 0) return;
+  constexpr int WARPS = THREADS / 32;
+  __shared__ int s_list[THREADS];
+  __shared__ int s_n;
+  const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+  const int32_t n = min(*n_sel, cap);
+  const int64_t ld = d.ld, rs = 3 * ld;
+  const int nvec = (int)(ld >> 2);
+  const int parts = (nvec + 31) >> 5;
+  for (int base = blockIdx.x * THREADS; base < n; base += gridDim.x * THREADS) {
+    if (tid == 0) s_n = 0;
+    __syncthreads();
+    const int c = base + tid;
+    if (c < n && (cflag[c] & CF_APPLY)) s_list[atomicAdd(&s_n, 1)] = c;
+    __syncthreads();
+    const int n_items = s_n * parts;
+    for (int it = wib; it < n_items; it += WARPS) {
+      const int c0 = s_list[it / parts], part_i = it % parts;
+      const uint32_t k = ckey[c0];
+      int J = 1;
+      while (J < pr.G && c0 + J < n && ckey[c0 + J] == k) J++;
+      const int v = part_i * 32 + lane;
+      float *row = tab + (int64_t)k * rs;
+      if (v < nvec) {
+        float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+        for (int j = 0; j < J; j++) {
+          const float4 *e = reinterpret_cast<const float4 *>(inbox + (int64_t)(c0 + j) * 2 * ld);
+          const float4 g0 = __ldcs(e + v);
+          float4 g1;
+          if (cflag[c0 + j] & CF_SINGLE) g1 = make_float4(g0.x * g0.x, g0.y * g0.y, g0.z * g0.z, g0.w * g0.w);
+          else g1 = __ldcs(e + nvec + v);
+          s0.x += g0.x; s0.y += g0.y; s0.z += g0.z; s0.w += g0.w;
+          s1.x += g1.x; s1.y += g1.y; s1.z += g1.z; s1.w += g1.w;
+        }
+        const bool any = s0.x != 0.f || s0.y != 0.f || s0.z != 0.f || s0.w != 0.f || s1.x != 0.f || s1.y != 0.f ||
+                         s1.z != 0.f || s1.w != 0.f;
+        if (any) {
+          float4 z = reinterpret_cast<float4 *>(row)[v], nn = reinterpret_cast<float4 *>(row + ld)[v];
+          const float4 w = reinterpret_cast<float4 *>(row + 2 * ld)[v];
+          ftrl_apply<PRECISE>(z.x, nn.x, w.x, s0.x, s1.x, h);
+          ftrl_apply<PRECISE>(z.y, nn.y, w.y, s0.y, s1.y, h);
+          ftrl_apply<PRECISE>(z.z, nn.z, w.z, s0.z, s1.z, h);
+          ftrl_apply<PRECISE>(z.w, nn.w, w.w, s0.w, s1.w, h);
+          reinterpret_cast<float4 *>(row)[v] = z;
+          reinterpret_cast<float4 *>(row + ld)[v] = nn;
+        }
+      }
+      if (part_i == 0 && lane == 0) {
+        float sg = 0.f, sg2 = 0.f;
+        for (int j = 0; j < J; j++) {
+          const float2 t = inbox_lin[c0 + j];
+          sg += t.x;
+          sg2 += t.y;
+        }
+        float4 e = lin[k];
+        ftrl_apply<PRECISE>(e.x, e.y, e.z, sg, sg2, h);
+        lin[k] = e;
+      }
+    }
+    __syncthreads();
+  }
 }
 
 // local partial sums -> every peer's SyncArea.red[rank]   (runs after the local k_batch_reduce partials)
