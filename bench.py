@@ -302,7 +302,8 @@ def main():
     torch.cuda.synchronize()
     prof = m.profile()
     m.profile_enable(False)
-    hot = ["materialise", "sample", "rows", "combine", "generic"]  # forward + FTRL update kernels
+    # forward + FTRL update kernels (sharded runs: + the row pull, the owner-side materialise and apply)
+    hot = ["materialise", "sample", "rows", "combine", "generic", "exchange", "pull", "apply"]
     hot_ms = sum(prof[p]["ms"] for p in hot if p in prof) / args.steps
     Ubar = float(np.mean([U[i % len(U)] for i in range(args.steps)]))
     bytes_alg = alg_bytes(model, n_fields, k, Ubar, nnz * world, B * world) / world  # per GPU
@@ -312,13 +313,15 @@ def main():
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get(f"{args.workload}-{args.dist}")
+            traffic = json.load(open(tp)).get(f"{args.workload}-{args.dist}") if world == 1 else None
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src,
-                "kernels": "k_row_touch + k_row_materialise + k_ffm_tile + k_ffm_staged_rows + k_ffm_combine "
-                           "(forward + FTRL update)" if model == "FFM"
+                "kernels": ("k_row_touch + k_row_materialise + k_ffm_tile + k_ffm_staged_rows + k_ffm_combine "
+                            "(forward + FTRL update)" if world == 1 else
+                            "owner select/sort/k_owner_materialise + k_pull + k_ffm_tile + k_ffm_staged_rows + "
+                            "k_ffm_combine + k_owner_apply (forward + FTRL update + row exchange)") if model == "FFM"
                 else "k_lrfm_sample + k_lrfm_rows + k_lrfm_combine",
                 "alg_bytes_per_step": bytes_alg, "kernel_ms_per_step": hot_ms,
                 "phase_ms_per_step": {p: v["ms"] / args.steps for p, v in prof.items() if v["ms"] > 0},
@@ -420,7 +423,7 @@ def main():
                        "l2": "inputs larger than L2 (rows touched per step >> 126 MB), no explicit flush",
                        "parallelism": "single GPU" if world == 1 else
                        f"{world} GPUs: tables sharded by feature id (feat mod {world}), samples split across ranks, "
-                       f"rows pulled/pushed over NVLink peer memory inside the kernels, global batch {B * world}",
+                       f"duplicates reduced where the samples live, one w plane in / one gradient sum out per distinct (row, rank) over NVLink peer memory, global batch {B * world}",
                        "distinct_batches": len(batches), "fused_rows_per_step": fused_rows},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_per_step) * args.steps,
             "roofline": roofline, "roofline_uniform_ids": roofline_uniform, "cpu_baseline": cpu,

@@ -74,7 +74,7 @@ def test_shard_state_round_trip():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_shard_count_invariance_on_one_gpu(world):
     rng = np.random.default_rng(5)
     nf, nfl, k, B = 3000, 13, 8, 512
