@@ -80,10 +80,26 @@ __device__ __forceinline__ void named_bar_sync(int id, int n_threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory");
 }
 
+// position in a ring of `n` slots, advanced without division: slot index and the mbarrier phase parity
+struct RingCursor {
+  int slot, round;
+  __device__ __forceinline__ void init(int start, int n) { slot = start % n; round = start / n; }
+  __device__ __forceinline__ void advance(int by, int n) {
+    slot += by;
+    while (slot >= n) {
+      slot -= n;
+      round++;
+    }
+  }
+  __device__ __forceinline__ uint32_t parity() const { return (uint32_t)(round & 1); }
+  __device__ __forceinline__ uint32_t prev_parity() const { return (uint32_t)((round - 1) & 1); }
+};
+
 // ---- tile geometry ------------------------------------------------------------------------------
 constexpr int TILE_META_WARPS = 2;   // warps prefetching sample metadata (CSR, occurrence class, linear records)
 // + one row-loader warp and one row-storer warp (TMA bulk copies)
 __host__ __device__ constexpr int tile_threads(int consumers) { return consumers + 32 * (2 + TILE_META_WARPS); }
+constexpr int TILE_MAX_CONSUMERS = 512;
 constexpr int TILE_MAX_STAGE = 4;    // row stages
 constexpr int TILE_MAX_META = 8;     // metadata slots
 
@@ -169,8 +185,8 @@ __device__ __forceinline__ void apply4(float4 &z, float4 &n, const float4 &w, co
 // Thread roles: [0, consumers) compute; warp `consumers/32` is the row producer (bulk loads / bulk
 // stores of the row ring); the next TILE_META_WARPS warps prefetch sample metadata into a deeper
 // ring so that the row producer never waits on a dependent global-load chain.
-template <bool PRECISE, int IPT>
-__global__ void __launch_bounds__(tile_threads(512), 1)
+template <bool PRECISE, int IPT, bool CACHE>
+__global__ void __launch_bounds__(tile_threads(TILE_MAX_CONSUMERS), 1)
 k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t *__restrict__ batch_flags,
            const __grid_constant__ RowSpace rsp, const float4 *__restrict__ bias, const uint32_t *__restrict__ pair_lut,
            const int32_t *__restrict__ occ_pos, const SegScan *__restrict__ scan, float *__restrict__ g_out,
@@ -229,16 +245,18 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
   }
   __syncthreads();
 
-  const int64_t n_mine = b.n_rows > blockIdx.x ? (b.n_rows - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int n_mine = b.n_rows > blockIdx.x ? (int)((b.n_rows - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
 
   if (role == 2) {
     // =========================== metadata warps ===========================
     const int mw = (tid - n_cons - 32 * (NL + NSW)) >> 5;
-    for (int64_t it = mw; it < n_mine; it += TILE_META_WARPS) {
-      const int slot = (int)(it % MD);
-      if (it >= MD) mbar_wait(&bar_mfree[slot], (uint32_t)(((it / MD) - 1) & 1));
+    RingCursor mc;
+    mc.init(mw, MD);
+    for (int it = mw; it < n_mine; it += TILE_META_WARPS, mc.advance(TILE_META_WARPS, MD)) {
+      const int slot = mc.slot;
+      if (mc.round > 0) mbar_wait(&bar_mfree[slot], mc.prev_parity());
       SampleMeta m = sample_meta(slot);
-      const int64_t s = blockIdx.x + it * gridDim.x;
+      const int64_t s = blockIdx.x + (int64_t)it * gridDim.x;
       const int64_t r0 = b.row_ptr[s];
       const int F = (int)min((int64_t)1 << 20, b.row_ptr[s + 1] - r0);
       int nv = 0;
@@ -294,12 +312,15 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
 
   if (role == 1) {
     // =========================== row loader warps ===========================
-    for (int64_t it = 0; it < n_mine; it++) {
-      const int st = (int)(it % NS);
+    RingCursor sc, mc;
+    sc.init(0, NS);
+    mc.init(0, MD);
+    for (int it = 0; it < n_mine; it++, sc.advance(1, NS), mc.advance(1, MD)) {
+      const int st = sc.slot;
       float *rows = stage_rows(st);
-      if (it >= NS) mbar_wait(&bar_free[st], (uint32_t)(((it / NS) - 1) & 1));  // previous occupant stored
-      const int slot = (int)(it % MD);
-      mbar_wait(&bar_mfull[slot], (uint32_t)((it / MD) & 1));
+      if (sc.round > 0) mbar_wait(&bar_free[st], sc.prev_parity());  // previous occupant stored
+      const int slot = mc.slot;
+      mbar_wait(&bar_mfull[slot], mc.parity());
       SampleMeta m = sample_meta(slot);
       const int nv = m.hdr[0];
       {
@@ -326,12 +347,15 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
     // =========================== row storer warps ===========================
     // retire samples in order: wait for the consumers, bulk-store the rows / gradient images, then hand the
     // stage back to the loader and the metadata slot back to the metadata warps
-    for (int64_t it = 0; it < n_mine; it++) {
-      const int st = (int)(it % NS);
-      const int slot = (int)(it % MD);
+    RingCursor sc, mc;
+    sc.init(0, NS);
+    mc.init(0, MD);
+    for (int it = 0; it < n_mine; it++, sc.advance(1, NS), mc.advance(1, MD)) {
+      const int st = sc.slot;
+      const int slot = mc.slot;
       float *rows = stage_rows(st);
       SampleMeta m = sample_meta(slot);
-      mbar_wait(&bar_done[st], (uint32_t)((it / NS) & 1));
+      mbar_wait(&bar_done[st], sc.parity());
       const int nv = m.hdr[0];
       for (int r = lane; r < nv && !(geo.dbg & 2); r += 32) {
         const RowMeta rm = m.row[r];
@@ -355,31 +379,47 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
     const float4 bz = *bias;
     return weight_from<PRECISE>(bz.x, f_sqrt<PRECISE>(bz.y), h);
   }();
-  for (int64_t it = 0; it < n_mine; it++) {
-    const int st = (int)(it % NS);
-    const int slot = (int)(it % MD);
-    const int64_t s = blockIdx.x + it * gridDim.x;
+  RingCursor sc, mc;
+  sc.init(0, NS);
+  mc.init(0, MD);
+  for (int it = 0; it < n_mine; it++, sc.advance(1, NS), mc.advance(1, MD)) {
+    const int st = sc.slot;
+    const int slot = mc.slot;
+    const int64_t s = blockIdx.x + (int64_t)it * gridDim.x;
     float *rows = stage_rows(st);
     SampleMeta m = sample_meta(slot);
-    mbar_wait(&bar_mfull[slot], (uint32_t)((it / MD) & 1));
-    mbar_wait(&bar_full[st], (uint32_t)((it / NS) & 1));
+    mbar_wait(&bar_mfull[slot], mc.parity());
+    mbar_wait(&bar_full[st], sc.parity());
     const int nv = m.hdr[0];
     const uint32_t n_items = (uint32_t)nv * (uint32_t)(nv - 1) / 2u * dec.C;
 
     // ---- pass 1: w, logit ----
     float acc = 0.f;
     float4 wAc[IPT], wBc[IPT];
+    // CACHE: pass 2 reuses the item's slice offsets / classes from pass 1 instead of decoding it again
+    int offA[CACHE ? IPT : 1], offB[CACHE ? IPT : 1], cls[CACHE ? IPT : 1];  // bit 0/1: row m / n fused, bit 2: valid
+    float xx[CACHE ? IPT : 1];
 #pragma unroll
     for (int j = 0; j < IPT; j++) {
       const uint32_t item = tid + j * n_cons;
+      if (CACHE) cls[j] = 0;
       if (item < n_items) {
         uint32_t p, c;
         dec(item, p, c);
         const uint32_t e = s_lut[p];
         const int mi = e & 0xff, ni = e >> 8;
         const RowMeta rmm = m.row[mi], rmn = m.row[ni];
-        const float *sa = rows + (size_t)mi * stride + rmn.fk + c * 4;  // slice A = (row m, field n)
-        const float *sb = rows + (size_t)ni * stride + rmm.fk + c * 4;  // slice B = (row n, field m)
+        const int oA = mi * stride + rmn.fk + (int)c * 4;  // slice A = (row m, field n)
+        const int oB = ni * stride + rmm.fk + (int)c * 4;  // slice B = (row n, field m)
+        const float xmn = rmm.x * rmn.x;
+        if (CACHE) {
+          offA[j] = oA;
+          offB[j] = oB;
+          xx[j] = xmn;
+          cls[j] = 4 | (rmm.pos < 0 ? 1 : 0) | (rmn.pos < 0 ? 2 : 0);
+        }
+        const float *sa = rows + oA;
+        const float *sb = rows + oB;
         // staged rows hold w itself in the z-plane slot; fused rows hold (z, n): w = W(n, z), stored as the
         // stale-by-one w the reference keeps (ffm.cpp:72-88)
         float4 wA = *reinterpret_cast<const float4 *>(sa), wB = *reinterpret_cast<const float4 *>(sb);
@@ -394,7 +434,7 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
         wAc[j] = wA;
         wBc[j] = wB;
         const float dot = fmaf(wA.x, wB.x, fmaf(wA.y, wB.y, fmaf(wA.z, wB.z, wA.w * wB.w)));
-        acc = fmaf(dot, rmm.x * rmn.x, acc);
+        acc = fmaf(dot, xmn, acc);
       }
     }
     for (int r = tid; r < nv; r += n_cons) {
@@ -425,18 +465,31 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
     //      every (row, field) slice is read and written by exactly one item (fields are distinct) ----
 #pragma unroll
     for (int j = 0; j < IPT; j++) {
-      const uint32_t item = tid + j * n_cons;
-      if (item < n_items) {
-        uint32_t p, c;
-        dec(item, p, c);
-        const uint32_t e = s_lut[p];
-        const int mi = e & 0xff, ni = e >> 8;
-        const RowMeta rmm = m.row[mi], rmn = m.row[ni];
-        float *sa = rows + (size_t)mi * stride + rmn.fk + c * 4;
-        float *sb = rows + (size_t)ni * stride + rmm.fk + c * 4;
-        const float gx = g * (rmm.x * rmn.x);
+      int oA, oB, cl;
+      float xmn;
+      if (CACHE) {
+        oA = offA[j]; oB = offB[j]; cl = cls[j]; xmn = xx[j];
+      } else {
+        const uint32_t item = tid + j * n_cons;
+        cl = 0; oA = oB = 0; xmn = 0.f;
+        if (item < n_items) {
+          uint32_t p, c;
+          dec(item, p, c);
+          const uint32_t e = s_lut[p];
+          const int mi = e & 0xff, ni = e >> 8;
+          const RowMeta rmm = m.row[mi], rmn = m.row[ni];
+          oA = mi * stride + rmn.fk + (int)c * 4;
+          oB = ni * stride + rmm.fk + (int)c * 4;
+          xmn = rmm.x * rmn.x;
+          cl = 4 | (rmm.pos < 0 ? 1 : 0) | (rmn.pos < 0 ? 2 : 0);
+        }
+      }
+      if (cl & 4) {
+        float *sa = rows + oA;
+        float *sb = rows + oB;
+        const float gx = g * xmn;
         const float4 wA = wAc[j], wB = wBc[j];
-        if (rmm.pos < 0) {
+        if (cl & 1) {
           float4 zA = *reinterpret_cast<const float4 *>(sa), nA = *reinterpret_cast<const float4 *>(sa + ld);
           apply4<PRECISE>(zA, nA, wA, wB, gx, h);
           *reinterpret_cast<float4 *>(sa) = zA;
@@ -444,7 +497,7 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
         } else {
           *reinterpret_cast<float4 *>(sa) = make_float4(gx * wB.x, gx * wB.y, gx * wB.z, gx * wB.w);
         }
-        if (rmn.pos < 0) {
+        if (cl & 2) {
           float4 zB = *reinterpret_cast<const float4 *>(sb), nB = *reinterpret_cast<const float4 *>(sb + ld);
           apply4<PRECISE>(zB, nB, wB, wA, gx, h);
           *reinterpret_cast<float4 *>(sb) = zB;
@@ -470,13 +523,24 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
     }
     // staged rows: slices no partner touches (own field, absent fields) must read as 0 in the image.
     // They are disjoint from the slices written above, so no barrier is needed.
-    for (int q = tid; q < nv * d.n_fields; q += n_cons) {
-      const int r = q / d.n_fields, f = q - r * d.n_fields;
-      const RowMeta rm = m.row[r];
-      if (rm.pos < 0) continue;
-      if (m.present[f] && f * k != rm.fk) continue;
-      float4 *zp = reinterpret_cast<float4 *>(rows + (size_t)r * stride + f * k);
-      for (int v = 0; v < (k >> 2); v++) zp[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (nv == d.n_fields) {
+      // every field is present (fields are distinct): only the own-field slice is untouched
+      for (int r = tid; r < nv; r += n_cons) {
+        const RowMeta rm = m.row[r];
+        if (rm.pos < 0) continue;
+        float4 *zp = reinterpret_cast<float4 *>(rows + (size_t)r * stride + rm.fk);
+        for (int v = 0; v < (k >> 2); v++) zp[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    } else {
+      for (int r = tid >> 5; r < nv; r += n_cons_warps) {
+        const RowMeta rm = m.row[r];
+        if (rm.pos < 0) continue;
+        for (int f = lane; f < d.n_fields; f += 32) {
+          if (m.present[f] && f * k != rm.fk) continue;
+          float4 *zp = reinterpret_cast<float4 *>(rows + (size_t)r * stride + f * k);
+          for (int v = 0; v < (k >> 2); v++) zp[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
     }
     fence_async_smem();
     __syncwarp();

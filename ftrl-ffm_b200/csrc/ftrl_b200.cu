@@ -358,8 +358,12 @@ static void run_ffm_batch(ftrl_handle *h, const Batch &b, float *logit_out) {
       geo.smem_bytes = h->tile_smem;
       const int tgrid = (int)std::min<int64_t>(b.n_rows, (int64_t)h->n_sms * h->tile_ctas_per_sm);
 #define FFM_TILE(I)                                                                                              \
-  k_ffm_tile<PRECISE, I><<<tgrid, tile_threads(geo.consumers), geo.smem_bytes, h->compute>>>(                   \
-      b, d, h->hyper, dec, geo, h->batch_flags.p, h->rowspace, h->bias, h->pair_lut, h->occ_pos.p, h->scan.p, h->g.p, logit_out)
+  if (h->tile_cache)                                                                                              \
+    k_ffm_tile<PRECISE, I, true><<<tgrid, tile_threads(geo.consumers), geo.smem_bytes, h->compute>>>(             \
+        b, d, h->hyper, dec, geo, h->batch_flags.p, h->rowspace, h->bias, h->pair_lut, h->occ_pos.p, h->scan.p, h->g.p, logit_out); \
+  else                                                                                                            \
+    k_ffm_tile<PRECISE, I, false><<<tgrid, tile_threads(geo.consumers), geo.smem_bytes, h->compute>>>(            \
+        b, d, h->hyper, dec, geo, h->batch_flags.p, h->rowspace, h->bias, h->pair_lut, h->occ_pos.p, h->scan.p, h->g.p, logit_out)
       if (h->tile_ipt <= 1) FFM_TILE(1);
       else if (h->tile_ipt == 2) FFM_TILE(2);
       else if (h->tile_ipt == 3) FFM_TILE(3);
@@ -815,8 +819,12 @@ static void train_device_sharded(ftrl_handle *h, const Batch &b, float *logit_ou
       geo.smem_bytes = h->tile_smem;
       const int tgrid = (int)std::min<int64_t>(b.n_rows, (int64_t)h->n_sms * h->tile_ctas_per_sm);
 #define FFM_TILE(I)                                                                                            \
-  k_ffm_tile<PRECISE, I><<<tgrid, tile_threads(geo.consumers), geo.smem_bytes, h->compute>>>(                  \
-      b, d, h->hyper, dec, geo, h->batch_flags.p, h->rowspace, h->bias, h->pair_lut, h->occ_pos.p, h->scan.p, h->g.p, logit_out)
+  if (h->tile_cache)                                                                                              \
+    k_ffm_tile<PRECISE, I, true><<<tgrid, tile_threads(geo.consumers), geo.smem_bytes, h->compute>>>(             \
+        b, d, h->hyper, dec, geo, h->batch_flags.p, h->rowspace, h->bias, h->pair_lut, h->occ_pos.p, h->scan.p, h->g.p, logit_out); \
+  else                                                                                                            \
+    k_ffm_tile<PRECISE, I, false><<<tgrid, tile_threads(geo.consumers), geo.smem_bytes, h->compute>>>(            \
+        b, d, h->hyper, dec, geo, h->batch_flags.p, h->rowspace, h->bias, h->pair_lut, h->occ_pos.p, h->scan.p, h->g.p, logit_out)
       if (h->tile_ipt <= 1) FFM_TILE(1);
       else if (h->tile_ipt == 2) FFM_TILE(2);
       else if (h->tile_ipt == 3) FFM_TILE(3);
@@ -991,9 +999,12 @@ int ftrl_create(const ftrl_config *cfg, ftrl_handle **out) {
         h->tile_ctas_per_sm = ctas;
         h->tile_smem = tile_smem_bytes(d.n_fields, stride, stages, metas);
         const int sm = (int)h->tile_smem;
-#define TILE_ATTR(P, I) FTRL_CUDA(cudaFuncSetAttribute(k_ffm_tile<P, I>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm))
+#define TILE_ATTR(P, I)                                                                                              \
+  FTRL_CUDA(cudaFuncSetAttribute(k_ffm_tile<P, I, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm)); \
+  FTRL_CUDA(cudaFuncSetAttribute(k_ffm_tile<P, I, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm))
         TILE_ATTR(false, 1); TILE_ATTR(false, 2); TILE_ATTR(false, 3); TILE_ATTR(false, 4);
         TILE_ATTR(true, 1); TILE_ATTR(true, 2); TILE_ATTR(true, 3); TILE_ATTR(true, 4);
+        h->tile_cache = env_int("FTRL_B200_TILE_CACHE", 1);
 #undef TILE_ATTR
       }
     }
@@ -1411,6 +1422,16 @@ __global__ void k_batch_stats(int32_t nnz, uint32_t sentinel, const uint32_t *sk
   if (blockIdx.x == 0 && threadIdx.x == 0) out[3] = *n_chunks;
 }
 
+// sharded runs: distinct rows this rank OWNS among the rows the global batch touches = runs of the sorted
+// contribution list
+__global__ void k_count_runs(int32_t cap, const int32_t *n_sel, uint32_t lsent, const uint32_t *ckey, int64_t *out) {
+  const int32_t n = min(*n_sel, cap);
+  unsigned long long u = 0;
+  for (int32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x)
+    if (ckey[c] != lsent && (c == 0 || ckey[c - 1] != ckey[c])) u++;
+  if (u) atomicAdd(reinterpret_cast<unsigned long long *>(out), u);
+}
+
 int ftrl_last_batch_stats(ftrl_handle *h, ftrl_batch_stats *out) {
   if (!h || !out) return FTRL_ERR_ARG;
   return guarded(h, [&] {
@@ -1421,12 +1442,17 @@ int ftrl_last_batch_stats(ftrl_handle *h, ftrl_batch_stats *out) {
     DevBuf<int64_t> tmp;
     tmp.alloc(4);
     FTRL_CUDA(cudaMemset(tmp.p, 0, sizeof(int64_t) * 4));
-    // sharded runs: the sorted list is the owner-side list (rows this rank owns, from all ranks' samples)
-    int32_t nnz = h->G > 1 ? (int32_t)h->ow_cap : (int32_t)h->last_nnz;
+    int32_t nnz = (int32_t)h->last_nnz;
     if (nnz > 0) {
       const bool have_single = h->dims.model_type == FTRL_FFM && h->fuse;
-      k_batch_stats<<<256, 256, 0, h->compute>>>(nnz, h->G > 1 ? (uint32_t)h->n_local : (uint32_t)h->dims.n_feats, h->skey.p, h->scan.p,
+      k_batch_stats<<<256, 256, 0, h->compute>>>(nnz, (uint32_t)h->dims.n_feats, h->skey.p, h->scan.p,
                                                  have_single ? h->fused_sorted.p : nullptr, h->n_chunks.p, tmp.p);
+      FTRL_CUDA(cudaGetLastError());
+    }
+    if (h->G > 1) {
+      // n_unique: rows this rank owns (each distinct row of the global batch is counted on exactly one rank)
+      FTRL_CUDA(cudaMemsetAsync(tmp.p + 1, 0, sizeof(int64_t), h->compute));
+      k_count_runs<<<256, 256, 0, h->compute>>>((int32_t)h->ow_cap, h->n_sel.p, (uint32_t)h->n_local, h->ckey.p, tmp.p + 1);
       FTRL_CUDA(cudaGetLastError());
     }
     int64_t r[4] = {0, 0, 0, 0};
