@@ -798,13 +798,6 @@ static void train_device_sharded(ftrl_handle *h, const Batch &b, float *logit_ou
     launched(h, PH_SEGMENT);
     peer_barrier(h);  // 2: classes / inbox slots are known everywhere, w of the touched slices is materialised
   }
-  {
-    PhaseScope ps(h, PH_PULL);
-    k_pull<8><<<grid, 256, 0, h->compute>>>(h->peers, d, nnz, sentinel, h->batch_flags.p, h->uhead.p, h->n_uall.p, h->skey.p,
-                                            h->rc_w.p, h->rc_lin.p);
-    FTRL_CUDA(cudaGetLastError());
-    launched(h, PH_PULL);
-  }
   const ItemDecode dec = make_item_decode(d.k, 4);
   {
     PhaseScope ps(h, PH_SAMPLE);
@@ -872,14 +865,14 @@ static void train_device_sharded(ftrl_handle *h, const Batch &b, float *logit_ou
   h->stats.kernel_launches = h->launches_this_call;
 }
 
-constexpr int PEER_BUFS = 9;
+constexpr int PEER_BUFS = 11;
 struct PeerBlob {  // FTRL_PEER_BLOB_BYTES
   uint32_t magic;
   int32_t rank, world, device;
   int64_t pid;
   int64_t nnz_cap, ow_cap;
   void *raw[PEER_BUFS];                // same-process attach
-  cudaIpcMemHandle_t ipc[PEER_BUFS];   // tab, lin, ukey, uinfo, umask, dst_at, inbox, inbox_lin, sync
+  cudaIpcMemHandle_t ipc[PEER_BUFS];   // tab, lin, ukey, uinfo, umask, dst_at, inbox, inbox_lin, sync, rc_w, rc_lin
 };
 static_assert(sizeof(PeerBlob) <= FTRL_PEER_BLOB_BYTES, "peer blob too large");
 
@@ -1468,7 +1461,8 @@ int ftrl_last_batch_stats(ftrl_handle *h, ftrl_batch_stats *out) {
 
 // ---- multi-GPU ------------------------------------------------------------------------------
 static void peer_buffers(ftrl_handle *h, void **ptrs) {
-  void *mine[PEER_BUFS] = {h->tab, h->lin, h->ukey.p, h->uinfo.p, h->umask.p, h->dst_at.p, h->inbox.p, h->inbox_lin.p, h->sync};
+  void *mine[PEER_BUFS] = {h->tab, h->lin, h->ukey.p, h->uinfo.p, h->umask.p, h->dst_at.p, h->inbox.p, h->inbox_lin.p, h->sync,
+                           h->rc_w.p, h->rc_lin.p};
   memcpy(ptrs, mine, sizeof(mine));
 }
 
@@ -1478,7 +1472,7 @@ int ftrl_export_peer_blob(ftrl_handle *h, void *blob) {
     if (h->G <= 1) throw StateFail{"not a multi-GPU handle (world_size <= 1)"};
     PeerBlob pb;
     memset(&pb, 0, sizeof(pb));
-    pb.magic = 0xF7B20002u;
+    pb.magic = 0xF7B20003u;
     pb.rank = h->rank;
     pb.world = h->G;
     pb.device = h->cfg.device;
@@ -1500,8 +1494,6 @@ int ftrl_export_peer_blob(ftrl_handle *h, void *blob) {
 static void wire_peer(ftrl_handle *, Shards &sh, Peers &pr, Export &ex, int q, void *const *ptr) {
   sh.tab[q] = static_cast<float *>(ptr[0]);
   sh.lin[q] = static_cast<float4 *>(ptr[1]);
-  pr.tab[q] = static_cast<const float *>(ptr[0]);
-  pr.lin[q] = static_cast<const float4 *>(ptr[1]);
   pr.ukey[q] = static_cast<const uint32_t *>(ptr[2]);
   pr.uinfo[q] = static_cast<const uint32_t *>(ptr[3]);
   pr.umask[q] = static_cast<const unsigned long long *>(ptr[4]);
@@ -1509,6 +1501,8 @@ static void wire_peer(ftrl_handle *, Shards &sh, Peers &pr, Export &ex, int q, v
   ex.inbox[q] = static_cast<float *>(ptr[6]);
   ex.inbox_lin[q] = static_cast<float2 *>(ptr[7]);
   pr.sync[q] = static_cast<SyncArea *>(ptr[8]);
+  pr.rc_w[q] = static_cast<float *>(ptr[9]);
+  pr.rc_lin[q] = static_cast<float *>(ptr[10]);
 }
 
 static void set_rowspace(ftrl_handle *h, int log2G, int rank, int G) {
@@ -1543,7 +1537,7 @@ int ftrl_attach_peers(ftrl_handle *h, const void *blobs) {
     for (int q = 0; q < h->G; q++) {
       PeerBlob pb;
       memcpy(&pb, static_cast<const char *>(blobs) + (size_t)q * FTRL_PEER_BLOB_BYTES, sizeof(pb));
-      if (pb.magic != 0xF7B20002u || pb.rank != q || pb.world != h->G) throw ArgFail{fmt("peer blob %d is not from rank %d of %d", q, q, h->G)};
+      if (pb.magic != 0xF7B20003u || pb.rank != q || pb.world != h->G) throw ArgFail{fmt("peer blob %d is not from rank %d of %d", q, q, h->G)};
       if (pb.nnz_cap != h->nnz_cap) throw ArgFail{"all ranks must use the same max_batch_nnz"};
       void *ptr[PEER_BUFS];
       if (q == h->rank) {

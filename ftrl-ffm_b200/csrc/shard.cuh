@@ -14,10 +14,10 @@
 //       k_contrib_class: a row touched once, by its owner only, is finalised inside that sample ("fused");
 //       a row touched by its owner only is reduced and applied there; every other contribution gets a slot
 //       of the owner's inbox (written into the contributing rank's dst_at); k_owner_materialise writes
-//       w = W(n,z) for the slices the global batch touches
+//       w = W(n,z) for the slices the global batch touches into the table and pushes it into the row cache
+//       of every remote rank that touches the row (one NVLink store stream per distinct (row, rank))
 //   --  barrier 2
-//   S3  k_pull: w plane of every distinct remote row -> local row cache (one NVLink read per distinct row);
-//       k_ffm_tile over the local samples (all addresses local: shard rows, row cache, staging);
+//   S3  k_ffm_tile over the local samples (all addresses local: shard rows, row cache, staging);
 //       k_ffm_staged_rows / k_ffm_combine reduce the local duplicates and store each row's (sum g, sum g^2)
 //       into the owner's inbox (Export); the local (sum g, sum g^2, loss) of the bias goes to every peer
 //   --  barrier 3
@@ -51,8 +51,8 @@ struct Peers {
   const uint32_t *uinfo[MAX_SHARDS];             // [u] sorted head position | single-occurrence flag
   const unsigned long long *umask[MAX_SHARDS];   // [u] fields of the row the rank's batch touches
   int32_t *dst_at[MAX_SHARDS];                   // [sorted head position] inbox slot, written by the owner
-  const float *tab[MAX_SHARDS];
-  const float4 *lin[MAX_SHARDS];
+  float *rc_w[MAX_SHARDS];                       // [sorted head position][ld] that rank's cache of remote rows
+  float *rc_lin[MAX_SHARDS];                     // [sorted head position]
 };
 
 // ---- S1: distinct rows of the local batch --------------------------------------------------------
@@ -208,7 +208,9 @@ __global__ void k_contrib_class(Peers pr, int32_t cap, const int32_t *__restrict
 }
 
 // w = W(n,z) (ffm.cpp:72-88, ftrl_model.cpp:52-59) for exactly the slices the global batch touches, and the
-// linear w: run heads are compacted per block, then one warp per row
+// linear w: run heads are compacted per block, then one warp per row.  The fresh w goes into the table AND,
+// with posted stores over NVLink, into the row cache of every remote rank that touches the row -- one
+// transfer per distinct (row, rank), overlapped with the table reads of the other rows.
 template <bool PRECISE, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 k_owner_materialise(Peers pr, Dims d, Hyper h, int32_t cap, const int32_t *__restrict__ n_sel,
@@ -234,57 +236,46 @@ k_owner_materialise(Peers pr, Dims d, Hyper h, int32_t cap, const int32_t *__res
       const int c0 = s_list[li];
       const uint32_t k = ckey[c0];
       unsigned long long m = 0ull;
+      int my_q = -1, my_head = 0;  // lane j < J: the j-th contributor of the row
       if (lane < pr.G && c0 + lane < n && ckey[c0 + lane] == k) {
         const uint32_t src = csrc[c0 + lane];
-        m = pr.umask[src >> SRC_SHIFT][src & SRC_MASK];
+        my_q = (int)(src >> SRC_SHIFT);
+        m = pr.umask[my_q][src & SRC_MASK];
+        my_head = (int)(pr.uinfo[my_q][src & SRC_MASK] & UINFO_POS);
       }
       const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)m);
       const unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(m >> 32));
       const unsigned long long mask = ((unsigned long long)hi << 32) | lo;
+      const unsigned remote = __ballot_sync(0xffffffffu, my_q >= 0 && my_q != pr.rank);
+      // the remote contributors' caches, broadcast once (warp-uniform; the loop below diverges on the mask)
+      float *rcw[MAX_SHARDS];
+#pragma unroll
+      for (int j = 0; j < MAX_SHARDS; j++) {
+        const int q = __shfl_sync(0xffffffffu, my_q, j), head = __shfl_sync(0xffffffffu, my_head, j);
+        rcw[j] = nullptr;
+        if ((remote >> j) & 1u) rcw[j] = pr.rc_w[q] + (int64_t)head * ld;
+      }
       float *row = tab + (int64_t)k * rs;
       for (int v = lane; v < d.n_fields * vpf; v += 32) {
         if (!((mask >> (v / vpf)) & 1ull)) continue;
         const float4 z = reinterpret_cast<const float4 *>(row)[v], nn = reinterpret_cast<const float4 *>(row + ld)[v];
-        reinterpret_cast<float4 *>(row + 2 * ld)[v] = weight4<PRECISE>(z, nn, h);
+        const float4 w = weight4<PRECISE>(z, nn, h);
+        reinterpret_cast<float4 *>(row + 2 * ld)[v] = w;
+#pragma unroll
+        for (int j = 0; j < MAX_SHARDS; j++)
+          if (rcw[j]) reinterpret_cast<float4 *>(rcw[j])[v] = w;
       }
+      __syncwarp();
+      float wl = 0.f;
       if (lane == 0) {
         const float4 e = lin[k];
-        lin[k].z = weight_from<PRECISE>(e.x, f_sqrt<PRECISE>(e.y), h);
+        wl = weight_from<PRECISE>(e.x, f_sqrt<PRECISE>(e.y), h);
+        lin[k].z = wl;
       }
+      wl = __shfl_sync(0xffffffffu, wl, 0);
+      if (my_q >= 0 && my_q != pr.rank) pr.rc_lin[my_q][my_head] = wl;
     }
     __syncthreads();
-  }
-}
-
-// ---- S3: pull the w plane of every distinct remote row into the local row cache ----------------------
-template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
-k_pull(Peers pr, Dims d, int32_t nnz, uint32_t sentinel, const int32_t *__restrict__ batch_flags,
-       const int32_t *__restrict__ uhead, const int32_t *__restrict__ n_uall_p, const uint32_t *__restrict__ skey,
-       float *__restrict__ rc_w, float *__restrict__ rc_lin) {
-  if (batch_flags[0] == 0) return;
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int32_t n_uall = nnz > 0 ? *n_uall_p : 0;
-  const int64_t ld = d.ld, rs = 3 * ld;
-  const int nvec = (int)(ld >> 2);
-  for (int32_t u = blockIdx.x * WARPS + wib; u < n_uall; u += gridDim.x * WARPS) {
-    const int32_t p = uhead[u];
-    const uint32_t key = skey[p];
-    if (key == sentinel) continue;
-    const int q = (int)(key & (uint32_t)(pr.G - 1));
-    if (q == pr.rank) continue;
-    const int64_t lrow = (int64_t)(key >> pr.log2G);
-    const float4 *src = reinterpret_cast<const float4 *>(pr.tab[q] + lrow * rs + 2 * ld);
-    float4 *dst = reinterpret_cast<float4 *>(rc_w + (int64_t)p * ld);
-    float4 buf[4];
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-      if (lane + 32 * i < nvec) buf[i] = __ldcs(src + lane + 32 * i);
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-      if (lane + 32 * i < nvec) dst[lane + 32 * i] = buf[i];
-    for (int v = lane + 128; v < nvec; v += 32) dst[v] = __ldcs(src + v);
-    if (lane == 0) rc_lin[p] = pr.lin[q][lrow].z;
   }
 }
 
