@@ -72,6 +72,11 @@ __device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, u
                "r"(bytes)
                : "memory");
 }
+// L2 prefetch of a span the row loader will bulk-copy a few samples later (hides the DRAM latency of the
+// 2-stage row ring: metadata runs several samples ahead of the rows)
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src_gmem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -290,6 +295,7 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
           }
           m.row[sl] = rm;
           m.present[fl] = 1;
+
         }
         nv += __popc(okm);
       }
@@ -339,6 +345,20 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_full[st]);
+      // L2 prefetch of the NEXT sample's rows: its stage is still occupied, but its metadata is ready (the
+      // metadata ring runs ahead); one sample ahead keeps the prefetched footprint at ~100 KB per SM
+      if (it + 1 < n_mine && !(geo.dbg & 32)) {
+        RingCursor nx = mc;
+        nx.advance(1, MD);
+        mbar_wait(&bar_mfull[nx.slot], nx.parity());
+        SampleMeta m2 = sample_meta(nx.slot);
+        const int nv2 = m2.hdr[0];
+        for (int r = lane; r < nv2; r += 32) {
+          const RowMeta rm = m2.row[r];
+          if (rm.pos < 0) bulk_prefetch_l2(rsp.tab + (int64_t)rm.loc * rs, row_bytes);
+          else bulk_prefetch_l2(w_plane(rm.loc), row_bytes / 2);
+        }
+      }
     }
     return;
   }
