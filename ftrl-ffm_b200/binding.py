@@ -13,7 +13,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libftrl_b200.so")
+# FTRL_B200_LIB: load another build of the same library (A/B timing of two builds in one GPU session)
+LIB_PATH = os.environ.get("FTRL_B200_LIB") or os.path.join(HERE, "libftrl_b200.so")
 
 MODEL_TYPES = {"LR": 0, "FM": 1, "FFM": 2}
 MODE_BATCH, MODE_SEQUENTIAL = 0, 1

@@ -210,6 +210,6 @@ struct ftrl_handle {
   int tile = 1;     // FFM: TMA-staged per-sample kernel for batches of distinct-field samples
   bool tile_ok = false;
   int tile_ctas_per_sm = 1;
-  int tile_f_cap = 0, tile_stride = 0, tile_stages = 0, tile_consumers = 0, tile_ipt = 1, tile_meta = 4, tile_dbg = 0, tile_cache = 1;
+  int tile_f_cap = 0, tile_stride = 0, tile_stride1 = 0, tile_stages = 0, tile_consumers = 0, tile_ipt = 1, tile_meta = 4, tile_dbg = 0, tile_cache = 1, tile_inflight = 4;
   size_t tile_smem = 0;
 };

@@ -105,13 +105,15 @@ constexpr int TILE_META_WARPS = 2;   // warps prefetching sample metadata (CSR, 
 // + one row-loader warp and one row-storer warp (TMA bulk copies)
 __host__ __device__ constexpr int tile_threads(int consumers) { return consumers + 32 * (2 + TILE_META_WARPS); }
 constexpr int TILE_MAX_CONSUMERS = 512;
-constexpr int TILE_MAX_STAGE = 4;    // row stages
+constexpr int TILE_MAX_STAGE = 4;    // samples in flight in the row ring (power of two)
 constexpr int TILE_MAX_META = 8;     // metadata slots
 
 struct TileGeom {
   int f_cap;        // rows per stage (= n_fields: samples with distinct fields have at most that many)
-  int stride;       // floats between consecutive rows of a stage (2*ld + pad), conflict-free columns
-  int n_stage;      // row stages (each f_cap * stride floats)
+  int stride;       // floats a fused row (z and n planes) takes in the row ring: 2*ld + pad, conflict-free columns
+  int stride1;      // floats a staged row (w plane only) takes: ld + pad1, same residue as `stride` modulo 32 floats
+  int n_stage;      // the row ring holds n_stage * f_cap * stride floats
+  int inflight;     // samples that may share the ring (2..TILE_MAX_STAGE)
   int n_meta;       // metadata slots (> n_stage: metadata runs ahead of the row ring)
   int consumers;    // consumer threads (multiple of 32)
   int dbg;          // experiment switches (FTRL_B200_TILE_DBG): 1 skip w stores, 2 skip row/image stores, 4 local lin only
@@ -119,7 +121,7 @@ struct TileGeom {
 };
 
 struct RowMeta {   // one 16-byte record per row of a sample
-  int32_t fk;      // field * k
+  int32_t fk;      // field * k | (offset of the row inside its sample's span of the row ring, floats) << 16
   float x;         // value
   int32_t pos;     // -1: row finalised here, >= 0: sorted position for the staged gradient image
   int32_t loc;     // row locator (RowSpace): >= 0 local row, < 0: -1 - head position in the remote-row cache
@@ -127,7 +129,7 @@ struct RowMeta {   // one 16-byte record per row of a sample
 struct SampleMeta {
   RowMeta *row;     // [f_cap]
   float4 *lin;      // [f_cap] {z, n, w, -} of the linear coordinate, prefetched
-  int32_t *hdr;     // [0] n valid rows, [1] label
+  int32_t *hdr;     // [0] n valid rows, [1] label, [2] floats of the row ring the sample needs
   uint8_t *present; // [n_fields] 1 when some valid row of the sample carries that field
 };
 
@@ -167,6 +169,14 @@ __host__ inline int tile_stride(int ld, int k) {
     if (ok) return 2 * ld + pad;
   }
   return 2 * ld;
+}
+
+// span of a staged row (w plane only): >= ld floats, same residue as the fused-row span modulo 8 16-byte units,
+// so consecutive rows keep landing in distinct bank groups whatever the mix of fused and staged rows
+__host__ inline int tile_stride1(int ld, int stride) {
+  int s1 = ld;
+  while (((s1 / 4) % 8) != ((stride / 4) % 8)) s1 += 4;
+  return s1;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -210,15 +220,23 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
   constexpr int NL = 1, NSW = 1;
   const int role = tid < n_cons ? 0 : (tid < n_cons + 32 * NL ? 1 : (tid < n_cons + 32 * (NL + NSW) ? 3 : 2));
   const int ld = d.ld, k = d.k;
-  const int stride = geo.stride, f_cap = geo.f_cap, NS = geo.n_stage, MD = geo.n_meta;
+  const int stride = geo.stride, stride1 = geo.stride1, f_cap = geo.f_cap, NS = geo.n_stage, MD = geo.n_meta;
   const size_t stage_bytes = tile_stage_bytes(f_cap, stride);
+  // The row ring: NS * stage_bytes of shared memory handed out in sample-sized spans.  A fused row takes
+  // `stride` floats (z, n), a staged row `stride1` (w only), so batches with many duplicated rows keep 3-4
+  // samples in flight where all-fused samples keep 2.  Up to TILE_MAX_STAGE samples share the ring.
+  constexpr int NSLOT = TILE_MAX_STAGE;
+  const int ring_floats = (int)((size_t)NS * stage_bytes / sizeof(float));
+  float *ring = reinterpret_cast<float *>(smem_raw);
+  __shared__ int s_base[NSLOT], s_need[NSLOT];
   const size_t meta_bytes = tile_meta_bytes(f_cap);
   const int64_t rs = 3 * (int64_t)ld;
   const uint32_t row_bytes = (uint32_t)(2 * ld * sizeof(float));
   unsigned char *meta_base = smem_raw + (size_t)NS * stage_bytes;
   uint16_t *s_lut = reinterpret_cast<uint16_t *>(meta_base + (size_t)MD * meta_bytes);
 
-  auto stage_rows = [&](int st) -> float * { return reinterpret_cast<float *>(smem_raw + (size_t)st * stage_bytes); };
+  auto row_off = [](const RowMeta &rm) { return rm.fk >> 16; };
+  auto row_fk = [](const RowMeta &rm) { return rm.fk & 0xffff; };
   auto sample_meta = [&](int slot) {
     SampleMeta m;
     unsigned char *p = meta_base + (size_t)slot * meta_bytes;
@@ -233,7 +251,7 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
   };
 
   if (tid == 0) {
-    for (int st = 0; st < NS; st++) {
+    for (int st = 0; st < NSLOT; st++) {
       mbar_init(&bar_full[st], NL);
       mbar_init(&bar_done[st], n_cons_warps);
       mbar_init(&bar_free[st], NSW);
@@ -301,9 +319,29 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
       }
       nv = min(nv, f_cap);
       __syncwarp();
+      // offsets of the rows inside the sample's span (exclusive prefix sum of the row sizes)
+      int need = 0;
+      for (int base = 0; base < nv; base += 32) {
+        const int r = base + lane;
+        RowMeta rm;
+        int sz = 0;
+        if (r < nv) {
+          rm = m.row[r];
+          sz = rm.pos < 0 ? stride : stride1;
+        }
+        int inc = sz;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += t;
+        }
+        if (r < nv) m.row[r].fk = rm.fk | ((need + inc - sz) << 16);
+        need += __shfl_sync(0xffffffffu, inc, 31);
+      }
       if (lane == 0) {
         m.hdr[0] = nv;
         m.hdr[1] = b.label[s];
+        m.hdr[2] = need;
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_mfull[slot]);
@@ -318,17 +356,42 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
 
   if (role == 1) {
     // =========================== row loader warps ===========================
-    RingCursor sc, mc;
-    sc.init(0, NS);
+    RingCursor mc;
     mc.init(0, MD);
-    for (int it = 0; it < n_mine; it++, sc.advance(1, NS), mc.advance(1, MD)) {
-      const int st = sc.slot;
-      float *rows = stage_rows(st);
-      if (sc.round > 0) mbar_wait(&bar_free[st], sc.prev_parity());  // previous occupant stored
+    int head = 0;     // next free float of the ring
+    int tail_it = 0;  // oldest sample whose span has not been handed back by the storer
+    for (int it = 0; it < n_mine; it++, mc.advance(1, MD)) {
+      const int st = it & (NSLOT - 1);
       const int slot = mc.slot;
       mbar_wait(&bar_mfull[slot], mc.parity());
       SampleMeta m = sample_meta(slot);
       const int nv = m.hdr[0];
+      const int need = m.hdr[2];
+      // a span for this sample: contiguous, after `head` or wrapped to the start of the ring; wait (in order)
+      // for older samples to retire until the sample slot is free and the span overlaps no live span
+      while (it - tail_it >= geo.inflight) {
+        mbar_wait(&bar_free[tail_it & (NSLOT - 1)], (uint32_t)((tail_it >> 2) & 1));
+        tail_it++;
+      }
+      const int base = head + need <= ring_floats ? head : 0;
+      for (;;) {
+        bool clash = false;
+        for (int j = tail_it; j < it; j++) {
+          const int bj = s_base[j & (NSLOT - 1)], nj = s_need[j & (NSLOT - 1)];
+          clash = clash || (base < bj + nj && bj < base + need);
+        }
+        if (!clash) break;
+        mbar_wait(&bar_free[tail_it & (NSLOT - 1)], (uint32_t)((tail_it >> 2) & 1));
+        tail_it++;
+      }
+      head = base + need;
+      __syncwarp();
+      if (lane == 0) {
+        s_base[st] = base;
+        s_need[st] = need;
+      }
+      __syncwarp();
+      float *rows = ring + base;
       {
         // TMA bulk copies.  Fused rows bring z and n (they are updated here); staged rows bring only the w
         // plane their owner materialised, into the z-plane slot of the stage
@@ -339,15 +402,15 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
         __syncwarp();
         for (int r = lane; r < nv; r += 32) {
           const RowMeta rm = m.row[r];
-          if (rm.pos < 0) bulk_g2s(rows + (size_t)r * stride, rsp.tab + (int64_t)rm.loc * rs, row_bytes, &bar_full[st]);
-          else bulk_g2s(rows + (size_t)r * stride, w_plane(rm.loc), row_bytes / 2, &bar_full[st]);
+          if (rm.pos < 0) bulk_g2s(rows + row_off(rm), rsp.tab + (int64_t)rm.loc * rs, row_bytes, &bar_full[st]);
+          else bulk_g2s(rows + row_off(rm), w_plane(rm.loc), row_bytes / 2, &bar_full[st]);
         }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_full[st]);
       // L2 prefetch of the NEXT sample's rows: its stage is still occupied, but its metadata is ready (the
       // metadata ring runs ahead); one sample ahead keeps the prefetched footprint at ~100 KB per SM
-      if (it + 1 < n_mine && !(geo.dbg & 32)) {
+      if (it + 1 < n_mine && (geo.dbg & 32)) {  // off by default: with the variable-span ring the loads themselves run ahead
         RingCursor nx = mc;
         nx.advance(1, MD);
         mbar_wait(&bar_mfull[nx.slot], nx.parity());
@@ -367,20 +430,19 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
     // =========================== row storer warps ===========================
     // retire samples in order: wait for the consumers, bulk-store the rows / gradient images, then hand the
     // stage back to the loader and the metadata slot back to the metadata warps
-    RingCursor sc, mc;
-    sc.init(0, NS);
+    RingCursor mc;
     mc.init(0, MD);
-    for (int it = 0; it < n_mine; it++, sc.advance(1, NS), mc.advance(1, MD)) {
-      const int st = sc.slot;
+    for (int it = 0; it < n_mine; it++, mc.advance(1, MD)) {
+      const int st = it & (NSLOT - 1);
       const int slot = mc.slot;
-      float *rows = stage_rows(st);
       SampleMeta m = sample_meta(slot);
-      mbar_wait(&bar_done[st], sc.parity());
+      mbar_wait(&bar_done[st], (uint32_t)((it >> 2) & 1));
+      float *rows = ring + s_base[st];
       const int nv = m.hdr[0];
       for (int r = lane; r < nv && !(geo.dbg & 2); r += 32) {
         const RowMeta rm = m.row[r];
-        if (rm.pos < 0) bulk_s2g(rsp.tab + (int64_t)rm.loc * rs, rows + (size_t)r * stride, row_bytes);
-        else bulk_s2g(rsp.staging + (int64_t)rm.pos * ld, rows + (size_t)r * stride, (uint32_t)(ld * sizeof(float)));
+        if (rm.pos < 0) bulk_s2g(rsp.tab + (int64_t)rm.loc * rs, rows + row_off(rm), row_bytes);
+        else bulk_s2g(rsp.staging + (int64_t)rm.pos * ld, rows + row_off(rm), (uint32_t)(ld * sizeof(float)));
       }
       bulk_commit();
       bulk_wait_read_all();
@@ -399,17 +461,16 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
     const float4 bz = *bias;
     return weight_from<PRECISE>(bz.x, f_sqrt<PRECISE>(bz.y), h);
   }();
-  RingCursor sc, mc;
-  sc.init(0, NS);
+  RingCursor mc;
   mc.init(0, MD);
-  for (int it = 0; it < n_mine; it++, sc.advance(1, NS), mc.advance(1, MD)) {
-    const int st = sc.slot;
+  for (int it = 0; it < n_mine; it++, mc.advance(1, MD)) {
+    const int st = it & (NSLOT - 1);
     const int slot = mc.slot;
     const int64_t s = blockIdx.x + (int64_t)it * gridDim.x;
-    float *rows = stage_rows(st);
     SampleMeta m = sample_meta(slot);
     mbar_wait(&bar_mfull[slot], mc.parity());
-    mbar_wait(&bar_full[st], sc.parity());
+    mbar_wait(&bar_full[st], (uint32_t)((it >> 2) & 1));
+    float *rows = ring + s_base[st];
     const int nv = m.hdr[0];
     const uint32_t n_items = (uint32_t)nv * (uint32_t)(nv - 1) / 2u * dec.C;
 
@@ -429,8 +490,8 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
         const uint32_t e = s_lut[p];
         const int mi = e & 0xff, ni = e >> 8;
         const RowMeta rmm = m.row[mi], rmn = m.row[ni];
-        const int oA = mi * stride + rmn.fk + (int)c * 4;  // slice A = (row m, field n)
-        const int oB = ni * stride + rmm.fk + (int)c * 4;  // slice B = (row n, field m)
+        const int oA = row_off(rmm) + row_fk(rmn) + (int)c * 4;  // slice A = (row m, field n)
+        const int oB = row_off(rmn) + row_fk(rmm) + (int)c * 4;  // slice B = (row n, field m)
         const float xmn = rmm.x * rmn.x;
         if (CACHE) {
           offA[j] = oA;
@@ -445,11 +506,11 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
         float4 wA = *reinterpret_cast<const float4 *>(sa), wB = *reinterpret_cast<const float4 *>(sb);
         if (rmm.pos < 0) {
           wA = weight4<PRECISE>(wA, *reinterpret_cast<const float4 *>(sa + ld), h);
-          *reinterpret_cast<float4 *>(rsp.tab + (int64_t)rmm.loc * rs + 2 * ld + rmn.fk + c * 4) = wA;
+          *reinterpret_cast<float4 *>(rsp.tab + (int64_t)rmm.loc * rs + 2 * ld + row_fk(rmn) + c * 4) = wA;
         }
         if (rmn.pos < 0) {
           wB = weight4<PRECISE>(wB, *reinterpret_cast<const float4 *>(sb + ld), h);
-          *reinterpret_cast<float4 *>(rsp.tab + (int64_t)rmn.loc * rs + 2 * ld + rmm.fk + c * 4) = wB;
+          *reinterpret_cast<float4 *>(rsp.tab + (int64_t)rmn.loc * rs + 2 * ld + row_fk(rmm) + c * 4) = wB;
         }
         wAc[j] = wA;
         wBc[j] = wB;
@@ -498,8 +559,8 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
           const uint32_t e = s_lut[p];
           const int mi = e & 0xff, ni = e >> 8;
           const RowMeta rmm = m.row[mi], rmn = m.row[ni];
-          oA = mi * stride + rmn.fk + (int)c * 4;
-          oB = ni * stride + rmm.fk + (int)c * 4;
+          oA = row_off(rmm) + row_fk(rmn) + (int)c * 4;
+          oB = row_off(rmn) + row_fk(rmm) + (int)c * 4;
           xmn = rmm.x * rmn.x;
           cl = 4 | (rmm.pos < 0 ? 1 : 0) | (rmn.pos < 0 ? 2 : 0);
         }
@@ -548,7 +609,7 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
       for (int r = tid; r < nv; r += n_cons) {
         const RowMeta rm = m.row[r];
         if (rm.pos < 0) continue;
-        float4 *zp = reinterpret_cast<float4 *>(rows + (size_t)r * stride + rm.fk);
+        float4 *zp = reinterpret_cast<float4 *>(rows + row_off(rm) + row_fk(rm));
         for (int v = 0; v < (k >> 2); v++) zp[v] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     } else {
@@ -556,8 +617,8 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
         const RowMeta rm = m.row[r];
         if (rm.pos < 0) continue;
         for (int f = lane; f < d.n_fields; f += 32) {
-          if (m.present[f] && f * k != rm.fk) continue;
-          float4 *zp = reinterpret_cast<float4 *>(rows + (size_t)r * stride + f * k);
+          if (m.present[f] && f * k != row_fk(rm)) continue;
+          float4 *zp = reinterpret_cast<float4 *>(rows + row_off(rm) + f * k);
           for (int v = 0; v < (k >> 2); v++) zp[v] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }

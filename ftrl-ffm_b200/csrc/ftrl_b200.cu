@@ -351,6 +351,8 @@ static void run_ffm_batch(ftrl_handle *h, const Batch &b, float *logit_out) {
       TileGeom geo;
       geo.f_cap = h->tile_f_cap;
       geo.stride = h->tile_stride;
+      geo.stride1 = h->tile_stride1;
+      geo.inflight = h->tile_inflight;
       geo.n_stage = h->tile_stages;
       geo.n_meta = h->tile_meta;
       geo.consumers = h->tile_consumers;
@@ -805,6 +807,8 @@ static void train_device_sharded(ftrl_handle *h, const Batch &b, float *logit_ou
       TileGeom geo;
       geo.f_cap = h->tile_f_cap;
       geo.stride = h->tile_stride;
+      geo.stride1 = h->tile_stride1;
+      geo.inflight = h->tile_inflight;
       geo.n_stage = h->tile_stages;
       geo.n_meta = h->tile_meta;
       geo.consumers = h->tile_consumers;
@@ -986,6 +990,7 @@ int ftrl_create(const ftrl_config *cfg, ftrl_handle **out) {
         h->tile_ok = true;
         h->tile_f_cap = d.n_fields;
         h->tile_stride = stride;
+        h->tile_stride1 = tile_stride1(d.ld, stride);
         h->tile_stages = stages;
         h->tile_consumers = cons;
         h->tile_ipt = std::max(1, ipt);
@@ -998,6 +1003,7 @@ int ftrl_create(const ftrl_config *cfg, ftrl_handle **out) {
         TILE_ATTR(false, 1); TILE_ATTR(false, 2); TILE_ATTR(false, 3); TILE_ATTR(false, 4);
         TILE_ATTR(true, 1); TILE_ATTR(true, 2); TILE_ATTR(true, 3); TILE_ATTR(true, 4);
         h->tile_cache = env_int("FTRL_B200_TILE_CACHE", 1);
+        h->tile_inflight = std::max(2, std::min(TILE_MAX_STAGE, env_int("FTRL_B200_TILE_INFLIGHT", TILE_MAX_STAGE)));
 #undef TILE_ATTR
       }
     }
