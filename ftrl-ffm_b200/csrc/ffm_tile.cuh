@@ -104,7 +104,7 @@ struct RingCursor {
 constexpr int TILE_META_WARPS = 2;   // warps prefetching sample metadata (CSR, occurrence class, linear records)
 // + one row-loader warp and one row-storer warp (TMA bulk copies)
 __host__ __device__ constexpr int tile_threads(int consumers) { return consumers + 32 * (2 + TILE_META_WARPS); }
-constexpr int TILE_MAX_CONSUMERS = 512;
+constexpr int TILE_MAX_CONSUMERS = 768;
 constexpr int TILE_MAX_STAGE = 4;    // samples in flight in the row ring (power of two)
 constexpr int TILE_MAX_META = 8;     // metadata slots
 

@@ -973,6 +973,7 @@ int ftrl_create(const ftrl_config *cfg, ftrl_handle **out) {
       const int64_t items = (int64_t)d.n_fields * (d.n_fields - 1) / 2 * (d.k / 4);
       int cons = 64;
       while (cons < 512 && cons * 3 < items) cons *= 2;
+      if (cons == 512 && items > 2 * 512) cons = TILE_MAX_CONSUMERS;  // 24 consumer warps, 2 items per thread at cfg4
       cons = env_int("FTRL_B200_TILE_CONSUMERS", cons);
       const int ipt = (int)((items + cons - 1) / cons);
       const size_t lut = tile_lut_bytes(d.n_fields) + 4 * tile_meta_bytes(d.n_fields);  // + minimal meta ring
