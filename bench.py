@@ -89,6 +89,13 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def mark(self):
+        """lines before the mark (warm-up) are dropped when later ones exist"""
+        self.n_mark = len(self.lines)
+
+    def since_mark(self):
+        return len(self.lines) - getattr(self, "n_mark", 0)
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -100,7 +107,7 @@ class ClockSampler:
             pass
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in self.lines[getattr(self, "n_mark", 0):]:
             p = [x.strip() for x in ln.split(",")]
             if len(p) < 8:
                 continue
@@ -285,11 +292,14 @@ def main():
         U.append(u)
     launches_per_step = st["kernel_launches"]
     fused_rows = st["n_fused_rows"]
+    # the sampler starts before the warm-up (same load as the timed steps): nvidia-smi needs ~100 ms to deliver
+    # its first line and K steps can be shorter than that
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for i in range(args.warmup):
         step_dev(i)
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for i in range(args.steps):
@@ -297,11 +307,18 @@ def main():
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop()
+    missing = 0 if sampler.since_mark() else 1
     if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        t = torch.tensor([ms, float(missing)], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+        ms, missing = float(t[0].item()), int(t[1].item())
+    if missing:
+        # no nvidia-smi line fell inside the timed region on some rank: keep the same load running (untimed,
+        # the same number of steps on every rank -- the sharded step is collective) for about 0.4 s
+        for j in range(min(400, max(8, int(400.0 / max(ms / args.steps, 0.05))))):
+            step_dev(j)
+        barrier()
+    clocks = sampler.stop()
     ms_per_step = ms / args.steps
     value = world * B * args.steps / (ms / 1e3)
 
@@ -331,7 +348,7 @@ def main():
                 "traffic": traffic, "peak_source": peak_src,
                 "kernels": ("k_row_touch + k_row_materialise + k_ffm_tile + k_ffm_staged_rows + k_ffm_combine "
                             "(forward + FTRL update)" if world == 1 else
-                            "owner select/sort/k_owner_materialise + k_pull + k_ffm_tile + k_ffm_staged_rows + "
+                            "owner select/sort/k_owner_materialise (pushes w to the row caches) + k_ffm_tile + k_ffm_staged_rows + "
                             "k_ffm_combine + k_owner_apply (forward + FTRL update + row exchange)") if model == "FFM"
                 else "k_lrfm_sample + k_lrfm_rows + k_lrfm_combine",
                 "alg_bytes_per_step": bytes_alg, "kernel_ms_per_step": hot_ms,
