@@ -172,12 +172,26 @@ def cpu_baseline(wl, dist, n_samples, threads=None):
             secs += time.perf_counter() - t0
             passes += 1
         cores = 1
+    one = None
+    if kind == "reference" and cores > 1:
+        n1 = max(256, n_samples // 8)
+        sub = pkg.synth.slice_csr(data, 0, n1)
+        m1 = CpuModel("ref", model, fold, n_fields, k, fast_init=True)
+        m1.stage_csr(**sub)
+        m1.train_staged(n_threads=1)
+        s1, p1 = 0.0, 0
+        while s1 < 2.0 and p1 < 1000:
+            dt, _ = m1.train_staged(n_threads=1)
+            s1 += dt
+            p1 += 1
+        one = p1 * n1 / s1
+        m1.close()
     sample = (f"{passes} training passes over {n_samples} samples of the step-0 distribution, {model} F={n_fields} "
               f"k={k}, ids folded into {fold} rows, after one warm-up pass; reference train() from {cores} threads "
               "with the chunking of ftrl_offline.cpp:63-103 (constructor replaced by a zero fill, see "
               "oracle/ref_shim.cpp)")
     return {"value": passes * n_samples / secs, "unit": "samples/s", "cores": cores, "kind": kind, "sample": sample,
-            "seconds": secs}
+            "seconds": secs, "value_1_thread": one}
 
 
 def run_reference(args, rank, world):
@@ -345,7 +359,8 @@ def main():
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src,
+                "traffic": traffic, "peak_source": peak_src, "frac_of_nominal_8000": achieved / 8000.0,
+                "dram_gbs_from_traffic": (traffic / (hot_ms / 1e3) / 1e9) if traffic else None,
                 "kernels": ("k_row_touch + k_row_materialise + k_ffm_tile + k_ffm_staged_rows + k_ffm_combine "
                             "(forward + FTRL update)" if world == 1 else
                             "owner select/sort/k_owner_materialise (pushes w to the row caches) + k_ffm_tile + k_ffm_staged_rows + "

@@ -1,25 +1,26 @@
 // ffm_tile.cuh -- the FFM fast path for batches whose samples all have distinct fields
 // (Criteo-shaped data): "load rows -> compute in shared memory -> store rows".
 //
-//  k_ffm_tile        persistent CTAs, one producer warp + consumer warps, NSTAGE-deep ring.
-//                    producer : per sample, one cp.async.bulk (TMA bulk copy, 2*ld*4 bytes) per
-//                               feature row brings the row's z and n planes into shared memory,
-//                               completion on an mbarrier; after the consumers are done, one bulk
-//                               store per row writes either the updated (z',n') row back into the
-//                               table (row occurs once in the batch) or the row's per-occurrence
-//                               gradient image into the staging buffer at its sorted position.
-//                    consumers: pass 1 materialises w = W(n,z) for every slice the sample touches
-//                               (ffm.cpp:72-88), stores w, forms the logit (ffm.cpp:57-70) and
-//                               g = sigmoid(logit) - y; pass 2 applies the FTRL update in place in
-//                               shared memory (ffm.cpp:90-136 telescoped) or deposits
-//                               g_s w_partner x_m x_n.
-//  k_ffm_staged_rows one warp per chunk of <= 32 occurrences of one row: streams the staged
-//                    gradient images (coalesced 128-bit loads), accumulates sum g and sum g^2 in
-//                    registers, applies the closed form or parks a partial for k_ffm_combine.
+//  k_ffm_tile        persistent CTAs (one per SM), warp-specialised:
+//                    metadata warps : prefetch, several samples ahead, each sample's CSR row, the class of
+//                                     every occurrence (fused / sorted position), row locators, linear records
+//                    loader warp    : hands out sample-sized spans of the shared-memory row ring and issues
+//                                     one cp.async.bulk (TMA bulk copy, mbarrier expect_tx) per feature row:
+//                                     z and n planes of a fused row, the materialised w plane of a staged row
+//                    consumer warps : pass 1 w = W(n,z) for fused rows (ffm.cpp:72-88, stored as the stale
+//                                     w the reference keeps), logit (ffm.cpp:57-70), g = sigmoid(logit) - y;
+//                                     pass 2 FTRL update in place in shared memory (ffm.cpp:90-136
+//                                     telescoped) or the gradient image g_s w_partner x_m x_n
+//                    storer warp    : one bulk store per row: updated (z',n') back into the table, or the
+//                                     gradient image into the staging buffer at its sorted position
+//  k_row_touch / k_row_materialise   owner-side pre-pass: w of the staged rows, only the touched slices
+//  k_ffm_staged_rows streaming segmented reduction of the staged gradient images: work item = (chunk of
+//                    <= 32 occurrences of one row, 32 float4 vectors); closed-form update, a partial for
+//                    k_ffm_combine, or (sharded runs) the row's sum into its owner's inbox
 //
-// HBM traffic per touched coordinate: rows that occur once: 8 B read (z,n) + 12 B written
-// (z',n',w) = the algorithmic 20 B; other rows: 8 B read + 4 B (w) + 4 B (gradient image) per
-// occurrence, then 4 B per occurrence + 20 B per distinct coordinate in the reduce.
+// HBM traffic per touched coordinate: rows that occur once: 8 B read (z,n) + 12 B written (z',n',w) = the
+// algorithmic 20 B; other rows: 12 B once (materialise) + 4 B (w) + 4 B (gradient image) per occurrence,
+// then 4 B per occurrence + 16 B per distinct coordinate in the reduce.
 #pragma once
 #include "common.cuh"
 #include "ffm.cuh"

@@ -123,7 +123,7 @@ def write_text(b: dict, path: str, fmt: str = "libffm") -> None:
         for r in range(len(rp) - 1):
             toks = [str(int(b["label"][r]))]
             for t in range(int(rp[r]), int(rp[r + 1])):
-                v = repr(float(b["val"][t]))
+                v = str(np.float32(b["val"][t]))  # shortest text that round-trips in fp32 ("1.0", "0.5489")
                 if fmt == "libffm":
                     toks.append(f"{int(b['field'][t])}:{int(b['feat'][t])}:{v}")
                 else:
