@@ -134,6 +134,12 @@ def make_batches(wl, dist, batch, n_distinct, rank):
 CPU_BASELINE_SECONDS = 10.0
 
 
+def workload_name(wl, model, n_fields, n_feats, k, B):
+    """config.workload -- identical on the GPU arm and on the `--impl reference` arm"""
+    tag = " (BASELINE.json configs[3])" if wl == "cfg4" else ""
+    return f"{wl}: {model} n_fields={n_fields} n_feats={n_feats} k={k} batch={B}/GPU{tag}"
+
+
 def alg_bytes(model, F, k, U, nnz, B):
     """20 B per touched coordinate (read z,n; write z,n,w) + CSR bytes"""
     lat = U * (F - 1) * k if model == "FFM" else U * k if model == "FM" else 0
@@ -233,8 +239,9 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "FTRL-FFM train samples/sec", "value": value, "unit": "samples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {model} n_fields={n_fields} n_feats={n_feats} k={k}",
-                   "dist": args.dist, "samples_per_step": n},
+        "config": {"workload": workload_name(args.workload, model, n_fields, n_feats, k, b0),
+                   "ids": f"{args.dist}" + (" s=1.2" if args.dist == "zipf" else ""),
+                   "samples_per_step": n, "note": "CPU arm: each step is a bounded sample of the minibatch"},
         "cpu_baseline": {"value": value, "unit": "samples/s", "cores": used, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -458,9 +465,7 @@ def main():
             "metric": "FTRL-FFM train samples/sec", "value": value, "unit": "samples/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {model} n_fields={n_fields} n_feats={n_feats} k={k} "
-                                   f"batch={B}/GPU (BASELINE.json configs[3])" if args.workload == "cfg4" else
-                       f"{args.workload}: {model} n_fields={n_fields} n_feats={n_feats} k={k} batch={B}/GPU",
+            "config": {"workload": workload_name(args.workload, model, n_fields, n_feats, k, B),
                        "ids": f"{args.dist}" + (" s=1.2" if args.dist == "zipf" else ""),
                        "state": "randomized live z/n (ftrl_randomize_state)", "mode": "minibatch",
                        "l2": "inputs larger than L2 (rows touched per step >> 126 MB), no explicit flush",
