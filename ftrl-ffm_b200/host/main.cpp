@@ -175,9 +175,14 @@ class Trainer {
 };
 
 // Reader::load_from_file (src/data/reader.cpp:50-91)
-void load_file(const std::string &path, bool libffm, int n_threads, host::Csr &out) {
+void load_file(const std::string &path, bool libffm, int n_threads, bool csr_cache, host::Csr &out) {
   printf("Loading data from file: %s\n", path.c_str());
   const auto t0 = clk::now();
+  if (csr_cache && host::load_csr_cache(path, libffm, out)) {
+    printf("Total number of samples loaded: %zu\n", out.rows());
+    printf("parsing data time: %.4lfs (binary image %s.csr)\n", since(t0), path.c_str());
+    return;
+  }
   std::vector<char> buf;
   if (!host::read_file(path, buf)) {
     fprintf(stderr, "fail to open %s\n", path.c_str());
@@ -186,6 +191,7 @@ void load_file(const std::string &path, bool libffm, int n_threads, host::Csr &o
   host::parse_buffer(buf.data(), buf.size(), libffm, n_threads, out);
   printf("Total number of samples loaded: %zu\n", out.rows());
   printf("parsing data time: %.4lfs\n", since(t0));
+  if (csr_cache && !host::save_csr_cache(path, libffm, out)) fprintf(stderr, "could not write %s.csr\n", path.c_str());
 }
 
 // FtrlOffline::train / evaluate / one_epoch (src/task/ftrl_offline.cpp:44-103)
@@ -193,8 +199,8 @@ void run_offline(const host::Options &o) {
   Trainer tr(o);
   const bool libffm = o.file_type == "libffm";
   host::Csr train, eval;
-  load_file(o.train_path, libffm, o.thread_num, train);
-  if (!o.eval_path.empty()) load_file(o.eval_path, libffm, o.thread_num, eval);
+  load_file(o.train_path, libffm, o.thread_num, o.csr_cache, train);
+  if (!o.eval_path.empty()) load_file(o.eval_path, libffm, o.thread_num, o.csr_cache, eval);
   std::mt19937 gen(o.seed ? (uint32_t)o.seed : std::random_device{}());
   std::vector<int32_t> order(train.rows());
   for (int ep = 1; ep <= o.epoch; ep++) {
@@ -265,13 +271,26 @@ void run_online(const host::Options &o) {
   Trainer tr(o);
   const bool libffm = o.file_type == "libffm";
   if (o.cmd) return;  // `// todo: online learning` in the reference (ftrl_online.cpp:55-57)
+  // --csr_cache: the files are parsed (or their binary images read) once and every epoch walks them in file
+  // order from memory; otherwise each epoch streams and parses the text again like the reference
+  host::Csr train, eval;
+  if (o.csr_cache) {
+    load_file(o.train_path, libffm, o.thread_num, true, train);
+    if (!o.eval_path.empty()) load_file(o.eval_path, libffm, o.thread_num, true, eval);
+  }
+  auto one_pass = [&](const host::Csr &mem, const std::string &path, bool is_train) {
+    if (!o.csr_cache) return stream_file(tr, path, libffm, o.thread_num, is_train);
+    tr.begin_epoch(mem.rows() / std::max<long>(1, o.batch_size) + 1);
+    tr.run_block(mem, nullptr, mem.rows(), is_train);
+    return tr.take_loss();
+  };
   for (int ep = 1; ep <= o.epoch; ep++) {
     const auto t0 = clk::now();
-    const double loss = stream_file(tr, o.train_path, libffm, o.thread_num, true);
+    const double loss = one_pass(train, o.train_path, true);
     printf("epoch %d train time: %.4lfs, train loss: %.4lf\n", ep, since(t0), loss);
     if (!o.eval_path.empty()) {
       const auto t1 = clk::now();
-      const double el = stream_file(tr, o.eval_path, libffm, o.thread_num, false);
+      const double el = one_pass(eval, o.eval_path, false);
       printf("epoch %d eval time: %.4lfs, eval loss: %.4lf\n", ep, since(t1), el);
     }
   }

@@ -9,6 +9,8 @@
 // Whole-file loading splits the byte range across n_threads at line boundaries like
 // Reader::get_data_partition (src/data/reader.cpp:22-48) and keeps file order.
 #pragma once
+#include <sys/stat.h>
+
 #include <charconv>
 #include <cstdint>
 #include <cstdio>
@@ -236,6 +238,75 @@ inline bool read_file(const std::string &path, std::vector<char> &buf) {
   const size_t got = n ? fread(buf.data(), 1, (size_t)n, f) : 0;
   fclose(f);
   return got == (size_t)n;
+}
+
+// ---- binary CSR image of a parsed text file (at GPU speed the text front-end is the
+// bottleneck; parse once, reuse while the text is unchanged).  `<text>.csr` = header + raw arrays; the header
+// carries the size and mtime of the text file it was made from and the format it was parsed as.
+struct CsrCacheHeader {
+  char magic[8];  // "FTRLCSR1"
+  int64_t src_size, src_mtime_ns;
+  int64_t rows, nnz;
+  int32_t libffm, pad;
+};
+
+inline bool file_fingerprint(const std::string &path, int64_t &size, int64_t &mtime_ns) {
+  struct stat st;
+  if (stat(path.c_str(), &st) != 0) return false;
+  size = (int64_t)st.st_size;
+  mtime_ns = (int64_t)st.st_mtim.tv_sec * 1000000000ll + st.st_mtim.tv_nsec;
+  return true;
+}
+
+inline bool save_csr_cache(const std::string &text_path, bool libffm, const Csr &c) {
+  CsrCacheHeader h{};
+  memcpy(h.magic, "FTRLCSR1", 8);
+  if (!file_fingerprint(text_path, h.src_size, h.src_mtime_ns)) return false;
+  h.rows = (int64_t)c.rows();
+  h.nnz = (int64_t)c.feat.size();
+  h.libffm = libffm ? 1 : 0;
+  const std::string tmp = text_path + ".csr.tmp", dst = text_path + ".csr";
+  FILE *f = fopen(tmp.c_str(), "wb");
+  if (!f) return false;
+  bool ok = fwrite(&h, sizeof(h), 1, f) == 1;
+  ok = ok && fwrite(c.row_ptr.data(), sizeof(int64_t), c.row_ptr.size(), f) == c.row_ptr.size();
+  ok = ok && fwrite(c.label.data(), sizeof(int32_t), c.label.size(), f) == c.label.size();
+  ok = ok && fwrite(c.field.data(), sizeof(int32_t), c.field.size(), f) == c.field.size();
+  ok = ok && fwrite(c.feat.data(), sizeof(int32_t), c.feat.size(), f) == c.feat.size();
+  ok = ok && fwrite(c.val.data(), sizeof(float), c.val.size(), f) == c.val.size();
+  ok = (fclose(f) == 0) && ok;
+  if (!ok || rename(tmp.c_str(), dst.c_str()) != 0) {
+    remove(tmp.c_str());
+    return false;
+  }
+  return true;
+}
+
+// false when there is no image, it belongs to another version of the text, or it is truncated
+inline bool load_csr_cache(const std::string &text_path, bool libffm, Csr &c) {
+  int64_t size = 0, mtime = 0;
+  if (!file_fingerprint(text_path, size, mtime)) return false;
+  FILE *f = fopen((text_path + ".csr").c_str(), "rb");
+  if (!f) return false;
+  CsrCacheHeader h{};
+  bool ok = fread(&h, sizeof(h), 1, f) == 1 && memcmp(h.magic, "FTRLCSR1", 8) == 0 && h.src_size == size &&
+            h.src_mtime_ns == mtime && h.libffm == (libffm ? 1 : 0) && h.rows >= 0 && h.nnz >= 0;
+  if (ok) {
+    c.row_ptr.resize((size_t)h.rows + 1);
+    c.label.resize((size_t)h.rows);
+    c.field.resize((size_t)h.nnz);
+    c.feat.resize((size_t)h.nnz);
+    c.val.resize((size_t)h.nnz);
+    ok = fread(c.row_ptr.data(), sizeof(int64_t), c.row_ptr.size(), f) == c.row_ptr.size();
+    ok = ok && fread(c.label.data(), sizeof(int32_t), c.label.size(), f) == c.label.size();
+    ok = ok && fread(c.field.data(), sizeof(int32_t), c.field.size(), f) == c.field.size();
+    ok = ok && fread(c.feat.data(), sizeof(int32_t), c.feat.size(), f) == c.feat.size();
+    ok = ok && fread(c.val.data(), sizeof(float), c.val.size(), f) == c.val.size();
+    ok = ok && c.row_ptr.front() == 0 && c.row_ptr.back() == h.nnz;
+  }
+  fclose(f);
+  if (!ok) c.clear();
+  return ok;
 }
 
 }  // namespace host

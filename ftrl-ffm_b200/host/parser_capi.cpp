@@ -15,6 +15,20 @@ int64_t host_parse_text(const char *buf, int64_t len, int libffm, int n_threads)
   host::parse_buffer(buf, (size_t)len, libffm != 0, n_threads, g_csr);
   return (int64_t)g_csr.rows();
 }
+// whole file, optionally through the binary CSR image next to it; *from_cache tells which path was taken
+int64_t host_load_file(const char *path, int libffm, int n_threads, int use_cache, int *from_cache) {
+  g_csr.clear();
+  if (from_cache) *from_cache = 0;
+  if (use_cache && host::load_csr_cache(path, libffm != 0, g_csr)) {
+    if (from_cache) *from_cache = 1;
+    return (int64_t)g_csr.rows();
+  }
+  std::vector<char> buf;
+  if (!host::read_file(path, buf)) return -1;
+  host::parse_buffer(buf.data(), buf.size(), libffm != 0, n_threads, g_csr);
+  if (use_cache) host::save_csr_cache(path, libffm != 0, g_csr);
+  return (int64_t)g_csr.rows();
+}
 int64_t host_parse_nnz() { return (int64_t)g_csr.feat.size(); }
 void host_parse_fetch(int64_t *row_ptr, int32_t *field, int32_t *feat, float *val, int32_t *label) {
   memcpy(row_ptr, g_csr.row_ptr.data(), sizeof(int64_t) * g_csr.row_ptr.size());

@@ -46,6 +46,21 @@ def test_main_sequential_reproduces_reference_epoch_lines(mt, libffm):
         assert re.search(r"epoch 1 train time: [0-9.]+s, train loss: 0\.69", out)
 
 
+def test_main_csr_cache_gives_the_same_epoch_lines():
+    """--csr_cache true (additive flag): epochs run from the parsed / cached CSR in file order and print the
+    same losses as the streaming text path; the second run is served from <file>.csr"""
+    with tempfile.TemporaryDirectory() as tmp:
+        g, path = cfg1_text(tmp, True)
+        common = ["--train_data", path, "--eval_data", path, "--model_type", "FFM", "--n_epochs", 2, "--batch_size", 1]
+        ref = run_main(*common)
+        first = run_main(*common, "--csr_cache", "true")
+        assert os.path.exists(path + ".csr") and "binary image" not in first
+        second = run_main(*common, "--csr_cache", "true")
+        assert "binary image" in second
+        losses = lambda out: re.findall(r"(train|eval) loss: ([0-9.]+)", out)
+        assert losses(ref) == losses(first) == losses(second) and len(losses(ref)) == 4
+
+
 def test_main_offline_minibatch_and_model_path():
     with tempfile.TemporaryDirectory() as tmp:
         g, path = cfg1_text(tmp, True)

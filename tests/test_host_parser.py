@@ -116,3 +116,45 @@ def test_against_reference_parser_line_by_line():
             np.testing.assert_array_equal(got["field"][a:e], fi[:n])
             np.testing.assert_array_equal(got["feat"][a:e], fe[:n])
             np.testing.assert_array_equal(got["val"][a:e], va[:n])
+
+
+def test_csr_cache_round_trip_and_invalidation(tmp_path):
+    """--csr_cache: the binary image next to a data file reproduces the parsed CSR exactly and is ignored once
+    the text changes (size / mtime fingerprint) or is asked for in the other format"""
+    import os
+    lib = parser_lib()
+    lib.host_load_file.restype = C.c_int64
+    lib.host_load_file.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
+    rng = np.random.default_rng(3)
+    b = pkg.synth.random_csr(rng, 700, 500, 7, max_nnz=7, oob_frac=0.0)
+    path = str(tmp_path / "d.ffm")
+    pkg.synth.write_text(b, path, "libffm")
+
+    def load(use_cache, libffm=1):
+        hit = C.c_int(-1)
+        n = lib.host_load_file(path.encode(), libffm, 3, use_cache, C.byref(hit))
+        nnz = lib.host_parse_nnz()
+        rp = np.zeros(n + 1, np.int64)
+        fi, fe, va, la = np.zeros(nnz, np.int32), np.zeros(nnz, np.int32), np.zeros(nnz, np.float32), np.zeros(n, np.int32)
+        lib.host_parse_fetch(*(a.ctypes.data_as(C.c_void_p) for a in (rp, fi, fe, va, la)))
+        return hit.value, {"row_ptr": rp, "field": fi, "feat": fe, "val": va, "label": la}
+
+    hit0, d0 = load(0)
+    assert hit0 == 0 and not os.path.exists(path + ".csr")
+    hit1, d1 = load(1)            # parses and writes the image
+    assert hit1 == 0 and os.path.exists(path + ".csr")
+    hit2, d2 = load(1)            # served from the image
+    assert hit2 == 1
+    for k in d0:
+        np.testing.assert_array_equal(d0[k], d1[k])
+        np.testing.assert_array_equal(d0[k], d2[k])
+    with open(path, "a") as f:    # the text changes: the image is stale
+        f.write("1 0:1:1.0\n")
+    hit3, d3 = load(1)
+    assert hit3 == 0 and len(d3["label"]) == len(d0["label"]) + 1
+    hit4, _ = load(1)
+    assert hit4 == 1
+    with open(path + ".csr", "r+b") as f:   # truncated image: ignored, rebuilt
+        f.truncate(100)
+    hit5, d5 = load(1)
+    assert hit5 == 0 and len(d5["label"]) == len(d3["label"])
