@@ -417,12 +417,72 @@ k_ffm_combine(Dims d, Hyper h, int32_t nnz, float *__restrict__ tab, float4 *__r
     }
     __syncthreads();
     const int n_list = s_n;
-    for (int li = 0; li < n_list; li++) {
-      // the order of s_list is arbitrary, but every row is handled exactly once and rows are independent
+    // (the order of s_list is arbitrary, but every row is handled exactly once and rows are independent)
+    // Rows of up to WARPS chunks: one warp per row, chunks added in order -- the same order of additions as the
+    // block-cooperative path below, which gives every warp one chunk of such a row.
+    for (int li = wib; li < n_list; li += WARPS) {
       const int c0 = s_list[li];
       const ChunkInfo ci = chunk_head_info(c0, nnz, sentinel, ch, chunk_pos, skey, scan);
-      int J = 1;  // number of chunks of this row
-      while (c0 + J < n_chunks && skey[chunk_pos[c0 + J]] == ci.key) J++;
+      int J = 1;
+      while (J <= WARPS && c0 + J < n_chunks && skey[chunk_pos[c0 + J]] == ci.key) J++;
+      if (J > WARPS) continue;
+      const int32_t dst = ex.on ? ex.dst_at[ci.p0] : -2;
+      const int64_t lrow = (int64_t)(ci.key >> ex.log2G);
+      float *row = tab + lrow * rs;
+      float *o = dst >= 0 ? ex.inbox[ci.key & ex.Gm1] + (int64_t)dst * 2 * ld : nullptr;
+      const float4 *p0 = reinterpret_cast<const float4 *>(part + (int64_t)ci.slot * 2 * ld);
+      for (int v = lane; v < nvec; v += 32) {
+        float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+        for (int j = 0; j < J; j++) {
+          const float4 t0 = __ldcs(p0 + (int64_t)j * 2 * nvec + v), t1 = __ldcs(p0 + (int64_t)j * 2 * nvec + nvec + v);
+          s0.x += t0.x; s0.y += t0.y; s0.z += t0.z; s0.w += t0.w;
+          s1.x += t1.x; s1.y += t1.y; s1.z += t1.z; s1.w += t1.w;
+        }
+        const bool any = s0.x != 0.f || s0.y != 0.f || s0.z != 0.f || s0.w != 0.f || s1.x != 0.f || s1.y != 0.f ||
+                         s1.z != 0.f || s1.w != 0.f;
+        if (o) {
+          reinterpret_cast<float4 *>(o)[v] = s0;
+          reinterpret_cast<float4 *>(o + ld)[v] = s1;
+        } else if (any) {
+          float4 z = reinterpret_cast<float4 *>(row)[v], n = reinterpret_cast<float4 *>(row + ld)[v];
+          const float4 w = reinterpret_cast<float4 *>(row + 2 * ld)[v];
+          ftrl_apply<PRECISE>(z.x, n.x, w.x, s0.x, s1.x, h);
+          ftrl_apply<PRECISE>(z.y, n.y, w.y, s0.y, s1.y, h);
+          ftrl_apply<PRECISE>(z.z, n.z, w.z, s0.z, s1.z, h);
+          ftrl_apply<PRECISE>(z.w, n.w, w.w, s0.w, s1.w, h);
+          reinterpret_cast<float4 *>(row)[v] = z;
+          reinterpret_cast<float4 *>(row + ld)[v] = n;
+        }
+      }
+      float sg = 0.f, sg2 = 0.f;
+      for (int j = lane; j < J; j += 32) {
+        const float2 t = part_lin[ci.slot + j];
+        sg += t.x; sg2 += t.y;
+      }
+      sg = warp_sum(sg);
+      sg2 = warp_sum(sg2);
+      if (lane == 0) {
+        if (dst >= 0) {
+          ex.inbox_lin[ci.key & ex.Gm1][dst] = make_float2(sg, sg2);
+        } else {
+          float4 e = lin[lrow];
+          ftrl_apply<PRECISE>(e.x, e.y, e.z, sg, sg2, h);
+          lin[lrow] = e;
+        }
+      }
+    }
+    // longer rows: the whole block per row, chunks split over the warps
+    for (int li = 0; li < n_list; li++) {
+      const int c0 = s_list[li];
+      const ChunkInfo ci = chunk_head_info(c0, nnz, sentinel, ch, chunk_pos, skey, scan);
+      // number of chunks of this row: keys are sorted, binary search for the first chunk of the next row
+      int lo = c0 + 1, hi = n_chunks;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (skey[chunk_pos[mid]] == ci.key) lo = mid + 1; else hi = mid;
+      }
+      const int J = lo - c0;
+      if (J <= WARPS) continue;
       const int32_t dst = ex.on ? ex.dst_at[ci.p0] : -2;  // sharded: >= 0 -> the sum goes to the owner's inbox
       const int64_t lrow = (int64_t)(ci.key >> ex.log2G);
       float *row = tab + lrow * rs;

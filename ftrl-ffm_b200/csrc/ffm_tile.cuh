@@ -211,7 +211,7 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint64_t bar_full[TILE_MAX_STAGE], bar_done[TILE_MAX_STAGE], bar_free[TILE_MAX_STAGE];
   __shared__ uint64_t bar_mfull[TILE_MAX_META], bar_mfree[TILE_MAX_META];
-  __shared__ float s_red[40];
+  __shared__ float s_red[2][32];  // per-warp partial logits, double-buffered by sample parity
 
   const int tid = threadIdx.x;
   const int n_cons = geo.consumers;
@@ -526,22 +526,19 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
       acc = fmaf(w, rm.x, acc);
     }
     // consumer-wide sum
+    // one barrier per sample: every warp adds the per-warp partials itself (same values, same order -> the
+    // same logit in every warp).  The buffer of sample `it` is next written for sample it + 2, i.e. by a warp
+    // that has passed the barrier of sample it + 1, which every warp reaches only after this read.
+    float *red = s_red[it & 1];
     acc = warp_sum(acc);
-    if (lane == 0) s_red[tid >> 5] = acc;
+    if (lane == 0) red[tid >> 5] = acc;
     named_bar_sync(1, n_cons);
-    if (tid < 32) {
-      float t = lane < n_cons_warps ? s_red[lane] : 0.f;
-      t = warp_sum(t);
-      if (lane == 0) {
-        const float logit = t + bias_w;
-        const float g = sigmoid_f(logit) - (float)m.hdr[1];
-        s_red[32] = g;
-        g_out[s] = g;
-        logit_out[s] = logit;
-      }
+    const float logit = warp_sum(lane < n_cons_warps ? red[lane] : 0.f) + bias_w;
+    const float g = sigmoid_f(logit) - (float)m.hdr[1];
+    if (tid == 0) {
+      g_out[s] = g;
+      logit_out[s] = logit;
     }
-    named_bar_sync(1, n_cons);
-    const float g = s_red[32];
 
     // ---- pass 2: FTRL update in place (fused rows) or gradient image into the z plane (staged rows);
     //      every (row, field) slice is read and written by exactly one item (fields are distinct) ----
