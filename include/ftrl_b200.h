@@ -196,9 +196,17 @@ int ftrl_last_batch_stats(ftrl_handle *h, ftrl_batch_stats *out);
 int ftrl_randomize_state(ftrl_handle *h, uint64_t seed, float z_scale, float n_lo, float n_hi);
 
 /* ---- multi-GPU (feature-sharded tables, peer memory over NVLink) ----------------- */
-/* Opaque, fixed-size descriptor of this rank's device tables that peers can map
- * (cudaIpcMemHandle-based).  Exchange the blobs out of band (e.g. an all-gather over
- * torch.distributed / MPI), then hand all world_size blobs to ftrl_attach_peers. */
+/* Replaces the shared-memory Hogwild workers of src/task/ftrl_offline.cpp:63-103 across GPUs: the samples of a
+ * global minibatch are split over the ranks, rows live on rank feat % world_size (config.rank / world_size,
+ * FFM with max_batch_rows / max_batch_nnz fixed at ftrl_create).  After ftrl_attach_peers every
+ * ftrl_train_batch(_device) call is COLLECTIVE: all ranks call it once per step with their share of the
+ * minibatch; the result equals one GPU training on the concatenated minibatch up to fp32 re-association of
+ * the per-rank partial sums (deterministic for a given world_size).  A rank that stops calling makes the
+ * others fail with FTRL_ERR_STATE after FTRL_B200_BARRIER_TIMEOUT_S (default 20 s) instead of hanging.
+ *
+ * ftrl_export_peer_blob: opaque, fixed-size descriptor of this rank's device buffers that peers can map
+ * (cudaIpcMemHandle-based).  Exchange the blobs out of band (e.g. an all-gather over torch.distributed /
+ * MPI), then hand all world_size blobs, in rank order, to ftrl_attach_peers. */
 #define FTRL_PEER_BLOB_BYTES 1024
 int ftrl_export_peer_blob(ftrl_handle *h, void *blob /* FTRL_PEER_BLOB_BYTES */);
 int ftrl_attach_peers(ftrl_handle *h, const void *blobs /* world_size * FTRL_PEER_BLOB_BYTES */);
