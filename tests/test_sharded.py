@@ -99,3 +99,42 @@ def test_shard_count_invariance_on_one_gpu(world):
         assert_state_close(sharded.get_state(), single.get_state(), rtol=2e-5, atol=2e-6, atol_z=2e-4,
                            name=f"G={world} step {step}")
     sharded.close()
+
+
+def _ragged(b, rng, nf, drop=0.3, oob=0.02):
+    """criteo-shaped batch -> samples with a random SUBSET of the fields (still distinct), a few out-of-range ids"""
+    keep = rng.random(len(b["feat"])) >= drop
+    rows = np.repeat(np.arange(len(b["label"])), np.diff(b["row_ptr"]))
+    cnt = np.bincount(rows[keep], minlength=len(b["label"]))
+    feat = b["feat"][keep].copy()
+    bad = rng.random(len(feat)) < oob
+    feat[bad] = nf + 7            # dropped by the validity mask (ffm.cpp:30-36)
+    return {"row_ptr": np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64), "field": b["field"][keep].copy(),
+            "feat": feat, "val": b["val"][keep].copy(), "label": b["label"].copy()}
+
+
+@pytest.mark.gpu
+def test_sharded_ragged_samples_and_field_masks():
+    """samples that carry different subsets of the fields on different ranks: the owner must materialise w for the
+    UNION of the slices the ranks touch, and only for those (cold slices keep their initial w)"""
+    rng = np.random.default_rng(11)
+    world, nf, nfl, k, B = 2, 600, 9, 4, 256
+    kw = dict(model_type="FFM", n_feats=nf, n_fields=nfl, n_factors=k)
+    single = pkg.FtrlModel(**kw)
+    sharded = pkg.LogicalShards(world, max_batch_rows=B, max_batch_nnz=B * nfl, **kw)
+    st = pkg.synth.random_state(rng, nf, nfl * k)
+    single.set_state(st)
+    sharded.set_state(st)
+    for step in range(3):
+        parts = [_ragged(pkg.synth.criteo_batch(B, nfl, nf, seed=50 * step + r, dist="zipf"), rng, nf)
+                 for r in range(world)]
+        off = np.cumsum([0] + [len(p["feat"]) for p in parts])
+        glob = {"row_ptr": np.concatenate([[0]] + [p["row_ptr"][1:] + off[i] for i, p in enumerate(parts)]),
+                "field": np.concatenate([p["field"] for p in parts]), "feat": np.concatenate([p["feat"] for p in parts]),
+                "val": np.concatenate([p["val"] for p in parts]), "label": np.concatenate([p["label"] for p in parts])}
+        lg1, loss1 = single.train(**glob)
+        outs = sharded.train(parts)
+        assert_close(np.concatenate([o[0] for o in outs]), lg1, 1e-5, 2e-6, f"logits step {step}")
+        assert_state_close(sharded.get_state(), single.get_state(), rtol=2e-5, atol=2e-6, atol_z=2e-4,
+                           name=f"ragged step {step}")
+    sharded.close()
