@@ -138,3 +138,30 @@ def test_sharded_ragged_samples_and_field_masks():
         assert_state_close(sharded.get_state(), single.get_state(), rtol=2e-5, atol=2e-6, atol_z=2e-4,
                            name=f"ragged step {step}")
     sharded.close()
+
+
+@pytest.mark.gpu
+def test_sharded_rank_with_an_empty_share():
+    """the last step of an epoch may leave some ranks without samples: the collective step must still complete
+    and equal one GPU training on the samples that exist"""
+    rng = np.random.default_rng(12)
+    world, nf, nfl, k, B = 2, 500, 7, 4, 128
+    kw = dict(model_type="FFM", n_feats=nf, n_fields=nfl, n_factors=k)
+    single = pkg.FtrlModel(**kw)
+    sharded = pkg.LogicalShards(world, max_batch_rows=B, max_batch_nnz=B * nfl, **kw)
+    st = pkg.synth.random_state(rng, nf, nfl * k)
+    single.set_state(st)
+    sharded.set_state(st)
+    empty = {"row_ptr": np.zeros(1, np.int64), "field": np.zeros(0, np.int32), "feat": np.zeros(0, np.int32),
+             "val": np.zeros(0, np.float32), "label": np.zeros(0, np.int32)}
+    for step in range(2):
+        full = pkg.synth.criteo_batch(B, nfl, nf, seed=70 + step, dist="zipf")
+        parts = [full, empty] if step == 0 else [empty, full]
+        lg1, loss1 = single.train(**full)
+        outs = sharded.train(parts)
+        lg = outs[0][0] if step == 0 else outs[1][0]
+        assert_close(lg, lg1, 1e-5, 2e-6, f"logits step {step}")
+        assert abs(sum(o[1] for o in outs) - loss1) <= 1e-6 * max(1.0, abs(loss1))
+        assert_state_close(sharded.get_state(), single.get_state(), rtol=2e-5, atol=2e-6, atol_z=2e-4,
+                           name=f"empty share step {step}")
+    sharded.close()
