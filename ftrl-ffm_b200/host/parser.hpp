@@ -134,8 +134,30 @@ inline void parse_line(const char *b, const char *e, bool libffm, Csr &out) {
       float v;
       long iv = 0;
       const char *r = q;
-      if (fast_uint(r, e, iv) && iv < (1 << 24) && (r == e || *r == ' ')) {
-        v = (float)iv;  // "1", "37": exact
+      bool have = false;
+      if (fast_uint(r, e, iv) && iv < (1 << 24)) {
+        if (r == e || *r == ' ') {
+          v = (float)iv;  // "1", "37": exact
+          have = true;
+        } else if (*r == '.') {
+          // "0.5489": mantissa < 2^24 and 10^digits <= 10^10 are exact in fp32, so ONE correctly rounded
+          // division gives the correctly rounded value (Clinger's fast path) -- the same float stof returns
+          static const float kPow10[11] = {1.f, 1e1f, 1e2f, 1e3f, 1e4f, 1e5f, 1e6f, 1e7f, 1e8f, 1e9f, 1e10f};
+          const char *f = r + 1;
+          unsigned long mant = (unsigned long)iv;
+          int nd = 0;
+          while (f < e && (unsigned)(*f - '0') <= 9u && nd < 10 && mant < (1ul << 24)) {
+            mant = mant * 10 + (unsigned)(*f++ - '0');
+            nd++;
+          }
+          if (mant < (1ul << 24) && (f == e || *f == ' ')) {
+            v = (float)mant / kPow10[nd];
+            r = f;
+            have = true;
+          }
+        }
+      }
+      if (have) {
         q = r;
       } else {
         auto fr = std::from_chars(q, e, v);

@@ -158,3 +158,22 @@ def test_csr_cache_round_trip_and_invalidation(tmp_path):
         f.truncate(100)
     hit5, d5 = load(1)
     assert hit5 == 0 and len(d5["label"]) == len(d3["label"])
+
+
+def test_decimal_fast_path_is_correctly_rounded():
+    """short decimals take a one-division fast path; it must return the float std::stof returns (the correctly
+    rounded fp32), including values whose nearest double and nearest float disagree in the last bit"""
+    rng = np.random.default_rng(9)
+    toks = []
+    for _ in range(20000):
+        nd = int(rng.integers(1, 8))
+        ip = int(rng.integers(0, 200)) if rng.random() < 0.5 else 0
+        frac = "".join(str(int(d)) for d in rng.integers(0, 10, nd))
+        toks.append(f"{ip}.{frac}")
+    toks += ["0.1", "0.3", "16777215.0", "16777216.5", "0.0000001", "1.0000001", "9.9999999", "0.5489", "123.456"]
+    text = "".join(f"1 {i + 1}:{t}\n" for i, t in enumerate(toks))
+    d = parse(text, False, 2)
+    want = np.array([np.float32(t) for t in toks], np.float32)
+    keep = want != 0
+    np.testing.assert_array_equal(d["val"], want[keep])
+    assert list(d["feat"]) == [i + 1 for i in range(len(toks)) if keep[i]]
