@@ -242,7 +242,7 @@ static void ensure_workspace(ftrl_handle *h, int64_t n_rows, int64_t nnz) {
     h->ckey.ensure(oc);
     h->csrc.ensure(oc);
     h->cflag.ensure(oc);
-    h->sel.ensure(oc);
+    h->sel.ensure(std::max<int64_t>(oc, (int64_t)h->G * nc));  // DeviceSelect may keep every candidate (all rows owned here)
     h->n_sel.ensure(4);
     h->red4.ensure(4);
     h->mscan.ensure(nc);
