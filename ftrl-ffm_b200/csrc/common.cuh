@@ -43,7 +43,7 @@ struct Shards {   // every shard's tables (predict reads rows where they live)
 };
 
 // What the per-sample training kernel sees: the local shard, the per-step cache of remote rows (their w
-// plane, pulled once per distinct row: shard.cuh) and the local staging area of gradient images.
+// plane, pushed by its owner once per distinct row: shard.cuh) and the local staging area of gradient images.
 // A row is named by a locator: >= 0 local row index; < 0: -1 - (sorted head position of the remote row).
 struct RowSpace {
   float *tab;            // [n_local][3][ld]
