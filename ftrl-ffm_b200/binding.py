@@ -54,7 +54,7 @@ ABI_SYMBOLS = [
     "ftrl_load_model", "ftrl_save_model_text", "ftrl_load_model_text", "ftrl_set_stream",
     "ftrl_profile_enable", "ftrl_profile_reset", "ftrl_profile_read", "ftrl_last_batch_stats",
     "ftrl_randomize_state", "ftrl_alloc_pinned", "ftrl_free_pinned",
-    "ftrl_export_peer_blob", "ftrl_attach_peers",
+    "ftrl_export_peer_blob", "ftrl_attach_peers", "ftrl_eval_auc", "ftrl_eval_auc_device",
 ]
 
 _lib = None
@@ -107,6 +107,8 @@ def load_library(path: str | None = None):
     lib.ftrl_alloc_pinned.restype = vp
     lib.ftrl_free_pinned.argtypes = [vp]
     lib.ftrl_free_pinned.restype = None
+    for n in ("ftrl_eval_auc", "ftrl_eval_auc_device"):
+        getattr(lib, n).argtypes = [vp, i64, f32p, i32p, C.POINTER(C.c_double)]
     lib.ftrl_export_peer_blob.argtypes = [vp, vp]
     lib.ftrl_attach_peers.argtypes = [vp, vp]
     if path is None:
@@ -272,6 +274,14 @@ class FtrlModel:
     @property
     def vec_w(self):
         return self._get(0)[2]
+
+    def auc(self, scores, labels) -> float:
+        """ROC AUC on the device (ftrl_eval_auc): ties get average ranks"""
+        sc = np.ascontiguousarray(scores, np.float32)
+        la = np.ascontiguousarray(labels, np.int32)
+        out = C.c_double(0.0)
+        self._check(self.lib.ftrl_eval_auc(self.h, len(sc), _np_ptr(sc), _np_ptr(la), C.byref(out)))
+        return float(out.value)
 
     def has_zero_weights(self) -> bool:
         out = C.c_int(0)

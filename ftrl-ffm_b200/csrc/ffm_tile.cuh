@@ -3,24 +3,26 @@
 //
 //  k_ffm_tile        persistent CTAs (one per SM), warp-specialised:
 //                    metadata warps : prefetch, several samples ahead, each sample's CSR row, the class of
-//                                     every occurrence (fused / sorted position), row locators, linear records
+//                                     every occurrence (fused / staged), row locators, linear records; rows
+//                                     are kept sorted by class so that warps rarely mix classes
 //                    loader warp    : hands out sample-sized spans of the shared-memory row ring and issues
 //                                     one cp.async.bulk (TMA bulk copy, mbarrier expect_tx) per feature row:
 //                                     z and n planes of a fused row, the materialised w plane of a staged row
 //                    consumer warps : pass 1 w = W(n,z) for fused rows (ffm.cpp:72-88, stored as the stale
 //                                     w the reference keeps), logit (ffm.cpp:57-70), g = sigmoid(logit) - y;
-//                                     pass 2 FTRL update in place in shared memory (ffm.cpp:90-136
-//                                     telescoped) or the gradient image g_s w_partner x_m x_n
-//                    storer warp    : one bulk store per row: updated (z',n') back into the table, or the
-//                                     gradient image into the staging buffer at its sorted position
+//                                     pass 2 FTRL update of the fused rows in place in shared memory
+//                                     (ffm.cpp:90-136 telescoped)
+//                    storer warp    : one bulk store per fused row: updated (z',n') back into the table
 //  k_row_touch / k_row_materialise   owner-side pre-pass: w of the staged rows, only the touched slices
-//  k_ffm_staged_rows streaming segmented reduction of the staged gradient images: work item = (chunk of
-//                    <= 32 occurrences of one row, 32 float4 vectors); closed-form update, a partial for
-//                    k_ffm_combine, or (sharded runs) the row's sum into its owner's inbox
+//  k_ffm_regrad_rows row-centric update of the staged rows: the per-occurrence gradients are re-derived from
+//                    the partner rows' w slices (32-byte gathers, mostly L2 hits) and reduced in registers:
+//                    closed-form update, a partial for k_ffm_combine, or (sharded runs) the row's sum into
+//                    its owner's inbox
 //
 // HBM traffic per touched coordinate: rows that occur once: 8 B read (z,n) + 12 B written (z',n',w) = the
-// algorithmic 20 B; other rows: 12 B once (materialise) + 4 B (w) + 4 B (gradient image) per occurrence,
-// then 4 B per occurrence + 16 B per distinct coordinate in the reduce.
+// algorithmic 20 B; other rows: 12 B once (materialise) + 20 B once (update) per distinct coordinate; per
+// occurrence only the w plane is read (twice: row-wise by the sample kernel, slice-wise by the row kernel),
+// which L2 serves for the rows that make up most occurrences.
 #pragma once
 #include "common.cuh"
 #include "ffm.cuh"
@@ -117,26 +119,28 @@ struct TileGeom {
   int inflight;     // samples that may share the ring (2..TILE_MAX_STAGE)
   int n_meta;       // metadata slots (> n_stage: metadata runs ahead of the row ring)
   int consumers;    // consumer threads (multiple of 32)
-  int dbg;          // experiment switches (FTRL_B200_TILE_DBG): 1 skip w stores, 2 skip row/image stores, 4 local lin only
+  int dbg;          // experiment switches (FTRL_B200_TILE_DBG): 1 skip w stores, 2 skip row stores, 64 L2 cache hints
   size_t smem_bytes;
 };
 
 struct RowMeta {   // one 16-byte record per row of a sample
   int32_t fk;      // field * k | (offset of the row inside its sample's span of the row ring, floats) << 16
   float x;         // value
-  int32_t pos;     // -1: row finalised here, >= 0: sorted position for the staged gradient image
+  int32_t pos;     // -1: row finalised here (fused), >= 0: sorted position (staged: reduced by k_ffm_regrad_rows)
   int32_t loc;     // row locator (RowSpace): >= 0 local row, < 0: -1 - head position in the remote-row cache
 };
+// Rows of a sample are kept sorted by class: fused rows take slots 0, 1, ... (hdr nf of them), staged rows
+// take slots f_cap-1, f_cap-2, ... (hdr ns of them), so that the work items of a sample fall into three
+// homogeneous ranges (fused x fused, fused x staged, staged x staged) and a warp rarely mixes classes.
 struct SampleMeta {
   RowMeta *row;     // [f_cap]
   float4 *lin;      // [f_cap] {z, n, w, -} of the linear coordinate, prefetched
-  int32_t *hdr;     // [0] n valid rows, [1] label, [2] floats of the row ring the sample needs
-  uint8_t *present; // [n_fields] 1 when some valid row of the sample carries that field
+  int32_t *hdr;     // [0] fused rows, [1] label, [2] floats of the row ring the sample needs, [3] staged rows
 };
 
 __host__ __device__ inline size_t tile_meta_bytes(int f_cap) {
-  // RowMeta (16 B) + lin (16 B) per row, + header 16 B, + present[f_cap] rounded to 16
-  return (size_t)f_cap * 32 + 16 + 2 * (size_t)((f_cap + 15) / 16) * 16;
+  // RowMeta (16 B) + lin (16 B) per row, + header 16 B
+  return (size_t)f_cap * 32 + 16;
 }
 __host__ __device__ inline size_t tile_stage_bytes(int f_cap, int stride) {
   return (size_t)f_cap * stride * sizeof(float);
@@ -180,6 +184,31 @@ __host__ inline int tile_stride1(int ld, int stride) {
   return s1;
 }
 
+// L2 eviction policies for the bulk copies (experiment switch 64): rows that are touched once per step stream
+// through (evict_first) so that the w planes of the hot rows, read once per occurrence, stay resident
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_s2g_hint(void *dst_gmem, const void *src_smem, uint32_t bytes, uint64_t pol) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst_gmem),
+               "r"(smem_u32(src_smem)), "r"(bytes), "l"(pol)
+               : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // k_ffm_tile.  IPT = items (pair, factor chunk) per consumer thread; w of pass 1 is kept in registers
 // for pass 2 (IPT * 8 floats).
@@ -198,10 +227,16 @@ __device__ __forceinline__ void apply4(float4 &z, float4 &n, const float4 &w, co
   gv = gx * wp.w; ftrl_apply<PRECISE>(z.w, n.w, w.w, gv, gv * gv, h);
 }
 
-// Thread roles: [0, consumers) compute; warp `consumers/32` is the row producer (bulk loads / bulk
-// stores of the row ring); the next TILE_META_WARPS warps prefetch sample metadata into a deeper
-// ring so that the row producer never waits on a dependent global-load chain.
-template <bool PRECISE, int IPT, bool CACHE>
+// Thread roles: [0, consumers) compute; then one row-loader warp (bulk loads into the row ring), one
+// row-storer warp (bulk stores of the updated fused rows) and TILE_META_WARPS warps that prefetch sample
+// metadata into a deeper ring so that the row loader never waits on a dependent global-load chain.
+//
+// Rows that occur once in the batch ("fused") are read (z, n), materialised, updated and written back here:
+// the algorithmic 20 B per coordinate.  Rows that occur several times ("staged") only lend their w plane
+// (materialised by k_row_materialise before this kernel) to the dot products; their gradient is re-derived
+// row by row in k_ffm_regrad_rows from the w slices of the partner rows, so nothing per occurrence is
+// written to HBM.
+template <bool PRECISE, int IPT>
 __global__ void __launch_bounds__(tile_threads(TILE_MAX_CONSUMERS), 1)
 k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t *__restrict__ batch_flags,
            const __grid_constant__ RowSpace rsp, const float4 *__restrict__ bias, const uint32_t *__restrict__ pair_lut,
@@ -246,10 +281,10 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
     m.lin = reinterpret_cast<float4 *>(p);
     p += (size_t)f_cap * 16;
     m.hdr = reinterpret_cast<int32_t *>(p);
-    p += 16;
-    m.present = p;
     return m;
   };
+  // r-th row of a sample with nf fused rows: fused rows from the front, staged rows from the back
+  auto row_slot = [&](int r, int nf) { return r < nf ? r : f_cap - 1 - (r - nf); };
 
   if (tid == 0) {
     for (int st = 0; st < NSLOT; st++) {
@@ -283,12 +318,10 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
       const int64_t s = blockIdx.x + (int64_t)it * gridDim.x;
       const int64_t r0 = b.row_ptr[s];
       const int F = (int)min((int64_t)1 << 20, b.row_ptr[s + 1] - r0);
-      int nv = 0;
-      for (int f = lane; f < f_cap; f += 32) m.present[f] = 0;
-      __syncwarp();
+      int nf = 0, ns = 0;
       for (int base = 0; base < F; base += 32) {
         const int t = base + lane;
-        int32_t fl = 0, ft = -1;
+        int32_t fl = 0, ft = -1, pos = 0;
         float x = 0.f;
         bool ok = false;
         if (t < F) {
@@ -296,39 +329,46 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
           ft = b.feat[r0 + t];
           x = b.val[r0 + t];
           ok = feat_valid(d, fl, ft);
+          if (ok) pos = occ_pos[r0 + t];
         }
-        const unsigned okm = __ballot_sync(0xffffffffu, ok);
-        const int sl = nv + __popc(okm & ((1u << lane) - 1));
-        if (ok && sl < f_cap) {
+        const bool fz = ok && pos < 0, sg = ok && pos >= 0;
+        const unsigned fm = __ballot_sync(0xffffffffu, fz), sm = __ballot_sync(0xffffffffu, sg);
+        const unsigned below = (1u << lane) - 1;
+        const int idx = fz ? nf + __popc(fm & below) : ns + __popc(sm & below);
+        if (ok && idx < f_cap) {
+          const int sl = fz ? idx : f_cap - 1 - idx;
           RowMeta rm;
           rm.fk = fl * k;
           rm.x = x;
-          rm.pos = occ_pos[r0 + t];
+          rm.pos = pos;
           if ((ft & rsp.Gm1) == rsp.rank) {
             rm.loc = ft >> rsp.log2G;
             m.lin[sl] = rsp.lin[rm.loc];
           } else {  // remote rows are never fused: pos >= 0, the row's cache slot is its sorted head position
-            const int32_t head = scan[rm.pos].start;
+            const int32_t head = scan[pos].start;
             rm.loc = -1 - head;
             m.lin[sl] = make_float4(0.f, 0.f, rsp.rc_lin[head], 0.f);
           }
           m.row[sl] = rm;
-          m.present[fl] = 1;
-
         }
-        nv += __popc(okm);
+        nf += __popc(fm);
+        ns += __popc(sm);
       }
-      nv = min(nv, f_cap);
+      // distinct fields: nf + ns <= f_cap (the clamps only guard malformed input)
+      nf = min(nf, f_cap);
+      ns = min(ns, f_cap - nf);
+      const int nv = nf + ns;
       __syncwarp();
       // offsets of the rows inside the sample's span (exclusive prefix sum of the row sizes)
       int need = 0;
       for (int base = 0; base < nv; base += 32) {
         const int r = base + lane;
+        const int sl = row_slot(r, nf);
         RowMeta rm;
         int sz = 0;
         if (r < nv) {
-          rm = m.row[r];
-          sz = rm.pos < 0 ? stride : stride1;
+          rm = m.row[sl];
+          sz = r < nf ? stride : stride1;
         }
         int inc = sz;
 #pragma unroll
@@ -336,13 +376,14 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
           const int t = __shfl_up_sync(0xffffffffu, inc, o);
           if (lane >= o) inc += t;
         }
-        if (r < nv) m.row[r].fk = rm.fk | ((need + inc - sz) << 16);
+        if (r < nv) m.row[sl].fk = rm.fk | ((need + inc - sz) << 16);
         need += __shfl_sync(0xffffffffu, inc, 31);
       }
       if (lane == 0) {
-        m.hdr[0] = nv;
+        m.hdr[0] = nf;
         m.hdr[1] = b.label[s];
         m.hdr[2] = need;
+        m.hdr[3] = ns;
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_mfull[slot]);
@@ -350,13 +391,11 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
     return;
   }
 
-  // w plane of a staged row: the local table, or the cache of remote rows
-  auto w_plane = [&](int32_t loc) -> const float * {
-    return loc >= 0 ? rsp.tab + (int64_t)loc * rs + 2 * ld : rsp.rc_w + (int64_t)(-1 - loc) * ld;
-  };
+  const bool hints = (geo.dbg & 64) != 0;
 
   if (role == 1) {
-    // =========================== row loader warps ===========================
+    // =========================== row loader warp ===========================
+    const uint64_t pol_stream = policy_evict_first(), pol_keep = policy_evict_last();
     RingCursor mc;
     mc.init(0, MD);
     int head = 0;     // next free float of the ring
@@ -366,7 +405,7 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
       const int slot = mc.slot;
       mbar_wait(&bar_mfull[slot], mc.parity());
       SampleMeta m = sample_meta(slot);
-      const int nv = m.hdr[0];
+      const int nf = m.hdr[0], nv = nf + m.hdr[3];
       const int need = m.hdr[2];
       // a span for this sample: contiguous, after `head` or wrapped to the start of the ring; wait (in order)
       // for older samples to retire until the sample slot is free and the span overlaps no live span
@@ -393,44 +432,31 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
       }
       __syncwarp();
       float *rows = ring + base;
-      {
-        // TMA bulk copies.  Fused rows bring z and n (they are updated here); staged rows bring only the w
-        // plane their owner materialised, into the z-plane slot of the stage
-        int bytes = 0;
-        for (int r = lane; r < nv; r += 32) bytes += m.row[r].pos < 0 ? (int)row_bytes : (int)(row_bytes / 2);
-        bytes = (int)warp_sum((float)bytes);
-        if (lane == 0) mbar_expect_tx(&bar_full[st], (uint32_t)bytes);
-        __syncwarp();
-        for (int r = lane; r < nv; r += 32) {
-          const RowMeta rm = m.row[r];
-          if (rm.pos < 0) bulk_g2s(rows + row_off(rm), rsp.tab + (int64_t)rm.loc * rs, row_bytes, &bar_full[st]);
-          else bulk_g2s(rows + row_off(rm), w_plane(rm.loc), row_bytes / 2, &bar_full[st]);
+      // TMA bulk copies.  Fused rows bring z and n (they are updated here); staged rows bring only the w plane
+      // their owner materialised
+      if (lane == 0) mbar_expect_tx(&bar_full[st], (uint32_t)(nf * (int)row_bytes + (nv - nf) * (int)(row_bytes / 2)));
+      __syncwarp();
+      for (int r = lane; r < nv; r += 32) {
+        const RowMeta rm = m.row[row_slot(r, nf)];
+        if (r < nf) {
+          if (hints) bulk_g2s_hint(rows + row_off(rm), rsp.tab + (int64_t)rm.loc * rs, row_bytes, &bar_full[st], pol_stream);
+          else bulk_g2s(rows + row_off(rm), rsp.tab + (int64_t)rm.loc * rs, row_bytes, &bar_full[st]);
+        } else {
+          if (hints) bulk_g2s_hint(rows + row_off(rm), rsp.w_plane(rm.loc, ld), row_bytes / 2, &bar_full[st], pol_keep);
+          else bulk_g2s(rows + row_off(rm), rsp.w_plane(rm.loc, ld), row_bytes / 2, &bar_full[st]);
         }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_full[st]);
-      // L2 prefetch of the NEXT sample's rows: its stage is still occupied, but its metadata is ready (the
-      // metadata ring runs ahead); one sample ahead keeps the prefetched footprint at ~100 KB per SM
-      if (it + 1 < n_mine && (geo.dbg & 32)) {  // off by default: with the variable-span ring the loads themselves run ahead
-        RingCursor nx = mc;
-        nx.advance(1, MD);
-        mbar_wait(&bar_mfull[nx.slot], nx.parity());
-        SampleMeta m2 = sample_meta(nx.slot);
-        const int nv2 = m2.hdr[0];
-        for (int r = lane; r < nv2; r += 32) {
-          const RowMeta rm = m2.row[r];
-          if (rm.pos < 0) bulk_prefetch_l2(rsp.tab + (int64_t)rm.loc * rs, row_bytes);
-          else bulk_prefetch_l2(w_plane(rm.loc), row_bytes / 2);
-        }
-      }
     }
     return;
   }
 
   if (role == 3) {
-    // =========================== row storer warps ===========================
-    // retire samples in order: wait for the consumers, bulk-store the rows / gradient images, then hand the
+    // =========================== row storer warp ===========================
+    // retire samples in order: wait for the consumers, bulk-store the updated fused rows, then hand the
     // stage back to the loader and the metadata slot back to the metadata warps
+    const uint64_t pol_stream = policy_evict_first();
     RingCursor mc;
     mc.init(0, MD);
     for (int it = 0; it < n_mine; it++, mc.advance(1, MD)) {
@@ -439,11 +465,11 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
       SampleMeta m = sample_meta(slot);
       mbar_wait(&bar_done[st], (uint32_t)((it >> 2) & 1));
       float *rows = ring + s_base[st];
-      const int nv = m.hdr[0];
-      for (int r = lane; r < nv && !(geo.dbg & 2); r += 32) {
+      const int nf = m.hdr[0];
+      for (int r = lane; r < nf && !(geo.dbg & 2); r += 32) {
         const RowMeta rm = m.row[r];
-        if (rm.pos < 0) bulk_s2g(rsp.tab + (int64_t)rm.loc * rs, rows + row_off(rm), row_bytes);
-        else bulk_s2g(rsp.staging + (int64_t)rm.pos * ld, rows + row_off(rm), (uint32_t)(ld * sizeof(float)));
+        if (hints) bulk_s2g_hint(rsp.tab + (int64_t)rm.loc * rs, rows + row_off(rm), row_bytes, pol_stream);
+        else bulk_s2g(rsp.tab + (int64_t)rm.loc * rs, rows + row_off(rm), row_bytes);
       }
       bulk_commit();
       bulk_wait_read_all();
@@ -472,58 +498,74 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
     mbar_wait(&bar_mfull[slot], mc.parity());
     mbar_wait(&bar_full[st], (uint32_t)((it >> 2) & 1));
     float *rows = ring + s_base[st];
-    const int nv = m.hdr[0];
+    const int nf = m.hdr[0], ns = m.hdr[3], nv = nf + ns;
+    // items of the sample in three ranges: fused x fused pairs, fused x staged, staged x staged
+    const uint32_t n_ff = (uint32_t)nf * (uint32_t)(nf - 1) / 2u * dec.C;
+    const uint32_t n_fs = (uint32_t)nf * (uint32_t)ns * dec.C;
     const uint32_t n_items = (uint32_t)nv * (uint32_t)(nv - 1) / 2u * dec.C;
+    const float inv_nf = nf > 0 ? 1.0f / (float)nf : 0.f;
 
     // ---- pass 1: w, logit ----
     float acc = 0.f;
     float4 wAc[IPT], wBc[IPT];
-    // CACHE: pass 2 reuses the item's slice offsets / classes from pass 1 instead of decoding it again
-    int offA[CACHE ? IPT : 1], offB[CACHE ? IPT : 1], cls[CACHE ? IPT : 1];  // bit 0/1: row m / n fused, bit 2: valid
-    float xx[CACHE ? IPT : 1];
+    // pass 2 reuses the item's slice offsets / classes from pass 1 instead of decoding it again
+    int offA[IPT], offB[IPT], cls[IPT];  // bit 0/1: row m / n fused
+    float xx[IPT];
 #pragma unroll
     for (int j = 0; j < IPT; j++) {
       const uint32_t item = tid + j * n_cons;
-      if (CACHE) cls[j] = 0;
+      cls[j] = 0;
       if (item < n_items) {
         uint32_t p, c;
-        dec(item, p, c);
-        const uint32_t e = s_lut[p];
-        const int mi = e & 0xff, ni = e >> 8;
+        int mi, ni;
+        if (item < n_ff) {
+          dec(item, p, c);
+          const uint32_t e = s_lut[p];
+          mi = e & 0xff;
+          ni = e >> 8;
+        } else if (item < n_ff + n_fs) {
+          dec(item - n_ff, p, c);
+          // p = n' * nf + m : exact for these ranges (p < 64 * 64, nf <= 64)
+          const int nq = __float2int_rd(((float)p + 0.5f) * inv_nf);
+          mi = (int)p - nq * nf;
+          ni = f_cap - 1 - nq;
+        } else {
+          dec(item - n_ff - n_fs, p, c);
+          const uint32_t e = s_lut[p];
+          mi = f_cap - 1 - (int)(e & 0xff);
+          ni = f_cap - 1 - (int)(e >> 8);
+        }
         const RowMeta rmm = m.row[mi], rmn = m.row[ni];
         const int oA = row_off(rmm) + row_fk(rmn) + (int)c * 4;  // slice A = (row m, field n)
         const int oB = row_off(rmn) + row_fk(rmm) + (int)c * 4;  // slice B = (row n, field m)
-        const float xmn = rmm.x * rmn.x;
-        if (CACHE) {
-          offA[j] = oA;
-          offB[j] = oB;
-          xx[j] = xmn;
-          cls[j] = 4 | (rmm.pos < 0 ? 1 : 0) | (rmn.pos < 0 ? 2 : 0);
-        }
+        offA[j] = oA;
+        offB[j] = oB;
+        xx[j] = rmm.x * rmn.x;
+        cls[j] = (rmm.pos < 0 ? 1 : 0) | (rmn.pos < 0 ? 2 : 0);
         const float *sa = rows + oA;
         const float *sb = rows + oB;
-        // staged rows hold w itself in the z-plane slot; fused rows hold (z, n): w = W(n, z), stored as the
-        // stale-by-one w the reference keeps (ffm.cpp:72-88)
+        // staged rows hold w itself; fused rows hold (z, n): w = W(n, z), stored as the stale-by-one w the
+        // reference keeps (ffm.cpp:72-88)
         float4 wA = *reinterpret_cast<const float4 *>(sa), wB = *reinterpret_cast<const float4 *>(sb);
         if (rmm.pos < 0) {
           wA = weight4<PRECISE>(wA, *reinterpret_cast<const float4 *>(sa + ld), h);
-          *reinterpret_cast<float4 *>(rsp.tab + (int64_t)rmm.loc * rs + 2 * ld + row_fk(rmn) + c * 4) = wA;
+          if (!(geo.dbg & 1)) *reinterpret_cast<float4 *>(rsp.tab + (int64_t)rmm.loc * rs + 2 * ld + row_fk(rmn) + c * 4) = wA;
         }
         if (rmn.pos < 0) {
           wB = weight4<PRECISE>(wB, *reinterpret_cast<const float4 *>(sb + ld), h);
-          *reinterpret_cast<float4 *>(rsp.tab + (int64_t)rmn.loc * rs + 2 * ld + row_fk(rmm) + c * 4) = wB;
+          if (!(geo.dbg & 1)) *reinterpret_cast<float4 *>(rsp.tab + (int64_t)rmn.loc * rs + 2 * ld + row_fk(rmm) + c * 4) = wB;
         }
         wAc[j] = wA;
         wBc[j] = wB;
         const float dot = fmaf(wA.x, wB.x, fmaf(wA.y, wB.y, fmaf(wA.z, wB.z, wA.w * wB.w)));
-        acc = fmaf(dot, xmn, acc);
+        acc = fmaf(dot, xx[j], acc);
       }
     }
     for (int r = tid; r < nv; r += n_cons) {
-      const float4 e = m.lin[r];
-      const RowMeta rm = m.row[r];
-      const float w = rm.pos < 0 ? weight_from<PRECISE>(e.x, f_sqrt<PRECISE>(e.y), h) : e.z;
-      acc = fmaf(w, rm.x, acc);
+      const int sl = row_slot(r, nf);
+      const float4 e = m.lin[sl];
+      const float w = r < nf ? weight_from<PRECISE>(e.x, f_sqrt<PRECISE>(e.y), h) : e.z;
+      acc = fmaf(w, m.row[sl].x, acc);
     }
     // consumer-wide sum
     // one barrier per sample: every warp adds the per-warp partials itself (same values, same order -> the
@@ -540,86 +582,39 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
       logit_out[s] = logit;
     }
 
-    // ---- pass 2: FTRL update in place (fused rows) or gradient image into the z plane (staged rows);
-    //      every (row, field) slice is read and written by exactly one item (fields are distinct) ----
+    // ---- pass 2: FTRL update of the fused rows in place; every (row, field) slice is read and written by
+    //      exactly one item (fields are distinct) ----
 #pragma unroll
     for (int j = 0; j < IPT; j++) {
-      int oA, oB, cl;
-      float xmn;
-      if (CACHE) {
-        oA = offA[j]; oB = offB[j]; cl = cls[j]; xmn = xx[j];
-      } else {
-        const uint32_t item = tid + j * n_cons;
-        cl = 0; oA = oB = 0; xmn = 0.f;
-        if (item < n_items) {
-          uint32_t p, c;
-          dec(item, p, c);
-          const uint32_t e = s_lut[p];
-          const int mi = e & 0xff, ni = e >> 8;
-          const RowMeta rmm = m.row[mi], rmn = m.row[ni];
-          oA = row_off(rmm) + row_fk(rmn) + (int)c * 4;
-          oB = row_off(rmn) + row_fk(rmm) + (int)c * 4;
-          xmn = rmm.x * rmn.x;
-          cl = 4 | (rmm.pos < 0 ? 1 : 0) | (rmn.pos < 0 ? 2 : 0);
-        }
-      }
-      if (cl & 4) {
-        float *sa = rows + oA;
-        float *sb = rows + oB;
-        const float gx = g * xmn;
+      const int cl = cls[j];
+      if (cl) {
+        const float gx = g * xx[j];
         const float4 wA = wAc[j], wB = wBc[j];
         if (cl & 1) {
+          float *sa = rows + offA[j];
           float4 zA = *reinterpret_cast<const float4 *>(sa), nA = *reinterpret_cast<const float4 *>(sa + ld);
           apply4<PRECISE>(zA, nA, wA, wB, gx, h);
           *reinterpret_cast<float4 *>(sa) = zA;
           *reinterpret_cast<float4 *>(sa + ld) = nA;
-        } else {
-          *reinterpret_cast<float4 *>(sa) = make_float4(gx * wB.x, gx * wB.y, gx * wB.z, gx * wB.w);
         }
         if (cl & 2) {
+          float *sb = rows + offB[j];
           float4 zB = *reinterpret_cast<const float4 *>(sb), nB = *reinterpret_cast<const float4 *>(sb + ld);
           apply4<PRECISE>(zB, nB, wB, wA, gx, h);
           *reinterpret_cast<float4 *>(sb) = zB;
           *reinterpret_cast<float4 *>(sb + ld) = nB;
-        } else {
-          *reinterpret_cast<float4 *>(sb) = make_float4(gx * wA.x, gx * wA.y, gx * wA.z, gx * wA.w);
         }
       }
     }
-    // linear coordinate: fused -> full update; staged -> w now, gradient to staging_lin
-    for (int r = tid; r < nv; r += n_cons) {
+    // linear coordinate of the fused rows (staged rows: k_ffm_regrad_rows)
+    for (int r = tid; r < nf; r += n_cons) {
       float4 e = m.lin[r];
       const RowMeta rm = m.row[r];
       const float gi = g * rm.x;
-      if (rm.pos < 0) {
-        const float w = weight_from<PRECISE>(e.x, f_sqrt<PRECISE>(e.y), h);
-        e.z = w;
-        ftrl_apply<PRECISE>(e.x, e.y, w, gi, gi * gi, h);
-        rsp.lin[rm.loc] = e;
-      } else {
-        rsp.staging_lin[rm.pos] = gi;  // w of staged rows: materialised by their owner
-      }
-    }
-    // staged rows: slices no partner touches (own field, absent fields) must read as 0 in the image.
-    // They are disjoint from the slices written above, so no barrier is needed.
-    if (nv == d.n_fields) {
-      // every field is present (fields are distinct): only the own-field slice is untouched
-      for (int r = tid; r < nv; r += n_cons) {
-        const RowMeta rm = m.row[r];
-        if (rm.pos < 0) continue;
-        float4 *zp = reinterpret_cast<float4 *>(rows + row_off(rm) + row_fk(rm));
-        for (int v = 0; v < (k >> 2); v++) zp[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    } else {
-      for (int r = tid >> 5; r < nv; r += n_cons_warps) {
-        const RowMeta rm = m.row[r];
-        if (rm.pos < 0) continue;
-        for (int f = lane; f < d.n_fields; f += 32) {
-          if (m.present[f] && f * k != row_fk(rm)) continue;
-          float4 *zp = reinterpret_cast<float4 *>(rows + row_off(rm) + f * k);
-          for (int v = 0; v < (k >> 2); v++) zp[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      }
+      const float w = weight_from<PRECISE>(e.x, f_sqrt<PRECISE>(e.y), h);
+      e.z = w;
+      ftrl_apply<PRECISE>(e.x, e.y, w, gi, gi * gi, h);
+      rsp.lin[rm.loc] = e;
     }
     fence_async_smem();
     __syncwarp();
@@ -680,18 +675,28 @@ k_row_materialise(Dims d, Hyper h, int32_t nnz, uint32_t sentinel, int32_t ch, c
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_ffm_staged_rows: streaming segmented reduction over the staged gradient images.
-// Work item = (chunk of <= 32 occurrences of one row, part of 32 float4 vectors of the row): one warp,
-// one 512-byte coalesced load per occurrence, all loads of the chunk independent (unrolled by 8), so a
-// row of 78 vectors is reduced by three warps in parallel.  Part 0 also reduces the linear coordinate.
+// k_ffm_regrad_rows: the update of the staged rows (rows that occur more than once in the batch, or whose
+// owner is another rank), row by row.  For an occurrence of row i (field f_i) in sample s the gradient of
+// slice (i, field n) is g_s x_i x_n w[row of field n in s][f_i, :] (ffm.cpp:112,117); instead of having the
+// sample kernel write that per-occurrence image to HBM and reading it back, it is re-derived here from the
+// partner rows' w slices -- 32-byte gathers that mostly hit L2, because the partners of a duplicated row are
+// themselves mostly duplicated (hot) rows.  The partner of (s, n) comes from the canonical table (prep.cuh).
+// Work item = (chunk of <= 32 occurrences of one row, part of 32 float4 vectors of the row): one warp; lane v
+// owns destination vector v = (partner field n, factor chunk), accumulates (sum g, sum g^2) in registers over
+// the occurrences in sorted (= sample) order -> deterministic.  Then the closed-form update (row fits one
+// chunk), a partial for k_ffm_combine, or (sharded runs) the row's sum into its owner's inbox.
 // ---------------------------------------------------------------------------------------------
+constexpr int REGRAD_U = 4;  // occurrences per pipeline stage: their canon entries / w gathers are in flight together
+
 template <bool PRECISE, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
-k_ffm_staged_rows(Dims d, Hyper h, int32_t nnz, const int32_t *__restrict__ batch_flags, float *__restrict__ tab,
-                  float4 *__restrict__ lin, int32_t ch, const int32_t *__restrict__ n_chunks_p,
+__global__ void __launch_bounds__(WARPS * 32, 3)
+k_ffm_regrad_rows(Dims d, Hyper h, int32_t nnz, const int32_t *__restrict__ batch_flags,
+                  const __grid_constant__ RowSpace rsp, int32_t ch, const int32_t *__restrict__ n_chunks_p,
                   const int32_t *__restrict__ chunk_pos, const uint32_t *__restrict__ skey,
-                  const SegScan *__restrict__ scan, const float *__restrict__ staging,
-                  const float *__restrict__ staging_lin, float *__restrict__ part, float2 *__restrict__ part_lin,
+                  const uint32_t *__restrict__ socc, const SegScan *__restrict__ scan,
+                  const int32_t *__restrict__ occ_row, const int32_t *__restrict__ field,
+                  const float *__restrict__ val, const float *__restrict__ g_in,
+                  const CanonEntry *__restrict__ canon, float *__restrict__ part, float2 *__restrict__ part_lin,
                   const __grid_constant__ Export ex) {
   if (batch_flags[0] == 0) return;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -700,6 +705,10 @@ k_ffm_staged_rows(Dims d, Hyper h, int32_t nnz, const int32_t *__restrict__ batc
   const uint32_t sentinel = (uint32_t)d.n_feats;
   const int nvec = (int)(ld >> 2);
   const int parts = (nvec + 31) >> 5;
+  const int vpf = d.k >> 2;  // float4 vectors per field slice
+  const int NF = d.n_fields;
+  float *tab = rsp.tab;
+  float4 *lin = rsp.lin;
   const int64_t n_items = (int64_t)n_chunks * parts;
   for (int64_t item = (int64_t)blockIdx.x * WARPS + wib; item < n_items; item += (int64_t)gridDim.x * WARPS) {
     const int c = (int)(item / parts), part_i = (int)(item - (int64_t)c * parts);
@@ -707,33 +716,73 @@ k_ffm_staged_rows(Dims d, Hyper h, int32_t nnz, const int32_t *__restrict__ batc
     if (!ci.valid) continue;
     const bool whole_row = ci.row_head && ci.row_last;
     const int v = part_i * 32 + lane;
-    const bool on = v < nvec;
-    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
-    const float4 *src = reinterpret_cast<const float4 *>(staging + (int64_t)ci.p0 * ld) + (on ? v : 0);
+    const int nfld = v / vpf;                 // destination slice = partner field
+    const bool on = v < nvec && nfld < NF;
+    const int col = (v - nfld * vpf) * 4;     // float offset inside a slice
+    const int own = nfld * d.k;
     const int n_occ = ci.p1 - ci.p0;
-    int p = 0;
-    for (; p + 8 <= n_occ; p += 8) {
-      float4 gq[8];
-#pragma unroll
-      for (int u = 0; u < 8; u++) gq[u] = on ? __ldcs(src + (int64_t)(p + u) * nvec) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int u = 0; u < 8; u++) {
-        a0.x += gq[u].x; a0.y += gq[u].y; a0.z += gq[u].z; a0.w += gq[u].w;
-        a1.x = fmaf(gq[u].x, gq[u].x, a1.x); a1.y = fmaf(gq[u].y, gq[u].y, a1.y);
-        a1.z = fmaf(gq[u].z, gq[u].z, a1.z); a1.w = fmaf(gq[u].w, gq[u].w, a1.w);
-      }
-    }
-    for (; p < n_occ; p++) {
-      const float4 gq = on ? __ldcs(src + (int64_t)p * nvec) : make_float4(0.f, 0.f, 0.f, 0.f);
-      a0.x += gq.x; a0.y += gq.y; a0.z += gq.z; a0.w += gq.w;
-      a1.x = fmaf(gq.x, gq.x, a1.x); a1.y = fmaf(gq.y, gq.y, a1.y);
-      a1.z = fmaf(gq.z, gq.z, a1.z); a1.w = fmaf(gq.w, gq.w, a1.w);
+    // lane l holds the metadata of occurrence p0 + l
+    int my_s = 0, my_fk = -1;
+    float my_gx = 0.f;
+    if (lane < n_occ) {
+      const uint32_t t = socc[ci.p0 + lane];
+      my_s = occ_row[t];
+      my_gx = g_in[my_s] * val[t];
+      my_fk = field[t] * d.k;
     }
     // sharded runs: the sum goes to the row's owner unless this rank owns the row and is its only contributor
     const int32_t dst = (ex.on && whole_row) ? ex.dst_at[ci.p0] : -2;
     const int64_t lrow = (int64_t)(ci.key >> ex.log2G);
     float *row = tab + lrow * rs;
-    if (on) {
+    // the row's own planes are needed only at the very end: fetch them now, under the gathers
+    const bool apply_here = whole_row && dst < 0 && v < nvec;
+    float4 rz = make_float4(0.f, 0.f, 0.f, 0.f), rn = rz, rw = rz;
+    if (apply_here) {
+      rz = __ldcs(reinterpret_cast<const float4 *>(row) + v);
+      rn = __ldcs(reinterpret_cast<const float4 *>(row + ld) + v);
+      rw = __ldcs(reinterpret_cast<const float4 *>(row + 2 * ld) + v);
+    }
+    // software pipeline over stages of REGRAD_U occurrences: the canon entries of stage b + 1 are requested
+    // before the w gathers of stage b are consumed, so one L2 round trip per stage is exposed instead of two
+    auto load_canon = [&](int p, CanonEntry (&e)[REGRAD_U]) {
+#pragma unroll
+      for (int u = 0; u < REGRAD_U; u++) {
+        const int sj = __shfl_sync(0xffffffffu, my_s, (p + u) & 31);
+        e[u].loc = CANON_NONE;
+        e[u].x = 0.f;
+        if (on && p + u < n_occ) {
+          const int2 t = __ldg(reinterpret_cast<const int2 *>(canon + (int64_t)sj * NF + nfld));
+          e[u].loc = t.x;
+          e[u].x = __int_as_float(t.y);
+        }
+      }
+    };
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+    CanonEntry e[REGRAD_U], en[REGRAD_U] = {};
+    load_canon(0, e);
+    for (int p = 0; p < n_occ; p += REGRAD_U) {
+      float4 w[REGRAD_U];
+      float gxx[REGRAD_U];
+#pragma unroll
+      for (int u = 0; u < REGRAD_U; u++) {
+        const int fk = __shfl_sync(0xffffffffu, my_fk, (p + u) & 31);
+        gxx[u] = __shfl_sync(0xffffffffu, my_gx, (p + u) & 31) * e[u].x;
+        // the slice of the row's own field is touched by no partner (fields are distinct)
+        const bool take = e[u].loc != CANON_NONE && fk != own;
+        w[u] = take ? __ldg(reinterpret_cast<const float4 *>(rsp.w_plane(e[u].loc, ld) + fk + col))
+                    : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      if (p + REGRAD_U < n_occ) load_canon(p + REGRAD_U, en);
+#pragma unroll
+      for (int u = 0; u < REGRAD_U; u++) {
+        const float4 gv = make_float4(gxx[u] * w[u].x, gxx[u] * w[u].y, gxx[u] * w[u].z, gxx[u] * w[u].w);
+        a0.x += gv.x; a0.y += gv.y; a0.z += gv.z; a0.w += gv.w;
+        a1.x = fmaf(gv.x, gv.x, a1.x); a1.y = fmaf(gv.y, gv.y, a1.y);
+        a1.z = fmaf(gv.z, gv.z, a1.z); a1.w = fmaf(gv.w, gv.w, a1.w);
+        e[u] = en[u];
+      }
+    }
+    if (v < nvec) {
       if (whole_row && dst >= 0) {
         // one occurrence: sum g^2 = g^2, the owner squares it (half the bytes over NVLink)
         float *o = ex.inbox[ci.key & ex.Gm1] + (int64_t)dst * 2 * ld;
@@ -743,14 +792,12 @@ k_ffm_staged_rows(Dims d, Hyper h, int32_t nnz, const int32_t *__restrict__ batc
         const bool any = a1.x != 0.f || a1.y != 0.f || a1.z != 0.f || a1.w != 0.f || a0.x != 0.f || a0.y != 0.f ||
                          a0.z != 0.f || a0.w != 0.f;
         if (any) {
-          float4 z = reinterpret_cast<float4 *>(row)[v], n = reinterpret_cast<float4 *>(row + ld)[v];
-          const float4 w = reinterpret_cast<float4 *>(row + 2 * ld)[v];
-          ftrl_apply<PRECISE>(z.x, n.x, w.x, a0.x, a1.x, h);
-          ftrl_apply<PRECISE>(z.y, n.y, w.y, a0.y, a1.y, h);
-          ftrl_apply<PRECISE>(z.z, n.z, w.z, a0.z, a1.z, h);
-          ftrl_apply<PRECISE>(z.w, n.w, w.w, a0.w, a1.w, h);
-          reinterpret_cast<float4 *>(row)[v] = z;
-          reinterpret_cast<float4 *>(row + ld)[v] = n;
+          ftrl_apply<PRECISE>(rz.x, rn.x, rw.x, a0.x, a1.x, h);
+          ftrl_apply<PRECISE>(rz.y, rn.y, rw.y, a0.y, a1.y, h);
+          ftrl_apply<PRECISE>(rz.z, rn.z, rw.z, a0.z, a1.z, h);
+          ftrl_apply<PRECISE>(rz.w, rn.w, rw.w, a0.w, a1.w, h);
+          __stcs(reinterpret_cast<float4 *>(row) + v, rz);
+          __stcs(reinterpret_cast<float4 *>(row + ld) + v, rn);
         }
       } else {
         float *pdst = part + (int64_t)ci.slot * 2 * ld;
@@ -759,22 +806,15 @@ k_ffm_staged_rows(Dims d, Hyper h, int32_t nnz, const int32_t *__restrict__ batc
       }
     }
     if (part_i == 0) {
-      // linear coordinate
-      float sg = 0.f, sg2 = 0.f;
-      for (int q = ci.p0 + lane; q < ci.p1; q += 32) {
-        const float gi = staging_lin[q];
-        sg += gi;
-        sg2 = fmaf(gi, gi, sg2);
-      }
-      sg = warp_sum(sg);
-      sg2 = warp_sum(sg2);
+      // linear coordinate: g_s x_i per occurrence
+      const float sg = warp_sum(my_gx), sg2 = warp_sum(my_gx * my_gx);
       if (lane == 0) {
         if (whole_row && dst >= 0) {
           ex.inbox_lin[ci.key & ex.Gm1][dst] = make_float2(sg, sg2);
         } else if (whole_row) {
-          float4 e = lin[lrow];
-          ftrl_apply<PRECISE>(e.x, e.y, e.z, sg, sg2, h);
-          lin[lrow] = e;
+          float4 le = lin[lrow];
+          ftrl_apply<PRECISE>(le.x, le.y, le.z, sg, sg2, h);
+          lin[lrow] = le;
         } else {
           part_lin[ci.slot] = make_float2(sg, sg2);
         }

@@ -192,7 +192,7 @@ static int key_bits(int32_t n_feats) {
   return bits;
 }
 
-// single-GPU handles: the one shard is this handle itself (staging buffers may have been reallocated)
+// single-GPU handles: the one shard is this handle itself (workspace buffers may have been reallocated)
 static void refresh_shards(ftrl_handle *h) {
   if (h->G > 1 && h->attached) return;
   Shards &sh = h->shards;
@@ -206,8 +206,6 @@ static void refresh_shards(ftrl_handle *h) {
   rsp = RowSpace{};
   rsp.tab = h->tab;
   rsp.lin = h->lin;
-  rsp.staging = h->staging.p;
-  rsp.staging_lin = h->staging_lin.p;
   h->exportd = Export{};
 }
 
@@ -264,10 +262,7 @@ static void ensure_workspace(ftrl_handle *h, int64_t n_rows, int64_t nnz) {
     h->pmask.ensure(nc);
     h->rowmask.ensure(nc + 2);
   }
-  if (h->tile_ok) {
-    h->staging.ensure((size_t)nc * h->dims.ld);
-    h->staging_lin.ensure(nc);
-  }
+  if (h->tile_ok) h->canon.ensure((size_t)rc * h->dims.n_fields);
   h->scan.ensure(nc);
   h->chunk_pos.ensure(nc + 2);
   h->n_chunks.ensure(4);
@@ -336,6 +331,51 @@ static void launch_ffm_sample(ftrl_handle *h, const Batch &b, float *logit_out, 
   FTRL_CUDA(cudaGetLastError());
 }
 
+// the sample kernel and the row kernel of the tile path (ffm_tile.cuh), shared by the single-GPU and the sharded step
+template <bool PRECISE>
+static void launch_tile(ftrl_handle *h, const Batch &b, const ItemDecode &dec, float *logit_out) {
+  TileGeom geo;
+  geo.f_cap = h->tile_f_cap;
+  geo.stride = h->tile_stride;
+  geo.stride1 = h->tile_stride1;
+  geo.inflight = h->tile_inflight;
+  geo.n_stage = h->tile_stages;
+  geo.n_meta = h->tile_meta;
+  geo.consumers = h->tile_consumers;
+  geo.dbg = h->tile_dbg;
+  geo.smem_bytes = h->tile_smem;
+  const int tgrid = (int)std::min<int64_t>(b.n_rows, (int64_t)h->n_sms * h->tile_ctas_per_sm);
+#define FFM_TILE(I)                                                                                   \
+  k_ffm_tile<PRECISE, I><<<tgrid, tile_threads(geo.consumers), geo.smem_bytes, h->compute>>>(        \
+      b, h->dims, h->hyper, dec, geo, h->batch_flags.p, h->rowspace, h->bias, h->pair_lut, h->occ_pos.p, h->scan.p, h->g.p, logit_out)
+  if (h->tile_ipt <= 1) FFM_TILE(1);
+  else if (h->tile_ipt == 2) FFM_TILE(2);
+  else if (h->tile_ipt == 3) FFM_TILE(3);
+  else FFM_TILE(4);
+#undef FFM_TILE
+  FTRL_CUDA(cudaGetLastError());
+  launched(h, PH_SAMPLE);
+}
+
+template <bool PRECISE>
+static void launch_regrad(ftrl_handle *h, const Batch &b) {
+  const int grid = h->n_sms * 16;
+  k_ffm_regrad_rows<PRECISE, 8><<<grid, 256, 0, h->compute>>>(h->dims, h->hyper, (int32_t)b.nnz, h->batch_flags.p, h->rowspace,
+                                                             h->chunk, h->n_chunks.p, h->chunk_pos.p, h->skey.p, h->socc.p,
+                                                             h->scan.p, h->occ_row.p, b.field, b.val, h->g.p, h->canon.p,
+                                                             h->part.p, h->part_lin.p, h->exportd);
+  FTRL_CUDA(cudaGetLastError());
+  launched(h, PH_ROWS);
+}
+
+// canonical (sample, field) -> row table of the tile path (prep.cuh); needs occ_pos / scan in sharded runs
+static void launch_canon(ftrl_handle *h, const Batch &b) {
+  if (b.n_rows <= 0) return;
+  const unsigned grid = (unsigned)((b.n_rows * 32 + 255) / 256);
+  k_build_canon<<<grid, 256, 0, h->compute>>>(b, h->dims, h->log2G, h->rank, h->occ_pos.p, h->scan.p, h->canon.p);
+  FTRL_CUDA(cudaGetLastError());
+}
+
 // FFM minibatch: when every sample of the batch has distinct fields (device-side flag) the tile kernels
 // (ffm_tile.cuh) process it; otherwise the generic LDG kernels do.  Both sets are enqueued, the one that
 // does not apply returns at once -- no host round trip.
@@ -348,46 +388,11 @@ static void run_ffm_batch(ftrl_handle *h, const Batch &b, float *logit_out) {
   if (tile) {
     {
       PhaseScope ps(h, PH_SAMPLE);
-      TileGeom geo;
-      geo.f_cap = h->tile_f_cap;
-      geo.stride = h->tile_stride;
-      geo.stride1 = h->tile_stride1;
-      geo.inflight = h->tile_inflight;
-      geo.n_stage = h->tile_stages;
-      geo.n_meta = h->tile_meta;
-      geo.consumers = h->tile_consumers;
-      geo.dbg = h->tile_dbg;
-      geo.smem_bytes = h->tile_smem;
-      const int tgrid = (int)std::min<int64_t>(b.n_rows, (int64_t)h->n_sms * h->tile_ctas_per_sm);
-#define FFM_TILE(I)                                                                                              \
-  if (h->tile_cache)                                                                                              \
-    k_ffm_tile<PRECISE, I, true><<<tgrid, tile_threads(geo.consumers), geo.smem_bytes, h->compute>>>(             \
-        b, d, h->hyper, dec, geo, h->batch_flags.p, h->rowspace, h->bias, h->pair_lut, h->occ_pos.p, h->scan.p, h->g.p, logit_out); \
-  else                                                                                                            \
-    k_ffm_tile<PRECISE, I, false><<<tgrid, tile_threads(geo.consumers), geo.smem_bytes, h->compute>>>(            \
-        b, d, h->hyper, dec, geo, h->batch_flags.p, h->rowspace, h->bias, h->pair_lut, h->occ_pos.p, h->scan.p, h->g.p, logit_out)
-      if (h->tile_ipt <= 1) FFM_TILE(1);
-      else if (h->tile_ipt == 2) FFM_TILE(2);
-      else if (h->tile_ipt == 3) FFM_TILE(3);
-      else FFM_TILE(4);
-#undef FFM_TILE
-      FTRL_CUDA(cudaGetLastError());
-      launched(h, PH_SAMPLE);
+      launch_tile<PRECISE>(h, b, dec, logit_out);
     }
     {
       PhaseScope ps(h, PH_ROWS);
-      if (h->precise)
-        k_ffm_staged_rows<true, 8><<<grid * 4, 256, 0, h->compute>>>(d, h->hyper, (int32_t)b.nnz, h->batch_flags.p, h->tab, h->lin,
-                                                                    h->chunk, h->n_chunks.p, h->chunk_pos.p, h->skey.p,
-                                                                    h->scan.p, h->staging.p, h->staging_lin.p, h->part.p,
-                                                                    h->part_lin.p, h->exportd);
-      else
-        k_ffm_staged_rows<false, 8><<<grid * 4, 256, 0, h->compute>>>(d, h->hyper, (int32_t)b.nnz, h->batch_flags.p, h->tab, h->lin,
-                                                                     h->chunk, h->n_chunks.p, h->chunk_pos.p, h->skey.p,
-                                                                     h->scan.p, h->staging.p, h->staging_lin.p, h->part.p,
-                                                                     h->part_lin.p, h->exportd);
-      FTRL_CUDA(cudaGetLastError());
-      launched(h, PH_ROWS);
+      launch_regrad<PRECISE>(h, b);
     }
   }
   {
@@ -520,7 +525,11 @@ static void run_prep(ftrl_handle *h, const Batch &b) {
     launched(h, PH_SEGMENT);
     FTRL_CUDA(cudaGetLastError());
   }
-  if (d.model_type == FTRL_FFM && h->tile_ok) run_row_prepass(h, nnz, sentinel);
+  if (d.model_type == FTRL_FFM && h->tile_ok) {
+    run_row_prepass(h, nnz, sentinel);
+    launch_canon(h, b);
+    launched(h, PH_MATERIALISE);
+  }
 }
 
 template <bool PRECISE>
@@ -618,6 +627,83 @@ static void predict_device(ftrl_handle *h, const Batch &b, int output_prob, floa
 }
 
 // ---------------------------------------------------------------------------------------------
+// ROC AUC on device (the reference has none -- only eval/loss.h:8-12; north_star asks for logloss AND AUC):
+// radix sort of the scores, one scan for (head of the tie group, positives so far), then the Mann-Whitney
+// rank sum with average ranks over ties, accumulated in integers (2 * rank sum), hence exact and
+// independent of the order of the additions.
+// ---------------------------------------------------------------------------------------------
+struct AucScan {
+  int32_t start;  // position of the head of the tie group at or before this position
+  int32_t cum;    // positives at or before this position
+};
+struct AucScanOp {
+  __device__ __forceinline__ AucScan operator()(const AucScan &a, const AucScan &b) const {
+    return AucScan{a.start > b.start ? a.start : b.start, a.cum + b.cum};
+  }
+};
+struct AucIn {
+  const uint32_t *skey, *slab;
+  __device__ __forceinline__ AucScan operator()(int32_t p) const {
+    const bool head = p == 0 || skey[p] != skey[p - 1];
+    return AucScan{head ? p : 0, (int32_t)slab[p]};
+  }
+};
+__global__ void k_auc_keys(int32_t n, const float *__restrict__ score, const int32_t *__restrict__ label,
+                           uint32_t *__restrict__ key, uint32_t *__restrict__ lab) {
+  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t u = __float_as_uint(score[i] + 0.0f);  // -0 and +0 tie
+  key[i] = (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // ascending order of the floats
+  lab[i] = label[i] > 0 ? 1u : 0u;
+}
+// out[0] += sum over tie groups of positives(group) * (2 * start + length + 1) ; out[1] = positives
+__global__ void k_auc_ranksum(int32_t n, const uint32_t *__restrict__ skey, const AucScan *__restrict__ sc,
+                              unsigned long long *__restrict__ out) {
+  unsigned long long acc = 0;
+  for (int32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+    if (p + 1 < n && skey[p + 1] == skey[p]) continue;  // not the tail of its group
+    const AucScan e = sc[p];
+    const long long len = p - e.start + 1;
+    const long long pos = e.cum - (e.start > 0 ? sc[e.start - 1].cum : 0);
+    acc += (unsigned long long)(pos * (2ll * e.start + len + 1));
+    if (p == n - 1) out[1] = (unsigned long long)e.cum;
+  }
+  if (acc) atomicAdd(out, acc);
+}
+
+static double auc_device(ftrl_handle *h, int64_t n64, const float *d_score, const int32_t *d_label) {
+  if (n64 <= 0) return std::nan("");
+  if (n64 >= (1ll << 31) - 64) throw ArgFail{"ftrl_eval_auc: n must be < 2^31"};
+  const int32_t n = (int32_t)n64;
+  DevBuf<uint32_t> key, lab, skey, slab;
+  DevBuf<AucScan> sc;
+  DevBuf<unsigned long long> out;
+  DevBuf<uint8_t> tmp;
+  key.alloc(n); lab.alloc(n); skey.alloc(n); slab.alloc(n); sc.alloc(n); out.alloc(2);
+  size_t a = 0, b = 0;
+  thrust::counting_iterator<int32_t> cnt(0);
+  cub::DeviceRadixSort::SortPairs(nullptr, a, key.p, skey.p, lab.p, slab.p, n, 0, 32);
+  auto it = thrust::make_transform_iterator(cnt, AucIn{skey.p, slab.p});
+  cub::DeviceScan::InclusiveScan(nullptr, b, it, sc.p, AucScanOp(), n);
+  size_t bytes = std::max(a, b) + 256;
+  tmp.alloc(bytes);
+  FTRL_CUDA(cudaMemsetAsync(out.p, 0, 2 * sizeof(unsigned long long), h->compute));
+  k_auc_keys<<<(n + 255) / 256, 256, 0, h->compute>>>(n, d_score, d_label, key.p, lab.p);
+  size_t t = bytes;
+  FTRL_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, t, key.p, skey.p, lab.p, slab.p, n, 0, 32, h->compute));
+  t = bytes;
+  FTRL_CUDA(cub::DeviceScan::InclusiveScan(tmp.p, t, it, sc.p, AucScanOp(), n, h->compute));
+  k_auc_ranksum<<<std::min(1024, (n + 255) / 256), 256, 0, h->compute>>>(n, skey.p, sc.p, out.p);
+  FTRL_CUDA(cudaGetLastError());
+  unsigned long long r[2] = {0, 0};
+  FTRL_CUDA(cudaMemcpyAsync(r, out.p, sizeof(r), cudaMemcpyDeviceToHost, h->compute));
+  FTRL_CUDA(cudaStreamSynchronize(h->compute));
+  const long double n_pos = (long double)r[1], n_neg = (long double)n - n_pos;
+  if (n_pos == 0 || n_neg == 0) return std::nan("");
+  return (double)(((long double)r[0] - n_pos * (n_pos + 1)) / (2 * n_pos * n_neg));
+}
+
+// ---------------------------------------------------------------------------------------------
 // host-pointer path: CSR staged through slots, async copies on the copy stream
 // ---------------------------------------------------------------------------------------------
 static void retire_slot(ftrl_handle *h, Slot &s) {
@@ -693,7 +779,7 @@ static void check_device_err(ftrl_handle *h) {
   if (e) {
     FTRL_CUDA(cudaMemset(h->d_err, 0, sizeof(e)));
     if (e == 2) throw ArgFail{"multi-GPU run: a sample repeats a field (the sharded path needs distinct fields per sample)"};
-    if (e == 3) throw ArgFail{"multi-GPU run: the rows owned by this rank exceed the workspace (extreme id skew)"};
+    if (e == 3) throw ArgFail{"multi-GPU run: the rows owned by one rank exceed its workspace (extreme id skew): the step was skipped on every rank, no state was changed"};
     if (e == 4) throw StateFail{"multi-GPU run: a peer did not reach the device barrier in time"};
     throw ArgFail{"sequential mode: a sample exceeds the supported size (more than 96 valid features, or FM n_factors > 1024)"};
   }
@@ -725,6 +811,7 @@ static void train_device_sharded(ftrl_handle *h, const Batch &b, float *logit_ou
   const int grid = h->n_sms * 4;
   thrust::counting_iterator<int32_t> cnt(0);
   if (!logit_out) logit_out = h->logit_ws.p;
+  const uint32_t step_tag = h->epoch + 1;  // the first barrier epoch of this step: the same on every rank, never 0
   {
     PhaseScope ps(h, PH_PREP);
     FTRL_CUDA(cudaMemsetAsync(h->batch_flags.p, 0x01, sizeof(int32_t), h->compute));
@@ -770,8 +857,8 @@ static void train_device_sharded(ftrl_handle *h, const Batch &b, float *logit_ou
     size_t bytes = h->cub_bytes;
     FTRL_CUDA(cub::DeviceSelect::If(h->cub_tmp.p, bytes, cnt, h->sel.p, h->n_sel.p, h->G * nnz_max,
                                     OwnedPred{h->peers, nnz_max}, h->compute));
-    k_fill_owned<<<(oc + 255) / 256, 256, 0, h->compute>>>(h->peers, nnz_max, oc, lsent, h->sel.p, h->n_sel.p, h->okey.p,
-                                                          h->osrc.p, h->d_err);
+    k_fill_owned<<<(oc + 255) / 256, 256, 0, h->compute>>>(h->peers, nnz_max, oc, lsent, step_tag, h->sel.p, h->n_sel.p,
+                                                          h->okey.p, h->osrc.p, h->d_err);
     bytes = h->cub_bytes;
     FTRL_CUDA(cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, bytes, h->okey.p, h->ckey.p, h->osrc.p, h->csrc.p, oc, 0,
                                               key_bits((int32_t)h->n_local), h->compute));
@@ -798,38 +885,16 @@ static void train_device_sharded(ftrl_handle *h, const Batch &b, float *logit_ou
     }
     FTRL_CUDA(cudaGetLastError());
     launched(h, PH_SEGMENT);
+    launch_canon(h, b);
+    launched(h, PH_SEGMENT);
     peer_barrier(h);  // 2: classes / inbox slots are known everywhere, w of the touched slices is materialised
+    k_check_abort<<<1, 1, 0, h->compute>>>(h->peers, step_tag, h->batch_flags.p, h->d_err);
+    FTRL_CUDA(cudaGetLastError());
   }
   const ItemDecode dec = make_item_decode(d.k, 4);
   {
     PhaseScope ps(h, PH_SAMPLE);
-    if (b.n_rows > 0) {
-      TileGeom geo;
-      geo.f_cap = h->tile_f_cap;
-      geo.stride = h->tile_stride;
-      geo.stride1 = h->tile_stride1;
-      geo.inflight = h->tile_inflight;
-      geo.n_stage = h->tile_stages;
-      geo.n_meta = h->tile_meta;
-      geo.consumers = h->tile_consumers;
-      geo.dbg = h->tile_dbg;
-      geo.smem_bytes = h->tile_smem;
-      const int tgrid = (int)std::min<int64_t>(b.n_rows, (int64_t)h->n_sms * h->tile_ctas_per_sm);
-#define FFM_TILE(I)                                                                                            \
-  if (h->tile_cache)                                                                                              \
-    k_ffm_tile<PRECISE, I, true><<<tgrid, tile_threads(geo.consumers), geo.smem_bytes, h->compute>>>(             \
-        b, d, h->hyper, dec, geo, h->batch_flags.p, h->rowspace, h->bias, h->pair_lut, h->occ_pos.p, h->scan.p, h->g.p, logit_out); \
-  else                                                                                                            \
-    k_ffm_tile<PRECISE, I, false><<<tgrid, tile_threads(geo.consumers), geo.smem_bytes, h->compute>>>(            \
-        b, d, h->hyper, dec, geo, h->batch_flags.p, h->rowspace, h->bias, h->pair_lut, h->occ_pos.p, h->scan.p, h->g.p, logit_out)
-      if (h->tile_ipt <= 1) FFM_TILE(1);
-      else if (h->tile_ipt == 2) FFM_TILE(2);
-      else if (h->tile_ipt == 3) FFM_TILE(3);
-      else FFM_TILE(4);
-#undef FFM_TILE
-      FTRL_CUDA(cudaGetLastError());
-      launched(h, PH_SAMPLE);
-    }
+    if (b.n_rows > 0) launch_tile<PRECISE>(h, b, dec, logit_out);
   }
   {
     PhaseScope ps(h, PH_REDUCE);
@@ -842,12 +907,7 @@ static void train_device_sharded(ftrl_handle *h, const Batch &b, float *logit_ou
   {
     // local duplicates are reduced here; each row's sum goes to its owner's inbox (or is applied here)
     PhaseScope ps(h, PH_ROWS);
-    k_ffm_staged_rows<PRECISE, 8><<<grid * 4, 256, 0, h->compute>>>(d, h->hyper, nnz, h->batch_flags.p, h->tab, h->lin, h->chunk,
-                                                                   h->n_chunks.p, h->chunk_pos.p, h->skey.p, h->scan.p,
-                                                                   h->staging.p, h->staging_lin.p, h->part.p, h->part_lin.p,
-                                                                   h->exportd);
-    FTRL_CUDA(cudaGetLastError());
-    launched(h, PH_ROWS);
+    launch_regrad<PRECISE>(h, b);
   }
   {
     PhaseScope ps(h, PH_COMBINE);
@@ -862,7 +922,7 @@ static void train_device_sharded(ftrl_handle *h, const Batch &b, float *logit_ou
     PhaseScope ps(h, PH_APPLY);
     k_owner_apply<PRECISE, 256><<<grid, 256, 0, h->compute>>>(h->peers, d, h->hyper, oc, h->n_sel.p, h->batch_flags.p, h->ckey.p,
                                                               h->cflag.p, h->inbox.p, h->inbox_lin.p, h->tab, h->lin);
-    k_bias_apply<PRECISE><<<1, 1, 0, h->compute>>>(h->peers, h->hyper, h->bias);
+    k_bias_apply<PRECISE><<<1, 1, 0, h->compute>>>(h->peers, h->hyper, h->batch_flags.p, h->bias);
     FTRL_CUDA(cudaGetLastError());
     launched(h, PH_APPLY, 2);
   }
@@ -998,12 +1058,9 @@ int ftrl_create(const ftrl_config *cfg, ftrl_handle **out) {
         h->tile_ctas_per_sm = ctas;
         h->tile_smem = tile_smem_bytes(d.n_fields, stride, stages, metas);
         const int sm = (int)h->tile_smem;
-#define TILE_ATTR(P, I)                                                                                              \
-  FTRL_CUDA(cudaFuncSetAttribute(k_ffm_tile<P, I, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm)); \
-  FTRL_CUDA(cudaFuncSetAttribute(k_ffm_tile<P, I, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm))
+#define TILE_ATTR(P, I) FTRL_CUDA(cudaFuncSetAttribute(k_ffm_tile<P, I>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm))
         TILE_ATTR(false, 1); TILE_ATTR(false, 2); TILE_ATTR(false, 3); TILE_ATTR(false, 4);
         TILE_ATTR(true, 1); TILE_ATTR(true, 2); TILE_ATTR(true, 3); TILE_ATTR(true, 4);
-        h->tile_cache = env_int("FTRL_B200_TILE_CACHE", 1);
         h->tile_inflight = std::max(2, std::min(TILE_MAX_STAGE, env_int("FTRL_B200_TILE_INFLIGHT", TILE_MAX_STAGE)));
 #undef TILE_ATTR
       }
@@ -1264,6 +1321,31 @@ int ftrl_randomize_state(ftrl_handle *h, uint64_t seed, float z_scale, float n_l
   });
 }
 
+// ---- evaluation metric -----------------------------------------------------------------------
+int ftrl_eval_auc_device(ftrl_handle *h, int64_t n, const float *scores, const int32_t *label, double *auc_out) {
+  if (!h || !auc_out) return FTRL_ERR_ARG;
+  return guarded(h, [&] {
+    if (n > 0 && (!scores || !label)) throw ArgFail{"scores/label is NULL"};
+    *auc_out = auc_device(h, n, scores, label);
+  });
+}
+int ftrl_eval_auc(ftrl_handle *h, int64_t n, const float *scores, const int32_t *label, double *auc_out) {
+  if (!h || !auc_out) return FTRL_ERR_ARG;
+  return guarded(h, [&] {
+    if (n > 0 && (!scores || !label)) throw ArgFail{"scores/label is NULL"};
+    if (n < 0) throw ArgFail{"negative size"};
+    DevBuf<float> ds;
+    DevBuf<int32_t> dl;
+    ds.alloc((size_t)n);
+    dl.alloc((size_t)n);
+    if (n > 0) {
+      FTRL_CUDA(cudaMemcpyAsync(ds.p, scores, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, h->compute));
+      FTRL_CUDA(cudaMemcpyAsync(dl.p, label, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, h->compute));
+    }
+    *auc_out = auc_device(h, n, ds.p, dl.p);
+  });
+}
+
 // ---- model files ----------------------------------------------------------------------------
 int ftrl_save_model(ftrl_handle *h, const char *path, int compress_level) {
   if (!h || !path) return FTRL_ERR_ARG;
@@ -1517,8 +1599,6 @@ static void set_rowspace(ftrl_handle *h, int log2G, int rank, int G) {
   rsp = RowSpace{};
   rsp.tab = h->tab;
   rsp.lin = h->lin;
-  rsp.staging = h->staging.p;
-  rsp.staging_lin = h->staging_lin.p;
   rsp.rc_w = h->rc_w.p;
   rsp.rc_lin = h->rc_lin.p;
   rsp.log2G = log2G;
@@ -1581,6 +1661,12 @@ int ftrl_attach_peers(ftrl_handle *h, const void *blobs) {
       self_ex.dst_at = h->dst_at.p;
       void *mine[PEER_BUFS];
       peer_buffers(h, mine);
+      // the dry run synchronises on a PRIVATE SyncArea: a peer that finished attaching earlier may already be
+      // writing its first step's flag / row counts into this rank's real one, which must not be reset here
+      DevBuf<SyncArea> scratch_sync;
+      scratch_sync.alloc(1);
+      FTRL_CUDA(cudaMemset(scratch_sync.p, 0, sizeof(SyncArea)));
+      mine[8] = scratch_sync.p;
       wire_peer(h, self_sh, me, self_ex, 0, mine);
       const int G = h->G, log2G = h->log2G, rank = h->rank;
       h->shards = self_sh;
@@ -1609,8 +1695,7 @@ int ftrl_attach_peers(ftrl_handle *h, const void *blobs) {
       h->G = G; h->log2G = log2G; h->rank = rank;
       FTRL_CUDA(cudaMemcpy(h->bias, &bias_save, sizeof(float4), cudaMemcpyHostToDevice));
       FTRL_CUDA(cudaMemset(h->d_err, 0, sizeof(int32_t)));
-      FTRL_CUDA(cudaMemset(h->sync, 0, sizeof(SyncArea)));
-      h->epoch = 0;
+      h->epoch = 0;  // the real SyncArea (zeroed by ftrl_create) has not been touched
     }
     h->shards = sh;
     h->peers = pr;

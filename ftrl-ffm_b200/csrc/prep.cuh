@@ -155,6 +155,28 @@ __global__ void k_occ_class(int32_t nnz, uint32_t sentinel, int fuse, const uint
   occ_pos[t] = fused ? -1 : p;
 }
 
+// canon[s][f] = (row locator, value) of the valid feature of sample s that carries field f, CANON_NONE when
+// there is none.  Meaningful for samples with distinct fields (the tile path).  Warp per sample.  Remote rows
+// (sharded runs) are named by the sorted head position of the row in the local batch: their w plane sits in
+// the row cache at that position (shard.cuh).
+__global__ void k_build_canon(Batch b, Dims d, int log2G, int rank, const int32_t *__restrict__ occ_pos,
+                              const SegScan *__restrict__ scan, CanonEntry *__restrict__ canon) {
+  const int lane = threadIdx.x & 31;
+  const int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (s >= b.n_rows) return;
+  CanonEntry *row = canon + s * d.n_fields;
+  for (int f = lane; f < d.n_fields; f += 32) row[f] = CanonEntry{CANON_NONE, 0.f};
+  __syncwarp();
+  const int Gm1 = (1 << log2G) - 1;
+  const int64_t r0 = b.row_ptr[s], r1 = b.row_ptr[s + 1];
+  for (int64_t t = r0 + lane; t < r1; t += 32) {
+    const int32_t fld = b.field[t], ft = b.feat[t];
+    if (!feat_valid(d, fld, ft)) continue;
+    const int32_t loc = (ft & Gm1) == rank ? (ft >> log2G) : -1 - scan[occ_pos[t]].start;
+    row[fld] = CanonEntry{loc, b.val[t]};
+  }
+}
+
 // everything a chunk-level kernel needs to know about chunk c
 struct ChunkInfo {
   int32_t p0, p1;    // sorted-position range of this chunk

@@ -17,8 +17,8 @@
 //       w = W(n,z) for the slices the global batch touches into the table and pushes it into the row cache
 //       of every remote rank that touches the row (one NVLink store stream per distinct (row, rank))
 //   --  barrier 2
-//   S3  k_ffm_tile over the local samples (all addresses local: shard rows, row cache, staging);
-//       k_ffm_staged_rows / k_ffm_combine reduce the local duplicates and store each row's (sum g, sum g^2)
+//   S3  k_ffm_tile over the local samples (all addresses local: shard rows, row cache);
+//       k_ffm_regrad_rows / k_ffm_combine reduce the local duplicates and store each row's (sum g, sum g^2)
 //       into the owner's inbox (Export); the local (sum g, sum g^2, loss) of the bias goes to every peer
 //   --  barrier 3
 //   S4  owner side: k_owner_apply sums the <= G inbox entries of a row in rank order and applies the
@@ -39,6 +39,7 @@ struct SyncArea {
   int32_t n_uniq[MAX_SHARDS];     // n_uniq[q] = distinct rows of rank q's current batch (written by q)
   int32_t simple[MAX_SHARDS];     // simple[q] != 0: every sample of rank q's batch has distinct fields
   double red[MAX_SHARDS][4];      // red[q] = {sum g, sum g^2, sum loss, n_rows} of rank q's batch
+  uint32_t abort_at[MAX_SHARDS];  // abort_at[q] = step tag at which rank q asked every rank to skip the step (written by q)
 };
 
 constexpr uint32_t UINFO_SINGLE = 1u << 30;  // uinfo = sorted head position | UINFO_SINGLE
@@ -136,6 +137,17 @@ __global__ void k_merge_flags(Peers pr, int32_t *batch_flags, int32_t *err) {
   if (!all) *err = 2;  // sharded mode has no generic fallback yet
 }
 
+// after barrier 2: some rank called the step off (k_fill_owned) -> nothing of this step may change z / n
+__global__ void k_check_abort(Peers pr, uint32_t step_tag, int32_t *batch_flags, int32_t *err) {
+  bool any = false;
+  for (int q = 0; q < pr.G; q++)
+    any = any || *reinterpret_cast<const volatile uint32_t *>(&pr.sync[pr.rank]->abort_at[q]) == step_tag;
+  if (any) {
+    batch_flags[0] = 0;
+    if (*err == 0) *err = 3;
+  }
+}
+
 // ---- S2: owner side ---------------------------------------------------------------------------------
 struct OwnedPred {
   Peers pr;
@@ -147,14 +159,20 @@ struct OwnedPred {
   }
 };
 
-// (local row, source) pairs of the owned contributions; the tail up to `cap` is padded with the sentinel
-__global__ void k_fill_owned(Peers pr, int32_t nnz_max, int32_t cap, uint32_t local_sentinel,
+// (local row, source) pairs of the owned contributions; the tail up to `cap` is padded with the sentinel.
+// More contributions than the workspace holds (ids concentrated on one residue mod G): the whole step is
+// called off on EVERY rank before any z / n is touched -- the tag goes to every peer, k_check_abort reads it
+// after barrier 2 and turns the remaining kernels of the step into no-ops (batch_flags[0] = 0).
+__global__ void k_fill_owned(Peers pr, int32_t nnz_max, int32_t cap, uint32_t local_sentinel, uint32_t step_tag,
                              const int32_t *__restrict__ sel, const int32_t *__restrict__ n_sel,
                              uint32_t *__restrict__ okey, uint32_t *__restrict__ osrc, int32_t *__restrict__ err) {
   const int32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= cap) return;
   const int32_t n = *n_sel;
-  if (j == 0 && n > cap) *err = 3;  // owned contributions exceed the workspace (extreme skew)
+  if (j == 0 && n > cap) {
+    *err = 3;  // owned contributions exceed the workspace (extreme skew)
+    for (int q = 0; q < pr.G; q++) *reinterpret_cast<volatile uint32_t *>(&pr.sync[q]->abort_at[pr.rank]) = step_tag;
+  }
   if (j < n) {
     const int32_t idx = sel[j];
     const int q = idx / nnz_max, u = idx - q * nnz_max;
@@ -359,7 +377,8 @@ __global__ void k_publish_red(Peers pr, const double *__restrict__ local4) {
 
 // bias update from the G partials, in rank order (identical on every rank)
 template <bool PRECISE>
-__global__ void k_bias_apply(Peers pr, Hyper h, float4 *__restrict__ bias) {
+__global__ void k_bias_apply(Peers pr, Hyper h, const int32_t *__restrict__ batch_flags, float4 *__restrict__ bias) {
+  if (batch_flags[0] == 0) return;  // the step was called off
   double a = 0.0, q2 = 0.0, n = 0.0;
   for (int q = 0; q < pr.G; q++) {
     a += pr.sync[pr.rank]->red[q][0];

@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <numeric>
 #include <random>
 #include <stdexcept>
@@ -126,7 +127,13 @@ class Trainer {
     if (train)
       rc = ftrl_train_batch(h_, (int64_t)rows, p.row_ptr, p.field, p.feat, p.val, p.label, nullptr, slot);
     else {
-      rc = ftrl_predict_batch(h_, (int64_t)rows, p.row_ptr, p.field, p.feat, p.val, p.label, 0, score_sink(rows), slot);
+      float *out = score_sink(rows);
+      if (opt_.auc) {  // keep every score and label of the pass: one block per call, never moved while in flight
+        scores_.emplace_back(rows);
+        out = scores_.back().data();
+        labels_.emplace_back(p.label, p.label + rows);
+      }
+      rc = ftrl_predict_batch(h_, (int64_t)rows, p.row_ptr, p.field, p.feat, p.val, p.label, 0, out, slot);
     }
     if (rc != FTRL_OK) die(h_, train ? "ftrl_train_batch" : "ftrl_predict_batch");
     n_submitted_ += rows;
@@ -151,6 +158,20 @@ class Trainer {
     return r;
   }
 
+  // ROC AUC over the scores collected since the last call (evaluation passes with --auc true); NaN if none
+  double take_auc() {
+    sync();
+    std::vector<float> sc;
+    std::vector<int32_t> la;
+    for (auto &b : scores_) sc.insert(sc.end(), b.begin(), b.end());
+    for (auto &b : labels_) la.insert(la.end(), b.begin(), b.end());
+    scores_.clear();
+    labels_.clear();
+    double auc = 0.0;
+    if (ftrl_eval_auc(h_, (int64_t)sc.size(), sc.data(), la.data(), &auc) != FTRL_OK) die(h_, "ftrl_eval_auc");
+    return auc;
+  }
+
   void begin_epoch(size_t expected_calls) { loss_parts_.reserve(std::max<size_t>(expected_calls + 8, 4096)); }
   ftrl_handle *handle() { return h_; }
 
@@ -170,6 +191,8 @@ class Trainer {
   std::vector<float> sink_[kPins];
   int next_pin_ = 0;
   std::vector<double> loss_parts_;
+  std::deque<std::vector<float>> scores_;
+  std::deque<std::vector<int32_t>> labels_;
   double loss_total_ = 0.0;
   size_t n_submitted_ = 0;
 };
@@ -216,6 +239,7 @@ void run_offline(const host::Options &o) {
       tr.run_block(eval, nullptr, eval.rows(), false);
       const double el = tr.take_loss();
       printf("epoch %d eval time: %.4lfs, eval loss: %.4lf\n", ep, since(t1), el);
+      if (o.auc) printf("epoch %d eval auc: %.6lf\n", ep, tr.take_auc());
     }
   }
   if (!o.model_path.empty() && ftrl_save_model(tr.handle(), o.model_path.c_str(), 10) != FTRL_OK)
@@ -292,6 +316,7 @@ void run_online(const host::Options &o) {
       const auto t1 = clk::now();
       const double el = one_pass(eval, o.eval_path, false);
       printf("epoch %d eval time: %.4lfs, eval loss: %.4lf\n", ep, since(t1), el);
+      if (o.auc) printf("epoch %d eval auc: %.6lf\n", ep, tr.take_auc());
     }
   }
   if (!o.model_path.empty() && ftrl_save_model(tr.handle(), o.model_path.c_str(), 10) != FTRL_OK)

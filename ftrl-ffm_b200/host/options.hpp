@@ -1,7 +1,7 @@
 // options.hpp -- command line of the drop-in `main`.
 // Same flags, defaults and input-type sniffing as the reference: src/utils/cmd_option.cpp:61-113,
 // src/include/utils/cmd_option.h:7-63.  Additive flags (default = reference-compatible): --batch_size,
-// --device, --seed, --csr_cache.
+// --device, --seed, --csr_cache, --auc.
 #pragma once
 #include <algorithm>
 #include <cctype>
@@ -39,7 +39,8 @@ static const char *kHelp =
     "--device <ordinal>: CUDA device\tdefault:0\n"
     "--seed <n>: shuffle / init seed (0 = from std::random_device)\tdefault:0\n"
     "--csr_cache <bool>: keep a binary image <file>.csr of each parsed data file and reuse it while the text is "
-    "unchanged\tdefault:false\n";
+    "unchanged\tdefault:false\n"
+    "--auc <bool>: also print `epoch N eval auc: ...` after every evaluation pass (computed on the GPU)\tdefault:false\n";
 
 struct Options {  // mirrors config_options (cmd_option.h:29-63)
   std::string model_path, train_path, eval_path, model_type = "FFM", file_type;
@@ -49,6 +50,7 @@ struct Options {  // mirrors config_options (cmd_option.h:29-63)
   // additive
   long batch_size = 1024;
   bool csr_cache = false;
+  bool auc = false;
   int device = 0;
   unsigned long long seed = 0;
 };
@@ -116,6 +118,7 @@ inline void parse_options(int argc, char **argv, Options &o) {
     else if (k == "--device") o.device = std::stoi(v);
     else if (k == "--seed") o.seed = std::stoull(v);
     else if (k == "--csr_cache") o.csr_cache = assign_bool(v);
+    else if (k == "--auc") o.auc = assign_bool(v);
     else throw std::invalid_argument("unknown argument: " + k + "\n");
   }
   o.file_type = detect_file_type(o.train_path);

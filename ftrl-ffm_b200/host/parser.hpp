@@ -94,6 +94,9 @@ inline void parse_token_general(const char *b, const char *e, const char *p, con
   q = c2 + 1;
   if (q >= tok_end) wrong_input(b, e);
   if (!parse_float(q, tok_end, v)) wrong_input(b, e);
+  // ids beyond the int range: std::stoi throws std::out_of_range in the reference (parser.cpp:26,33,76,83),
+  // which ends the run -- never let such an id wrap into [0, n_feats)
+  if (fld > 0x7fffffffL || fld < -0x80000000L || ft > 0x7fffffffL || ft < -0x80000000L) wrong_input(b, e);
   if (v != 0.0f) {
     out.field.push_back((int32_t)fld);
     out.feat.push_back((int32_t)ft);
@@ -314,6 +317,12 @@ inline bool load_csr_cache(const std::string &text_path, bool libffm, Csr &c) {
   bool ok = fread(&h, sizeof(h), 1, f) == 1 && memcmp(h.magic, "FTRLCSR1", 8) == 0 && h.src_size == size &&
             h.src_mtime_ns == mtime && h.libffm == (libffm ? 1 : 0) && h.rows >= 0 && h.nnz >= 0;
   if (ok) {
+    // the header must agree with the length of the image before anything is sized from it
+    struct stat st;
+    const __int128 want = (__int128)sizeof(h) + ((__int128)h.rows + 1) * 8 + (__int128)h.rows * 4 + (__int128)h.nnz * 12;
+    ok = fstat(fileno(f), &st) == 0 && (__int128)st.st_size == want;
+  }
+  if (ok) {
     c.row_ptr.resize((size_t)h.rows + 1);
     c.label.resize((size_t)h.rows);
     c.field.resize((size_t)h.nnz);
@@ -325,6 +334,7 @@ inline bool load_csr_cache(const std::string &text_path, bool libffm, Csr &c) {
     ok = ok && fread(c.feat.data(), sizeof(int32_t), c.feat.size(), f) == c.feat.size();
     ok = ok && fread(c.val.data(), sizeof(float), c.val.size(), f) == c.val.size();
     ok = ok && c.row_ptr.front() == 0 && c.row_ptr.back() == h.nnz;
+    for (size_t r = 0; ok && r + 1 < c.row_ptr.size(); r++) ok = c.row_ptr[r] <= c.row_ptr[r + 1];  // monotone
   }
   fclose(f);
   if (!ok) c.clear();

@@ -105,7 +105,8 @@ const char *ftrl_last_error(const ftrl_handle *h);
  * into an internal device slot and kernels are enqueued; logits_out (pre-update logits,
  * nullable, host) and *loss_sum_out (fp64 sum of eval/loss.h:8-12, nullable, host) are
  * valid after ftrl_sync().  Input buffers may be reused as soon as the call returns when
- * pageable, after ftrl_sync() or two further train calls when pinned. */
+ * pageable, after ftrl_sync() or THREE further train / predict calls when pinned (three
+ * CSR slots rotate; the copy of call i is only known to be complete when call i + 3 starts). */
 int ftrl_train_batch(ftrl_handle *h, int64_t n_rows, const int64_t *row_ptr, const int32_t *field,
                      const int32_t *feat, const float *val, const int32_t *label,
                      float *logits_out, double *loss_sum_out);
@@ -127,6 +128,15 @@ int ftrl_predict_batch_device(ftrl_handle *h, int64_t n_rows, int64_t nnz, const
                               const int32_t *field, const int32_t *feat, const float *val,
                               const int32_t *label, int output_prob, float *out,
                               double *loss_sum_out);
+
+/* ROC AUC of n scores (logits or probabilities: any monotone score) against 0/1 labels, computed on the
+ * device: radix sort + Mann-Whitney rank sum with average ranks over ties (exact integer arithmetic).
+ * The reference reports only the mean log-loss (src/include/eval/loss.h:8-12, evaluate.cpp:39-49); this is
+ * the second quality metric the evaluation pass reports (`main --auc true`).  Synchronous; *auc_out is a
+ * host double, NaN when only one class is present.  Host pointers / device pointers. */
+int ftrl_eval_auc(ftrl_handle *h, int64_t n, const float *scores, const int32_t *label, double *auc_out);
+int ftrl_eval_auc_device(ftrl_handle *h, int64_t n, const float *scores, const int32_t *label,
+                         double *auc_out);
 
 /* Blocks until every enqueued batch has finished and host outputs are written.
  * Replaces ThreadPool::synchronize (thread_pool.h:82-88) / the epoch join. */
@@ -206,7 +216,9 @@ int ftrl_randomize_state(ftrl_handle *h, uint64_t seed, float z_scale, float n_l
  *
  * ftrl_export_peer_blob: opaque, fixed-size descriptor of this rank's device buffers that peers can map
  * (cudaIpcMemHandle-based).  Exchange the blobs out of band (e.g. an all-gather over torch.distributed /
- * MPI), then hand all world_size blobs, in rank order, to ftrl_attach_peers. */
+ * MPI), then hand all world_size blobs, in rank order, to ftrl_attach_peers.  No host-side barrier is needed
+ * between ftrl_attach_peers and the first collective call: a rank that is still attaching is waited for by
+ * the device-side barrier of the step. */
 #define FTRL_PEER_BLOB_BYTES 1024
 int ftrl_export_peer_blob(ftrl_handle *h, void *blob /* FTRL_PEER_BLOB_BYTES */);
 int ftrl_attach_peers(ftrl_handle *h, const void *blobs /* world_size * FTRL_PEER_BLOB_BYTES */);
