@@ -9,8 +9,11 @@ Workload (config.workload): BASELINE.json configs[3] -- synthetic Criteo-shaped 
   value  : samples/s with the CSR minibatches already resident in HBM (CUDA-event time, max over ranks)
   e2e    : samples/s through ftrl_train_batch() with PINNED HOST buffers: H2D copies of the CSR and the
            D2H read of the loss are inside the timed region (3 batches in flight)
-  roofline: forward+update kernels (k_ffm_sample + k_ffm_rows + k_ffm_combine), algorithmic bytes of
-           SURVEY.md 8(d) / DESIGN.md divided by their CUDA-event time, against MEASURED_PEAKS.json
+  roofline: forward+update kernels (k_row_touch + k_row_materialise + k_build_canon + k_ffm_tile +
+           k_ffm_regrad_rows + k_ffm_combine; LR/FM: k_lrfm_sample + k_lrfm_rows + k_lrfm_combine), algorithmic
+           bytes of SURVEY.md 8(d) / DESIGN.md divided by their CUDA-event time, against MEASURED_PEAKS.json;
+           `traffic` = DRAM bytes of the same kernels from the ncu capture in profiles/traffic.json, used only
+           when that capture was made from the kernel sources the loaded library was built from
   cpu_baseline: the reference's train() (oracle/_ref, all host cores) on a bounded sample
 """
 from __future__ import annotations
@@ -53,6 +56,18 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the extra uniform-id roofline measurement")
     return ap.parse_args()
+
+
+def kernel_source_sha16():
+    """identifies the kernel sources a profile was captured from (profiles/traffic.json carries the same stamp)"""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "ftrl-ffm_b200", "csrc")
+    for name in sorted(os.listdir(d)):
+        if name.endswith((".cu", ".cuh", ".h")):
+            h.update(name.encode())
+            h.update(open(os.path.join(d, name), "rb").read())
+    return h.hexdigest()[:16]
 
 
 def peaks():
@@ -358,19 +373,24 @@ def main():
     bytes_alg = alg_bytes(model, n_fields, k, Ubar, nnz * world, B * world) / world  # per GPU
     peak, peak_src = peaks()
     achieved = bytes_alg / (hot_ms / 1e3) / 1e9
-    traffic = None
+    traffic, traffic_note = None, "no ncu capture for this workload"
     tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
+    if os.path.exists(tp) and world == 1:
         try:
-            traffic = json.load(open(tp)).get(f"{args.workload}-{args.dist}") if world == 1 else None
+            tj = json.load(open(tp))
+            if tj.get("_kernel_source_sha16") != kernel_source_sha16():
+                traffic_note = "profiles/traffic.json was captured from other kernel sources: not reported"
+            else:
+                traffic = tj.get(f"{args.workload}-{args.dist}")
+                traffic_note = tj.get("_source") if traffic else traffic_note
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "frac_of_nominal_8000": achieved / 8000.0,
+                "traffic": traffic, "traffic_source": traffic_note, "peak_source": peak_src, "frac_of_nominal_8000": achieved / 8000.0,
                 "dram_gbs_from_traffic": (traffic / (hot_ms / 1e3) / 1e9) if traffic else None,
-                "kernels": ("k_row_touch + k_row_materialise + k_ffm_tile + k_ffm_staged_rows + k_ffm_combine "
+                "kernels": ("k_row_touch + k_row_materialise + k_build_canon + k_ffm_tile + k_ffm_regrad_rows + k_ffm_combine "
                             "(forward + FTRL update)" if world == 1 else
-                            "owner select/sort/k_owner_materialise (pushes w to the row caches) + k_ffm_tile + k_ffm_staged_rows + "
+                            "owner select/sort/k_owner_materialise (pushes w to the row caches) + k_ffm_tile + k_ffm_regrad_rows + "
                             "k_ffm_combine + k_owner_apply (forward + FTRL update + row exchange)") if model == "FFM"
                 else "k_lrfm_sample + k_lrfm_rows + k_lrfm_combine",
                 "alg_bytes_per_step": bytes_alg, "kernel_ms_per_step": hot_ms,

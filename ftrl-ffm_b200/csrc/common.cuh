@@ -66,6 +66,12 @@ struct __align__(8) CanonEntry {
   float x;
 };
 constexpr int32_t CANON_NONE = (int32_t)0x80000000;
+// A partner row that is FUSED (occurs once in the batch) is not looked up in the table by the row kernel: its w
+// slice would be a 32-byte DRAM read nobody else shares.  The sample kernel, which has the row in shared
+// memory, leaves the finished gradient slice g x x w in a compact per-occurrence image instead, and the entry
+// names the slot of that image: CANON_FUSED | rank of the row among the fused rows of its sample.
+constexpr uint32_t CANON_FUSED = 0xA0000000u;  // top three bits 101 (remote locators are small negatives: 111)
+__device__ __forceinline__ bool canon_is_fused(int32_t loc) { return ((uint32_t)loc >> 29) == 5u; }
 
 // Where the reduced (sum g, sum g^2) of a row goes (k_ffm_regrad_rows / k_ffm_combine).  Single GPU: applied
 // in place.  Sharded: dst_at[sorted head position] = -2 apply here (this rank owns the row and is its only

@@ -62,6 +62,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// the same on a precomputed shared-memory address (the generic -> shared conversion costs ~10 instructions
+// per use); `hint_ns` > 0: the hardware may suspend the warp for about that long before it reports "not yet"
+// -- the helper warps wait with a long hint so that their polling does not take issue slots from the consumers
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar_addr, uint32_t parity, uint32_t hint_ns = 0) {
+  uint32_t ok;
+  do {
+    if (hint_ns)
+      asm volatile(
+          "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}\n"
+          : "=r"(ok) : "r"(bar_addr), "r"(parity), "r"(hint_ns) : "memory");
+    else
+      asm volatile(
+          "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+          : "=r"(ok) : "r"(bar_addr), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar_addr) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_addr) : "memory");
+}
 // global -> shared, completion (bytes) signalled on an mbarrier
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -105,8 +124,8 @@ struct RingCursor {
 
 // ---- tile geometry ------------------------------------------------------------------------------
 constexpr int TILE_META_WARPS = 2;   // warps prefetching sample metadata (CSR, occurrence class, linear records)
-// + one row-loader warp and one row-storer warp (TMA bulk copies)
-__host__ __device__ constexpr int tile_threads(int consumers) { return consumers + 32 * (2 + TILE_META_WARPS); }
+// + one row-loader warp (TMA bulk copies)
+__host__ __device__ constexpr int tile_threads(int consumers) { return consumers + 32 * (1 + TILE_META_WARPS); }
 constexpr int TILE_MAX_CONSUMERS = 768;
 constexpr int TILE_MAX_STAGE = 4;    // samples in flight in the row ring (power of two)
 constexpr int TILE_MAX_META = 8;     // metadata slots
@@ -120,37 +139,41 @@ struct TileGeom {
   int n_meta;       // metadata slots (> n_stage: metadata runs ahead of the row ring)
   int consumers;    // consumer threads (multiple of 32)
   int dbg;          // experiment switches (FTRL_B200_TILE_DBG): 1 skip w stores, 2 skip row stores, 64 L2 cache hints
+  uint32_t helper_ns;  // suspend hint (ns) of the helper warps' mbarrier waits, 0: plain polling
   size_t smem_bytes;
 };
 
-struct RowMeta {   // one 16-byte record per row of a sample
-  int32_t fk;      // field * k | (offset of the row inside its sample's span of the row ring, floats) << 16
-  float x;         // value
-  int32_t pos;     // -1: row finalised here (fused), >= 0: sorted position (staged: reduced by k_ffm_regrad_rows)
+// Per-sample metadata, one slot per FIELD (samples of the tile path have distinct fields, so a field names at
+// most one row of the sample): work items are fixed (field pair, factor chunk) triples, the same for every
+// sample, and the only per-sample indirection left in the inner loops is the row's offset in the row ring.
+struct RowEnt {    // 8 bytes
+  int32_t off;     // offset of the row inside its sample's span of the row ring (floats); 0 when the field is absent
+  float x;         // value; 0 when the field is absent (the aliased span start then contributes 0)
+};
+struct RowAux {    // 8 bytes
   int32_t loc;     // row locator (RowSpace): >= 0 local row, < 0: -1 - head position in the remote-row cache
+  int32_t pos;     // -1: row finalised here (fused); staged (reduced by k_ffm_regrad_rows): base of the occurrence's
+                   // image of fused-partner gradient slices (in slices of k floats)
 };
-// Rows of a sample are kept sorted by class: fused rows take slots 0, 1, ... (hdr nf of them), staged rows
-// take slots f_cap-1, f_cap-2, ... (hdr ns of them), so that the work items of a sample fall into three
-// homogeneous ranges (fused x fused, fused x staged, staged x staged) and a warp rarely mixes classes.
 struct SampleMeta {
-  RowMeta *row;     // [f_cap]
+  RowEnt *ent;      // [f_cap]
+  RowAux *aux;      // [f_cap]
   float4 *lin;      // [f_cap] {z, n, w, -} of the linear coordinate, prefetched
-  int32_t *hdr;     // [0] fused rows, [1] label, [2] floats of the row ring the sample needs, [3] staged rows
+  int32_t *hdr;     // [0] fused rows, [1] label, [2] floats of the row ring the sample needs, [3] present rows,
+                    // [4],[5] present-field mask lo/hi, [6],[7] fused-field mask lo/hi
+  uint8_t *flist;   // [f_cap] fields of the fused rows, ascending
 };
+constexpr int TILE_MAX_FR = 8;  // fused-row vectors per consumer thread (z kept in registers between the passes)
 
 __host__ __device__ inline size_t tile_meta_bytes(int f_cap) {
-  // RowMeta (16 B) + lin (16 B) per row, + header 16 B
-  return (size_t)f_cap * 32 + 16;
+  // RowEnt (8 B) + RowAux (8 B) + lin (16 B) per field, + header 32 B, + flist[f_cap] rounded to 16
+  return (size_t)f_cap * 32 + 32 + (size_t)((f_cap + 15) / 16) * 16;
 }
 __host__ __device__ inline size_t tile_stage_bytes(int f_cap, int stride) {
   return (size_t)f_cap * stride * sizeof(float);
 }
-// the pair table (m | n << 8) as uint16 for f_cap rows
-__host__ __device__ inline size_t tile_lut_bytes(int f_cap) {
-  return (((size_t)f_cap * (f_cap - 1) / 2 * 2) + 15) / 16 * 16;
-}
 __host__ __device__ inline size_t tile_smem_bytes(int f_cap, int stride, int n_stage, int n_meta) {
-  return tile_stage_bytes(f_cap, stride) * n_stage + tile_meta_bytes(f_cap) * n_meta + tile_lut_bytes(f_cap);
+  return tile_stage_bytes(f_cap, stride) * n_stage + tile_meta_bytes(f_cap) * n_meta;
 }
 
 // choose stride = 2*ld + pad (floats) such that column accesses of consecutive rows by the lanes of
@@ -227,24 +250,34 @@ __device__ __forceinline__ void apply4(float4 &z, float4 &n, const float4 &w, co
   gv = gx * wp.w; ftrl_apply<PRECISE>(z.w, n.w, w.w, gv, gv * gv, h);
 }
 
-// Thread roles: [0, consumers) compute; then one row-loader warp (bulk loads into the row ring), one
-// row-storer warp (bulk stores of the updated fused rows) and TILE_META_WARPS warps that prefetch sample
-// metadata into a deeper ring so that the row loader never waits on a dependent global-load chain.
+// Thread roles: [0, consumers) compute; then one row-loader warp (bulk loads into the row ring) and
+// TILE_META_WARPS warps that prefetch sample metadata into a deeper ring so that the row loader never waits
+// on a dependent global-load chain.
 //
 // Rows that occur once in the batch ("fused") are read (z, n), materialised, updated and written back here:
 // the algorithmic 20 B per coordinate.  Rows that occur several times ("staged") only lend their w plane
 // (materialised by k_row_materialise before this kernel) to the dot products; their gradient is re-derived
 // row by row in k_ffm_regrad_rows from the w slices of the partner rows, so nothing per occurrence is
 // written to HBM.
-template <bool PRECISE, int IPT>
-__global__ void __launch_bounds__(tile_threads(TILE_MAX_CONSUMERS), 1)
+//
+// Per sample the consumers run three passes:
+//   pass 0  fused rows, row-centric (thread = one float4 vector of one fused row, coalesced): w = W(n, z)
+//           (ffm.cpp:72-88) written over the z slot in shared memory and to the table (the stale-by-one w the
+//           reference keeps); z stays in registers
+//   pass 1  every (field pair, factor chunk) item, identical work for fused and staged rows: both slices are w
+//           now; logit (ffm.cpp:57-70), g = sigmoid(logit) - y
+//   pass 2  fused rows, same thread mapping as pass 0: FTRL update (ffm.cpp:90-136 telescoped)
+//           with the partner's w slice from shared memory; z', n' stored straight to the table (512 B per warp)
+template <bool PRECISE, int IPT, int FR, int MAXC>
+__global__ void __launch_bounds__(tile_threads(MAXC), 1)
 k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t *__restrict__ batch_flags,
            const __grid_constant__ RowSpace rsp, const float4 *__restrict__ bias, const uint32_t *__restrict__ pair_lut,
-           const int32_t *__restrict__ occ_pos, const SegScan *__restrict__ scan, float *__restrict__ g_out,
+           const int32_t *__restrict__ occ_pos, const SegScan *__restrict__ scan,
+           const int32_t *__restrict__ sbase, float *__restrict__ sparse, float *__restrict__ g_out,
            float *__restrict__ logit_out) {
   if (batch_flags[0] == 0) return;  // some sample repeats a field: the generic kernels take this batch
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ uint64_t bar_full[TILE_MAX_STAGE], bar_done[TILE_MAX_STAGE], bar_free[TILE_MAX_STAGE];
+  __shared__ uint64_t bar_full[TILE_MAX_STAGE], bar_done[TILE_MAX_STAGE];
   __shared__ uint64_t bar_mfull[TILE_MAX_META], bar_mfree[TILE_MAX_META];
   __shared__ float s_red[2][32];  // per-warp partial logits, double-buffered by sample parity
 
@@ -252,10 +285,9 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
   const int n_cons = geo.consumers;
   const int n_cons_warps = n_cons >> 5;
   const int lane = tid & 31;
-  // 0 consumer, 1 row loader, 3 row storer, 2 metadata
-  constexpr int NL = 1, NSW = 1;
-  const int role = tid < n_cons ? 0 : (tid < n_cons + 32 * NL ? 1 : (tid < n_cons + 32 * (NL + NSW) ? 3 : 2));
-  const int ld = d.ld, k = d.k;
+  // 0 consumer, 1 row loader, 2 metadata
+  const int role = tid < n_cons ? 0 : (tid < n_cons + 32 ? 1 : 2);
+  const int ld = d.ld, k = d.k, NF = d.n_fields;
   const int stride = geo.stride, stride1 = geo.stride1, f_cap = geo.f_cap, NS = geo.n_stage, MD = geo.n_meta;
   const size_t stage_bytes = tile_stage_bytes(f_cap, stride);
   // The row ring: NS * stage_bytes of shared memory handed out in sample-sized spans.  A fused row takes
@@ -264,43 +296,37 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
   constexpr int NSLOT = TILE_MAX_STAGE;
   const int ring_floats = (int)((size_t)NS * stage_bytes / sizeof(float));
   float *ring = reinterpret_cast<float *>(smem_raw);
-  __shared__ int s_base[NSLOT], s_need[NSLOT];
+  __shared__ int s_need[NSLOT];
   const size_t meta_bytes = tile_meta_bytes(f_cap);
   const int64_t rs = 3 * (int64_t)ld;
   const uint32_t row_bytes = (uint32_t)(2 * ld * sizeof(float));
   unsigned char *meta_base = smem_raw + (size_t)NS * stage_bytes;
-  uint16_t *s_lut = reinterpret_cast<uint16_t *>(meta_base + (size_t)MD * meta_bytes);
 
-  auto row_off = [](const RowMeta &rm) { return rm.fk >> 16; };
-  auto row_fk = [](const RowMeta &rm) { return rm.fk & 0xffff; };
   auto sample_meta = [&](int slot) {
     SampleMeta m;
     unsigned char *p = meta_base + (size_t)slot * meta_bytes;
-    m.row = reinterpret_cast<RowMeta *>(p);
-    p += (size_t)f_cap * 16;
+    m.ent = reinterpret_cast<RowEnt *>(p);
+    p += (size_t)f_cap * 8;
+    m.aux = reinterpret_cast<RowAux *>(p);
+    p += (size_t)f_cap * 8;
     m.lin = reinterpret_cast<float4 *>(p);
     p += (size_t)f_cap * 16;
     m.hdr = reinterpret_cast<int32_t *>(p);
+    p += 32;
+    m.flist = p;
     return m;
   };
-  // r-th row of a sample with nf fused rows: fused rows from the front, staged rows from the back
-  auto row_slot = [&](int r, int nf) { return r < nf ? r : f_cap - 1 - (r - nf); };
 
   if (tid == 0) {
     for (int st = 0; st < NSLOT; st++) {
-      mbar_init(&bar_full[st], NL);
+      mbar_init(&bar_full[st], 1);
       mbar_init(&bar_done[st], n_cons_warps);
-      mbar_init(&bar_free[st], NSW);
     }
     for (int sl = 0; sl < MD; sl++) {
       mbar_init(&bar_mfull[sl], 1);
-      mbar_init(&bar_mfree[sl], NSW);
+      mbar_init(&bar_mfree[sl], n_cons_warps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  for (int p = tid; p < f_cap * (f_cap - 1) / 2; p += blockDim.x) {
-    const uint32_t e = pair_lut[p];
-    s_lut[p] = (uint16_t)((e & 0xffu) | ((e >> 16) << 8));
   }
   __syncthreads();
 
@@ -308,82 +334,61 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
 
   if (role == 2) {
     // =========================== metadata warps ===========================
-    const int mw = (tid - n_cons - 32 * (NL + NSW)) >> 5;
+    const int mw = (tid - n_cons - 32) >> 5;
     RingCursor mc;
     mc.init(mw, MD);
     for (int it = mw; it < n_mine; it += TILE_META_WARPS, mc.advance(TILE_META_WARPS, MD)) {
       const int slot = mc.slot;
-      if (mc.round > 0) mbar_wait(&bar_mfree[slot], mc.prev_parity());
+      if (mc.round > 0) mbar_wait_a(smem_u32(&bar_mfree[slot]), mc.prev_parity(), geo.helper_ns);
       SampleMeta m = sample_meta(slot);
       const int64_t s = blockIdx.x + (int64_t)it * gridDim.x;
       const int64_t r0 = b.row_ptr[s];
       const int F = (int)min((int64_t)1 << 20, b.row_ptr[s + 1] - r0);
-      int nf = 0, ns = 0;
+      for (int f = lane; f < NF; f += 32) m.ent[f] = RowEnt{0, 0.f};
+      __syncwarp();
+      unsigned long long present = 0ull, fusedm = 0ull;
       for (int base = 0; base < F; base += 32) {
         const int t = base + lane;
-        int32_t fl = 0, ft = -1, pos = 0;
-        float x = 0.f;
-        bool ok = false;
+        unsigned long long pbit = 0ull, fbit = 0ull;
         if (t < F) {
-          fl = b.field[r0 + t];
-          ft = b.feat[r0 + t];
-          x = b.val[r0 + t];
-          ok = feat_valid(d, fl, ft);
-          if (ok) pos = occ_pos[r0 + t];
-        }
-        const bool fz = ok && pos < 0, sg = ok && pos >= 0;
-        const unsigned fm = __ballot_sync(0xffffffffu, fz), sm = __ballot_sync(0xffffffffu, sg);
-        const unsigned below = (1u << lane) - 1;
-        const int idx = fz ? nf + __popc(fm & below) : ns + __popc(sm & below);
-        if (ok && idx < f_cap) {
-          const int sl = fz ? idx : f_cap - 1 - idx;
-          RowMeta rm;
-          rm.fk = fl * k;
-          rm.x = x;
-          rm.pos = pos;
-          if ((ft & rsp.Gm1) == rsp.rank) {
-            rm.loc = ft >> rsp.log2G;
-            m.lin[sl] = rsp.lin[rm.loc];
-          } else {  // remote rows are never fused: pos >= 0, the row's cache slot is its sorted head position
-            const int32_t head = scan[pos].start;
-            rm.loc = -1 - head;
-            m.lin[sl] = make_float4(0.f, 0.f, rsp.rc_lin[head], 0.f);
+          const int32_t fl = b.field[r0 + t], ft = b.feat[r0 + t];
+          if (feat_valid(d, fl, ft)) {
+            const int32_t pos = occ_pos[r0 + t];
+            RowAux a;
+            a.pos = pos < 0 ? -1 : sbase[pos];  // staged rows: base of the occurrence's image of fused-partner slices
+            if ((ft & rsp.Gm1) == rsp.rank) {
+              a.loc = ft >> rsp.log2G;
+              m.lin[fl] = rsp.lin[a.loc];
+            } else {  // remote rows are never fused: pos >= 0, the row's cache slot is its sorted head position
+              const int32_t head = scan[pos].start;
+              a.loc = -1 - head;
+              m.lin[fl] = make_float4(0.f, 0.f, rsp.rc_lin[head], 0.f);
+            }
+            m.aux[fl] = a;
+            m.ent[fl].x = b.val[r0 + t];
+            pbit = 1ull << fl;
+            if (pos < 0) fbit = pbit;
           }
-          m.row[sl] = rm;
         }
-        nf += __popc(fm);
-        ns += __popc(sm);
+        present |= ((unsigned long long)__reduce_or_sync(0xffffffffu, (unsigned)(pbit >> 32)) << 32) |
+                   __reduce_or_sync(0xffffffffu, (unsigned)pbit);
+        fusedm |= ((unsigned long long)__reduce_or_sync(0xffffffffu, (unsigned)(fbit >> 32)) << 32) |
+                  __reduce_or_sync(0xffffffffu, (unsigned)fbit);
       }
-      // distinct fields: nf + ns <= f_cap (the clamps only guard malformed input)
-      nf = min(nf, f_cap);
-      ns = min(ns, f_cap - nf);
-      const int nv = nf + ns;
       __syncwarp();
-      // offsets of the rows inside the sample's span (exclusive prefix sum of the row sizes)
-      int need = 0;
-      for (int base = 0; base < nv; base += 32) {
-        const int r = base + lane;
-        const int sl = row_slot(r, nf);
-        RowMeta rm;
-        int sz = 0;
-        if (r < nv) {
-          rm = m.row[sl];
-          sz = r < nf ? stride : stride1;
-        }
-        int inc = sz;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int t = __shfl_up_sync(0xffffffffu, inc, o);
-          if (lane >= o) inc += t;
-        }
-        if (r < nv) m.row[sl].fk = rm.fk | ((need + inc - sz) << 16);
-        need += __shfl_sync(0xffffffffu, inc, 31);
-      }
+      // the list of fused fields (the loader places the rows in the ring and fills in their offsets)
+      for (int f = lane; f < NF; f += 32)
+        if ((fusedm >> f) & 1ull) m.flist[__popcll(fusedm & ((1ull << f) - 1ull))] = (uint8_t)f;
+      const int need = __popcll(fusedm) * stride + (__popcll(present) - __popcll(fusedm)) * stride1;
       if (lane == 0) {
-        m.hdr[0] = nf;
+        m.hdr[0] = __popcll(fusedm);
         m.hdr[1] = b.label[s];
         m.hdr[2] = need;
-        m.hdr[3] = ns;
+        m.hdr[3] = __popcll(present);
+        m.hdr[4] = (int32_t)(uint32_t)present;
+        m.hdr[5] = (int32_t)(uint32_t)(present >> 32);
+        m.hdr[6] = (int32_t)(uint32_t)fusedm;
+        m.hdr[7] = (int32_t)(uint32_t)(fusedm >> 32);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_mfull[slot]);
@@ -398,52 +403,74 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
     const uint64_t pol_stream = policy_evict_first(), pol_keep = policy_evict_last();
     RingCursor mc;
     mc.init(0, MD);
+    // The row ring is a circular buffer of floats: rows are placed one after another (a row that would cross
+    // the end starts over at 0), samples retire in order.  `live` = floats between the oldest live row and
+    // `head`, wrap waste included; a sample is admitted when its rows plus one worst-case wrap gap fit.
     int head = 0;     // next free float of the ring
-    int tail_it = 0;  // oldest sample whose span has not been handed back by the storer
+    int live = 0;
+    int tail_it = 0;  // oldest sample whose rows have not been handed back by the consumers
     for (int it = 0; it < n_mine; it++, mc.advance(1, MD)) {
       const int st = it & (NSLOT - 1);
       const int slot = mc.slot;
-      mbar_wait(&bar_mfull[slot], mc.parity());
+      mbar_wait_a(smem_u32(&bar_mfull[slot]), mc.parity(), geo.helper_ns);
       SampleMeta m = sample_meta(slot);
-      const int nf = m.hdr[0], nv = nf + m.hdr[3];
+      const int nf = m.hdr[0], np = m.hdr[3];
       const int need = m.hdr[2];
-      // a span for this sample: contiguous, after `head` or wrapped to the start of the ring; wait (in order)
-      // for older samples to retire until the sample slot is free and the span overlaps no live span
-      while (it - tail_it >= geo.inflight) {
-        mbar_wait(&bar_free[tail_it & (NSLOT - 1)], (uint32_t)((tail_it >> 2) & 1));
+      const unsigned long long present = ((unsigned long long)(uint32_t)m.hdr[5] << 32) | (uint32_t)m.hdr[4];
+      const unsigned long long fusedm = ((unsigned long long)(uint32_t)m.hdr[7] << 32) | (uint32_t)m.hdr[6];
+      while (it - tail_it >= geo.inflight || (tail_it < it && live + need + stride > ring_floats)) {
+        mbar_wait_a(smem_u32(&bar_done[tail_it & (NSLOT - 1)]), (uint32_t)((tail_it >> 2) & 1), geo.helper_ns);
+        live -= s_need[tail_it & (NSLOT - 1)];
         tail_it++;
       }
-      const int base = head + need <= ring_floats ? head : 0;
-      for (;;) {
-        bool clash = false;
-        for (int j = tail_it; j < it; j++) {
-          const int bj = s_base[j & (NSLOT - 1)], nj = s_need[j & (NSLOT - 1)];
-          clash = clash || (base < bj + nj && bj < base + need);
+      // place the rows in field order
+      int used = 0;
+      for (int base = 0; base < NF; base += 32) {
+        const int f = base + lane;
+        const bool here = f < NF && ((present >> f) & 1ull);
+        const int sz = here ? (((fusedm >> f) & 1ull) ? stride : stride1) : 0;
+        int inc = sz;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += t;
         }
-        if (!clash) break;
-        mbar_wait(&bar_free[tail_it & (NSLOT - 1)], (uint32_t)((tail_it >> 2) & 1));
-        tail_it++;
+        int pos = head + inc - sz;
+        const unsigned over = __ballot_sync(0xffffffffu, here && pos + sz > ring_floats);
+        if (over) {  // the first row that does not fit before the end, and every row after it, start over at 0
+          const int fs = __ffs(over) - 1;
+          const int wrap_pos = __shfl_sync(0xffffffffu, pos, fs);
+          if (lane >= fs) pos -= wrap_pos;
+          used += ring_floats - wrap_pos;
+        }
+        if (here) m.ent[f].off = pos;
+        head = __shfl_sync(0xffffffffu, pos + sz, 31);
+        used += __shfl_sync(0xffffffffu, inc, 31);
       }
-      head = base + need;
+      live += used;
       __syncwarp();
-      if (lane == 0) {
-        s_base[st] = base;
-        s_need[st] = need;
-      }
+      if (lane == 0) s_need[st] = used;
       __syncwarp();
-      float *rows = ring + base;
       // TMA bulk copies.  Fused rows bring z and n (they are updated here); staged rows bring only the w plane
       // their owner materialised
-      if (lane == 0) mbar_expect_tx(&bar_full[st], (uint32_t)(nf * (int)row_bytes + (nv - nf) * (int)(row_bytes / 2)));
+      // (experiment switches: 8 = staged rows are not loaded at all, 16 = loaded as two half copies)
+      if (lane == 0)
+        mbar_expect_tx(&bar_full[st], (uint32_t)(nf * (int)row_bytes + ((geo.dbg & 8) ? 0 : (np - nf) * (int)(row_bytes / 2))));
       __syncwarp();
-      for (int r = lane; r < nv; r += 32) {
-        const RowMeta rm = m.row[row_slot(r, nf)];
-        if (r < nf) {
-          if (hints) bulk_g2s_hint(rows + row_off(rm), rsp.tab + (int64_t)rm.loc * rs, row_bytes, &bar_full[st], pol_stream);
-          else bulk_g2s(rows + row_off(rm), rsp.tab + (int64_t)rm.loc * rs, row_bytes, &bar_full[st]);
-        } else {
-          if (hints) bulk_g2s_hint(rows + row_off(rm), rsp.w_plane(rm.loc, ld), row_bytes / 2, &bar_full[st], pol_keep);
-          else bulk_g2s(rows + row_off(rm), rsp.w_plane(rm.loc, ld), row_bytes / 2, &bar_full[st]);
+      for (int f = lane; f < NF; f += 32) {
+        if (!((present >> f) & 1ull)) continue;
+        float *dst = ring + m.ent[f].off;
+        const int32_t loc = m.aux[f].loc;
+        if ((fusedm >> f) & 1ull) {
+          if (hints) bulk_g2s_hint(dst, rsp.tab + (int64_t)loc * rs, row_bytes, &bar_full[st], pol_stream);
+          else bulk_g2s(dst, rsp.tab + (int64_t)loc * rs, row_bytes, &bar_full[st]);
+        } else if (geo.dbg & 16) {
+          const uint32_t h1 = (row_bytes / 4) & ~15u;
+          bulk_g2s(dst, rsp.w_plane(loc, ld), h1, &bar_full[st]);
+          bulk_g2s(reinterpret_cast<char *>(dst) + h1, reinterpret_cast<const char *>(rsp.w_plane(loc, ld)) + h1, row_bytes / 2 - h1, &bar_full[st]);
+        } else if (!(geo.dbg & 8)) {
+          if (hints) bulk_g2s_hint(dst, rsp.w_plane(loc, ld), row_bytes / 2, &bar_full[st], pol_keep);
+          else bulk_g2s(dst, rsp.w_plane(loc, ld), row_bytes / 2, &bar_full[st]);
         }
       }
       __syncwarp();
@@ -452,42 +479,45 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
     return;
   }
 
-  if (role == 3) {
-    // =========================== row storer warp ===========================
-    // retire samples in order: wait for the consumers, bulk-store the updated fused rows, then hand the
-    // stage back to the loader and the metadata slot back to the metadata warps
-    const uint64_t pol_stream = policy_evict_first();
-    RingCursor mc;
-    mc.init(0, MD);
-    for (int it = 0; it < n_mine; it++, mc.advance(1, MD)) {
-      const int st = it & (NSLOT - 1);
-      const int slot = mc.slot;
-      SampleMeta m = sample_meta(slot);
-      mbar_wait(&bar_done[st], (uint32_t)((it >> 2) & 1));
-      float *rows = ring + s_base[st];
-      const int nf = m.hdr[0];
-      for (int r = lane; r < nf && !(geo.dbg & 2); r += 32) {
-        const RowMeta rm = m.row[r];
-        if (hints) bulk_s2g_hint(rsp.tab + (int64_t)rm.loc * rs, rows + row_off(rm), row_bytes, pol_stream);
-        else bulk_s2g(rsp.tab + (int64_t)rm.loc * rs, rows + row_off(rm), row_bytes);
-      }
-      bulk_commit();
-      bulk_wait_read_all();
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&bar_free[st]);
-        mbar_arrive(&bar_mfree[slot]);
-      }
-    }
-    bulk_wait_all();
-    return;
-  }
-
   // =========================== consumer warps ===========================
   const float bias_w = [&] {
     const float4 bz = *bias;
     return weight_from<PRECISE>(bz.x, f_sqrt<PRECISE>(bz.y), h);
   }();
+  // the thread's pair items, fixed for the whole kernel: (field m, field n, factor chunk c), m < n
+  const uint32_t n_items = (uint32_t)NF * (uint32_t)(NF - 1) / 2u * dec.C;
+  // (packed: registers are the scarce resource of this kernel)
+  uint32_t pmn[IPT], pcol[IPT];  // m | n << 8 (0xffff: no item) ; column of slice A | column of slice B << 16
+#pragma unroll
+  for (int j = 0; j < IPT; j++) {
+    const uint32_t item = tid + j * n_cons;
+    pmn[j] = 0xffffu;
+    pcol[j] = 0;
+    if (item < n_items) {
+      uint32_t p, c;
+      dec(item, p, c);
+      const uint32_t e = pair_lut[p];
+      const uint32_t mi = e & 0xffffu, ni = e >> 16;
+      pmn[j] = mi | (ni << 8);
+      // slice A = (row of field m, field n), slice B = (row of field n, field m)
+      pcol[j] = (ni * k + c * 4) | ((mi * k + c * 4) << 16);
+    }
+  }
+  // the thread's fused-row vectors: (i-th fused row of the sample, float4 vector v of the row)
+  const int nvec = ld >> 2, vpf = k >> 2;
+  uint32_t fpk[FR];  // vector v | partner field of that slice << 16 | index i of the fused row << 24
+#pragma unroll
+  for (int r = 0; r < FR; r++) {
+    const int fitem = tid + r * n_cons;
+    const int i = fitem / nvec, v = fitem - i * nvec;
+    fpk[r] = (uint32_t)v | ((uint32_t)(v / vpf) << 16) | ((uint32_t)min(i, 255) << 24);
+  }
+  auto f_v = [&](int r) { return (int)(fpk[r] & 0xffffu); };
+  auto f_n = [&](int r) { return (int)((fpk[r] >> 16) & 0xffu); };
+  auto f_i = [&](int r) { return (int)(fpk[r] >> 24); };
+
+  const uint32_t a_full = smem_u32(bar_full), a_done = smem_u32(bar_done);
+  const uint32_t a_mfull = smem_u32(bar_mfull), a_mfree = smem_u32(bar_mfree);
   RingCursor mc;
   mc.init(0, MD);
   for (int it = 0; it < n_mine; it++, mc.advance(1, MD)) {
@@ -495,82 +525,58 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
     const int slot = mc.slot;
     const int64_t s = blockIdx.x + (int64_t)it * gridDim.x;
     SampleMeta m = sample_meta(slot);
-    mbar_wait(&bar_mfull[slot], mc.parity());
-    mbar_wait(&bar_full[st], (uint32_t)((it >> 2) & 1));
-    float *rows = ring + s_base[st];
-    const int nf = m.hdr[0], ns = m.hdr[3], nv = nf + ns;
-    // items of the sample in three ranges: fused x fused pairs, fused x staged, staged x staged
-    const uint32_t n_ff = (uint32_t)nf * (uint32_t)(nf - 1) / 2u * dec.C;
-    const uint32_t n_fs = (uint32_t)nf * (uint32_t)ns * dec.C;
-    const uint32_t n_items = (uint32_t)nv * (uint32_t)(nv - 1) / 2u * dec.C;
-    const float inv_nf = nf > 0 ? 1.0f / (float)nf : 0.f;
+    mbar_wait_a(a_mfull + 8 * slot, mc.parity());
+    mbar_wait_a(a_full + 8 * st, (uint32_t)((it >> 2) & 1));
+    const int nf = m.hdr[0];
+    const unsigned long long present = ((unsigned long long)(uint32_t)m.hdr[5] << 32) | (uint32_t)m.hdr[4];
+    const unsigned long long fusedm = ((unsigned long long)(uint32_t)m.hdr[7] << 32) | (uint32_t)m.hdr[6];
 
-    // ---- pass 1: w, logit ----
+    // ---- pass 0: w of the fused rows, in place over z ----
+    float4 zreg[FR];
+    unsigned long long fm = ~0ull;  // byte r: field of the thread's r-th fused row in this sample, 0xff: nothing to do
+    if (nf > 0) {
+#pragma unroll
+      for (int r = 0; r < FR; r++) {
+        if (f_i(r) < nf) {
+          const int mf = m.flist[f_i(r)];
+          // slices no partner touches (own field, absent fields) keep their z, n, w (ffm.cpp:72-88 never visits them)
+          if (f_n(r) != mf && ((present >> f_n(r)) & 1ull)) {
+            fm = (fm & ~(0xffull << (8 * r))) | ((unsigned long long)mf << (8 * r));
+            float *zp = ring + m.ent[mf].off + f_v(r) * 4;
+            const float4 z = *reinterpret_cast<const float4 *>(zp);
+            const float4 w = weight4<PRECISE>(z, *reinterpret_cast<const float4 *>(zp + ld), h);
+            *reinterpret_cast<float4 *>(zp) = w;
+            if (!(geo.dbg & 1)) *reinterpret_cast<float4 *>(rsp.tab + (int64_t)m.aux[mf].loc * rs + 2 * ld + f_v(r) * 4) = w;
+            zreg[r] = z;
+          }
+        }
+      }
+      named_bar_sync(2, n_cons);  // every fused row's w is in place before any pair item reads it
+    }
+
+    // ---- pass 1: logit ----
     float acc = 0.f;
-    float4 wAc[IPT], wBc[IPT];
-    // pass 2 reuses the item's slice offsets / classes from pass 1 instead of decoding it again
-    int offA[IPT], offB[IPT], cls[IPT];  // bit 0/1: row m / n fused
-    float xx[IPT];
 #pragma unroll
     for (int j = 0; j < IPT; j++) {
-      const uint32_t item = tid + j * n_cons;
-      cls[j] = 0;
-      if (item < n_items) {
-        uint32_t p, c;
-        int mi, ni;
-        if (item < n_ff) {
-          dec(item, p, c);
-          const uint32_t e = s_lut[p];
-          mi = e & 0xff;
-          ni = e >> 8;
-        } else if (item < n_ff + n_fs) {
-          dec(item - n_ff, p, c);
-          // p = n' * nf + m : exact for these ranges (p < 64 * 64, nf <= 64)
-          const int nq = __float2int_rd(((float)p + 0.5f) * inv_nf);
-          mi = (int)p - nq * nf;
-          ni = f_cap - 1 - nq;
-        } else {
-          dec(item - n_ff - n_fs, p, c);
-          const uint32_t e = s_lut[p];
-          mi = f_cap - 1 - (int)(e & 0xff);
-          ni = f_cap - 1 - (int)(e >> 8);
-        }
-        const RowMeta rmm = m.row[mi], rmn = m.row[ni];
-        const int oA = row_off(rmm) + row_fk(rmn) + (int)c * 4;  // slice A = (row m, field n)
-        const int oB = row_off(rmn) + row_fk(rmm) + (int)c * 4;  // slice B = (row n, field m)
-        offA[j] = oA;
-        offB[j] = oB;
-        xx[j] = rmm.x * rmn.x;
-        cls[j] = (rmm.pos < 0 ? 1 : 0) | (rmn.pos < 0 ? 2 : 0);
-        const float *sa = rows + oA;
-        const float *sb = rows + oB;
-        // staged rows hold w itself; fused rows hold (z, n): w = W(n, z), stored as the stale-by-one w the
-        // reference keeps (ffm.cpp:72-88)
-        float4 wA = *reinterpret_cast<const float4 *>(sa), wB = *reinterpret_cast<const float4 *>(sb);
-        if (rmm.pos < 0) {
-          wA = weight4<PRECISE>(wA, *reinterpret_cast<const float4 *>(sa + ld), h);
-          if (!(geo.dbg & 1)) *reinterpret_cast<float4 *>(rsp.tab + (int64_t)rmm.loc * rs + 2 * ld + row_fk(rmn) + c * 4) = wA;
-        }
-        if (rmn.pos < 0) {
-          wB = weight4<PRECISE>(wB, *reinterpret_cast<const float4 *>(sb + ld), h);
-          if (!(geo.dbg & 1)) *reinterpret_cast<float4 *>(rsp.tab + (int64_t)rmn.loc * rs + 2 * ld + row_fk(rmm) + c * 4) = wB;
-        }
-        wAc[j] = wA;
-        wBc[j] = wB;
+      if (pmn[j] != 0xffffu) {
+        const RowEnt eA = m.ent[pmn[j] & 0xffu], eB = m.ent[pmn[j] >> 8];
+        const float4 wA = *reinterpret_cast<const float4 *>(ring + eA.off + (pcol[j] & 0xffffu));
+        const float4 wB = *reinterpret_cast<const float4 *>(ring + eB.off + (pcol[j] >> 16));
         const float dot = fmaf(wA.x, wB.x, fmaf(wA.y, wB.y, fmaf(wA.z, wB.z, wA.w * wB.w)));
-        acc = fmaf(dot, xx[j], acc);
+        // an absent field has x = 0 and aliases the start of the ring: whatever is read there must not count
+        const float xx = eA.x * eB.x;
+        acc = xx != 0.f ? fmaf(dot, xx, acc) : acc;
       }
     }
-    for (int r = tid; r < nv; r += n_cons) {
-      const int sl = row_slot(r, nf);
-      const float4 e = m.lin[sl];
-      const float w = r < nf ? weight_from<PRECISE>(e.x, f_sqrt<PRECISE>(e.y), h) : e.z;
-      acc = fmaf(w, m.row[sl].x, acc);
+    for (int f = tid; f < NF; f += n_cons) {
+      if (!((present >> f) & 1ull)) continue;
+      const float4 e = m.lin[f];
+      const float w = ((fusedm >> f) & 1ull) ? weight_from<PRECISE>(e.x, f_sqrt<PRECISE>(e.y), h) : e.z;
+      acc = fmaf(w, m.ent[f].x, acc);
     }
-    // consumer-wide sum
-    // one barrier per sample: every warp adds the per-warp partials itself (same values, same order -> the
-    // same logit in every warp).  The buffer of sample `it` is next written for sample it + 2, i.e. by a warp
-    // that has passed the barrier of sample it + 1, which every warp reaches only after this read.
+    // consumer-wide sum: every warp adds the per-warp partials itself (same values, same order -> the same
+    // logit in every warp).  The buffer of sample `it` is next written for sample it + 2, i.e. by a warp that
+    // has passed the barrier of sample it + 1, which every warp reaches only after this read.
     float *red = s_red[it & 1];
     acc = warp_sum(acc);
     if (lane == 0) red[tid >> 5] = acc;
@@ -582,43 +588,49 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
       logit_out[s] = logit;
     }
 
-    // ---- pass 2: FTRL update of the fused rows in place; every (row, field) slice is read and written by
-    //      exactly one item (fields are distinct) ----
+    // ---- pass 2: FTRL update of the fused rows; every (row, field) slice belongs to exactly one thread ----
+    if (nf > 0) {
 #pragma unroll
-    for (int j = 0; j < IPT; j++) {
-      const int cl = cls[j];
-      if (cl) {
-        const float gx = g * xx[j];
-        const float4 wA = wAc[j], wB = wBc[j];
-        if (cl & 1) {
-          float *sa = rows + offA[j];
-          float4 zA = *reinterpret_cast<const float4 *>(sa), nA = *reinterpret_cast<const float4 *>(sa + ld);
-          apply4<PRECISE>(zA, nA, wA, wB, gx, h);
-          *reinterpret_cast<float4 *>(sa) = zA;
-          *reinterpret_cast<float4 *>(sa + ld) = nA;
-        }
-        if (cl & 2) {
-          float *sb = rows + offB[j];
-          float4 zB = *reinterpret_cast<const float4 *>(sb), nB = *reinterpret_cast<const float4 *>(sb + ld);
-          apply4<PRECISE>(zB, nB, wB, wA, gx, h);
-          *reinterpret_cast<float4 *>(sb) = zB;
-          *reinterpret_cast<float4 *>(sb + ld) = nB;
+      for (int r = 0; r < FR; r++) {
+        const int mf = (int)((fm >> (8 * r)) & 0xffull);
+        if (mf != 0xff) {
+          const RowEnt eM = m.ent[mf], eP = m.ent[f_n(r)];
+          const float *zp = ring + eM.off + f_v(r) * 4;
+          const float4 w = *reinterpret_cast<const float4 *>(zp);
+          float4 nn = *reinterpret_cast<const float4 *>(zp + ld);
+          // partner slice = (row of field fn, field mf), same factor chunk
+          const float4 wp = *reinterpret_cast<const float4 *>(ring + eP.off + mf * k + (f_v(r) - f_n(r) * vpf) * 4);
+          float4 z = zreg[r];
+          const float gx = g * (eM.x * eP.x);
+          apply4<PRECISE>(z, nn, w, wp, gx, h);
+          // a staged partner's row kernel would have to fetch this row's slice from HBM just for this one
+          // occurrence: leave the finished gradient slice g x x w in the partner occurrence's image instead
+          if (!((fusedm >> f_n(r)) & 1ull))
+            __stcs(reinterpret_cast<float4 *>(sparse + ((int64_t)m.aux[f_n(r)].pos + f_i(r)) * k + (f_v(r) - f_n(r) * vpf) * 4),
+                   make_float4(gx * w.x, gx * w.y, gx * w.z, gx * w.w));
+          if (!(geo.dbg & 2)) {
+            float *grow = rsp.tab + (int64_t)m.aux[mf].loc * rs + f_v(r) * 4;
+            *reinterpret_cast<float4 *>(grow) = z;
+            *reinterpret_cast<float4 *>(grow + ld) = nn;
+          }
         }
       }
+      // linear coordinate of the fused rows (staged rows: k_ffm_regrad_rows)
+      for (int i = tid; i < nf; i += n_cons) {
+        const int mf = m.flist[i];
+        float4 e = m.lin[mf];
+        const float gi = g * m.ent[mf].x;
+        const float w = weight_from<PRECISE>(e.x, f_sqrt<PRECISE>(e.y), h);
+        e.z = w;
+        ftrl_apply<PRECISE>(e.x, e.y, w, gi, gi * gi, h);
+        rsp.lin[m.aux[mf].loc] = e;
+      }
     }
-    // linear coordinate of the fused rows (staged rows: k_ffm_regrad_rows)
-    for (int r = tid; r < nf; r += n_cons) {
-      float4 e = m.lin[r];
-      const RowMeta rm = m.row[r];
-      const float gi = g * rm.x;
-      const float w = weight_from<PRECISE>(e.x, f_sqrt<PRECISE>(e.y), h);
-      e.z = w;
-      ftrl_apply<PRECISE>(e.x, e.y, w, gi, gi * gi, h);
-      rsp.lin[rm.loc] = e;
-    }
-    fence_async_smem();
     __syncwarp();
-    if (lane == 0) mbar_arrive(&bar_done[st]);
+    if (lane == 0) {
+      mbar_arrive_a(a_done + 8 * st);     // the sample's rows go back to the loader
+      mbar_arrive_a(a_mfree + 8 * slot);  // the metadata slot goes back to the metadata warps
+    }
   }
 }
 
@@ -694,8 +706,8 @@ k_ffm_regrad_rows(Dims d, Hyper h, int32_t nnz, const int32_t *__restrict__ batc
                   const __grid_constant__ RowSpace rsp, int32_t ch, const int32_t *__restrict__ n_chunks_p,
                   const int32_t *__restrict__ chunk_pos, const uint32_t *__restrict__ skey,
                   const uint32_t *__restrict__ socc, const SegScan *__restrict__ scan,
-                  const int32_t *__restrict__ occ_row, const int32_t *__restrict__ field,
-                  const float *__restrict__ val, const float *__restrict__ g_in,
+                  const int4 *__restrict__ srec, const int32_t *__restrict__ sbase,
+                  const float *__restrict__ sparse, const float *__restrict__ g_in,
                   const CanonEntry *__restrict__ canon, float *__restrict__ part, float2 *__restrict__ part_lin,
                   const __grid_constant__ Export ex) {
   if (batch_flags[0] == 0) return;
@@ -709,9 +721,13 @@ k_ffm_regrad_rows(Dims d, Hyper h, int32_t nnz, const int32_t *__restrict__ batc
   const int NF = d.n_fields;
   float *tab = rsp.tab;
   float4 *lin = rsp.lin;
+  const uint64_t pol_keep = policy_evict_last();
   const int64_t n_items = (int64_t)n_chunks * parts;
   for (int64_t item = (int64_t)blockIdx.x * WARPS + wib; item < n_items; item += (int64_t)gridDim.x * WARPS) {
-    const int c = (int)(item / parts), part_i = (int)(item - (int64_t)c * parts);
+    // part-major order: rows are sorted by id, i.e. (Criteo-shaped ids) by field, so the warps in flight all
+    // gather the same column of the table (slice f of every partner row); one part at a time keeps that
+    // working set -- a third of the column and of the canonical table -- inside L2
+    const int part_i = (int)(item / n_chunks), c = (int)(item - (int64_t)part_i * n_chunks);
     const ChunkInfo ci = chunk_info<true>(c, nnz, sentinel, ch, chunk_pos, skey, scan);
     if (!ci.valid) continue;
     const bool whole_row = ci.row_head && ci.row_last;
@@ -722,13 +738,14 @@ k_ffm_regrad_rows(Dims d, Hyper h, int32_t nnz, const int32_t *__restrict__ batc
     const int own = nfld * d.k;
     const int n_occ = ci.p1 - ci.p0;
     // lane l holds the metadata of occurrence p0 + l
-    int my_s = 0, my_fk = -1;
+    int my_s = 0, my_fk = -1, my_sb = 0;
     float my_gx = 0.f;
     if (lane < n_occ) {
-      const uint32_t t = socc[ci.p0 + lane];
-      my_s = occ_row[t];
-      my_gx = g_in[my_s] * val[t];
-      my_fk = field[t] * d.k;
+      const int4 rec = __ldg(srec + ci.p0 + lane);  // {sample, value, field * k, -}: sequential along the sorted list
+      my_sb = __ldg(sbase + ci.p0 + lane);
+      my_s = rec.x;
+      my_gx = g_in[my_s] * __int_as_float(rec.y);
+      my_fk = rec.z;
     }
     // sharded runs: the sum goes to the row's owner unless this rank owns the row and is its only contributor
     const int32_t dst = (ex.on && whole_row) ? ex.dst_at[ci.p0] : -2;
@@ -751,7 +768,11 @@ k_ffm_regrad_rows(Dims d, Hyper h, int32_t nnz, const int32_t *__restrict__ batc
         e[u].loc = CANON_NONE;
         e[u].x = 0.f;
         if (on && p + u < n_occ) {
-          const int2 t = __ldg(reinterpret_cast<const int2 *>(canon + (int64_t)sj * NF + nfld));
+          // the canonical table is re-read once per field of a sample, spread over the whole kernel: keep it in L2
+          int2 t;
+          asm volatile("ld.global.nc.L2::cache_hint.v2.b32 {%0, %1}, [%2], %3;"
+                       : "=r"(t.x), "=r"(t.y)
+                       : "l"(canon + (int64_t)sj * NF + nfld), "l"(pol_keep));
           e[u].loc = t.x;
           e[u].x = __int_as_float(t.y);
         }
@@ -766,11 +787,18 @@ k_ffm_regrad_rows(Dims d, Hyper h, int32_t nnz, const int32_t *__restrict__ batc
 #pragma unroll
       for (int u = 0; u < REGRAD_U; u++) {
         const int fk = __shfl_sync(0xffffffffu, my_fk, (p + u) & 31);
+        const int sb = __shfl_sync(0xffffffffu, my_sb, (p + u) & 31);
         gxx[u] = __shfl_sync(0xffffffffu, my_gx, (p + u) & 31) * e[u].x;
         // the slice of the row's own field is touched by no partner (fields are distinct)
         const bool take = e[u].loc != CANON_NONE && fk != own;
-        w[u] = take ? __ldg(reinterpret_cast<const float4 *>(rsp.w_plane(e[u].loc, ld) + fk + col))
-                    : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (take && canon_is_fused(e[u].loc)) {
+          // fused partner: the sample kernel left the finished gradient slice in this occurrence's image
+          w[u] = __ldcs(reinterpret_cast<const float4 *>(sparse + ((int64_t)sb + (e[u].loc & 0xff)) * d.k + col));
+          gxx[u] = 1.0f;
+        } else {
+          w[u] = take ? __ldg(reinterpret_cast<const float4 *>(rsp.w_plane(e[u].loc, ld) + fk + col))
+                      : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
       }
       if (p + REGRAD_U < n_occ) load_canon(p + REGRAD_U, en);
 #pragma unroll

@@ -103,6 +103,20 @@ __global__ void k_lin_copy(float4 *lin, float *dense, int64_t row0, int64_t n_ro
   if (to_dense) dense[q] = *e; else *e = dense[q];
 }
 
+// the same by GLOBAL row over every shard (peer memory): a rank of an attached multi-GPU run reads the whole model
+__global__ void k_plane_gather(Shards sh, float *dense, int64_t row0, int64_t n_rows, int32_t row_len, int32_t ld, int plane) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n_rows * row_len) return;
+  const int64_t r = q / row_len;
+  const int c = (int)(q % row_len);
+  dense[q] = sh.row((int32_t)(row0 + r), 3 * (int64_t)ld)[(int64_t)plane * ld + c];
+}
+__global__ void k_lin_gather(Shards sh, float *dense, int64_t row0, int64_t n_rows, int plane) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n_rows) return;
+  dense[q] = reinterpret_cast<const float *>(sh.linp((int32_t)(row0 + q)))[plane];
+}
+
 __global__ void k_has_zero(const float *tab, const float4 *lin, int64_t n_rows, int32_t row_len, int32_t ld,
                            int32_t *flag) {
   const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -262,7 +276,15 @@ static void ensure_workspace(ftrl_handle *h, int64_t n_rows, int64_t nnz) {
     h->pmask.ensure(nc);
     h->rowmask.ensure(nc + 2);
   }
-  if (h->tile_ok) h->canon.ensure((size_t)rc * h->dims.n_fields);
+  if (h->tile_ok) {
+    h->canon.ensure((size_t)rc * h->dims.n_fields);
+    h->srec.ensure(nc);
+    h->n_fused.ensure(rc);
+    h->sbase.ensure(nc + 1);
+    // (staged occurrence, fused partner) pairs of a sample with F distinct fields: at most (F/2)^2
+    const int64_t nfl = h->dims.n_fields;
+    h->sparse.ensure((size_t)rc * (size_t)((nfl * nfl + 3) / 4) * h->dims.k);
+  }
   h->scan.ensure(nc);
   h->chunk_pos.ensure(nc + 2);
   h->n_chunks.ensure(4);
@@ -343,15 +365,20 @@ static void launch_tile(ftrl_handle *h, const Batch &b, const ItemDecode &dec, f
   geo.n_meta = h->tile_meta;
   geo.consumers = h->tile_consumers;
   geo.dbg = h->tile_dbg;
+  geo.helper_ns = (uint32_t)h->tile_helper_ns;
   geo.smem_bytes = h->tile_smem;
   const int tgrid = (int)std::min<int64_t>(b.n_rows, (int64_t)h->n_sms * h->tile_ctas_per_sm);
-#define FFM_TILE(I)                                                                                   \
-  k_ffm_tile<PRECISE, I><<<tgrid, tile_threads(geo.consumers), geo.smem_bytes, h->compute>>>(        \
-      b, h->dims, h->hyper, dec, geo, h->batch_flags.p, h->rowspace, h->bias, h->pair_lut, h->occ_pos.p, h->scan.p, h->g.p, logit_out)
-  if (h->tile_ipt <= 1) FFM_TILE(1);
-  else if (h->tile_ipt == 2) FFM_TILE(2);
-  else if (h->tile_ipt == 3) FFM_TILE(3);
-  else FFM_TILE(4);
+#define FFM_TILE(I, R, C)                                                                             \
+  k_ffm_tile<PRECISE, I, R, C><<<tgrid, tile_threads(geo.consumers), geo.smem_bytes, h->compute>>>(   \
+      b, h->dims, h->hyper, dec, geo, h->batch_flags.p, h->rowspace, h->bias, h->pair_lut, h->occ_pos.p, h->scan.p, h->sbase.p, h->sparse.p, h->g.p, logit_out)
+  switch (h->tile_variant) {
+    case 0: FFM_TILE(1, 4, 768); break;
+    case 1: FFM_TILE(2, 4, 768); break;
+    case 2: FFM_TILE(3, 4, 768); break;
+    case 3: FFM_TILE(4, 4, 768); break;
+    case 4: FFM_TILE(3, 6, 512); break;
+    default: FFM_TILE(4, 8, 384); break;
+  }
 #undef FFM_TILE
   FTRL_CUDA(cudaGetLastError());
   launched(h, PH_SAMPLE);
@@ -362,7 +389,7 @@ static void launch_regrad(ftrl_handle *h, const Batch &b) {
   const int grid = h->n_sms * 16;
   k_ffm_regrad_rows<PRECISE, 8><<<grid, 256, 0, h->compute>>>(h->dims, h->hyper, (int32_t)b.nnz, h->batch_flags.p, h->rowspace,
                                                              h->chunk, h->n_chunks.p, h->chunk_pos.p, h->skey.p, h->socc.p,
-                                                             h->scan.p, h->occ_row.p, b.field, b.val, h->g.p, h->canon.p,
+                                                             h->scan.p, h->srec.p, h->sbase.p, h->sparse.p, h->g.p, h->canon.p,
                                                              h->part.p, h->part_lin.p, h->exportd);
   FTRL_CUDA(cudaGetLastError());
   launched(h, PH_ROWS);
@@ -370,10 +397,16 @@ static void launch_regrad(ftrl_handle *h, const Batch &b) {
 
 // canonical (sample, field) -> row table of the tile path (prep.cuh); needs occ_pos / scan in sharded runs
 static void launch_canon(ftrl_handle *h, const Batch &b) {
-  if (b.n_rows <= 0) return;
+  if (b.n_rows <= 0 || b.nnz <= 0) return;
   const unsigned grid = (unsigned)((b.n_rows * 32 + 255) / 256);
-  k_build_canon<<<grid, 256, 0, h->compute>>>(b, h->dims, h->log2G, h->rank, h->occ_pos.p, h->scan.p, h->canon.p);
+  k_build_canon<<<grid, 256, 0, h->compute>>>(b, h->dims, h->log2G, h->rank, h->occ_pos.p, h->scan.p, h->canon.p,
+                                              h->n_fused.p);
   FTRL_CUDA(cudaGetLastError());
+  // where the sample kernel leaves the gradient slices of fused partners for the row kernel
+  thrust::counting_iterator<int32_t> cnt(0);
+  auto it = thrust::make_transform_iterator(cnt, SparseCount{h->fused_sorted.p, h->srec.p, h->n_fused.p});
+  size_t bytes = h->cub_bytes;
+  FTRL_CUDA(cub::DeviceScan::ExclusiveSum(h->cub_tmp.p, bytes, it, h->sbase.p, (int)b.nnz, h->compute));
 }
 
 // FFM minibatch: when every sample of the batch has distinct fields (device-side flag) the tile kernels
@@ -491,6 +524,7 @@ static void run_prep(ftrl_handle *h, const Batch &b) {
   {
     PhaseScope ps(h, PH_PREP);
     FTRL_CUDA(cudaMemsetAsync(h->batch_flags.p, 0x01, sizeof(int32_t), h->compute));  // != 0: all samples simple
+    FTRL_CUDA(cudaMemsetAsync(h->batch_flags.p + 1, 0, 3 * sizeof(int32_t), h->compute));  // [2]: fused rows
     const unsigned grid = (unsigned)((b.n_rows * 32 + 255) / 256);
     k_prep_rows<<<grid, 256, 0, h->compute>>>(b, d, h->key.p, h->occ_idx.p, h->occ_row.p, h->sflags.p,
                                               h->batch_flags.p, h->tile_ok ? h->pmask.p : nullptr);
@@ -511,7 +545,8 @@ static void run_prep(ftrl_handle *h, const Batch &b) {
     PhaseScope ps(h, PH_SEGMENT);
     const int fuse = (d.model_type == FTRL_FFM && h->fuse) ? 1 : 0;
     k_occ_class<<<(nnz + 255) / 256, 256, 0, h->compute>>>(nnz, sentinel, fuse, h->skey.p, h->socc.p, h->occ_row.p,
-                                                           h->sflags.p, h->fused_sorted.p, h->occ_pos.p);
+                                                           h->sflags.p, h->fused_sorted.p, h->occ_pos.p, h->batch_flags.p, b.field, b.val, d.k,
+                                                           h->tile_ok ? h->srec.p : nullptr);
     launched(h, PH_SEGMENT);
     size_t bytes = h->cub_bytes;
     thrust::counting_iterator<int32_t> cnt(0);
@@ -815,6 +850,7 @@ static void train_device_sharded(ftrl_handle *h, const Batch &b, float *logit_ou
   {
     PhaseScope ps(h, PH_PREP);
     FTRL_CUDA(cudaMemsetAsync(h->batch_flags.p, 0x01, sizeof(int32_t), h->compute));
+    FTRL_CUDA(cudaMemsetAsync(h->batch_flags.p + 1, 0, 3 * sizeof(int32_t), h->compute));  // [2]: fused rows
     if (b.n_rows > 0) {
       const unsigned pg = (unsigned)((b.n_rows * 32 + 255) / 256);
       k_prep_rows<<<pg, 256, 0, h->compute>>>(b, d, h->key.p, h->occ_idx.p, h->occ_row.p, h->sflags.p, h->batch_flags.p,
@@ -836,7 +872,7 @@ static void train_device_sharded(ftrl_handle *h, const Batch &b, float *logit_ou
     PhaseScope ps(h, PH_SEGMENT);
     if (nnz > 0) {
       k_occ_class<<<(nnz + 255) / 256, 256, 0, h->compute>>>(nnz, sentinel, 0, h->skey.p, h->socc.p, h->occ_row.p, h->sflags.p,
-                                                             h->fused_sorted.p, h->occ_pos.p);
+                                                             h->fused_sorted.p, h->occ_pos.p, h->batch_flags.p, b.field, b.val, d.k, h->srec.p);
       size_t bytes = h->cub_bytes;
       auto mit = thrust::make_transform_iterator(cnt, MaskIn{h->skey.p, h->socc.p, h->pmask.p});
       FTRL_CUDA(cub::DeviceScan::InclusiveScan(h->cub_tmp.p, bytes, mit, h->mscan.p, MaskScanOp(), nnz, h->compute));
@@ -863,7 +899,7 @@ static void train_device_sharded(ftrl_handle *h, const Batch &b, float *logit_ou
     FTRL_CUDA(cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, bytes, h->okey.p, h->ckey.p, h->osrc.p, h->csrc.p, oc, 0,
                                               key_bits((int32_t)h->n_local), h->compute));
     k_contrib_class<<<(oc + 255) / 256, 256, 0, h->compute>>>(h->peers, oc, h->n_sel.p, lsent, h->ckey.p, h->csrc.p, h->socc.p,
-                                                             h->cflag.p, h->fused_sorted.p, h->occ_pos.p);
+                                                             h->cflag.p, h->fused_sorted.p, h->occ_pos.p, h->batch_flags.p);
     k_owner_materialise<PRECISE, 256><<<grid, 256, 0, h->compute>>>(h->peers, d, h->hyper, oc, h->n_sel.p, h->batch_flags.p,
                                                                     h->ckey.p, h->csrc.p, h->cflag.p, h->tab, h->lin);
     FTRL_CUDA(cudaGetLastError());
@@ -1024,6 +1060,11 @@ int ftrl_create(const ftrl_config *cfg, ftrl_handle **out) {
     h->chunk = env_int("FTRL_B200_CHUNK", cfg->model_type == FTRL_FFM ? 32 : cfg->model_type == FTRL_FM ? 256 : 2048);
     if (h->chunk < 1) h->chunk = 1;
     if (cfg->model_type == FTRL_FFM && h->chunk > 32) h->chunk = 32;  // chunk ends are found with one ballot
+    {
+      // experiment switch: L2 fetch granularity hint (bytes; the row kernel gathers 32-byte slices)
+      const int fg = env_int("FTRL_B200_L2_FETCH", 0);
+      if (fg > 0) FTRL_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)fg));
+    }
     h->tile = env_int("FTRL_B200_TILE", 1);
     h->tile_dbg = env_int("FTRL_B200_TILE_DBG", 0);
     if (cfg->model_type == FTRL_FFM && h->tile && h->fuse && d.k % 4 == 0 && d.n_fields <= 64) {
@@ -1034,10 +1075,20 @@ int ftrl_create(const ftrl_config *cfg, ftrl_handle **out) {
       int cons = 64;
       while (cons < 512 && cons * 3 < items) cons *= 2;
       if (cons == 512 && items > 2 * 512) cons = TILE_MAX_CONSUMERS;  // 24 consumer warps, 2 items per thread at cfg4
+      // every consumer thread also owns up to FR float4 vectors of the sample's fused rows (z stays in registers)
+      const int64_t vectors = (int64_t)d.n_fields * (d.ld / 4);
+      while (cons < TILE_MAX_CONSUMERS && (int64_t)cons * 4 < vectors) cons += 32;
       cons = env_int("FTRL_B200_TILE_CONSUMERS", cons);
-      const int ipt = (int)((items + cons - 1) / cons);
-      const size_t lut = tile_lut_bytes(d.n_fields) + 4 * tile_meta_bytes(d.n_fields);  // + minimal meta ring
-      if (2 * stage + lut <= budget && ipt <= 4) {
+      cons = std::max(32, std::min(TILE_MAX_CONSUMERS, cons / 32 * 32));
+      const int ipt = (int)((items + cons - 1) / cons), fr = (int)((vectors + cons - 1) / cons);
+      // instantiations: (items, vectors) per thread and the block size their register budget was compiled for
+      int variant = -1;
+      if (fr <= 4 && ipt <= 4) variant = ipt - 1;
+      else if (fr <= 6 && ipt <= 3 && cons <= 512) variant = 4;
+      else if (fr <= 8 && ipt <= 4 && cons <= 384) variant = 5;
+      const size_t lut = 4 * tile_meta_bytes(d.n_fields);  // minimal meta ring
+      if (2 * stage + lut <= budget && variant >= 0) {
+        h->tile_variant = variant;
         int ctas = (int)std::min<size_t>(8, (size_t)prop.sharedMemPerMultiprocessor / (2 * stage + lut + 2048));
         ctas = std::max(1, std::min(ctas, 2048 / tile_threads(cons)));
         ctas = env_int("FTRL_B200_TILE_CTAS", ctas);
@@ -1058,10 +1109,17 @@ int ftrl_create(const ftrl_config *cfg, ftrl_handle **out) {
         h->tile_ctas_per_sm = ctas;
         h->tile_smem = tile_smem_bytes(d.n_fields, stride, stages, metas);
         const int sm = (int)h->tile_smem;
-#define TILE_ATTR(P, I) FTRL_CUDA(cudaFuncSetAttribute(k_ffm_tile<P, I>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm))
-        TILE_ATTR(false, 1); TILE_ATTR(false, 2); TILE_ATTR(false, 3); TILE_ATTR(false, 4);
-        TILE_ATTR(true, 1); TILE_ATTR(true, 2); TILE_ATTR(true, 3); TILE_ATTR(true, 4);
+#define TILE_ATTR(P) \
+  FTRL_CUDA(cudaFuncSetAttribute(k_ffm_tile<P, 1, 4, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm)); \
+  FTRL_CUDA(cudaFuncSetAttribute(k_ffm_tile<P, 2, 4, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm)); \
+  FTRL_CUDA(cudaFuncSetAttribute(k_ffm_tile<P, 3, 4, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm)); \
+  FTRL_CUDA(cudaFuncSetAttribute(k_ffm_tile<P, 4, 4, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm)); \
+  FTRL_CUDA(cudaFuncSetAttribute(k_ffm_tile<P, 3, 6, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm)); \
+  FTRL_CUDA(cudaFuncSetAttribute(k_ffm_tile<P, 4, 8, 384>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm))
+        TILE_ATTR(false);
+        TILE_ATTR(true);
         h->tile_inflight = std::max(2, std::min(TILE_MAX_STAGE, env_int("FTRL_B200_TILE_INFLIGHT", TILE_MAX_STAGE)));
+        h->tile_helper_ns = env_int("FTRL_B200_TILE_HELPER_NS", 0);
 #undef TILE_ATTR
       }
     }
@@ -1242,6 +1300,54 @@ static void xfer_rows(ftrl_handle *h, int which, int64_t row0, int64_t n_rows, f
   FTRL_CUDA(cudaGetLastError());
 }
 
+// rows [row0, row0 + n_rows) of the WHOLE model (global feature ids), read through the mapped peer shards
+static void get_rows_global(ftrl_handle *h, int which, int64_t row0, int64_t n_rows, float *lin, float *vec) {
+  const Dims &d = h->dims;
+  if (row0 < 0 || n_rows < 0 || row0 + n_rows > d.n_feats) throw ArgFail{"row range out of bounds"};
+  if (h->G > 1 && !h->attached) throw StateFail{"multi-GPU handle: call ftrl_attach_peers first"};
+  const int plane = plane_of(which);
+  FTRL_CUDA(cudaStreamSynchronize(h->compute));
+  const int64_t chunk_rows = std::max<int64_t>(1, (int64_t)(16 << 20) / std::max<int32_t>(1, d.row_len));
+  h->xfer.ensure((size_t)std::min<int64_t>(n_rows, chunk_rows) * std::max<int32_t>(1, d.row_len));
+  for (int64_t r = 0; r < n_rows; r += chunk_rows) {
+    const int64_t nr = std::min(chunk_rows, n_rows - r);
+    if (lin) {
+      k_lin_gather<<<(unsigned)((nr + 255) / 256), 256, 0, h->compute>>>(h->shards, h->xfer.p, row0 + r, nr, plane);
+      FTRL_CUDA(cudaMemcpyAsync(lin + r, h->xfer.p, sizeof(float) * nr, cudaMemcpyDeviceToHost, h->compute));
+      FTRL_CUDA(cudaStreamSynchronize(h->compute));
+    }
+    if (vec && d.row_len) {
+      const int64_t q = nr * d.row_len;
+      k_plane_gather<<<(unsigned)((q + 255) / 256), 256, 0, h->compute>>>(h->shards, h->xfer.p, row0 + r, nr, d.row_len, d.ld, plane);
+      FTRL_CUDA(cudaMemcpyAsync(vec + r * d.row_len, h->xfer.p, sizeof(float) * q, cudaMemcpyDeviceToHost, h->compute));
+      FTRL_CUDA(cudaStreamSynchronize(h->compute));
+    }
+  }
+  FTRL_CUDA(cudaGetLastError());
+}
+
+// rows [row0, row0 + n_rows) of the whole model arrive in `lin` / `vec`; this rank keeps the rows it owns
+static void set_rows_owned(ftrl_handle *h, int which, int64_t row0, int64_t n_rows, const float *lin, const float *vec) {
+  if (h->G == 1) {
+    xfer_rows(h, which, row0, n_rows, const_cast<float *>(lin), const_cast<float *>(vec), false);
+    return;
+  }
+  const int64_t G = h->G, rl = h->dims.row_len;
+  int64_t g0 = row0 + ((h->rank - row0 % G) % G + G) % G;  // first global row >= row0 owned by this rank
+  if (g0 >= row0 + n_rows) return;
+  const int64_t n_mine = (row0 + n_rows - g0 + G - 1) / G;
+  std::vector<float> l2, v2;
+  if (lin) {
+    l2.resize((size_t)n_mine);
+    for (int64_t i = 0; i < n_mine; i++) l2[(size_t)i] = lin[g0 - row0 + i * G];
+  }
+  if (vec && rl) {
+    v2.resize((size_t)(n_mine * rl));
+    for (int64_t i = 0; i < n_mine; i++) memcpy(&v2[(size_t)(i * rl)], vec + (g0 - row0 + i * G) * rl, sizeof(float) * (size_t)rl);
+  }
+  xfer_rows(h, which, g0 / G, n_mine, lin ? l2.data() : nullptr, (vec && rl) ? v2.data() : nullptr, false);
+}
+
 static void xfer_bias(ftrl_handle *h, int which, float *v, bool get) {
   if (!v) return;
   FTRL_CUDA(cudaStreamSynchronize(h->compute));
@@ -1350,7 +1456,7 @@ int ftrl_eval_auc(ftrl_handle *h, int64_t n, const float *scores, const int32_t 
 int ftrl_save_model(ftrl_handle *h, const char *path, int compress_level) {
   if (!h || !path) return FTRL_ERR_ARG;
   return guarded(h, [&] {
-    if (h->G > 1) throw StateFail{"model files of a feature-sharded run are not supported yet: save per shard with ftrl_get_rows"};
+    // multi-GPU: ONE attached rank writes the file, reading every shard through peer memory
     const Dims &d = h->dims;
     const uint64_t total = sizeof(float) * (1ull + (uint64_t)d.n_feats + (uint64_t)d.n_feats * d.row_len);
     ModelWriter w(path, compress_level, total);
@@ -1361,13 +1467,13 @@ int ftrl_save_model(ftrl_handle *h, const char *path, int compress_level) {
     std::vector<float> buf((size_t)chunk_rows * std::max<int32_t>(1, d.row_len));
     for (int64_t r = 0; r < d.n_feats; r += chunk_rows) {
       const int64_t nr = std::min<int64_t>(chunk_rows, d.n_feats - r);
-      xfer_rows(h, 0, r, nr, buf.data(), nullptr, true);
+      get_rows_global(h, 0, r, nr, buf.data(), nullptr);
       w.write(buf.data(), sizeof(float) * nr);
     }
     if (d.row_len)
       for (int64_t r = 0; r < d.n_feats; r += chunk_rows) {
         const int64_t nr = std::min<int64_t>(chunk_rows, d.n_feats - r);
-        xfer_rows(h, 0, r, nr, nullptr, buf.data(), true);
+        get_rows_global(h, 0, r, nr, nullptr, buf.data());
         w.write(buf.data(), sizeof(float) * nr * d.row_len);
       }
     const uint64_t csize = w.finish();
@@ -1378,7 +1484,7 @@ int ftrl_save_model(ftrl_handle *h, const char *path, int compress_level) {
 int ftrl_load_model(ftrl_handle *h, const char *path) {
   if (!h || !path) return FTRL_ERR_ARG;
   return guarded(h, [&] {
-    if (h->G > 1) throw StateFail{"model files of a feature-sharded run are not supported yet: save per shard with ftrl_get_rows"};
+    // multi-GPU: EVERY rank reads the file and keeps the rows it owns (and the replicated bias)
     const Dims &d = h->dims;
     const uint64_t total = sizeof(float) * (1ull + (uint64_t)d.n_feats + (uint64_t)d.n_feats * d.row_len);
     ModelReader rd(path);
@@ -1392,13 +1498,13 @@ int ftrl_load_model(ftrl_handle *h, const char *path) {
     for (int64_t r = 0; r < d.n_feats; r += chunk_rows) {
       const int64_t nr = std::min<int64_t>(chunk_rows, d.n_feats - r);
       rd.read(buf.data(), sizeof(float) * nr);
-      xfer_rows(h, 0, r, nr, buf.data(), nullptr, false);
+      set_rows_owned(h, 0, r, nr, buf.data(), nullptr);
     }
     if (d.row_len)
       for (int64_t r = 0; r < d.n_feats; r += chunk_rows) {
         const int64_t nr = std::min<int64_t>(chunk_rows, d.n_feats - r);
         rd.read(buf.data(), sizeof(float) * nr * d.row_len);
-        xfer_rows(h, 0, r, nr, nullptr, buf.data(), false);
+        set_rows_owned(h, 0, r, nr, nullptr, buf.data());
       }
     printf("loading from %s, before: %zu -> after: %zu \n", path, (size_t)rd.file_size(), (size_t)total);
   });
@@ -1407,12 +1513,11 @@ int ftrl_load_model(ftrl_handle *h, const char *path) {
 int ftrl_save_model_text(ftrl_handle *h, const char *path) {
   if (!h || !path) return FTRL_ERR_ARG;
   return guarded(h, [&] {
-    if (h->G > 1) throw StateFail{"model files of a feature-sharded run are not supported yet: save per shard with ftrl_get_rows"};
     const Dims &d = h->dims;
     std::vector<float> lin((size_t)d.n_feats), vec((size_t)d.n_feats * d.row_len);
     float b = 0.f;
     xfer_bias(h, 0, &b, true);
-    xfer_rows(h, 0, 0, d.n_feats, lin.data(), vec.empty() ? nullptr : vec.data(), true);
+    get_rows_global(h, 0, 0, d.n_feats, lin.data(), vec.empty() ? nullptr : vec.data());
     save_text_model(path, b, lin.data(), vec.data(), d.n_feats, d.row_len);
   });
 }
@@ -1420,13 +1525,12 @@ int ftrl_save_model_text(ftrl_handle *h, const char *path) {
 int ftrl_load_model_text(ftrl_handle *h, const char *path) {
   if (!h || !path) return FTRL_ERR_ARG;
   return guarded(h, [&] {
-    if (h->G > 1) throw StateFail{"model files of a feature-sharded run are not supported yet: save per shard with ftrl_get_rows"};
     const Dims &d = h->dims;
     std::vector<float> lin((size_t)d.n_feats), vec((size_t)d.n_feats * d.row_len);
     float b = 0.f;
     load_text_model(path, &b, lin.data(), vec.data(), d.n_feats, d.row_len);
     xfer_bias(h, 0, &b, false);
-    xfer_rows(h, 0, 0, d.n_feats, lin.data(), vec.empty() ? nullptr : vec.data(), false);
+    set_rows_owned(h, 0, 0, d.n_feats, lin.data(), vec.empty() ? nullptr : vec.data());
   });
 }
 

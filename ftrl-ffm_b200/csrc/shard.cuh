@@ -194,7 +194,8 @@ enum : uint8_t {
 __global__ void k_contrib_class(Peers pr, int32_t cap, const int32_t *__restrict__ n_sel, uint32_t lsent,
                                 const uint32_t *__restrict__ ckey, const uint32_t *__restrict__ csrc,
                                 const uint32_t *__restrict__ socc, uint8_t *__restrict__ cflag,
-                                uint8_t *__restrict__ fused_sorted, int32_t *__restrict__ occ_pos) {
+                                uint8_t *__restrict__ fused_sorted, int32_t *__restrict__ occ_pos,
+                                int32_t *__restrict__ batch_flags) {
   const int32_t c = blockIdx.x * blockDim.x + threadIdx.x;
   const int32_t n = min(*n_sel, cap);
   if (c >= n) return;
@@ -215,6 +216,7 @@ __global__ void k_contrib_class(Peers pr, int32_t cap, const int32_t *__restrict
       fused_sorted[p_head] = 1;
       occ_pos[socc[p_head]] = -1;
       cflag[c] = 0;
+      atomicAdd(&batch_flags[2], 1);  // count of fused rows (statistics)
     } else {       // reduced and applied by this rank's own row kernels
       pr.dst_at[q][p_head] = -2;
       cflag[c] = CF_MAT;

@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <deque>
+#include <future>
 #include <numeric>
 #include <random>
 #include <stdexcept>
@@ -247,7 +248,9 @@ void run_offline(const host::Options &o) {
 }
 
 // one streaming pass over a file in file order: PcTask::run (src/concurrent/pc_task.cpp:22-80) with
-// FtrlOnline::run_task (ftrl_online.cpp:70-80) / Evaluator::run_task (evaluate.cpp:23-33) as consumer
+// FtrlOnline::run_task (ftrl_online.cpp:70-80) / Evaluator::run_task (evaluate.cpp:23-33) as consumer.
+// Like the reference's producer / consumer pair, reading + parsing of block i+1 (a producer task on the parser
+// threads) overlaps the submission and the GPU work of block i (this thread).
 double stream_file(Trainer &tr, const std::string &path, bool libffm, int n_threads, bool train) {
   FILE *f = fopen(path.c_str(), "rb");
   if (!f) {
@@ -257,34 +260,46 @@ double stream_file(Trainer &tr, const std::string &path, bool libffm, int n_thre
   std::vector<char> buf(32u << 20);
   size_t have = 0;
   bool eof = false;
-  long lines = 0, next_log = 1000000;
-  host::Csr csr;
-  tr.begin_epoch(1u << 16);
-  while (!eof || have) {
-    if (!eof) {
-      const size_t got = fread(buf.data() + have, 1, buf.size() - have, f);
-      have += got;
-      if (got == 0) eof = true;
-    }
-    size_t use = have;
-    if (!eof) {  // cut at the last complete line
-      while (use > 0 && buf[use - 1] != '\n') use--;
-      if (use == 0) {
-        if (have == buf.size()) buf.resize(buf.size() * 2);
-        continue;
+  // producer: next block of complete lines -> CSR; false when the file is exhausted
+  auto produce = [&](host::Csr *out) -> bool {
+    out->clear();
+    while (!eof || have) {
+      if (!eof) {
+        const size_t got = fread(buf.data() + have, 1, buf.size() - have, f);
+        have += got;
+        if (got == 0) eof = true;
       }
+      size_t use = have;
+      if (!eof) {  // cut at the last complete line
+        while (use > 0 && buf[use - 1] != '\n') use--;
+        if (use == 0) {
+          if (have == buf.size()) buf.resize(buf.size() * 2);
+          continue;
+        }
+      }
+      if (use == 0) return false;
+      host::parse_buffer(buf.data(), use, libffm, n_threads, *out);
+      memmove(buf.data(), buf.data() + use, have - use);
+      have -= use;
+      return true;
     }
-    if (use == 0) break;
-    csr.clear();
-    host::parse_buffer(buf.data(), use, libffm, n_threads, csr);
-    tr.run_block(csr, nullptr, csr.rows(), train);  // copies into pinned staging: csr/buf are free again
+    return false;
+  };
+  long lines = 0, next_log = 1000000;
+  host::Csr blocks[2];
+  tr.begin_epoch(1u << 16);
+  int cur = 0;
+  std::future<bool> next = std::async(std::launch::async, produce, &blocks[cur]);
+  while (next.get()) {
+    host::Csr &csr = blocks[cur];
+    cur ^= 1;
+    next = std::async(std::launch::async, produce, &blocks[cur]);  // parse the next block while this one trains
+    tr.run_block(csr, nullptr, csr.rows(), train);  // copies into pinned staging
     lines += (long)csr.rows();
     while (lines >= next_log) {  // pc_task.cpp:47-49
       printf("%ld lines finished...\n", next_log);
       next_log += 1000000;
     }
-    memmove(buf.data(), buf.data() + use, have - use);
-    have -= use;
   }
   fclose(f);
   return tr.take_loss();

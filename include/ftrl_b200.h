@@ -167,7 +167,10 @@ int ftrl_has_zero_weights(ftrl_handle *h, int *out);
 /* Replaces LR/FFM::save_compressed_model / load_compressed_model (lr.cpp:26-39,
  * ffm.cpp:138-159, compression/compress.cpp:15-51): one zstd frame (content size in
  * the frame header) of little-endian fp32 [bias][lin_w][vec_w rows].  FM uses the same
- * layout with row_len = n_factors (the reference has no FM save). */
+ * layout with row_len = n_factors (the reference has no FM save).
+ * Multi-GPU handles write / read the SAME single-model file: ftrl_save_model is called on ONE attached
+ * rank (it reads every shard through peer memory; the other ranks must be idle, i.e. after a host barrier
+ * behind ftrl_sync), ftrl_load_model on EVERY rank (each keeps the rows it owns and the replicated bias). */
 int ftrl_save_model(ftrl_handle *h, const char *path, int compress_level);
 int ftrl_load_model(ftrl_handle *h, const char *path);
 /* Replaces FFM::save_model / load_model (ffm.cpp:161-200): text, line 1 bias, n_feats

@@ -326,3 +326,70 @@ def test_against_the_reference_binary_itself():
     want, _ = r.train_csr(**b)
     assert_close(got, want, RTOL, 1e-6, "logits")
     assert_state_close(m.get_state(), r.get_state(), RTOL, name="ref")
+
+
+# ---------------------------------------------------------------------------------------------
+# 6. device AUC (ftrl_eval_auc), Gaussian init (tests/test_utils.cpp:26-38), IEEE flavour of the kernels
+# ---------------------------------------------------------------------------------------------
+def test_device_auc_matches_rank_sum_with_ties():
+    rng = np.random.default_rng(12)
+    m = gpu_model("LR", 16, 1, 1)
+    for n, levels in ((1, 0), (2, 0), (1000, 0), (100_000, 0), (100_000, 17), (50_000, 1)):
+        s = rng.normal(0, 2, n).astype(np.float32)
+        if levels:  # heavy ties (cold-start models score every sample the same)
+            s = np.round(s * levels / 4).astype(np.float32) / levels
+        s[: n // 50] = -s[: n // 50]
+        if n > 10:
+            s[:5] = [0.0, -0.0, np.float32(1e-45), -np.float32(1e-45), 0.0]
+        y = (rng.random(n) < 0.3).astype(np.int32)
+        got, want = m.auc(s, y), pkg.synth.auc(y, s)
+        if np.isnan(want):
+            assert np.isnan(got)
+        else:
+            assert abs(got - want) <= 1e-12, (n, levels, got, want)
+    assert np.isnan(m.auc(np.zeros(4, np.float32), np.ones(4, np.int32)))  # one class only
+
+
+def test_gaussian_init_distribution_and_reference_shape_test():
+    """tests/test_utils.cpp:26-38 (init_weights(100, 10, 4, 0, 0.01): every row has a value in (-0.05, 0.05)) plus
+    the moments of the device generator; n = z = 0"""
+    m = gpu_model("FFM", 100, 10, 4, init_mean=0.0, init_stddev=0.01)
+    st = m.get_state()
+    assert st["vec_w"].shape == (100, 40)
+    assert all(((row > -0.05) & (row < 0.05)).any() for row in st["vec_w"])
+    assert not st["vec_n"].any() and not st["vec_z"].any() and not st["lin_n"].any() and not st["lin_z"].any()
+    m.close()
+    m = gpu_model("FFM", 20000, 8, 8, init_mean=0.25, init_stddev=0.02, seed=5)
+    w = m.vec_w.astype(np.float64).ravel()
+    lw = m.lin_w.astype(np.float64)
+    n = w.size
+    assert abs(w.mean() - 0.25) < 5 * 0.02 / np.sqrt(n) and abs(w.std() - 0.02) < 5 * 0.02 / np.sqrt(2 * n)
+    assert abs(lw.mean() - 0.25) < 5 * 0.02 / np.sqrt(lw.size)
+    zs = (w - 0.25) / 0.02
+    assert abs((zs ** 3).mean()) < 0.02 and abs((zs ** 4).mean() - 3.0) < 0.05   # skewness, kurtosis
+    assert 0.6826 - 0.005 < (np.abs(zs) < 1).mean() < 0.6826 + 0.005
+    # another seed gives another model; the same seed the same model
+    m2 = gpu_model("FFM", 20000, 8, 8, init_mean=0.25, init_stddev=0.02, seed=6)
+    m3 = gpu_model("FFM", 20000, 8, 8, init_mean=0.25, init_stddev=0.02, seed=5)
+    assert not np.array_equal(m2.lin_w, m.lin_w) and np.array_equal(m3.vec_w, m.vec_w)
+
+
+@pytest.mark.parametrize("mt,nfl,k,kw", [("FFM", 6, 4, {}), ("FFM", 39, 8, {"max_nnz": 39}), ("FFM", 4, 8, {"dup_field": True}),
+                                         ("FM", 1, 16, {"dup_feat": True, "max_nnz": 20}),
+                                         ("LR", 1, 1, {"dup_feat": True, "max_nnz": 20})])
+def test_minibatch_ieee_flavour(mt, nfl, k, kw, monkeypatch):
+    """FTRL_B200_PRECISE=1: the same minibatch kernels instantiated with IEEE sqrt / division"""
+    monkeypatch.setenv("FTRL_B200_PRECISE", "1")
+    rng = np.random.default_rng(70 + nfl + k)
+    nf = 300
+    m = gpu_model(mt, nf, nfl, k)
+    o = CpuModel("oracle", mt, nf, nfl, k)
+    st = pkg.synth.random_state(rng, nf, o.row_len)
+    m.set_state(st)
+    o.set_state(st)
+    for it, nrows in enumerate((5, 300, 2000)):
+        b = pkg.synth.random_csr(rng, nrows, nf, nfl, **kw)
+        got, gl = m.train(**b)
+        want, wl = o.train_batch_csr(**b)
+        assert_close(got, want, RTOL, 2e-6, f"logits batch {it}")
+        assert_state_close(m.get_state(), o.get_state(), rtol=2e-5, atol=2e-6, atol_z=2e-4, name=f"{mt} precise {it}")

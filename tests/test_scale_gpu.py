@@ -132,3 +132,60 @@ def test_criteo_shape_subsample_against_oracle():
         assert abs(gl - wl) <= 1e-6 * abs(wl)
     # hot rows collect thousands of fp32 contributions per coordinate (fp64 in the oracle)
     assert_state_close(m.get_state(), o.get_state(), rtol=1e-4, atol=1e-5, atol_z=5e-3, name="criteo subsample")
+
+
+@pytest.mark.parametrize("mt,k", [("LR", 1), ("FM", 16)])
+@pytest.mark.parametrize("dist", ["zipf", "uniform"])
+def test_cfg2_full_batch_against_oracle(mt, k, dist):
+    """config 2 shape (BASELINE.json configs[1]: libsvm LR + FM k 16, 1M features, 64K-sample minibatch): the
+    oracle's minibatch rule finishes a whole batch of this size in a second, so the full step is compared"""
+    nf = 1_000_000
+    rng = np.random.default_rng(31)
+    m = pkg.FtrlModel(mt, n_feats=nf, n_fields=1, n_factors=k)
+    o = CpuModel("oracle", mt, nf, 1, k)
+    st = pkg.synth.random_state(rng, nf, o.row_len)
+    m.set_state(st)
+    o.set_state(st)
+    for step in range(2):
+        b = pkg.synth.criteo_batch(65536, NFL, nf, seed=40 + step, dist=dist)
+        b["field"] = np.zeros_like(b["field"])  # libsvm: the parser forces field 0 (src/data/parser.cpp:20)
+        got, gl = m.train(**b)
+        want, wl = o.train_batch_csr(**b)
+        assert_close(got, want, 1e-5, 2e-6, f"{mt} logits step {step}")
+        assert abs(gl - wl) <= 1e-6 * abs(wl)
+    # hot ids collect thousands of fp32 contributions per coordinate (fp64 in the oracle)
+    assert_state_close(m.get_state(), o.get_state(), rtol=1e-4, atol=1e-5, atol_z=5e-3, name=f"cfg2 {mt} {dist}")
+
+
+@pytest.mark.parametrize("batch", [64, 1024])
+def test_live_latent_minibatch_quality_within_0p002_of_sequential_reference(batch):
+    """north_star criterion 3 where the latent vectors are ALIVE (from a cold start FFM == LR):
+    same injected non-cold state, same planted-signal data; the reference's own sequential train() (oracle/_ref
+    when it travelled, else its line-by-line restatement) against GPU minibatch training; held-out logloss and
+    AUC of the two final models must agree within 0.002."""
+    from oracle.cpu_model import have_ref
+    nfl, k = 10, 4
+    nf = nfl * 300
+    rng = np.random.default_rng(5)
+    train = pkg.synth.criteo_batch(20000, nfl, nf, seed=77, dist="zipf", n_numeric=3, planted=True)
+    held = pkg.synth.criteo_batch(5000, nfl, nf, seed=78, dist="zipf", n_numeric=3, planted=True)
+    st = pkg.synth.random_state(rng, nf, nfl * k)
+    ref = CpuModel("ref" if have_ref() else "oracle", "FFM", nf, nfl, k)
+    ref.set_state(st)
+    m = pkg.FtrlModel("FFM", n_feats=nf, n_fields=nfl, n_factors=k)
+    m.set_state(st)
+    for ep in range(2):
+        ref.train_csr(**train)   # one sample after another, file order: n_threads = 1 of the reference
+        for r0 in range(0, 20000, batch):
+            m.train(**pkg.synth.slice_csr(train, r0, min(r0 + batch, 20000)), want_logits=False)
+    args = (held["row_ptr"], held["field"], held["feat"], held["val"], held["label"])
+    p_ref, l_ref = ref.predict_csr(*args)
+    p_gpu, l_gpu = m.predict(*args)
+    st_ref, st_gpu = ref.get_state(), m.get_state()
+    assert np.abs(st_ref["vec_z"] - st["vec_z"]).max() > 1e-3, "latent state did not move: the test is vacuous"
+    assert np.isfinite(p_ref).all() and np.isfinite(p_gpu).all()
+    auc_ref, auc_gpu = pkg.synth.auc(held["label"], p_ref), pkg.synth.auc(held["label"], p_gpu)
+    print(f"batch {batch}: held-out logloss ref {l_ref / 5000:.6f} gpu {l_gpu / 5000:.6f}; auc ref {auc_ref:.6f} gpu {auc_gpu:.6f}")
+    assert abs(l_ref / 5000 - l_gpu / 5000) < 0.002
+    assert abs(auc_ref - auc_gpu) < 0.002
+    assert abs(m.auc(p_gpu, held["label"]) - auc_gpu) < 1e-9   # device AUC = harness AUC

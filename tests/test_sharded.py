@@ -165,3 +165,48 @@ def test_sharded_rank_with_an_empty_share():
         assert_state_close(sharded.get_state(), single.get_state(), rtol=2e-5, atol=2e-6, atol_z=2e-4,
                            name=f"empty share step {step}")
     sharded.close()
+
+
+@pytest.mark.gpu
+def test_sharded_model_file_is_the_single_model_file(tmp_path):
+    """save on ONE rank of a sharded run (peer reads), load on EVERY rank: the file is the reference's single-model
+    layout (ffm.cpp:138-159), byte-identical to what one GPU holding the same weights writes, and the reference's
+    own load_compressed_model reads it back"""
+    from oracle.cpu_model import CpuModel, have_ref
+    rng = np.random.default_rng(13)
+    world, nf, nfl, k, B = 4, 997, 6, 4, 128   # 997 rows: the shards differ in size
+    kw = dict(model_type="FFM", n_feats=nf, n_fields=nfl, n_factors=k)
+    single = pkg.FtrlModel(**kw)
+    sharded = pkg.LogicalShards(world, max_batch_rows=B, max_batch_nnz=B * nfl, **kw)
+    st = pkg.synth.random_state(rng, nf, nfl * k)
+    single.set_state(st)
+    sharded.set_state(st)
+    parts = [pkg.synth.criteo_batch(B, nfl, nf, seed=90 + r, dist="zipf") for r in range(world)]
+    sharded.train(parts)
+    f_sh, f_one = str(tmp_path / "sharded.zst"), str(tmp_path / "single.zst")
+    sharded.models[1].save_compressed_model(f_sh)         # any one rank
+    full = sharded.get_state()
+    single.set_state({"bias": full["bias"], "lin_w": full["lin_w"], "vec_w": full["vec_w"]})
+    single.save_compressed_model(f_one)
+    assert open(f_sh, "rb").read() == open(f_one, "rb").read()
+    # load on every rank of a fresh sharded run
+    again = pkg.LogicalShards(world, max_batch_rows=B, max_batch_nnz=B * nfl, **kw)
+    for m in again.models:
+        m.load_compressed_model(f_sh)
+    got = again.get_state()
+    assert np.array_equal(got["lin_w"], full["lin_w"]) and np.array_equal(got["vec_w"], full["vec_w"])
+    assert got["bias"][0] == full["bias"][0]
+    # text form
+    f_txt = str(tmp_path / "sharded.txt")
+    sharded.models[0].save_model(f_txt)
+    for m in again.models:
+        m.set_state({"lin_w": np.zeros(m.n_local, np.float32)})
+        m.load_model(f_txt)
+    assert_close(again.get_state()["lin_w"], full["lin_w"], 1e-5, 1e-7, "text lin_w")
+    if have_ref():
+        r = CpuModel("ref", "FFM", nf, nfl, k)
+        r._fn("load_compressed")(r.h, f_sh.encode())
+        rs = r.get_state()
+        assert np.array_equal(rs["lin_w"], full["lin_w"]) and np.array_equal(rs["vec_w"], full["vec_w"])
+    sharded.close()
+    again.close()
