@@ -38,6 +38,8 @@ WORKLOADS = {
     "cfg3": ("FFM", 39, 1_000_000, 4, 65536),    # configs[2]
     "cfg2-fm": ("FM", 39, 1_000_000, 16, 65536),  # configs[1]
     "cfg2-lr": ("LR", 39, 1_000_000, 1, 65536),
+    # BASELINE.json configs[4]: 100M features, k 8: 374 GB of w/z/n, feature-sharded over 8 GPUs (46.8 GB each)
+    "cfg5": ("FFM", 39, 100_000_000, 8, 65536),
 }
 
 
@@ -151,7 +153,8 @@ CPU_BASELINE_SECONDS = 10.0
 
 def workload_name(wl, model, n_fields, n_feats, k, B):
     """config.workload -- identical on the GPU arm and on the `--impl reference` arm"""
-    tag = " (BASELINE.json configs[3])" if wl == "cfg4" else ""
+    tag = {"cfg4": " (BASELINE.json configs[3])", "cfg5": " (BASELINE.json configs[4])", "cfg3": " (BASELINE.json configs[2])",
+           "cfg2-fm": " (BASELINE.json configs[1])", "cfg2-lr": " (BASELINE.json configs[1])"}.get(wl, "")
     return f"{wl}: {model} n_fields={n_fields} n_feats={n_feats} k={k} batch={B}/GPU{tag}"
 
 

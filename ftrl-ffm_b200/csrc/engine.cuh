@@ -195,7 +195,8 @@ struct ftrl_handle {
   int64_t ow_cap = 0;           // owner-side capacity: (row, rank) contributions this rank may own per step
   ftrl::DevBuf<uint32_t> okey, osrc, ckey, csrc;   // owned contributions, unsorted / sorted by local row
   ftrl::DevBuf<uint8_t> cflag;
-  ftrl::DevBuf<int32_t> sel, n_sel;
+  ftrl::DevBuf<int32_t> n_sel;
+  ftrl::DevBuf<uint32_t> bkey, bkey_s, bidx, perm;   // owner buckets of the distinct-row list (shard.cuh)
   ftrl::DevBuf<ftrl::MaskScan> mscan;              // segmented OR-scan of the field masks over the sorted list
   ftrl::DevBuf<int32_t> uhead, n_uall, dst_at;     // distinct rows of the local batch (sorted head positions)
   ftrl::DevBuf<uint32_t> ukey, uinfo;

@@ -254,8 +254,11 @@ static void ensure_workspace(ftrl_handle *h, int64_t n_rows, int64_t nnz) {
     h->ckey.ensure(oc);
     h->csrc.ensure(oc);
     h->cflag.ensure(oc);
-    h->sel.ensure(std::max<int64_t>(oc, (int64_t)h->G * nc));  // DeviceSelect may keep every candidate (all rows owned here)
     h->n_sel.ensure(4);
+    h->bkey.ensure(nc);
+    h->bkey_s.ensure(nc);
+    h->bidx.ensure(nc);
+    h->perm.ensure(nc);
     h->red4.ensure(4);
     h->mscan.ensure(nc);
     h->uhead.ensure(nc + 1);
@@ -291,7 +294,7 @@ static void ensure_workspace(ftrl_handle *h, int64_t n_rows, int64_t nnz) {
   const int64_t slots = 2 * (nc / h->chunk + 2);
   if (h->dims.row_len) h->part.ensure((size_t)slots * 2 * h->dims.ld);
   h->part_lin.ensure(slots);
-  h->cub_bytes = cub_temp_bytes(h->G > 1 ? std::max<int64_t>((int64_t)h->G * nc, oc) : nc, key_bits(h->dims.n_feats));
+  h->cub_bytes = cub_temp_bytes(h->G > 1 ? std::max<int64_t>(nc, oc) : nc, key_bits(h->dims.n_feats));
   h->cub_tmp.ensure(h->cub_bytes);
   h->rows_cap = rc;
   h->nnz_cap = nc;
@@ -838,8 +841,6 @@ static void train_device_sharded(ftrl_handle *h, const Batch &b, float *logit_ou
   const Dims &d = h->dims;
   if (b.n_rows > h->rows_cap || b.nnz > h->nnz_cap) throw ArgFail{"batch exceeds max_batch_rows / max_batch_nnz of a multi-GPU handle"};
   const int32_t nnz = (int32_t)b.nnz;
-  const int32_t nnz_max = (int32_t)h->cfg.max_batch_nnz;
-  const int32_t ucap = (int32_t)h->nnz_cap;
   const uint32_t sentinel = (uint32_t)d.n_feats;
   const uint32_t lsent = (uint32_t)h->n_local;  // sentinel in local-row space (n_local may differ by 1 across ranks)
   const int32_t oc = (int32_t)h->ow_cap;
@@ -879,23 +880,27 @@ static void train_device_sharded(ftrl_handle *h, const Batch &b, float *logit_ou
       bytes = h->cub_bytes;
       FTRL_CUDA(cub::DeviceSelect::If(h->cub_tmp.p, bytes, cnt, h->uhead.p, h->n_uall.p, nnz, RowHeadPred{h->skey.p}, h->compute));
     }
-    k_publish_unique<<<(std::max(nnz, 1) + 255) / 256, 256, 0, h->compute>>>(h->peers, nnz, sentinel, ucap, h->uhead.p, h->n_uall.p,
-                                                                             h->skey.p, h->mscan.p, h->batch_flags.p, h->ukey.p,
-                                                                             h->uinfo.p, h->umask.p);
+    if (nnz > 0) {
+      // the list goes out bucketed by owner: one stable radix pass over the owner bits
+      k_owner_keys<<<(nnz + 255) / 256, 256, 0, h->compute>>>(nnz, h->G, sentinel, h->uhead.p, h->n_uall.p, h->skey.p, h->bkey.p,
+                                                             h->bidx.p);
+      size_t bytes = h->cub_bytes;
+      FTRL_CUDA(cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, bytes, h->bkey.p, h->bkey_s.p, h->bidx.p, h->perm.p, nnz, 0,
+                                                h->log2G + 1, h->compute));
+      k_publish_unique<<<(nnz + 255) / 256, 256, 0, h->compute>>>(nnz, h->G, h->bkey_s.p, h->perm.p, h->uhead.p, h->n_uall.p, h->skey.p,
+                                                                 h->mscan.p, h->ukey.p, h->uinfo.p, h->umask.p);
+    }
+    k_publish_bounds<<<1, 32, 0, h->compute>>>(h->peers, nnz, h->bkey_s.p, h->batch_flags.p);
     FTRL_CUDA(cudaGetLastError());
-    launched(h, PH_SEGMENT, 2);
+    launched(h, PH_SEGMENT, 4);
     peer_barrier(h);  // 1: every rank's distinct-row list is published
   }
   {
     // owner side: contributions (row, rank) of the rows this rank owns
     PhaseScope ps(h, PH_EXCHANGE);
     k_merge_flags<<<1, 1, 0, h->compute>>>(h->peers, h->batch_flags.p, h->d_err);
+    k_fill_owned<<<(oc + 255) / 256, 256, 0, h->compute>>>(h->peers, oc, lsent, step_tag, h->n_sel.p, h->okey.p, h->osrc.p, h->d_err);
     size_t bytes = h->cub_bytes;
-    FTRL_CUDA(cub::DeviceSelect::If(h->cub_tmp.p, bytes, cnt, h->sel.p, h->n_sel.p, h->G * nnz_max,
-                                    OwnedPred{h->peers, nnz_max}, h->compute));
-    k_fill_owned<<<(oc + 255) / 256, 256, 0, h->compute>>>(h->peers, nnz_max, oc, lsent, step_tag, h->sel.p, h->n_sel.p,
-                                                          h->okey.p, h->osrc.p, h->d_err);
-    bytes = h->cub_bytes;
     FTRL_CUDA(cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, bytes, h->okey.p, h->ckey.p, h->osrc.p, h->csrc.p, oc, 0,
                                               key_bits((int32_t)h->n_local), h->compute));
     k_contrib_class<<<(oc + 255) / 256, 256, 0, h->compute>>>(h->peers, oc, h->n_sel.p, lsent, h->ckey.p, h->csrc.p, h->socc.p,
@@ -1790,12 +1795,9 @@ int ftrl_attach_peers(ftrl_handle *h, const void *blobs) {
       FTRL_CUDA(cudaMemcpy(ws.val.p, one, sizeof(one), cudaMemcpyHostToDevice));
       FTRL_CUDA(cudaMemcpy(ws.label.p, &lab, sizeof(lab), cudaMemcpyHostToDevice));
       Batch wb{1, 2, ws.row_ptr.p, ws.field.p, ws.feat.p, ws.val.p, ws.label.p};
-      const int64_t save_max = h->cfg.max_batch_nnz;
-      h->cfg.max_batch_nnz = std::min<int64_t>(save_max, 64);
-      h->G = 1;  // the owner-side select scans G * max_batch_nnz candidates: one shard here
+      h->G = 1;  // one shard: this rank against itself
       if (h->precise) train_device_sharded<true>(h, wb, nullptr, ws.loss.p); else train_device_sharded<false>(h, wb, nullptr, ws.loss.p);
       FTRL_CUDA(cudaStreamSynchronize(h->compute));
-      h->cfg.max_batch_nnz = save_max;
       h->G = G; h->log2G = log2G; h->rank = rank;
       FTRL_CUDA(cudaMemcpy(h->bias, &bias_save, sizeof(float4), cudaMemcpyHostToDevice));
       FTRL_CUDA(cudaMemset(h->d_err, 0, sizeof(int32_t)));

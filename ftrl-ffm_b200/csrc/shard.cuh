@@ -36,7 +36,8 @@ namespace ftrl {
 // lives in device memory of every rank, mapped by all peers
 struct SyncArea {
   uint32_t flag[MAX_SHARDS];      // flag[q] = last barrier epoch rank q has reached (written by q)
-  int32_t n_uniq[MAX_SHARDS];     // n_uniq[q] = distinct rows of rank q's current batch (written by q)
+  int32_t boff[MAX_SHARDS][MAX_SHARDS + 1];  // boff[q][r] .. boff[q][r+1]: the part of rank q's distinct-row list
+                                             // owned by rank r (the list is published bucketed by owner; written by q)
   int32_t simple[MAX_SHARDS];     // simple[q] != 0: every sample of rank q's batch has distinct fields
   double red[MAX_SHARDS][4];      // red[q] = {sum g, sum g^2, sum loss, n_rows} of rank q's batch
   uint32_t abort_at[MAX_SHARDS];  // abort_at[q] = step tag at which rank q asked every rank to skip the step (written by q)
@@ -84,30 +85,55 @@ struct RowHeadPred {
   __device__ __forceinline__ bool operator()(int32_t p) const { return p == 0 || skey[p] != skey[p - 1]; }
 };
 
-// one thread per listed row head; thread 0 also tells every peer how many distinct rows this rank has
-__global__ void k_publish_unique(Peers pr, int32_t nnz, uint32_t sentinel, int32_t cap, const int32_t *__restrict__ uhead,
-                                 const int32_t *__restrict__ n_uall_p, const uint32_t *__restrict__ skey,
-                                 const MaskScan *__restrict__ mscan, const int32_t *__restrict__ batch_flags,
+// The distinct-row list is published BUCKETED BY OWNER (each bucket still sorted by feature id): an owner then
+// reads one contiguous run per peer instead of scanning every peer's whole list for its rows.
+//   k_owner_keys     : bucket of the u-th distinct row = its owner; G for the sentinel run and the unused tail
+//   (one stable radix-sort pass over log2(G) + 1 bits gives the bucketed order `perm`)
+//   k_publish_unique : one thread per slot v of the bucketed list
+//   k_publish_bounds : bucket boundaries + the "distinct fields" flag of this rank, to every peer
+__global__ void k_owner_keys(int32_t nnz, int G, uint32_t sentinel, const int32_t *__restrict__ uhead,
+                             const int32_t *__restrict__ n_uall_p, const uint32_t *__restrict__ skey,
+                             uint32_t *__restrict__ bkey, uint32_t *__restrict__ bidx) {
+  const int32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= nnz) return;
+  uint32_t bk = (uint32_t)G;
+  if (u < *n_uall_p) {
+    const uint32_t key = skey[uhead[u]];
+    if (key != sentinel) bk = key & (uint32_t)(G - 1);
+  }
+  bkey[u] = bk;
+  bidx[u] = (uint32_t)u;
+}
+
+__global__ void k_publish_unique(int32_t nnz, int G, const uint32_t *__restrict__ bkey_s, const uint32_t *__restrict__ perm,
+                                 const int32_t *__restrict__ uhead, const int32_t *__restrict__ n_uall_p,
+                                 const uint32_t *__restrict__ skey, const MaskScan *__restrict__ mscan,
                                  uint32_t *__restrict__ ukey, uint32_t *__restrict__ uinfo,
                                  unsigned long long *__restrict__ umask) {
-  const int32_t u = blockIdx.x * blockDim.x + threadIdx.x;
-  const int32_t n_uall = nnz > 0 ? *n_uall_p : 0;
-  if (u == 0) {
-    int32_t n = n_uall;
-    if (n > 0 && skey[uhead[n - 1]] == sentinel) n--;  // the run of invalid occurrences sorts last
-    for (int q = 0; q < pr.G; q++) {
-      pr.sync[q]->n_uniq[pr.rank] = n;
-      pr.sync[q]->simple[pr.rank] = batch_flags[0];
-    }
-  }
-  if (u >= n_uall || u >= cap) return;
+  const int32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= nnz || bkey_s[v] >= (uint32_t)G) return;
+  const int32_t u = (int32_t)perm[v], n_uall = *n_uall_p;
   const int32_t p = uhead[u];
-  const uint32_t key = skey[p];
-  if (key == sentinel) return;
   const int32_t next = u + 1 < n_uall ? uhead[u + 1] : nnz;
-  ukey[u] = key;
-  uinfo[u] = (uint32_t)p | (next - p == 1 ? UINFO_SINGLE : 0u);
-  umask[u] = mscan[next - 1].mask;
+  ukey[v] = skey[p];
+  uinfo[v] = (uint32_t)p | (next - p == 1 ? UINFO_SINGLE : 0u);
+  umask[v] = mscan[next - 1].mask;
+}
+
+// lane r <= G: first slot of bucket r (lower bound in the sorted bucket keys)
+__global__ void k_publish_bounds(Peers pr, int32_t nnz, const uint32_t *__restrict__ bkey_s,
+                                 const int32_t *__restrict__ batch_flags) {
+  const int r = threadIdx.x;
+  if (r > pr.G) return;
+  int32_t lo = 0, hi = nnz;
+  while (lo < hi) {
+    const int32_t mid = (lo + hi) >> 1;
+    if (bkey_s[mid] < (uint32_t)r) lo = mid + 1; else hi = mid;
+  }
+  for (int q = 0; q < pr.G; q++) {
+    pr.sync[q]->boff[pr.rank][r] = lo;
+    if (r == 0) pr.sync[q]->simple[pr.rank] = batch_flags[0];
+  }
 }
 
 // all ranks arrive; returns when every rank has reached `epoch`.  A peer that never arrives (crashed
@@ -149,33 +175,32 @@ __global__ void k_check_abort(Peers pr, uint32_t step_tag, int32_t *batch_flags,
 }
 
 // ---- S2: owner side ---------------------------------------------------------------------------------
-struct OwnedPred {
-  Peers pr;
-  int32_t nnz_max;
-  __device__ __forceinline__ bool operator()(int32_t idx) const {
-    const int q = idx / nnz_max, u = idx - q * nnz_max;
-    if (u >= pr.sync[pr.rank]->n_uniq[q]) return false;
-    return (int)(pr.ukey[q][u] & (uint32_t)(pr.G - 1)) == pr.rank;
-  }
-};
-
 // (local row, source) pairs of the owned contributions; the tail up to `cap` is padded with the sentinel.
 // More contributions than the workspace holds (ids concentrated on one residue mod G): the whole step is
 // called off on EVERY rank before any z / n is touched -- the tag goes to every peer, k_check_abort reads it
 // after barrier 2 and turns the remaining kernels of the step into no-ops (batch_flags[0] = 0).
-__global__ void k_fill_owned(Peers pr, int32_t nnz_max, int32_t cap, uint32_t local_sentinel, uint32_t step_tag,
-                             const int32_t *__restrict__ sel, const int32_t *__restrict__ n_sel,
-                             uint32_t *__restrict__ okey, uint32_t *__restrict__ osrc, int32_t *__restrict__ err) {
+// Contribution j is the (j - start_q)-th row of the run rank q published for this owner, runs in rank order.
+__global__ void k_fill_owned(Peers pr, int32_t cap, uint32_t local_sentinel, uint32_t step_tag,
+                             int32_t *__restrict__ n_sel, uint32_t *__restrict__ okey, uint32_t *__restrict__ osrc,
+                             int32_t *__restrict__ err) {
   const int32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= cap) return;
-  const int32_t n = *n_sel;
+  const SyncArea *sa = pr.sync[pr.rank];
+  int32_t n = 0, q = -1, u = 0;
+  for (int r = 0; r < pr.G; r++) {
+    const int32_t b0 = sa->boff[r][pr.rank], cnt = sa->boff[r][pr.rank + 1] - b0;
+    if (q < 0 && j < n + cnt) {
+      q = r;
+      u = b0 + (j - n);
+    }
+    n += cnt;
+  }
+  if (j == 0) *n_sel = n;
   if (j == 0 && n > cap) {
     *err = 3;  // owned contributions exceed the workspace (extreme skew)
     for (int q = 0; q < pr.G; q++) *reinterpret_cast<volatile uint32_t *>(&pr.sync[q]->abort_at[pr.rank]) = step_tag;
   }
   if (j < n) {
-    const int32_t idx = sel[j];
-    const int q = idx / nnz_max, u = idx - q * nnz_max;
     okey[j] = pr.ukey[q][u] >> pr.log2G;
     osrc[j] = ((uint32_t)q << SRC_SHIFT) | (uint32_t)u;
   } else {

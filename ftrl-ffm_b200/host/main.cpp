@@ -66,9 +66,13 @@ struct PinnedCsr {
   }
 };
 
+// One model on one GPU, or (--n_gpus N) one model whose tables are sharded by feature id over N GPUs of this box:
+// N handles in this process, peers attached in-process (ftrl_export_peer_blob / ftrl_attach_peers), every minibatch
+// split into N contiguous shares -- the reference's worker fan-out (ftrl_offline.cpp:85-91) across GPUs.
 class Trainer {
  public:
-  Trainer(const host::Options &o) : opt_(o) {
+  // max_row_nnz: longest sample of the data (sizes the fixed buffers of a multi-GPU run; ignored for one GPU)
+  Trainer(const host::Options &o, size_t max_row_nnz = 0) : opt_(o) {
     ftrl_config c;
     ftrl_config_default(&c);
     if (o.model_type == "LR") c.model_type = FTRL_LR;
@@ -88,56 +92,86 @@ class Trainer {
     c.w_beta = o.w_beta;
     c.w_l1 = o.w_l1;
     c.w_l2 = o.w_l2;
-    c.device = o.device;
     c.mode = o.batch_size == 1 ? FTRL_MODE_SEQUENTIAL : FTRL_MODE_BATCH;
     c.seed = o.seed ? o.seed : std::random_device{}();
-    if (ftrl_create(&c, &h_) != FTRL_OK) die(nullptr, "ftrl_create");
     // sequential mode walks the samples of a call in order on the device: hand over large blocks
     block_ = o.batch_size == 1 ? 8192 : (size_t)o.batch_size;
-  }
-  ~Trainer() { ftrl_destroy(h_); }
-
-  // trains (or scores) samples idx[begin..end) of `data`; losses are appended to loss_parts_
-  void submit(const host::Csr &data, const int32_t *order, size_t begin, size_t end, bool train) {
-    PinnedCsr &p = pin_[next_pin_];
-    next_pin_ = (next_pin_ + 1) % kPins;
-    const size_t rows = end - begin;
-    size_t nnz = 0;
-    for (size_t i = begin; i < end; i++) {
-      const size_t r = order ? (size_t)order[i] : i;
-      nnz += (size_t)(data.row_ptr[r + 1] - data.row_ptr[r]);
-    }
-    p.ensure(rows, nnz);
-    size_t w = 0;
-    p.row_ptr[0] = 0;
-    for (size_t i = begin; i < end; i++) {
-      const size_t r = order ? (size_t)order[i] : i;
-      const size_t a = (size_t)data.row_ptr[r], n = (size_t)data.row_ptr[r + 1] - a;
-      memcpy(p.field + w, data.field.data() + a, n * sizeof(int32_t));
-      memcpy(p.feat + w, data.feat.data() + a, n * sizeof(int32_t));
-      memcpy(p.val + w, data.val.data() + a, n * sizeof(float));
-      w += n;
-      p.row_ptr[i - begin + 1] = (int64_t)w;
-      p.label[i - begin] = data.label[r];
-    }
-    // the library writes through these pointers at ftrl_sync: never reallocate with calls in flight
-    if (loss_parts_.size() + 1 >= loss_parts_.capacity()) sync();
-    loss_parts_.push_back(0.0);
-    double *slot = &loss_parts_.back();
-    int rc;
-    if (train)
-      rc = ftrl_train_batch(h_, (int64_t)rows, p.row_ptr, p.field, p.feat, p.val, p.label, nullptr, slot);
-    else {
-      float *out = score_sink(rows);
-      if (opt_.auc) {  // keep every score and label of the pass: one block per call, never moved while in flight
-        scores_.emplace_back(rows);
-        out = scores_.back().data();
-        labels_.emplace_back(p.label, p.label + rows);
+    const int G = std::max(1, o.n_gpus);
+    ranks_.resize((size_t)G);
+    for (int r = 0; r < G; r++) {
+      c.device = o.device + r;
+      c.rank = r;
+      c.world_size = G;
+      if (G > 1) {
+        c.max_batch_rows = (int64_t)((block_ + G - 1) / G);
+        c.max_batch_nnz = c.max_batch_rows * (int64_t)std::max<size_t>(1, max_row_nnz);
       }
-      rc = ftrl_predict_batch(h_, (int64_t)rows, p.row_ptr, p.field, p.feat, p.val, p.label, 0, out, slot);
+      if (ftrl_create(&c, &ranks_[r].h) != FTRL_OK) die(nullptr, "ftrl_create");
     }
-    if (rc != FTRL_OK) die(h_, train ? "ftrl_train_batch" : "ftrl_predict_batch");
-    n_submitted_ += rows;
+    if (G > 1) {
+      std::vector<char> blobs((size_t)G * FTRL_PEER_BLOB_BYTES);
+      for (int r = 0; r < G; r++)
+        if (ftrl_export_peer_blob(ranks_[r].h, blobs.data() + (size_t)r * FTRL_PEER_BLOB_BYTES) != FTRL_OK)
+          die(ranks_[r].h, "ftrl_export_peer_blob");
+      for (int r = 0; r < G; r++)
+        if (ftrl_attach_peers(ranks_[r].h, blobs.data()) != FTRL_OK) die(ranks_[r].h, "ftrl_attach_peers");
+    }
+  }
+  ~Trainer() {
+    for (auto &r : ranks_) ftrl_destroy(r.h);
+  }
+
+  // trains (or scores) samples idx[begin..end) of `data`: rank r takes the r-th contiguous share
+  void submit(const host::Csr &data, const int32_t *order, size_t begin, size_t end, bool train) {
+    const size_t G = ranks_.size(), total = end - begin, share = (total + G - 1) / G;
+    // the library writes through these pointers at ftrl_sync: never reallocate with calls in flight
+    if (loss_parts_.size() + G >= loss_parts_.capacity()) sync();
+    const int pin = next_pin_;
+    next_pin_ = (next_pin_ + 1) % kPins;
+    for (size_t g = 0; g < G; g++) {
+      const size_t b0 = std::min(end, begin + g * share), b1 = std::min(end, b0 + share);
+      Rank &rk = ranks_[g];
+      PinnedCsr &p = rk.pin[pin];
+      const size_t rows = b1 - b0;
+      size_t nnz = 0;
+      for (size_t i = b0; i < b1; i++) {
+        const size_t r = order ? (size_t)order[i] : i;
+        nnz += (size_t)(data.row_ptr[r + 1] - data.row_ptr[r]);
+      }
+      p.ensure(rows, nnz);
+      size_t w = 0;
+      p.row_ptr[0] = 0;
+      for (size_t i = b0; i < b1; i++) {
+        const size_t r = order ? (size_t)order[i] : i;
+        const size_t a = (size_t)data.row_ptr[r], n = (size_t)data.row_ptr[r + 1] - a;
+        memcpy(p.field + w, data.field.data() + a, n * sizeof(int32_t));
+        memcpy(p.feat + w, data.feat.data() + a, n * sizeof(int32_t));
+        memcpy(p.val + w, data.val.data() + a, n * sizeof(float));
+        w += n;
+        p.row_ptr[i - b0 + 1] = (int64_t)w;
+        p.label[i - b0] = data.label[r];
+      }
+      loss_parts_.push_back(0.0);
+      double *slot = &loss_parts_.back();
+      int rc;
+      if (train) {
+        // a multi-GPU step is collective: every rank is called, also with an empty share
+        rc = ftrl_train_batch(rk.h, (int64_t)rows, p.row_ptr, p.field, p.feat, p.val, p.label, nullptr, slot);
+      } else if (rows == 0) {
+        rc = FTRL_OK;
+      } else {
+        if (rk.sink[pin].size() < share) rk.sink[pin].resize(std::max(share, block_));
+        float *out = rk.sink[pin].data();  // predictions are not needed by the driver (only the loss) ...
+        if (opt_.auc) {  // ... unless the AUC is asked for: one block per call, never moved while in flight
+          scores_.emplace_back(rows);
+          out = scores_.back().data();
+          labels_.emplace_back(p.label, p.label + rows);
+        }
+        rc = ftrl_predict_batch(rk.h, (int64_t)rows, p.row_ptr, p.field, p.feat, p.val, p.label, 0, out, slot);
+      }
+      if (rc != FTRL_OK) die(rk.h, train ? "ftrl_train_batch" : "ftrl_predict_batch");
+    }
+    n_submitted_ += total;
   }
 
   void run_block(const host::Csr &data, const int32_t *order, size_t n, bool train) {
@@ -145,7 +179,8 @@ class Trainer {
   }
 
   void sync() {
-    if (ftrl_sync(h_) != FTRL_OK) die(h_, "ftrl_sync");
+    for (auto &r : ranks_)
+      if (ftrl_sync(r.h) != FTRL_OK) die(r.h, "ftrl_sync");
     for (double v : loss_parts_) loss_total_ += v;
     loss_parts_.clear();
   }
@@ -169,27 +204,27 @@ class Trainer {
     scores_.clear();
     labels_.clear();
     double auc = 0.0;
-    if (ftrl_eval_auc(h_, (int64_t)sc.size(), sc.data(), la.data(), &auc) != FTRL_OK) die(h_, "ftrl_eval_auc");
+    if (ftrl_eval_auc(handle(), (int64_t)sc.size(), sc.data(), la.data(), &auc) != FTRL_OK) die(handle(), "ftrl_eval_auc");
     return auc;
   }
 
-  void begin_epoch(size_t expected_calls) { loss_parts_.reserve(std::max<size_t>(expected_calls + 8, 4096)); }
-  ftrl_handle *handle() { return h_; }
+  void begin_epoch(size_t expected_calls) {
+    loss_parts_.reserve(std::max<size_t>((expected_calls + 8) * ranks_.size(), 4096));
+  }
+  // the handle model files are written through (a multi-GPU run: one rank reads every shard over peer memory)
+  ftrl_handle *handle() { return ranks_[0].h; }
+  int n_gpus() const { return (int)ranks_.size(); }
 
  private:
-  float *score_sink(size_t rows) {
-    // predictions themselves are not needed by the driver (only the loss); fixed-size sink per slot
-    // (rows <= block_), never reallocated while calls are in flight
-    if (sink_[next_pin_].size() < block_) sink_[next_pin_].resize(block_);
-    (void)rows;
-    return sink_[next_pin_].data();
-  }
   static constexpr int kPins = 4;
+  struct Rank {
+    ftrl_handle *h = nullptr;
+    PinnedCsr pin[kPins];
+    std::vector<float> sink[kPins];
+  };
   host::Options opt_;
-  ftrl_handle *h_ = nullptr;
+  std::vector<Rank> ranks_;
   size_t block_ = 1024;
-  PinnedCsr pin_[kPins];
-  std::vector<float> sink_[kPins];
   int next_pin_ = 0;
   std::vector<double> loss_parts_;
   std::deque<std::vector<float>> scores_;
@@ -197,6 +232,12 @@ class Trainer {
   double loss_total_ = 0.0;
   size_t n_submitted_ = 0;
 };
+
+size_t max_row_nnz(const host::Csr &c) {
+  size_t m = 0;
+  for (size_t r = 0; r + 1 < c.row_ptr.size(); r++) m = std::max(m, (size_t)(c.row_ptr[r + 1] - c.row_ptr[r]));
+  return m;
+}
 
 // Reader::load_from_file (src/data/reader.cpp:50-91)
 void load_file(const std::string &path, bool libffm, int n_threads, bool csr_cache, host::Csr &out) {
@@ -220,11 +261,11 @@ void load_file(const std::string &path, bool libffm, int n_threads, bool csr_cac
 
 // FtrlOffline::train / evaluate / one_epoch (src/task/ftrl_offline.cpp:44-103)
 void run_offline(const host::Options &o) {
-  Trainer tr(o);
   const bool libffm = o.file_type == "libffm";
   host::Csr train, eval;
   load_file(o.train_path, libffm, o.thread_num, o.csr_cache, train);
   if (!o.eval_path.empty()) load_file(o.eval_path, libffm, o.thread_num, o.csr_cache, eval);
+  Trainer tr(o, std::max(max_row_nnz(train), max_row_nnz(eval)));
   std::mt19937 gen(o.seed ? (uint32_t)o.seed : std::random_device{}());
   std::vector<int32_t> order(train.rows());
   for (int ep = 1; ep <= o.epoch; ep++) {
@@ -307,7 +348,6 @@ double stream_file(Trainer &tr, const std::string &path, bool libffm, int n_thre
 
 // FtrlOnline::train / evaluate (src/task/ftrl_online.cpp:42-68)
 void run_online(const host::Options &o) {
-  Trainer tr(o);
   const bool libffm = o.file_type == "libffm";
   if (o.cmd) return;  // `// todo: online learning` in the reference (ftrl_online.cpp:55-57)
   // --csr_cache: the files are parsed (or their binary images read) once and every epoch walks them in file
@@ -316,7 +356,12 @@ void run_online(const host::Options &o) {
   if (o.csr_cache) {
     load_file(o.train_path, libffm, o.thread_num, true, train);
     if (!o.eval_path.empty()) load_file(o.eval_path, libffm, o.thread_num, true, eval);
+  } else if (o.n_gpus > 1) {
+    // the buffers peers map are sized at creation from the longest sample: the data must be known up front
+    fprintf(stderr, "--n_gpus > 1 needs the data in memory: use --online false or --csr_cache true\n");
+    exit(EXIT_FAILURE);
   }
+  Trainer tr(o, std::max(max_row_nnz(train), max_row_nnz(eval)));
   auto one_pass = [&](const host::Csr &mem, const std::string &path, bool is_train) {
     if (!o.csr_cache) return stream_file(tr, path, libffm, o.thread_num, is_train);
     tr.begin_epoch(mem.rows() / std::max<long>(1, o.batch_size) + 1);

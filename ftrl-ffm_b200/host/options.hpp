@@ -1,7 +1,7 @@
 // options.hpp -- command line of the drop-in `main`.
 // Same flags, defaults and input-type sniffing as the reference: src/utils/cmd_option.cpp:61-113,
 // src/include/utils/cmd_option.h:7-63.  Additive flags (default = reference-compatible): --batch_size,
-// --device, --seed, --csr_cache, --auc.
+// --device, --n_gpus, --seed, --csr_cache, --auc.
 #pragma once
 #include <algorithm>
 #include <cctype>
@@ -36,7 +36,9 @@ static const char *kHelp =
     "--n_epochs <epochs>: how many epochs to train\tdefault:1\n"
     "--online <online>: whether to online training mode\tdefault:true\n"
     "--batch_size <n>: samples per GPU minibatch; 1 = reference-exact sequential mode\tdefault:1024\n"
-    "--device <ordinal>: CUDA device\tdefault:0\n"
+    "--device <ordinal>: CUDA device (first device of a multi-GPU run)\tdefault:0\n"
+    "--n_gpus <n>: 1, 2, 4 or 8 GPUs of this box; the tables are sharded by feature id, every minibatch is split "
+    "across the GPUs (FFM, data in memory: --online false or --csr_cache true)\tdefault:1\n"
     "--seed <n>: shuffle / init seed (0 = from std::random_device)\tdefault:0\n"
     "--csr_cache <bool>: keep a binary image <file>.csr of each parsed data file and reuse it while the text is "
     "unchanged\tdefault:false\n"
@@ -52,6 +54,7 @@ struct Options {  // mirrors config_options (cmd_option.h:29-63)
   bool csr_cache = false;
   bool auc = false;
   int device = 0;
+  int n_gpus = 1;
   unsigned long long seed = 0;
 };
 
@@ -116,6 +119,7 @@ inline void parse_options(int argc, char **argv, Options &o) {
     else if (k == "--cmd") o.cmd = assign_bool(v);
     else if (k == "--batch_size") o.batch_size = std::stol(v);
     else if (k == "--device") o.device = std::stoi(v);
+    else if (k == "--n_gpus") o.n_gpus = std::stoi(v);
     else if (k == "--seed") o.seed = std::stoull(v);
     else if (k == "--csr_cache") o.csr_cache = assign_bool(v);
     else if (k == "--auc") o.auc = assign_bool(v);
