@@ -42,38 +42,20 @@ struct Shards {   // every shard's tables (predict reads rows where they live)
   __device__ __forceinline__ float4 *linp(int32_t feat) const { return lin[feat & (G - 1)] + (feat >> log2G); }
 };
 
-// What the training kernels address: the local shard and the per-step cache of remote rows (their w plane,
-// pushed by its owner once per distinct row: shard.cuh).
+// What the per-sample training kernel sees: the local shard, the per-step cache of remote rows (their w
+// plane, pushed by its owner once per distinct row: shard.cuh) and the local staging area of gradient images.
 // A row is named by a locator: >= 0 local row index; < 0: -1 - (sorted head position of the remote row).
 struct RowSpace {
   float *tab;            // [n_local][3][ld]
   float4 *lin;           // [n_local]
+  float *staging;        // [sorted position][ld]
+  float *staging_lin;    // [sorted position]
   const float *rc_w;     // [sorted head position][ld]   (null when G == 1)
   const float *rc_lin;   // [sorted head position]
   int log2G, rank, Gm1, pad;
-  // w plane of a row whose w has been materialised for this step
-  __device__ __forceinline__ const float *w_plane(int32_t loc, int64_t ld) const {
-    return loc >= 0 ? tab + (int64_t)loc * 3 * ld + 2 * ld : rc_w + (int64_t)(-1 - loc) * ld;
-  }
 };
 
-// One entry per (sample, field) of a batch whose samples have distinct fields: the row carried by that
-// field (locator as above) and its value; CANON_NONE when the sample has no valid feature of that field.
-// Built once per step (prep.cuh: k_build_canon); the row kernel (ffm_tile.cuh: k_ffm_regrad_rows) finds the
-// partner rows of an occurrence through it.
-struct __align__(8) CanonEntry {
-  int32_t loc;
-  float x;
-};
-constexpr int32_t CANON_NONE = (int32_t)0x80000000;
-// A partner row that is FUSED (occurs once in the batch) is not looked up in the table by the row kernel: its w
-// slice would be a 32-byte DRAM read nobody else shares.  The sample kernel, which has the row in shared
-// memory, leaves the finished gradient slice g x x w in a compact per-occurrence image instead, and the entry
-// names the slot of that image: CANON_FUSED | rank of the row among the fused rows of its sample.
-constexpr uint32_t CANON_FUSED = 0xA0000000u;  // top three bits 101 (remote locators are small negatives: 111)
-__device__ __forceinline__ bool canon_is_fused(int32_t loc) { return ((uint32_t)loc >> 29) == 5u; }
-
-// Where the reduced (sum g, sum g^2) of a row goes (k_ffm_regrad_rows / k_ffm_combine).  Single GPU: applied
+// Where the reduced (sum g, sum g^2) of a row goes (k_ffm_staged_rows / k_ffm_combine).  Single GPU: applied
 // in place.  Sharded: dst_at[sorted head position] = -2 apply here (this rank owns the row and is its only
 // contributor), >= 0: slot in the owner's inbox.
 struct Export {

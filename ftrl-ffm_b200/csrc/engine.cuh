@@ -154,10 +154,7 @@ struct ftrl_handle {
   ftrl::DevBuf<uint64_t> pmask;                 // per occurrence: fields of the other features of its sample
   ftrl::DevBuf<unsigned long long> rowmask;     // per segmented row: fields touched in this batch
   ftrl::PmaskSrc pmask_src{};
-  ftrl::DevBuf<ftrl::CanonEntry> canon;      // [sample][field] -> (row locator, value) of the tile path
-  ftrl::DevBuf<int4> srec;                   // [sorted position] {sample, value, field * k, -}
-  ftrl::DevBuf<int32_t> n_fused, sbase;      // fused rows per sample; image base per sorted position (slices)
-  ftrl::DevBuf<float> sparse;                // gradient slices (staged occurrence x fused partner), written by k_ffm_tile
+  ftrl::DevBuf<float> staging, staging_lin;  // per-occurrence gradient images (tile path)
   ftrl::DevBuf<ftrl::SegScan> scan;
   ftrl::DevBuf<float> g, S, part;
   ftrl::DevBuf<float2> part_lin;
@@ -214,6 +211,6 @@ struct ftrl_handle {
   int tile = 1;     // FFM: TMA-staged per-sample kernel for batches of distinct-field samples
   bool tile_ok = false;
   int tile_ctas_per_sm = 1;
-  int tile_f_cap = 0, tile_stride = 0, tile_stride1 = 0, tile_stages = 0, tile_consumers = 0, tile_ipt = 1, tile_meta = 4, tile_dbg = 0, tile_inflight = 4, tile_helper_ns = 0, tile_variant = 1;
+  int tile_f_cap = 0, tile_stride = 0, tile_stride1 = 0, tile_stages = 0, tile_consumers = 0, tile_ipt = 1, tile_meta = 4, tile_dbg = 0, tile_cache = 1, tile_inflight = 4;
   size_t tile_smem = 0;
 };

@@ -220,6 +220,8 @@ static void refresh_shards(ftrl_handle *h) {
   rsp = RowSpace{};
   rsp.tab = h->tab;
   rsp.lin = h->lin;
+  rsp.staging = h->staging.p;
+  rsp.staging_lin = h->staging_lin.p;
   h->exportd = Export{};
 }
 
@@ -280,13 +282,8 @@ static void ensure_workspace(ftrl_handle *h, int64_t n_rows, int64_t nnz) {
     h->rowmask.ensure(nc + 2);
   }
   if (h->tile_ok) {
-    h->canon.ensure((size_t)rc * h->dims.n_fields);
-    h->srec.ensure(nc);
-    h->n_fused.ensure(rc);
-    h->sbase.ensure(nc + 1);
-    // (staged occurrence, fused partner) pairs of a sample with F distinct fields: at most (F/2)^2
-    const int64_t nfl = h->dims.n_fields;
-    h->sparse.ensure((size_t)rc * (size_t)((nfl * nfl + 3) / 4) * h->dims.k);
+    h->staging.ensure((size_t)nc * h->dims.ld);
+    h->staging_lin.ensure(nc);
   }
   h->scan.ensure(nc);
   h->chunk_pos.ensure(nc + 2);
@@ -368,48 +365,34 @@ static void launch_tile(ftrl_handle *h, const Batch &b, const ItemDecode &dec, f
   geo.n_meta = h->tile_meta;
   geo.consumers = h->tile_consumers;
   geo.dbg = h->tile_dbg;
-  geo.helper_ns = (uint32_t)h->tile_helper_ns;
   geo.smem_bytes = h->tile_smem;
   const int tgrid = (int)std::min<int64_t>(b.n_rows, (int64_t)h->n_sms * h->tile_ctas_per_sm);
-#define FFM_TILE(I, R, C)                                                                             \
-  k_ffm_tile<PRECISE, I, R, C><<<tgrid, tile_threads(geo.consumers), geo.smem_bytes, h->compute>>>(   \
-      b, h->dims, h->hyper, dec, geo, h->batch_flags.p, h->rowspace, h->bias, h->pair_lut, h->occ_pos.p, h->scan.p, h->sbase.p, h->sparse.p, h->g.p, logit_out)
-  switch (h->tile_variant) {
-    case 0: FFM_TILE(1, 4, 768); break;
-    case 1: FFM_TILE(2, 4, 768); break;
-    case 2: FFM_TILE(3, 4, 768); break;
-    case 3: FFM_TILE(4, 4, 768); break;
-    case 4: FFM_TILE(3, 6, 512); break;
-    default: FFM_TILE(4, 8, 384); break;
-  }
+#define FFM_TILE(I)                                                                                              \
+  if (h->tile_cache)                                                                                              \
+    k_ffm_tile<PRECISE, I, true><<<tgrid, tile_threads(geo.consumers), geo.smem_bytes, h->compute>>>(             \
+        b, h->dims, h->hyper, dec, geo, h->batch_flags.p, h->rowspace, h->bias, h->pair_lut, h->occ_pos.p, h->scan.p, h->g.p, logit_out); \
+  else                                                                                                            \
+    k_ffm_tile<PRECISE, I, false><<<tgrid, tile_threads(geo.consumers), geo.smem_bytes, h->compute>>>(            \
+        b, h->dims, h->hyper, dec, geo, h->batch_flags.p, h->rowspace, h->bias, h->pair_lut, h->occ_pos.p, h->scan.p, h->g.p, logit_out)
+  if (h->tile_ipt <= 1) FFM_TILE(1);
+  else if (h->tile_ipt == 2) FFM_TILE(2);
+  else if (h->tile_ipt == 3) FFM_TILE(3);
+  else FFM_TILE(4);
 #undef FFM_TILE
   FTRL_CUDA(cudaGetLastError());
   launched(h, PH_SAMPLE);
 }
 
+// streaming segmented reduction of the staged gradient images (local duplicates); each row's sum is applied, parked
+// for k_ffm_combine, or (sharded runs) exported to its owner's inbox
 template <bool PRECISE>
-static void launch_regrad(ftrl_handle *h, const Batch &b) {
+static void launch_staged_rows(ftrl_handle *h, const Batch &b) {
   const int grid = h->n_sms * 16;
-  k_ffm_regrad_rows<PRECISE, 8><<<grid, 256, 0, h->compute>>>(h->dims, h->hyper, (int32_t)b.nnz, h->batch_flags.p, h->rowspace,
-                                                             h->chunk, h->n_chunks.p, h->chunk_pos.p, h->skey.p, h->socc.p,
-                                                             h->scan.p, h->srec.p, h->sbase.p, h->sparse.p, h->g.p, h->canon.p,
-                                                             h->part.p, h->part_lin.p, h->exportd);
+  k_ffm_staged_rows<PRECISE, 8><<<grid, 256, 0, h->compute>>>(h->dims, h->hyper, (int32_t)b.nnz, h->batch_flags.p, h->tab, h->lin,
+                                                             h->chunk, h->n_chunks.p, h->chunk_pos.p, h->skey.p, h->scan.p,
+                                                             h->staging.p, h->staging_lin.p, h->part.p, h->part_lin.p, h->exportd);
   FTRL_CUDA(cudaGetLastError());
   launched(h, PH_ROWS);
-}
-
-// canonical (sample, field) -> row table of the tile path (prep.cuh); needs occ_pos / scan in sharded runs
-static void launch_canon(ftrl_handle *h, const Batch &b) {
-  if (b.n_rows <= 0 || b.nnz <= 0) return;
-  const unsigned grid = (unsigned)((b.n_rows * 32 + 255) / 256);
-  k_build_canon<<<grid, 256, 0, h->compute>>>(b, h->dims, h->log2G, h->rank, h->occ_pos.p, h->scan.p, h->canon.p,
-                                              h->n_fused.p);
-  FTRL_CUDA(cudaGetLastError());
-  // where the sample kernel leaves the gradient slices of fused partners for the row kernel
-  thrust::counting_iterator<int32_t> cnt(0);
-  auto it = thrust::make_transform_iterator(cnt, SparseCount{h->fused_sorted.p, h->srec.p, h->n_fused.p});
-  size_t bytes = h->cub_bytes;
-  FTRL_CUDA(cub::DeviceScan::ExclusiveSum(h->cub_tmp.p, bytes, it, h->sbase.p, (int)b.nnz, h->compute));
 }
 
 // FFM minibatch: when every sample of the batch has distinct fields (device-side flag) the tile kernels
@@ -428,7 +411,7 @@ static void run_ffm_batch(ftrl_handle *h, const Batch &b, float *logit_out) {
     }
     {
       PhaseScope ps(h, PH_ROWS);
-      launch_regrad<PRECISE>(h, b);
+      launch_staged_rows<PRECISE>(h, b);
     }
   }
   {
@@ -527,7 +510,6 @@ static void run_prep(ftrl_handle *h, const Batch &b) {
   {
     PhaseScope ps(h, PH_PREP);
     FTRL_CUDA(cudaMemsetAsync(h->batch_flags.p, 0x01, sizeof(int32_t), h->compute));  // != 0: all samples simple
-    FTRL_CUDA(cudaMemsetAsync(h->batch_flags.p + 1, 0, 3 * sizeof(int32_t), h->compute));  // [2]: fused rows
     const unsigned grid = (unsigned)((b.n_rows * 32 + 255) / 256);
     k_prep_rows<<<grid, 256, 0, h->compute>>>(b, d, h->key.p, h->occ_idx.p, h->occ_row.p, h->sflags.p,
                                               h->batch_flags.p, h->tile_ok ? h->pmask.p : nullptr);
@@ -548,8 +530,7 @@ static void run_prep(ftrl_handle *h, const Batch &b) {
     PhaseScope ps(h, PH_SEGMENT);
     const int fuse = (d.model_type == FTRL_FFM && h->fuse) ? 1 : 0;
     k_occ_class<<<(nnz + 255) / 256, 256, 0, h->compute>>>(nnz, sentinel, fuse, h->skey.p, h->socc.p, h->occ_row.p,
-                                                           h->sflags.p, h->fused_sorted.p, h->occ_pos.p, h->batch_flags.p, b.field, b.val, d.k,
-                                                           h->tile_ok ? h->srec.p : nullptr);
+                                                           h->sflags.p, h->fused_sorted.p, h->occ_pos.p);
     launched(h, PH_SEGMENT);
     size_t bytes = h->cub_bytes;
     thrust::counting_iterator<int32_t> cnt(0);
@@ -563,11 +544,7 @@ static void run_prep(ftrl_handle *h, const Batch &b) {
     launched(h, PH_SEGMENT);
     FTRL_CUDA(cudaGetLastError());
   }
-  if (d.model_type == FTRL_FFM && h->tile_ok) {
-    run_row_prepass(h, nnz, sentinel);
-    launch_canon(h, b);
-    launched(h, PH_MATERIALISE);
-  }
+  if (d.model_type == FTRL_FFM && h->tile_ok) run_row_prepass(h, nnz, sentinel);
 }
 
 template <bool PRECISE>
@@ -851,7 +828,6 @@ static void train_device_sharded(ftrl_handle *h, const Batch &b, float *logit_ou
   {
     PhaseScope ps(h, PH_PREP);
     FTRL_CUDA(cudaMemsetAsync(h->batch_flags.p, 0x01, sizeof(int32_t), h->compute));
-    FTRL_CUDA(cudaMemsetAsync(h->batch_flags.p + 1, 0, 3 * sizeof(int32_t), h->compute));  // [2]: fused rows
     if (b.n_rows > 0) {
       const unsigned pg = (unsigned)((b.n_rows * 32 + 255) / 256);
       k_prep_rows<<<pg, 256, 0, h->compute>>>(b, d, h->key.p, h->occ_idx.p, h->occ_row.p, h->sflags.p, h->batch_flags.p,
@@ -873,7 +849,7 @@ static void train_device_sharded(ftrl_handle *h, const Batch &b, float *logit_ou
     PhaseScope ps(h, PH_SEGMENT);
     if (nnz > 0) {
       k_occ_class<<<(nnz + 255) / 256, 256, 0, h->compute>>>(nnz, sentinel, 0, h->skey.p, h->socc.p, h->occ_row.p, h->sflags.p,
-                                                             h->fused_sorted.p, h->occ_pos.p, h->batch_flags.p, b.field, b.val, d.k, h->srec.p);
+                                                             h->fused_sorted.p, h->occ_pos.p);
       size_t bytes = h->cub_bytes;
       auto mit = thrust::make_transform_iterator(cnt, MaskIn{h->skey.p, h->socc.p, h->pmask.p});
       FTRL_CUDA(cub::DeviceScan::InclusiveScan(h->cub_tmp.p, bytes, mit, h->mscan.p, MaskScanOp(), nnz, h->compute));
@@ -904,7 +880,7 @@ static void train_device_sharded(ftrl_handle *h, const Batch &b, float *logit_ou
     FTRL_CUDA(cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, bytes, h->okey.p, h->ckey.p, h->osrc.p, h->csrc.p, oc, 0,
                                               key_bits((int32_t)h->n_local), h->compute));
     k_contrib_class<<<(oc + 255) / 256, 256, 0, h->compute>>>(h->peers, oc, h->n_sel.p, lsent, h->ckey.p, h->csrc.p, h->socc.p,
-                                                             h->cflag.p, h->fused_sorted.p, h->occ_pos.p, h->batch_flags.p);
+                                                             h->cflag.p, h->fused_sorted.p, h->occ_pos.p);
     k_owner_materialise<PRECISE, 256><<<grid, 256, 0, h->compute>>>(h->peers, d, h->hyper, oc, h->n_sel.p, h->batch_flags.p,
                                                                     h->ckey.p, h->csrc.p, h->cflag.p, h->tab, h->lin);
     FTRL_CUDA(cudaGetLastError());
@@ -926,8 +902,6 @@ static void train_device_sharded(ftrl_handle *h, const Batch &b, float *logit_ou
     }
     FTRL_CUDA(cudaGetLastError());
     launched(h, PH_SEGMENT);
-    launch_canon(h, b);
-    launched(h, PH_SEGMENT);
     peer_barrier(h);  // 2: classes / inbox slots are known everywhere, w of the touched slices is materialised
     k_check_abort<<<1, 1, 0, h->compute>>>(h->peers, step_tag, h->batch_flags.p, h->d_err);
     FTRL_CUDA(cudaGetLastError());
@@ -948,7 +922,7 @@ static void train_device_sharded(ftrl_handle *h, const Batch &b, float *logit_ou
   {
     // local duplicates are reduced here; each row's sum goes to its owner's inbox (or is applied here)
     PhaseScope ps(h, PH_ROWS);
-    launch_regrad<PRECISE>(h, b);
+    launch_staged_rows<PRECISE>(h, b);
   }
   {
     PhaseScope ps(h, PH_COMBINE);
@@ -1065,11 +1039,6 @@ int ftrl_create(const ftrl_config *cfg, ftrl_handle **out) {
     h->chunk = env_int("FTRL_B200_CHUNK", cfg->model_type == FTRL_FFM ? 32 : cfg->model_type == FTRL_FM ? 256 : 2048);
     if (h->chunk < 1) h->chunk = 1;
     if (cfg->model_type == FTRL_FFM && h->chunk > 32) h->chunk = 32;  // chunk ends are found with one ballot
-    {
-      // experiment switch: L2 fetch granularity hint (bytes; the row kernel gathers 32-byte slices)
-      const int fg = env_int("FTRL_B200_L2_FETCH", 0);
-      if (fg > 0) FTRL_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)fg));
-    }
     h->tile = env_int("FTRL_B200_TILE", 1);
     h->tile_dbg = env_int("FTRL_B200_TILE_DBG", 0);
     if (cfg->model_type == FTRL_FFM && h->tile && h->fuse && d.k % 4 == 0 && d.n_fields <= 64) {
@@ -1080,20 +1049,10 @@ int ftrl_create(const ftrl_config *cfg, ftrl_handle **out) {
       int cons = 64;
       while (cons < 512 && cons * 3 < items) cons *= 2;
       if (cons == 512 && items > 2 * 512) cons = TILE_MAX_CONSUMERS;  // 24 consumer warps, 2 items per thread at cfg4
-      // every consumer thread also owns up to FR float4 vectors of the sample's fused rows (z stays in registers)
-      const int64_t vectors = (int64_t)d.n_fields * (d.ld / 4);
-      while (cons < TILE_MAX_CONSUMERS && (int64_t)cons * 4 < vectors) cons += 32;
       cons = env_int("FTRL_B200_TILE_CONSUMERS", cons);
-      cons = std::max(32, std::min(TILE_MAX_CONSUMERS, cons / 32 * 32));
-      const int ipt = (int)((items + cons - 1) / cons), fr = (int)((vectors + cons - 1) / cons);
-      // instantiations: (items, vectors) per thread and the block size their register budget was compiled for
-      int variant = -1;
-      if (fr <= 4 && ipt <= 4) variant = ipt - 1;
-      else if (fr <= 6 && ipt <= 3 && cons <= 512) variant = 4;
-      else if (fr <= 8 && ipt <= 4 && cons <= 384) variant = 5;
-      const size_t lut = 4 * tile_meta_bytes(d.n_fields);  // minimal meta ring
-      if (2 * stage + lut <= budget && variant >= 0) {
-        h->tile_variant = variant;
+      const int ipt = (int)((items + cons - 1) / cons);
+      const size_t lut = tile_lut_bytes(d.n_fields) + 4 * tile_meta_bytes(d.n_fields);  // + minimal meta ring
+      if (2 * stage + lut <= budget && ipt <= 4) {
         int ctas = (int)std::min<size_t>(8, (size_t)prop.sharedMemPerMultiprocessor / (2 * stage + lut + 2048));
         ctas = std::max(1, std::min(ctas, 2048 / tile_threads(cons)));
         ctas = env_int("FTRL_B200_TILE_CTAS", ctas);
@@ -1114,17 +1073,13 @@ int ftrl_create(const ftrl_config *cfg, ftrl_handle **out) {
         h->tile_ctas_per_sm = ctas;
         h->tile_smem = tile_smem_bytes(d.n_fields, stride, stages, metas);
         const int sm = (int)h->tile_smem;
-#define TILE_ATTR(P) \
-  FTRL_CUDA(cudaFuncSetAttribute(k_ffm_tile<P, 1, 4, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm)); \
-  FTRL_CUDA(cudaFuncSetAttribute(k_ffm_tile<P, 2, 4, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm)); \
-  FTRL_CUDA(cudaFuncSetAttribute(k_ffm_tile<P, 3, 4, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm)); \
-  FTRL_CUDA(cudaFuncSetAttribute(k_ffm_tile<P, 4, 4, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm)); \
-  FTRL_CUDA(cudaFuncSetAttribute(k_ffm_tile<P, 3, 6, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm)); \
-  FTRL_CUDA(cudaFuncSetAttribute(k_ffm_tile<P, 4, 8, 384>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm))
-        TILE_ATTR(false);
-        TILE_ATTR(true);
+#define TILE_ATTR(P, I)                                                                                              \
+  FTRL_CUDA(cudaFuncSetAttribute(k_ffm_tile<P, I, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm)); \
+  FTRL_CUDA(cudaFuncSetAttribute(k_ffm_tile<P, I, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm))
+        TILE_ATTR(false, 1); TILE_ATTR(false, 2); TILE_ATTR(false, 3); TILE_ATTR(false, 4);
+        TILE_ATTR(true, 1); TILE_ATTR(true, 2); TILE_ATTR(true, 3); TILE_ATTR(true, 4);
+        h->tile_cache = env_int("FTRL_B200_TILE_CACHE", 1);
         h->tile_inflight = std::max(2, std::min(TILE_MAX_STAGE, env_int("FTRL_B200_TILE_INFLIGHT", TILE_MAX_STAGE)));
-        h->tile_helper_ns = env_int("FTRL_B200_TILE_HELPER_NS", 0);
 #undef TILE_ATTR
       }
     }
@@ -1708,6 +1663,8 @@ static void set_rowspace(ftrl_handle *h, int log2G, int rank, int G) {
   rsp = RowSpace{};
   rsp.tab = h->tab;
   rsp.lin = h->lin;
+  rsp.staging = h->staging.p;
+  rsp.staging_lin = h->staging_lin.p;
   rsp.rc_w = h->rc_w.p;
   rsp.rc_lin = h->rc_lin.p;
   rsp.log2G = log2G;

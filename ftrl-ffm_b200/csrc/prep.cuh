@@ -137,83 +137,23 @@ __global__ void k_terminate(int32_t *chunk_pos, const int32_t *n_chunks, int32_t
 // in a sample with distinct fields, is "fused": its update is finalised by the per-sample kernel.
 //   fused_sorted[p] = 1 for such rows (p = sorted position)
 //   occ_pos[t]      = -1 when occurrence t is fused, else its sorted position p
-// batch_flags[2] += number of fused rows (integer count: the order of the additions does not matter)
-//   srec[p]         = {sample, value bits, field * k, -} of the occurrence at sorted position p (when asked for):
-//                     the row kernels walk the sorted list and read these 16-byte records sequentially instead
-//                     of chasing socc -> occ_row / val / field with three dependent random gathers per occurrence
 __global__ void k_occ_class(int32_t nnz, uint32_t sentinel, int fuse, const uint32_t *__restrict__ skey,
                             const uint32_t *__restrict__ socc, const int32_t *__restrict__ occ_row,
                             const uint8_t *__restrict__ sflags, uint8_t *__restrict__ fused_sorted,
-                            int32_t *__restrict__ occ_pos, int32_t *__restrict__ batch_flags,
-                            const int32_t *__restrict__ field, const float *__restrict__ val, int32_t kf,
-                            int4 *__restrict__ srec) {
+                            int32_t *__restrict__ occ_pos) {
   const int32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= nnz) return;
+  const uint32_t k = skey[p];
+  const uint32_t t = socc[p];
   bool fused = false;
-  if (p < nnz) {
-    const uint32_t k = skey[p];
-    const uint32_t t = socc[p];
-    if (srec) srec[p] = make_int4(occ_row[t], __float_as_int(val[t]), field[t] * kf, 0);
-    if (fuse && k != sentinel) {
-      const bool head = p == 0 || skey[p - 1] != k;
-      const bool last = p + 1 == nnz || skey[p + 1] != k;
-      fused = head && last && (sflags[occ_row[t]] & SF_FUSABLE);
-    }
-    fused_sorted[p] = fused ? 1 : 0;
-    occ_pos[t] = fused ? -1 : p;
+  if (fuse && k != sentinel) {
+    const bool head = p == 0 || skey[p - 1] != k;
+    const bool last = p + 1 == nnz || skey[p + 1] != k;
+    fused = head && last && (sflags[occ_row[t]] & SF_FUSABLE);
   }
-  const unsigned fm = __ballot_sync(0xffffffffu, fused);
-  if ((threadIdx.x & 31) == 0 && fm) atomicAdd(&batch_flags[2], __popc(fm));
+  fused_sorted[p] = fused ? 1 : 0;
+  occ_pos[t] = fused ? -1 : p;
 }
-
-// canon[s][f] = (row locator, value) of the valid feature of sample s that carries field f, CANON_NONE when
-// there is none.  Meaningful for samples with distinct fields (the tile path).  Warp per sample.  Remote rows
-// (sharded runs) are named by the sorted head position of the row in the local batch: their w plane sits in
-// the row cache at that position (shard.cuh).
-// Fused rows (occ_pos < 0) get CANON_FUSED | rank among the fused rows of the sample in field order -- the
-// slot of their gradient slices in the per-occurrence images (common.cuh); n_fused[s] = their number.
-__global__ void k_build_canon(Batch b, Dims d, int log2G, int rank, const int32_t *__restrict__ occ_pos,
-                              const SegScan *__restrict__ scan, CanonEntry *__restrict__ canon,
-                              int32_t *__restrict__ n_fused) {
-  const int lane = threadIdx.x & 31;
-  const int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (s >= b.n_rows) return;
-  CanonEntry *row = canon + s * d.n_fields;
-  for (int f = lane; f < d.n_fields; f += 32) row[f] = CanonEntry{CANON_NONE, 0.f};
-  const int Gm1 = (1 << log2G) - 1;
-  const int64_t r0 = b.row_ptr[s], r1 = b.row_ptr[s + 1];
-  // fields of the fused rows (n_fields <= 64 on the tile path; wider models never read the ranks)
-  unsigned long long fusedm = 0ull;
-  for (int64_t base = r0; base < r1; base += 32) {
-    const int64_t t = base + lane;
-    unsigned long long bit = 0ull;
-    if (t < r1) {
-      const int32_t fld = b.field[t];
-      if (feat_valid(d, fld, b.feat[t]) && occ_pos[t] < 0 && fld < 64) bit = 1ull << fld;
-    }
-    fusedm |= ((unsigned long long)__reduce_or_sync(0xffffffffu, (unsigned)(bit >> 32)) << 32) |
-              __reduce_or_sync(0xffffffffu, (unsigned)bit);
-  }
-  __syncwarp();
-  for (int64_t t = r0 + lane; t < r1; t += 32) {
-    const int32_t fld = b.field[t], ft = b.feat[t];
-    if (!feat_valid(d, fld, ft)) continue;
-    const int32_t pos = occ_pos[t];
-    int32_t loc;
-    if (pos < 0 && fld < 64) loc = (int32_t)(CANON_FUSED | (uint32_t)__popcll(fusedm & ((1ull << fld) - 1ull)));
-    else loc = (ft & Gm1) == rank ? (ft >> log2G) : -1 - scan[pos].start;
-    row[fld] = CanonEntry{loc, b.val[t]};
-  }
-  if (lane == 0) n_fused[s] = __popcll(fusedm);
-}
-
-// image base of every sorted position: sbase[p] = number of (staged occurrence, fused partner) pairs before p
-// in the sorted list = exclusive sum of "fused rows of p's sample" over the staged positions
-struct SparseCount {
-  const uint8_t *fused_sorted;
-  const int4 *srec;
-  const int32_t *n_fused;
-  __device__ __forceinline__ int32_t operator()(int32_t p) const { return fused_sorted[p] ? 0 : n_fused[srec[p].x]; }
-};
 
 // everything a chunk-level kernel needs to know about chunk c
 struct ChunkInfo {

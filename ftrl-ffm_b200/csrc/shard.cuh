@@ -17,8 +17,8 @@
 //       w = W(n,z) for the slices the global batch touches into the table and pushes it into the row cache
 //       of every remote rank that touches the row (one NVLink store stream per distinct (row, rank))
 //   --  barrier 2
-//   S3  k_ffm_tile over the local samples (all addresses local: shard rows, row cache);
-//       k_ffm_regrad_rows / k_ffm_combine reduce the local duplicates and store each row's (sum g, sum g^2)
+//   S3  k_ffm_tile over the local samples (all addresses local: shard rows, row cache, staging);
+//       k_ffm_staged_rows / k_ffm_combine reduce the local duplicates and store each row's (sum g, sum g^2)
 //       into the owner's inbox (Export); the local (sum g, sum g^2, loss) of the bias goes to every peer
 //   --  barrier 3
 //   S4  owner side: k_owner_apply sums the <= G inbox entries of a row in rank order and applies the
@@ -219,8 +219,7 @@ enum : uint8_t {
 __global__ void k_contrib_class(Peers pr, int32_t cap, const int32_t *__restrict__ n_sel, uint32_t lsent,
                                 const uint32_t *__restrict__ ckey, const uint32_t *__restrict__ csrc,
                                 const uint32_t *__restrict__ socc, uint8_t *__restrict__ cflag,
-                                uint8_t *__restrict__ fused_sorted, int32_t *__restrict__ occ_pos,
-                                int32_t *__restrict__ batch_flags) {
+                                uint8_t *__restrict__ fused_sorted, int32_t *__restrict__ occ_pos) {
   const int32_t c = blockIdx.x * blockDim.x + threadIdx.x;
   const int32_t n = min(*n_sel, cap);
   if (c >= n) return;
@@ -241,7 +240,6 @@ __global__ void k_contrib_class(Peers pr, int32_t cap, const int32_t *__restrict
       fused_sorted[p_head] = 1;
       occ_pos[socc[p_head]] = -1;
       cflag[c] = 0;
-      atomicAdd(&batch_flags[2], 1);  // count of fused rows (statistics)
     } else {       // reduced and applied by this rank's own row kernels
       pr.dst_at[q][p_head] = -2;
       cflag[c] = CF_MAT;
