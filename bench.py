@@ -294,8 +294,10 @@ def main():
 
     batches, (model, n_fields, n_feats, k, B) = make_batches(args.workload, args.dist, args.batch, args.n_distinct, rank)
     nnz = int(batches[0]["row_ptr"][-1])
+    # the synthetic minibatches are resident in HBM and never rewritten: the library may read the ids of batch i+1
+    # while batch i trains (ftrl_config.reserved[0], include/ftrl_b200.h)
     m = pkg.FtrlModel(model, n_feats=n_feats, n_fields=n_fields, n_factors=k, device=local_rank,
-                      max_batch_rows=B, max_batch_nnz=nnz, rank=rank, world_size=world)
+                      max_batch_rows=B, max_batch_nnz=nnz, rank=rank, world_size=world, stable_device_inputs=True)
     if world > 1:
         # feature-sharded tables: every rank maps every peer's shard (CUDA IPC); the blobs travel by all-gather
         blob = torch.frombuffer(bytearray(m.export_peer_blob()), dtype=torch.uint8).cuda()

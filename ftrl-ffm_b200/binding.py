@@ -139,7 +139,7 @@ class FtrlModel:
 
     def __init__(self, model_type="FFM", n_feats=10000, n_fields=8, n_factors=16, init_mean=0.0,
                  init_stddev=0.02, w_alpha=1e-4, w_beta=1.0, w_l1=0.1, w_l2=5.0, mode="batch",
-                 device=0, seed=42, max_batch_rows=0, max_batch_nnz=0, rank=0, world_size=1):
+                 device=0, seed=42, max_batch_rows=0, max_batch_nnz=0, rank=0, world_size=1, stable_device_inputs=False):
         self.lib = load_library()
         mt = str(model_type).upper()  # cmd_option.cpp:70 upper-cases --model_type
         if mt not in MODEL_TYPES:
@@ -154,6 +154,8 @@ class FtrlModel:
         cfg.device, cfg.seed = int(device), int(seed)
         cfg.max_batch_rows, cfg.max_batch_nnz = int(max_batch_rows), int(max_batch_nnz)
         cfg.rank, cfg.world_size = int(rank), int(world_size)
+        # ftrl_config.reserved[0] bit 0: device-resident CSR arrays are complete before the previous train call was made
+        cfg.reserved[0] = 1 if stable_device_inputs else 0
         self.cfg = cfg
         self.model_type = mt
         self.n_feats = int(n_feats)

@@ -75,6 +75,10 @@ struct DevBuf {
     p = nullptr;
     n = 0;
   }
+  void swap(DevBuf &o) {
+    T *tp = p; p = o.p; o.p = tp;
+    size_t tn = n; n = o.n; o.n = tn;
+  }
   ~DevBuf() { release(); }
 };
 
@@ -144,6 +148,27 @@ struct ftrl_handle {
   // streams
   cudaStream_t compute = nullptr, copy = nullptr;
   bool own_compute = true;
+
+  // Index workspace of a batch (everything the weight-independent phase writes: sort keys, sorted list, classes,
+  // chunk list, field masks).  Two sets alternate between consecutive batches: the index phase of batch i+1 runs on
+  // its own stream under the forward / update kernels of batch i (train_device, FTRL_B200_PIPELINE).  The members
+  // below are the CURRENT set; `alt` holds the other one (swap_idsets).
+  struct IdSet {
+    int64_t rows_cap = 0, nnz_cap = 0;
+    ftrl::DevBuf<uint32_t> key, occ_idx, skey, socc;
+    ftrl::DevBuf<int32_t> occ_row, chunk_pos, n_chunks;
+    ftrl::DevBuf<uint8_t> sflags, fused_sorted;
+    ftrl::DevBuf<int32_t> occ_pos, batch_flags;
+    ftrl::DevBuf<uint64_t> pmask;
+    ftrl::DevBuf<unsigned long long> rowmask;
+    ftrl::DevBuf<ftrl::SegScan> scan;
+  } alt;
+  int idset_cur = 0;
+  cudaStream_t idstream = nullptr;
+  cudaEvent_t ev_id_done[2] = {nullptr, nullptr}, ev_hot_done[2] = {nullptr, nullptr};
+  bool hot_recorded[2] = {false, false};
+  int pipeline = 1;             // FTRL_B200_PIPELINE
+  bool stable_device_inputs = false;
 
   // per-batch workspace (shared by consecutive batches: the compute stream is in-order)
   int64_t rows_cap = 0, nnz_cap = 0;

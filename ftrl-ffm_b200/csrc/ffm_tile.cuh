@@ -127,10 +127,15 @@ struct RowMeta {   // one 16-byte record per row of a sample
   int32_t pos;     // -1: row finalised here, >= 0: sorted position for the staged gradient image
   int32_t loc;     // row locator (RowSpace): >= 0 local row, < 0: -1 - head position in the remote-row cache
 };
+// Rows of a sample are kept sorted by class: fused rows take slots 0, 1, ... (hdr[0] of them), staged rows take
+// slots f_cap-1, f_cap-2, ... (hdr[3] of them), so that the work items of a sample fall into three homogeneous
+// ranges (fused x fused, fused x staged, staged x staged) and a warp rarely mixes classes: the fused path
+// (w = W(n,z), FTRL update: ~10x the instructions of the staged path) is then executed only by the warps whose
+// items need it instead of by every warp that happens to hold one fused row.
 struct SampleMeta {
   RowMeta *row;     // [f_cap]
   float4 *lin;      // [f_cap] {z, n, w, -} of the linear coordinate, prefetched
-  int32_t *hdr;     // [0] n valid rows, [1] label, [2] floats of the row ring the sample needs
+  int32_t *hdr;     // [0] fused rows, [1] label, [2] floats of the row ring the sample needs, [3] staged rows
   uint8_t *present; // [n_fields] 1 when some valid row of the sample carries that field
 };
 
@@ -251,6 +256,9 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
     return m;
   };
 
+  // r-th row of a sample with nf fused rows: fused rows from the front, staged rows from the back
+  auto row_slot = [&](int r, int nf) { return r < nf ? r : f_cap - 1 - (r - nf); };
+
   if (tid == 0) {
     for (int st = 0; st < NSLOT; st++) {
       mbar_init(&bar_full[st], NL);
@@ -283,12 +291,12 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
       const int64_t s = blockIdx.x + (int64_t)it * gridDim.x;
       const int64_t r0 = b.row_ptr[s];
       const int F = (int)min((int64_t)1 << 20, b.row_ptr[s + 1] - r0);
-      int nv = 0;
+      int nf = 0, ns = 0;
       for (int f = lane; f < f_cap; f += 32) m.present[f] = 0;
       __syncwarp();
       for (int base = 0; base < F; base += 32) {
         const int t = base + lane;
-        int32_t fl = 0, ft = -1;
+        int32_t fl = 0, ft = -1, pos = 0;
         float x = 0.f;
         bool ok = false;
         if (t < F) {
@@ -296,14 +304,18 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
           ft = b.feat[r0 + t];
           x = b.val[r0 + t];
           ok = feat_valid(d, fl, ft);
+          if (ok) pos = occ_pos[r0 + t];
         }
-        const unsigned okm = __ballot_sync(0xffffffffu, ok);
-        const int sl = nv + __popc(okm & ((1u << lane) - 1));
-        if (ok && sl < f_cap) {
+        const bool fz = ok && pos < 0, sg = ok && pos >= 0;
+        const unsigned fm = __ballot_sync(0xffffffffu, fz), sm = __ballot_sync(0xffffffffu, sg);
+        const unsigned below = (1u << lane) - 1;
+        const int idx = fz ? nf + __popc(fm & below) : ns + __popc(sm & below);
+        if (ok && idx < f_cap) {
+          const int sl = fz ? idx : f_cap - 1 - idx;
           RowMeta rm;
           rm.fk = fl * k;
           rm.x = x;
-          rm.pos = occ_pos[r0 + t];
+          rm.pos = pos;
           if ((ft & rsp.Gm1) == rsp.rank) {
             rm.loc = ft >> rsp.log2G;
             m.lin[sl] = rsp.lin[rm.loc];
@@ -314,21 +326,25 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
           }
           m.row[sl] = rm;
           m.present[fl] = 1;
-
         }
-        nv += __popc(okm);
+        nf += __popc(fm);
+        ns += __popc(sm);
       }
-      nv = min(nv, f_cap);
+      // distinct fields: nf + ns <= f_cap (the clamps only guard malformed input)
+      nf = min(nf, f_cap);
+      ns = min(ns, f_cap - nf);
+      const int nv = nf + ns;
       __syncwarp();
       // offsets of the rows inside the sample's span (exclusive prefix sum of the row sizes)
       int need = 0;
       for (int base = 0; base < nv; base += 32) {
         const int r = base + lane;
+        const int sl = row_slot(r, nf);
         RowMeta rm;
         int sz = 0;
         if (r < nv) {
-          rm = m.row[r];
-          sz = rm.pos < 0 ? stride : stride1;
+          rm = m.row[sl];
+          sz = r < nf ? stride : stride1;
         }
         int inc = sz;
 #pragma unroll
@@ -336,13 +352,14 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
           const int t = __shfl_up_sync(0xffffffffu, inc, o);
           if (lane >= o) inc += t;
         }
-        if (r < nv) m.row[r].fk = rm.fk | ((need + inc - sz) << 16);
+        if (r < nv) m.row[sl].fk = rm.fk | ((need + inc - sz) << 16);
         need += __shfl_sync(0xffffffffu, inc, 31);
       }
       if (lane == 0) {
-        m.hdr[0] = nv;
+        m.hdr[0] = nf;
         m.hdr[1] = b.label[s];
         m.hdr[2] = need;
+        m.hdr[3] = ns;
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_mfull[slot]);
@@ -366,7 +383,7 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
       const int slot = mc.slot;
       mbar_wait(&bar_mfull[slot], mc.parity());
       SampleMeta m = sample_meta(slot);
-      const int nv = m.hdr[0];
+      const int nf = m.hdr[0], nv = nf + m.hdr[3];
       const int need = m.hdr[2];
       // a span for this sample: contiguous, after `head` or wrapped to the start of the ring; wait (in order)
       // for older samples to retire until the sample slot is free and the span overlaps no live span
@@ -396,13 +413,10 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
       {
         // TMA bulk copies.  Fused rows bring z and n (they are updated here); staged rows bring only the w
         // plane their owner materialised, into the z-plane slot of the stage
-        int bytes = 0;
-        for (int r = lane; r < nv; r += 32) bytes += m.row[r].pos < 0 ? (int)row_bytes : (int)(row_bytes / 2);
-        bytes = (int)warp_sum((float)bytes);
-        if (lane == 0) mbar_expect_tx(&bar_full[st], (uint32_t)bytes);
+        if (lane == 0) mbar_expect_tx(&bar_full[st], (uint32_t)(nf * (int)row_bytes + (nv - nf) * (int)(row_bytes / 2)));
         __syncwarp();
         for (int r = lane; r < nv; r += 32) {
-          const RowMeta rm = m.row[r];
+          const RowMeta rm = m.row[row_slot(r, nf)];
           if (rm.pos < 0) bulk_g2s(rows + row_off(rm), rsp.tab + (int64_t)rm.loc * rs, row_bytes, &bar_full[st]);
           else bulk_g2s(rows + row_off(rm), w_plane(rm.loc), row_bytes / 2, &bar_full[st]);
         }
@@ -416,9 +430,9 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
         nx.advance(1, MD);
         mbar_wait(&bar_mfull[nx.slot], nx.parity());
         SampleMeta m2 = sample_meta(nx.slot);
-        const int nv2 = m2.hdr[0];
+        const int nf2 = m2.hdr[0], nv2 = nf2 + m2.hdr[3];
         for (int r = lane; r < nv2; r += 32) {
-          const RowMeta rm = m2.row[r];
+          const RowMeta rm = m2.row[row_slot(r, nf2)];
           if (rm.pos < 0) bulk_prefetch_l2(rsp.tab + (int64_t)rm.loc * rs, row_bytes);
           else bulk_prefetch_l2(w_plane(rm.loc), row_bytes / 2);
         }
@@ -439,9 +453,9 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
       SampleMeta m = sample_meta(slot);
       mbar_wait(&bar_done[st], (uint32_t)((it >> 2) & 1));
       float *rows = ring + s_base[st];
-      const int nv = m.hdr[0];
+      const int nf = m.hdr[0], nv = nf + m.hdr[3];
       for (int r = lane; r < nv && !(geo.dbg & 2); r += 32) {
-        const RowMeta rm = m.row[r];
+        const RowMeta rm = m.row[row_slot(r, nf)];
         if (rm.pos < 0) bulk_s2g(rsp.tab + (int64_t)rm.loc * rs, rows + row_off(rm), row_bytes);
         else bulk_s2g(rsp.staging + (int64_t)rm.pos * ld, rows + row_off(rm), (uint32_t)(ld * sizeof(float)));
       }
@@ -472,8 +486,33 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
     mbar_wait(&bar_mfull[slot], mc.parity());
     mbar_wait(&bar_full[st], (uint32_t)((it >> 2) & 1));
     float *rows = ring + s_base[st];
-    const int nv = m.hdr[0];
+    const int nf = m.hdr[0], ns = m.hdr[3], nv = nf + ns;
+    // items of the sample in three ranges: fused x fused pairs, fused x staged, staged x staged
+    const uint32_t n_ff = (uint32_t)nf * (uint32_t)(nf - 1) / 2u * dec.C;
+    const uint32_t n_fs = (uint32_t)nf * (uint32_t)ns * dec.C;
     const uint32_t n_items = (uint32_t)nv * (uint32_t)(nv - 1) / 2u * dec.C;
+    const float inv_nf = nf > 0 ? 1.0f / (float)nf : 0.f;
+    // (m, n) = row slots of item `item`
+    auto item_rows = [&](uint32_t item, int &mi, int &ni, uint32_t &c) {
+      uint32_t p;
+      if (item < n_ff) {
+        dec(item, p, c);
+        const uint32_t e = s_lut[p];
+        mi = e & 0xff;
+        ni = e >> 8;
+      } else if (item < n_ff + n_fs) {
+        dec(item - n_ff, p, c);
+        // p = n' * nf + m : exact for these ranges (p < 64 * 64, nf <= 64)
+        const int nq = __float2int_rd(((float)p + 0.5f) * inv_nf);
+        mi = (int)p - nq * nf;
+        ni = f_cap - 1 - nq;
+      } else {
+        dec(item - n_ff - n_fs, p, c);
+        const uint32_t e = s_lut[p];
+        mi = f_cap - 1 - (int)(e & 0xff);
+        ni = f_cap - 1 - (int)(e >> 8);
+      }
+    };
 
     // ---- pass 1: w, logit ----
     float acc = 0.f;
@@ -486,10 +525,9 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
       const uint32_t item = tid + j * n_cons;
       if (CACHE) cls[j] = 0;
       if (item < n_items) {
-        uint32_t p, c;
-        dec(item, p, c);
-        const uint32_t e = s_lut[p];
-        const int mi = e & 0xff, ni = e >> 8;
+        uint32_t c;
+        int mi, ni;
+        item_rows(item, mi, ni, c);
         const RowMeta rmm = m.row[mi], rmn = m.row[ni];
         const int oA = row_off(rmm) + row_fk(rmn) + (int)c * 4;  // slice A = (row m, field n)
         const int oB = row_off(rmn) + row_fk(rmm) + (int)c * 4;  // slice B = (row n, field m)
@@ -520,8 +558,9 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
       }
     }
     for (int r = tid; r < nv; r += n_cons) {
-      const float4 e = m.lin[r];
-      const RowMeta rm = m.row[r];
+      const int sl = row_slot(r, nf);
+      const float4 e = m.lin[sl];
+      const RowMeta rm = m.row[sl];
       const float w = rm.pos < 0 ? weight_from<PRECISE>(e.x, f_sqrt<PRECISE>(e.y), h) : e.z;
       acc = fmaf(w, rm.x, acc);
     }
@@ -552,10 +591,9 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
         const uint32_t item = tid + j * n_cons;
         cl = 0; oA = oB = 0; xmn = 0.f;
         if (item < n_items) {
-          uint32_t p, c;
-          dec(item, p, c);
-          const uint32_t e = s_lut[p];
-          const int mi = e & 0xff, ni = e >> 8;
+          uint32_t c;
+          int mi, ni;
+          item_rows(item, mi, ni, c);
           const RowMeta rmm = m.row[mi], rmn = m.row[ni];
           oA = row_off(rmm) + row_fk(rmn) + (int)c * 4;
           oB = row_off(rmn) + row_fk(rmm) + (int)c * 4;
@@ -588,8 +626,9 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
     }
     // linear coordinate: fused -> full update; staged -> w now, gradient to staging_lin
     for (int r = tid; r < nv; r += n_cons) {
-      float4 e = m.lin[r];
-      const RowMeta rm = m.row[r];
+      const int sl = row_slot(r, nf);
+      float4 e = m.lin[sl];
+      const RowMeta rm = m.row[sl];
       const float gi = g * rm.x;
       if (rm.pos < 0) {
         const float w = weight_from<PRECISE>(e.x, f_sqrt<PRECISE>(e.y), h);
@@ -604,16 +643,14 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
     // They are disjoint from the slices written above, so no barrier is needed.
     if (nv == d.n_fields) {
       // every field is present (fields are distinct): only the own-field slice is untouched
-      for (int r = tid; r < nv; r += n_cons) {
-        const RowMeta rm = m.row[r];
-        if (rm.pos < 0) continue;
+      for (int r = nf + tid; r < nv; r += n_cons) {   // staged rows
+        const RowMeta rm = m.row[row_slot(r, nf)];
         float4 *zp = reinterpret_cast<float4 *>(rows + row_off(rm) + row_fk(rm));
         for (int v = 0; v < (k >> 2); v++) zp[v] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     } else {
-      for (int r = tid >> 5; r < nv; r += n_cons_warps) {
-        const RowMeta rm = m.row[r];
-        if (rm.pos < 0) continue;
+      for (int r = nf + (tid >> 5); r < nv; r += n_cons_warps) {   // staged rows
+        const RowMeta rm = m.row[row_slot(r, nf)];
         for (int f = lane; f < d.n_fields; f += 32) {
           if (m.present[f] && f * k != row_fk(rm)) continue;
           float4 *zp = reinterpret_cast<float4 *>(rows + row_off(rm) + f * k);

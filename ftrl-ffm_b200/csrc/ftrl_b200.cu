@@ -225,9 +225,23 @@ static void refresh_shards(ftrl_handle *h) {
   h->exportd = Export{};
 }
 
+// the other index-workspace set becomes the current one (its capacity travels with it)
+static void swap_idsets(ftrl_handle *h) {
+  ftrl_handle::IdSet &a = h->alt;
+  std::swap(h->rows_cap, a.rows_cap);
+  std::swap(h->nnz_cap, a.nnz_cap);
+  h->key.swap(a.key); h->occ_idx.swap(a.occ_idx); h->skey.swap(a.skey); h->socc.swap(a.socc);
+  h->occ_row.swap(a.occ_row); h->chunk_pos.swap(a.chunk_pos); h->n_chunks.swap(a.n_chunks);
+  h->sflags.swap(a.sflags); h->fused_sorted.swap(a.fused_sorted);
+  h->occ_pos.swap(a.occ_pos); h->batch_flags.swap(a.batch_flags);
+  h->pmask.swap(a.pmask); h->rowmask.swap(a.rowmask); h->scan.swap(a.scan);
+  h->idset_cur ^= 1;
+}
+
 static void ensure_workspace(ftrl_handle *h, int64_t n_rows, int64_t nnz) {
   if (n_rows <= h->rows_cap && nnz <= h->nnz_cap) return;
   FTRL_CUDA(cudaStreamSynchronize(h->compute));
+  if (h->idstream) FTRL_CUDA(cudaStreamSynchronize(h->idstream));
   const int64_t rc = std::max<int64_t>(h->rows_cap, n_rows + n_rows / 8 + 16);
   const int64_t nc = std::max<int64_t>(h->nnz_cap, nnz + nnz / 8 + 64);
   if (nc >= (1ll << 31) - 64) throw ArgFail{"batch nnz must be < 2^31"};
@@ -484,13 +498,21 @@ static void run_lrfm_batch(ftrl_handle *h, const Batch &b, float *logit_out) {
 }
 
 // owner-side pre-pass of the tile path: materialise w of the segmented rows (ffm_tile.cuh)
-static void run_row_prepass(ftrl_handle *h, int32_t n_sorted, uint32_t sentinel) {
+// the two halves of the owner-side pre-pass: which slices of the staged rows does the batch touch (ids only) ...
+static void run_row_touch(ftrl_handle *h, int32_t n_sorted, uint32_t sentinel) {
   PhaseScope ps(h, PH_MATERIALISE);
-  const Dims &d = h->dims;
   const int grid = h->n_sms * 4;
   FTRL_CUDA(cudaMemsetAsync(h->rowmask.p, 0, sizeof(unsigned long long) * (size_t)(n_sorted + 2), h->compute));
   k_row_touch<8><<<grid, 256, 0, h->compute>>>(n_sorted, sentinel, h->chunk, h->batch_flags.p, h->n_chunks.p, h->chunk_pos.p,
                                                h->skey.p, h->socc.p, h->scan.p, h->pmask_src, h->rowmask.p);
+  FTRL_CUDA(cudaGetLastError());
+  launched(h, PH_MATERIALISE);
+}
+// ... and w = W(n, z) of exactly those slices (needs the weights of the previous step)
+static void run_row_materialise(ftrl_handle *h, int32_t n_sorted, uint32_t sentinel) {
+  PhaseScope ps(h, PH_MATERIALISE);
+  const Dims &d = h->dims;
+  const int grid = h->n_sms * 4;
   if (h->precise)
     k_row_materialise<true, 8><<<grid, 256, 0, h->compute>>>(d, h->hyper, n_sorted, sentinel, h->chunk, h->batch_flags.p,
                                                              h->n_chunks.p, h->chunk_pos.p, h->skey.p, h->scan.p,
@@ -500,7 +522,7 @@ static void run_row_prepass(ftrl_handle *h, int32_t n_sorted, uint32_t sentinel)
                                                               h->n_chunks.p, h->chunk_pos.p, h->skey.p, h->scan.p,
                                                               h->rowmask.p, h->tab, h->lin);
   FTRL_CUDA(cudaGetLastError());
-  launched(h, PH_MATERIALISE, 2);
+  launched(h, PH_MATERIALISE);
 }
 
 static void run_prep(ftrl_handle *h, const Batch &b) {
@@ -544,7 +566,7 @@ static void run_prep(ftrl_handle *h, const Batch &b) {
     launched(h, PH_SEGMENT);
     FTRL_CUDA(cudaGetLastError());
   }
-  if (d.model_type == FTRL_FFM && h->tile_ok) run_row_prepass(h, nnz, sentinel);
+  if (d.model_type == FTRL_FFM && h->tile_ok) run_row_touch(h, nnz, sentinel);
 }
 
 template <bool PRECISE>
@@ -567,7 +589,11 @@ static void run_model(ftrl_handle *h, const Batch &b, float *logit_out) {
 template <bool PRECISE>
 static void train_device_sharded(ftrl_handle *h, const Batch &b, float *logit_out, double *loss_sum_out);
 
-static void train_device(ftrl_handle *h, const Batch &b, float *logit_out, double *loss_sum_out) {
+// inputs_ready: event after which the CSR arrays of `b` may be read (host path: the slot's copy), or null: the arrays
+// are ready in the order of the compute stream.  With an event (or stable device inputs) the weight-independent
+// index phase of this batch runs on its own stream, under the forward / update kernels of the previous batch.
+static void train_device(ftrl_handle *h, const Batch &b, float *logit_out, double *loss_sum_out,
+                         cudaEvent_t inputs_ready = nullptr) {
   h->launches_this_call = 0;
   h->stats = ftrl_batch_stats{};
   h->stats.n_rows = b.n_rows;
@@ -577,13 +603,19 @@ static void train_device(ftrl_handle *h, const Batch &b, float *logit_out, doubl
     return;
   }
   if (h->G > 1) {
+    if (inputs_ready) FTRL_CUDA(cudaStreamWaitEvent(h->compute, inputs_ready, 0));
     if (h->precise) train_device_sharded<true>(h, b, logit_out, loss_sum_out);
     else train_device_sharded<false>(h, b, logit_out, loss_sum_out);
     return;
   }
+  const bool piped = h->pipeline && h->cfg.mode == FTRL_MODE_BATCH && !h->profiling && h->idstream &&
+                     (inputs_ready || h->stable_device_inputs);
+  if (piped) swap_idsets(h);
   ensure_workspace(h, b.n_rows, b.nnz);
+  if (piped) refresh_shards(h);
   const Dims &d = h->dims;
   if (h->cfg.mode == FTRL_MODE_SEQUENTIAL) {
+    if (inputs_ready) FTRL_CUDA(cudaStreamWaitEvent(h->compute, inputs_ready, 0));
     PhaseScope ps(h, PH_EXACT);
     k_exact_train<<<1, EX_THREADS, 0, h->compute>>>(b, d, h->hyper, h->tab, h->lin, h->bias, logit_out, loss_sum_out,
                                                     h->d_err);
@@ -592,7 +624,27 @@ static void train_device(ftrl_handle *h, const Batch &b, float *logit_out, doubl
     h->stats.kernel_launches = h->launches_this_call;
     return;
   }
-  run_prep(h, b);
+  if (piped) {
+    const int cur = h->idset_cur;
+    cudaStream_t main_stream = h->compute;
+    if (inputs_ready) FTRL_CUDA(cudaStreamWaitEvent(h->idstream, inputs_ready, 0));
+    // this index set was last read by the forward / update kernels two batches ago
+    if (h->hot_recorded[cur]) FTRL_CUDA(cudaStreamWaitEvent(h->idstream, h->ev_hot_done[cur], 0));
+    h->compute = h->idstream;  // everything run_prep enqueues goes to the index stream
+    try {
+      run_prep(h, b);
+    } catch (...) {
+      h->compute = main_stream;
+      throw;
+    }
+    h->compute = main_stream;
+    FTRL_CUDA(cudaEventRecord(h->ev_id_done[cur], h->idstream));
+    FTRL_CUDA(cudaStreamWaitEvent(h->compute, h->ev_id_done[cur], 0));
+  } else {
+    if (inputs_ready) FTRL_CUDA(cudaStreamWaitEvent(h->compute, inputs_ready, 0));
+    run_prep(h, b);
+  }
+  if (d.model_type == FTRL_FFM && h->tile_ok && b.nnz > 0) run_row_materialise(h, (int32_t)b.nnz, (uint32_t)d.n_feats);
   if (!logit_out) logit_out = h->logit_ws.p;
   const bool pr = h->precise != 0;
   if (pr) run_model<true>(h, b, logit_out); else run_model<false>(h, b, logit_out);
@@ -603,6 +655,10 @@ static void train_device(ftrl_handle *h, const Batch &b, float *logit_out, doubl
     else k_batch_reduce<false><<<rg, 256, 0, h->compute>>>(b.n_rows, h->hyper, h->g.p, logit_out, b.label, h->bias, 1, h->red_part.p, h->ticket.p, loss_sum_out, nullptr);
     FTRL_CUDA(cudaGetLastError());
     launched(h, PH_REDUCE);
+  }
+  if (h->idstream) {  // (also after an unpipelined call: it read the current index set on the compute stream)
+    FTRL_CUDA(cudaEventRecord(h->ev_hot_done[h->idset_cur], h->compute));
+    h->hot_recorded[h->idset_cur] = true;
   }
   h->stats.kernel_launches = h->launches_this_call;
 }
@@ -765,8 +821,7 @@ static Slot &stage_batch(ftrl_handle *h, int64_t n_rows, const int64_t *row_ptr,
     FTRL_CUDA(cudaMemcpyAsync(s.feat.p, feat, sizeof(int32_t) * nnz, cudaMemcpyHostToDevice, h->copy));
     FTRL_CUDA(cudaMemcpyAsync(s.val.p, val, sizeof(float) * nnz, cudaMemcpyHostToDevice, h->copy));
   }
-  FTRL_CUDA(cudaEventRecord(s.copied, h->copy));
-  FTRL_CUDA(cudaStreamWaitEvent(h->compute, s.copied, 0));
+  FTRL_CUDA(cudaEventRecord(s.copied, h->copy));  // the caller orders its kernels behind this event
   b.n_rows = n_rows;
   b.nnz = nnz;
   b.row_ptr = s.row_ptr.p;
@@ -1085,6 +1140,15 @@ int ftrl_create(const ftrl_config *cfg, ftrl_handle **out) {
     }
     FTRL_CUDA(cudaStreamCreateWithFlags(&h->compute, cudaStreamNonBlocking));
     FTRL_CUDA(cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking));
+    h->pipeline = env_int("FTRL_B200_PIPELINE", 1);
+    h->stable_device_inputs = (cfg->reserved[0] & 1) != 0;
+    if (h->pipeline && cfg->mode == FTRL_MODE_BATCH && h->cfg.world_size <= 1) {
+      FTRL_CUDA(cudaStreamCreateWithFlags(&h->idstream, cudaStreamNonBlocking));
+      for (int i = 0; i < 2; i++) {
+        FTRL_CUDA(cudaEventCreateWithFlags(&h->ev_id_done[i], cudaEventDisableTiming));
+        FTRL_CUDA(cudaEventCreateWithFlags(&h->ev_hot_done[i], cudaEventDisableTiming));
+      }
+    }
     if (h->G > 1 && !h->tile_ok) throw ArgFail{"multi-GPU runs need the tile path (n_factors % 4 == 0, sample tile must fit shared memory)"};
     const int64_t n = std::max<int64_t>(1, h->n_local);
     FTRL_CUDA(cudaMalloc(&h->lin, page_round(sizeof(float4) * n)));
@@ -1105,6 +1169,11 @@ int ftrl_create(const ftrl_config *cfg, ftrl_handle **out) {
       // no allocation on the hot path: workspace and the CSR staging slots are sized up front
       const int64_t mr = cfg->max_batch_rows, mn = std::max<int64_t>(cfg->max_batch_nnz, 0);
       ensure_workspace(h, mr, mn);
+      if (h->idstream) {  // both index sets
+        swap_idsets(h);
+        ensure_workspace(h, mr, mn);
+        swap_idsets(h);
+      }
       for (auto &sl : h->slots) {
         sl.row_ptr.ensure(mr + 1);
         sl.label.ensure(mr);
@@ -1154,6 +1223,11 @@ void ftrl_destroy(ftrl_handle *h) {
   if (h->bias) cudaFree(h->bias);
   if (h->pair_lut) cudaFree(h->pair_lut);
   if (h->d_err) cudaFree(h->d_err);
+  for (int i = 0; i < 2; i++) {
+    if (h->ev_id_done[i]) cudaEventDestroy(h->ev_id_done[i]);
+    if (h->ev_hot_done[i]) cudaEventDestroy(h->ev_hot_done[i]);
+  }
+  if (h->idstream) cudaStreamDestroy(h->idstream);
   if (h->compute && h->own_compute) cudaStreamDestroy(h->compute);
   if (h->copy) cudaStreamDestroy(h->copy);
   delete h;
@@ -1181,7 +1255,7 @@ int ftrl_train_batch(ftrl_handle *h, int64_t n_rows, const int64_t *row_ptr, con
     if (n_rows > 0 && !label) throw ArgFail{"label is NULL"};
     Batch b{};
     Slot &s = stage_batch(h, n_rows, row_ptr, field, feat, val, label, b);
-    train_device(h, b, logits_out ? s.out.p : nullptr, s.loss.p);
+    train_device(h, b, logits_out ? s.out.p : nullptr, s.loss.p, s.copied);
     finish_slot(h, s, n_rows, logits_out, loss_sum_out);
   });
 }
@@ -1207,6 +1281,7 @@ int ftrl_predict_batch(ftrl_handle *h, int64_t n_rows, const int64_t *row_ptr, c
     if (loss_sum_out && !label && n_rows > 0) throw ArgFail{"loss requested without labels"};
     Batch b{};
     Slot &s = stage_batch(h, n_rows, row_ptr, field, feat, val, label, b);
+    FTRL_CUDA(cudaStreamWaitEvent(h->compute, s.copied, 0));
     predict_device(h, b, output_prob, s.out.p, loss_sum_out ? s.loss.p : nullptr);
     finish_slot(h, s, n_rows, out, loss_sum_out);
   });

@@ -76,6 +76,11 @@ typedef struct ftrl_config {
    * feat % world_size == rank.  world_size <= 1: single GPU.                      */
   int32_t rank;
   int32_t world_size;
+  /* reserved[0] bit 0: the caller of ftrl_train_batch_device promises that the CSR arrays of a call are complete
+   * before the PREVIOUS train call on this handle was made (e.g. a data set resident in HBM).  The library may
+   * then read them -- not the weights -- while the previous batch is still being trained: the sort / segment work
+   * of batch i+1 overlaps the forward / update kernels of batch i.  ftrl_train_batch (host pointers) always
+   * does this; without the bit the device-pointer variant reads its inputs in stream order only. */
   int32_t reserved[8];
 } ftrl_config;
 
