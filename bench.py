@@ -9,8 +9,8 @@ Workload (config.workload): BASELINE.json configs[3] -- synthetic Criteo-shaped 
   value  : samples/s with the CSR minibatches already resident in HBM (CUDA-event time, max over ranks)
   e2e    : samples/s through ftrl_train_batch() with PINNED HOST buffers: H2D copies of the CSR and the
            D2H read of the loss are inside the timed region (3 batches in flight)
-  roofline: forward+update kernels (k_row_touch + k_row_materialise + k_build_canon + k_ffm_tile +
-           k_ffm_regrad_rows + k_ffm_combine; LR/FM: k_lrfm_sample + k_lrfm_rows + k_lrfm_combine), algorithmic
+  roofline: forward+update kernels (k_row_touch + k_row_materialise + k_ffm_tile +
+           k_ffm_staged_rows + k_ffm_combine; LR/FM: k_lrfm_sample + k_lrfm_rows + k_lrfm_combine), algorithmic
            bytes of SURVEY.md 8(d) / DESIGN.md divided by their CUDA-event time, against MEASURED_PEAKS.json;
            `traffic` = DRAM bytes of the same kernels from the ncu capture in profiles/traffic.json, used only
            when that capture was made from the kernel sources the loaded library was built from
@@ -393,9 +393,9 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_source": traffic_note, "peak_source": peak_src, "frac_of_nominal_8000": achieved / 8000.0,
                 "dram_gbs_from_traffic": (traffic / (hot_ms / 1e3) / 1e9) if traffic else None,
-                "kernels": ("k_row_touch + k_row_materialise + k_build_canon + k_ffm_tile + k_ffm_regrad_rows + k_ffm_combine "
+                "kernels": ("k_row_touch + k_row_materialise + k_ffm_tile + k_ffm_staged_rows + k_ffm_combine "
                             "(forward + FTRL update)" if world == 1 else
-                            "owner select/sort/k_owner_materialise (pushes w to the row caches) + k_ffm_tile + k_ffm_regrad_rows + "
+                            "owner select/sort/k_owner_materialise (pushes w to the row caches) + k_ffm_tile + k_ffm_staged_rows + "
                             "k_ffm_combine + k_owner_apply (forward + FTRL update + row exchange)") if model == "FFM"
                 else "k_lrfm_sample + k_lrfm_rows + k_lrfm_combine",
                 "alg_bytes_per_step": bytes_alg, "kernel_ms_per_step": hot_ms,

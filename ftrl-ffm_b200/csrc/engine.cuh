@@ -162,11 +162,17 @@ struct ftrl_handle {
     ftrl::DevBuf<uint64_t> pmask;
     ftrl::DevBuf<unsigned long long> rowmask;
     ftrl::DevBuf<ftrl::SegScan> scan;
+    ftrl::DevBuf<int4> cdesc;
+    // sharded runs: the sorted list of owned contributions (read by the owner-side weight kernels of the step)
+    ftrl::DevBuf<uint32_t> ckey, csrc;
+    ftrl::DevBuf<uint8_t> cflag;
+    ftrl::DevBuf<int32_t> n_sel;
   } alt;
   int idset_cur = 0;
   cudaStream_t idstream = nullptr;
   cudaEvent_t ev_id_done[2] = {nullptr, nullptr}, ev_hot_done[2] = {nullptr, nullptr};
-  bool hot_recorded[2] = {false, false};
+  cudaEvent_t ev_id_tail = nullptr;  // end of the last index phase, whichever stream it ran on
+  bool hot_recorded[2] = {false, false}, id_tail_recorded = false;
   int pipeline = 1;             // FTRL_B200_PIPELINE
   bool stable_device_inputs = false;
 
@@ -181,6 +187,7 @@ struct ftrl_handle {
   ftrl::PmaskSrc pmask_src{};
   ftrl::DevBuf<float> staging, staging_lin;  // per-occurrence gradient images (tile path)
   ftrl::DevBuf<ftrl::SegScan> scan;
+  ftrl::DevBuf<int4> cdesc;                  // one record per chunk of the chunk list (k_chunk_desc, prep.cuh)
   ftrl::DevBuf<float> g, S, part;
   ftrl::DevBuf<float2> part_lin;
   ftrl::DevBuf<float> logit_ws;
@@ -211,7 +218,9 @@ struct ftrl_handle {
   ftrl::Export exportd{};       // where reduced row sums go (single GPU: applied in place)
   ftrl::Peers peers{};
   ftrl::SyncArea *sync = nullptr;
-  uint32_t epoch = 0;
+  uint32_t epoch = 0;           // barrier epochs of the weight channel (compute stream)
+  uint32_t epoch_id = 0;        // ... of the index channel
+  uint32_t shard_step = 0;      // sharded steps made: its parity selects the published-list / index set of a step
   long long barrier_timeout_cycles = 40000000000ll;
   bool attached = false;
   int64_t ow_cap = 0;           // owner-side capacity: (row, rank) contributions this rank may own per step

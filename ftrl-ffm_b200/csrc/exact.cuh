@@ -78,6 +78,130 @@ __device__ __forceinline__ void ex_ffm_pair_factor(float *tab, int64_t a, int64_
   n2 = __fadd_rn(v_nif2, __fmul_rn(v_gif2, v_gif2));
 }
 
+// A sample the shared-memory path cannot hold (more than EX_CAP valid features, or FM with more than EX_KCAP
+// factors): one thread walks it straight from the CSR arrays in the reference's order -- the reference has no
+// cap (ffm.cpp:57-70, fm.cpp:40-67).  Same operations, same order as the paths of k_exact_train below.
+__device__ void ex_train_sample_serial(const Batch &b, const Dims &d, const Hyper &h, int64_t r0, int64_t r1, int y,
+                                       float *tab, float4 *lin, float4 *bias, float &logit_o) {
+  const int64_t ld = d.ld, rs = 3 * ld;
+  const int k = d.k;
+  auto valid = [&](int64_t t) { return feat_valid(d, b.field[t], b.feat[t]); };
+  // ---- materialise w (idempotent: repeated coordinates give the same value) ----
+  for (int64_t t = r0; t < r1; t++) {
+    if (!valid(t)) continue;
+    float4 e = lin[b.feat[t]];
+    lin[b.feat[t]].z = ex_weight(e.y, e.x, h);
+  }
+  {
+    float4 e = *bias;
+    e.z = ex_weight(e.y, e.x, h);
+    *bias = e;
+  }
+  if (d.model_type == 2) {
+    for (int64_t m = r0; m < r1; m++) {
+      if (!valid(m)) continue;
+      for (int64_t n = m + 1; n < r1; n++) {
+        if (!valid(n)) continue;
+        const int64_t a = (int64_t)b.feat[m] * rs + (int64_t)b.field[n] * k;
+        const int64_t c = (int64_t)b.feat[n] * rs + (int64_t)b.field[m] * k;
+        for (int f = 0; f < k; f++) {
+          tab[a + f + 2 * ld] = ex_weight(tab[a + f + ld], tab[a + f], h);
+          tab[c + f + 2 * ld] = ex_weight(tab[c + f + ld], tab[c + f], h);
+        }
+      }
+    }
+  } else if (d.model_type == 1) {
+    for (int64_t t = r0; t < r1; t++) {
+      if (!valid(t)) continue;
+      const int64_t a = (int64_t)b.feat[t] * rs;
+      for (int f = 0; f < k; f++) tab[a + f + 2 * ld] = ex_weight(tab[a + f + ld], tab[a + f], h);
+    }
+  }
+  // ---- logit: bias, linear terms, then the pair / factor terms in source order ----
+  float acc = bias->z;
+  for (int64_t t = r0; t < r1; t++)
+    if (valid(t)) acc = __fadd_rn(acc, __fmul_rn(lin[b.feat[t]].z, b.val[t]));
+  if (d.model_type == 2) {
+    for (int64_t m = r0; m < r1; m++) {
+      if (!valid(m)) continue;
+      for (int64_t n = m + 1; n < r1; n++) {
+        if (!valid(n)) continue;
+        const float *wa = tab + (int64_t)b.feat[m] * rs + 2 * ld + (int64_t)b.field[n] * k;
+        const float *wb = tab + (int64_t)b.feat[n] * rs + 2 * ld + (int64_t)b.field[m] * k;
+        float dot = 0.0f;
+        for (int f = 0; f < k; f++) dot = __fadd_rn(dot, __fmul_rn(wa[f], wb[f]));
+        acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(dot, b.val[m]), b.val[n]));
+      }
+    }
+  } else if (d.model_type == 1) {
+    for (int f = 0; f < k; f++) {
+      float s_vx = 0.0f, sum_sqr = 0.0f;
+      for (int64_t t = r0; t < r1; t++) {
+        if (!valid(t)) continue;
+        const float vx = __fmul_rn(tab[(int64_t)b.feat[t] * rs + 2 * ld + f], b.val[t]);
+        s_vx = __fadd_rn(s_vx, vx);
+        sum_sqr = __fadd_rn(sum_sqr, __fmul_rn(vx, vx));
+      }
+      acc = __fadd_rn(acc, __fmul_rn(0.5f, __fsub_rn(__fmul_rn(s_vx, s_vx), sum_sqr)));
+    }
+  }
+  logit_o = acc;
+  const float g = __fsub_rn(ex_sigmoid(acc), (float)y);
+  // ---- update_linear_nz + update_bias_nz (ftrl_model.cpp:66-85) ----
+  for (int64_t t = r0; t < r1; t++) {
+    if (!valid(t)) continue;
+    float4 e = lin[b.feat[t]];
+    const float gi = __fmul_rn(g, b.val[t]);
+    const float si = ex_sigma(e.y, gi, gi, h);
+    e.x = __fadd_rn(e.x, __fsub_rn(gi, __fmul_rn(si, e.z)));
+    e.y = __fadd_rn(e.y, __fmul_rn(gi, gi));
+    lin[b.feat[t]] = e;
+  }
+  {
+    float4 e = *bias;
+    const float si = ex_sigma(e.y, g, g, h);
+    e.x = __fadd_rn(e.x, __fsub_rn(g, __fmul_rn(si, e.z)));
+    e.y = __fadd_rn(e.y, __fmul_rn(g, g));
+    *bias = e;
+  }
+  // ---- latent n,z updates ----
+  if (d.model_type == 2) {
+    for (int64_t m = r0; m < r1; m++) {
+      if (!valid(m)) continue;
+      for (int64_t n = m + 1; n < r1; n++) {
+        if (!valid(n)) continue;
+        const float x = __fmul_rn(b.val[m], b.val[n]);
+        const int64_t a0 = (int64_t)b.feat[m] * rs + (int64_t)b.field[n] * k;
+        const int64_t c0 = (int64_t)b.feat[n] * rs + (int64_t)b.field[m] * k;
+        const bool alias = a0 == c0;
+        for (int f = 0; f < k; f++) {
+          float z1, n1, z2, n2;
+          ex_ffm_pair_factor(tab, a0 + f, c0 + f, ld, g, x, h, z1, n1, z2, n2);
+          if (!alias) { tab[a0 + f] = z1; tab[a0 + f + ld] = n1; }
+          tab[c0 + f] = z2; tab[c0 + f + ld] = n2;
+        }
+      }
+    }
+  } else if (d.model_type == 1) {
+    // fm.cpp:80-101.  sum_vx of a factor is recomputed from the stored w (the n,z updates do not touch w)
+    for (int f = 0; f < k; f++) {
+      float s_vx = 0.0f;
+      for (int64_t t = r0; t < r1; t++)
+        if (valid(t)) s_vx = __fadd_rn(s_vx, __fmul_rn(tab[(int64_t)b.feat[t] * rs + 2 * ld + f], b.val[t]));
+      for (int64_t t = r0; t < r1; t++) {
+        if (!valid(t)) continue;
+        const int64_t a = (int64_t)b.feat[t] * rs + f;
+        const float x = b.val[t];
+        const float vif = tab[a + 2 * ld], v_nif = tab[a + ld], v_zif = tab[a];
+        const float v_gif = __fmul_rn(g, __fsub_rn(__fmul_rn(x, s_vx), __fmul_rn(__fmul_rn(vif, x), x)));
+        const float v_sif = ex_sigma(v_nif, v_gif, v_gif, h);
+        tab[a] = __fsub_rn(__fadd_rn(v_zif, v_gif), __fmul_rn(v_sif, vif));
+        tab[a + ld] = __fadd_rn(v_nif, __fmul_rn(v_gif, v_gif));
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(EX_THREADS)
 k_exact_train(Batch b, Dims d, Hyper h, float *__restrict__ tab, float4 *__restrict__ lin,
               float4 *__restrict__ bias, float *__restrict__ logit_out, double *__restrict__ loss_sum_out,
@@ -105,7 +229,15 @@ k_exact_train(Batch b, Dims d, Hyper h, float *__restrict__ tab, float4 *__restr
         }
         fv++;
       }
-      if (overflow || (d.model_type == 1 && k > EX_KCAP)) { *err = 1; fv = fv < EX_CAP ? fv : EX_CAP; }
+      if (overflow || (d.model_type == 1 && k > EX_KCAP)) {
+        // wider than the shared-memory path: the whole sample serially, straight from the CSR arrays
+        float lg;
+        const int y = b.label[s];
+        ex_train_sample_serial(b, d, h, r0, r0 + F, y, tab, lin, bias, lg);
+        if (logit_out) logit_out[s] = lg;
+        loss_sum += logloss_d(y, lg);
+        fv = -1;
+      }
       sh.Fv = fv;
       bool par = true;
       for (int u = 0; u < fv && par; u++)
@@ -115,6 +247,7 @@ k_exact_train(Batch b, Dims d, Hyper h, float *__restrict__ tab, float4 *__restr
     }
     __syncthreads();
     const int Fv = sh.Fv;
+    if (Fv < 0) continue;  // done by ex_train_sample_serial (uniform: every thread reads the same sh.Fv)
     const int P = Fv * (Fv - 1) / 2;
 
     // ---- materialise w: update_linear_w, update_bias, update_vector_w (idempotent) ----

@@ -393,9 +393,8 @@ constexpr int COMB_VPL = 3;  // float4 vectors per lane and plane per block of t
 
 template <bool PRECISE, int THREADS>
 __global__ void __launch_bounds__(THREADS)
-k_ffm_combine(Dims d, Hyper h, int32_t nnz, float *__restrict__ tab, float4 *__restrict__ lin, int32_t ch,
-              const int32_t *__restrict__ n_chunks_p, const int32_t *__restrict__ chunk_pos,
-              const uint32_t *__restrict__ skey, const SegScan *__restrict__ scan,
+k_ffm_combine(Dims d, Hyper h, float *__restrict__ tab, float4 *__restrict__ lin,
+              const int32_t *__restrict__ n_chunks_p, const int4 *__restrict__ cdesc,
               const float *__restrict__ part, const float2 *__restrict__ part_lin, const __grid_constant__ Export ex) {
   constexpr int WARPS = THREADS / 32;
   constexpr int VB = 32 * COMB_VPL;  // vectors per block
@@ -412,7 +411,7 @@ k_ffm_combine(Dims d, Hyper h, int32_t nnz, float *__restrict__ tab, float4 *__r
     __syncthreads();
     const int c = base + tid;
     if (c < n_chunks) {
-      const ChunkInfo ci = chunk_head_info(c, nnz, sentinel, ch, chunk_pos, skey, scan);
+      const ChunkInfo ci = chunk_unpack(cdesc[c], sentinel);
       if (ci.valid && ci.row_head && !ci.row_last) s_list[atomicAdd(&s_n, 1)] = c;
     }
     __syncthreads();
@@ -422,9 +421,9 @@ k_ffm_combine(Dims d, Hyper h, int32_t nnz, float *__restrict__ tab, float4 *__r
     // block-cooperative path below, which gives every warp one chunk of such a row.
     for (int li = wib; li < n_list; li += WARPS) {
       const int c0 = s_list[li];
-      const ChunkInfo ci = chunk_head_info(c0, nnz, sentinel, ch, chunk_pos, skey, scan);
+      const ChunkInfo ci = chunk_unpack(cdesc[c0], sentinel);
       int J = 1;
-      while (J <= WARPS && c0 + J < n_chunks && skey[chunk_pos[c0 + J]] == ci.key) J++;
+      while (J <= WARPS && c0 + J < n_chunks && (uint32_t)cdesc[c0 + J].y == ci.key) J++;
       if (J > WARPS) continue;
       const int32_t dst = ex.on ? ex.dst_at[ci.p0] : -2;
       const int64_t lrow = (int64_t)(ci.key >> ex.log2G);
@@ -474,12 +473,12 @@ k_ffm_combine(Dims d, Hyper h, int32_t nnz, float *__restrict__ tab, float4 *__r
     // longer rows: the whole block per row, chunks split over the warps
     for (int li = 0; li < n_list; li++) {
       const int c0 = s_list[li];
-      const ChunkInfo ci = chunk_head_info(c0, nnz, sentinel, ch, chunk_pos, skey, scan);
+      const ChunkInfo ci = chunk_unpack(cdesc[c0], sentinel);
       // number of chunks of this row: keys are sorted, binary search for the first chunk of the next row
       int lo = c0 + 1, hi = n_chunks;
       while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        if (skey[chunk_pos[mid]] == ci.key) lo = mid + 1; else hi = mid;
+        if ((uint32_t)cdesc[mid].y == ci.key) lo = mid + 1; else hi = mid;
       }
       const int J = lo - c0;
       if (J <= WARPS) continue;

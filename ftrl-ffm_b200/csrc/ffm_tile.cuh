@@ -674,15 +674,14 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
 // ---------------------------------------------------------------------------------------------
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
-k_row_touch(int32_t nnz, uint32_t sentinel, int32_t ch, const int32_t *__restrict__ batch_flags,
-            const int32_t *__restrict__ n_chunks_p, const int32_t *__restrict__ chunk_pos,
-            const uint32_t *__restrict__ skey, const uint32_t *__restrict__ socc, const SegScan *__restrict__ scan,
-            PmaskSrc pm, unsigned long long *__restrict__ rowmask) {
+k_row_touch(uint32_t sentinel, int32_t ch, const int32_t *__restrict__ batch_flags, const int32_t *__restrict__ n_chunks_p,
+            const int4 *__restrict__ cdesc, const uint32_t *__restrict__ socc, PmaskSrc pm,
+            unsigned long long *__restrict__ rowmask) {
   if (batch_flags[0] == 0) return;
   const int wib = threadIdx.x >> 5;
   const int n_chunks = *n_chunks_p;
   for (int c = blockIdx.x * WARPS + wib; c < n_chunks; c += gridDim.x * WARPS) {
-    const ChunkInfo ci = chunk_info<true>(c, nnz, sentinel, ch, chunk_pos, skey, scan);
+    const ChunkInfo ci = chunk_unpack(cdesc[c], sentinel);
     if (!ci.valid) continue;
     row_touch_chunk(c, ci, ch, socc, pm, rowmask);
   }
@@ -690,29 +689,40 @@ k_row_touch(int32_t nnz, uint32_t sentinel, int32_t ch, const int32_t *__restric
 
 template <bool PRECISE, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
-k_row_materialise(Dims d, Hyper h, int32_t nnz, uint32_t sentinel, int32_t ch, const int32_t *__restrict__ batch_flags,
-                  const int32_t *__restrict__ n_chunks_p, const int32_t *__restrict__ chunk_pos,
-                  const uint32_t *__restrict__ skey, const SegScan *__restrict__ scan,
+k_row_materialise(Dims d, Hyper h, uint32_t sentinel, const int32_t *__restrict__ batch_flags,
+                  const int32_t *__restrict__ n_chunks_p, const int4 *__restrict__ cdesc,
                   const unsigned long long *__restrict__ rowmask, float *__restrict__ tab, float4 *__restrict__ lin) {
   if (batch_flags[0] == 0) return;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t ld = d.ld, rs = 3 * ld;
   const int n_chunks = *n_chunks_p;
   const int vpf = d.k >> 2;  // float4 vectors per field slice
+  const int nv = d.n_fields * vpf;
   for (int c = blockIdx.x * WARPS + wib; c < n_chunks; c += gridDim.x * WARPS) {
-    const ChunkInfo ci = chunk_head_info(c, nnz, sentinel, ch, chunk_pos, skey, scan);
+    const ChunkInfo ci = chunk_unpack(cdesc[c], sentinel);
     if (!ci.valid || !ci.row_head) continue;
     const unsigned long long mask = rowmask[c];
     float *row = tab + (int64_t)ci.key * rs;
-    for (int v = lane; v < d.n_fields * vpf; v += 32) {
-      if (!((mask >> (v / vpf)) & 1ull)) continue;
-      const float4 z = reinterpret_cast<const float4 *>(row)[v], n = reinterpret_cast<const float4 *>(row + ld)[v];
-      reinterpret_cast<float4 *>(row + 2 * ld)[v] = weight4<PRECISE>(z, n, h);
+    float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lane == 0) e = lin[ci.key];
+    for (int v0 = 0; v0 < nv; v0 += 128) {
+      // all loads of up to four vectors per lane first, then the arithmetic and the stores
+      float4 z[4], n[4];
+      bool act[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int v = v0 + u * 32 + lane;
+        act[u] = v < nv && ((mask >> (v / vpf)) & 1ull);
+        if (act[u]) {
+          z[u] = reinterpret_cast<const float4 *>(row)[v];
+          n[u] = reinterpret_cast<const float4 *>(row + ld)[v];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        if (act[u]) reinterpret_cast<float4 *>(row + 2 * ld)[v0 + u * 32 + lane] = weight4<PRECISE>(z[u], n[u], h);
     }
-    if (lane == 0) {
-      const float4 e = lin[ci.key];
-      lin[ci.key].z = weight_from<PRECISE>(e.x, f_sqrt<PRECISE>(e.y), h);
-    }
+    if (lane == 0) lin[ci.key].z = weight_from<PRECISE>(e.x, f_sqrt<PRECISE>(e.y), h);
   }
 }
 
@@ -724,12 +734,10 @@ k_row_materialise(Dims d, Hyper h, int32_t nnz, uint32_t sentinel, int32_t ch, c
 // ---------------------------------------------------------------------------------------------
 template <bool PRECISE, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
-k_ffm_staged_rows(Dims d, Hyper h, int32_t nnz, const int32_t *__restrict__ batch_flags, float *__restrict__ tab,
-                  float4 *__restrict__ lin, int32_t ch, const int32_t *__restrict__ n_chunks_p,
-                  const int32_t *__restrict__ chunk_pos, const uint32_t *__restrict__ skey,
-                  const SegScan *__restrict__ scan, const float *__restrict__ staging,
-                  const float *__restrict__ staging_lin, float *__restrict__ part, float2 *__restrict__ part_lin,
-                  const __grid_constant__ Export ex) {
+k_ffm_staged_rows(Dims d, Hyper h, const int32_t *__restrict__ batch_flags, float *__restrict__ tab,
+                  float4 *__restrict__ lin, const int32_t *__restrict__ n_chunks_p, const int4 *__restrict__ cdesc,
+                  const float *__restrict__ staging, const float *__restrict__ staging_lin, float *__restrict__ part,
+                  float2 *__restrict__ part_lin, const __grid_constant__ Export ex) {
   if (batch_flags[0] == 0) return;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t ld = d.ld, rs = 3 * ld;
@@ -740,7 +748,7 @@ k_ffm_staged_rows(Dims d, Hyper h, int32_t nnz, const int32_t *__restrict__ batc
   const int64_t n_items = (int64_t)n_chunks * parts;
   for (int64_t item = (int64_t)blockIdx.x * WARPS + wib; item < n_items; item += (int64_t)gridDim.x * WARPS) {
     const int c = (int)(item / parts), part_i = (int)(item - (int64_t)c * parts);
-    const ChunkInfo ci = chunk_info<true>(c, nnz, sentinel, ch, chunk_pos, skey, scan);
+    const ChunkInfo ci = chunk_unpack(cdesc[c], sentinel);
     if (!ci.valid) continue;
     const bool whole_row = ci.row_head && ci.row_last;
     const int v = part_i * 32 + lane;
@@ -748,6 +756,7 @@ k_ffm_staged_rows(Dims d, Hyper h, int32_t nnz, const int32_t *__restrict__ batc
     float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
     const float4 *src = reinterpret_cast<const float4 *>(staging + (int64_t)ci.p0 * ld) + (on ? v : 0);
     const int n_occ = ci.p1 - ci.p0;
+    float *row = tab + (int64_t)(ci.key >> ex.log2G) * rs;
     int p = 0;
     for (; p + 8 <= n_occ; p += 8) {
       float4 gq[8];
@@ -761,15 +770,14 @@ k_ffm_staged_rows(Dims d, Hyper h, int32_t nnz, const int32_t *__restrict__ batc
       }
     }
     for (; p < n_occ; p++) {
-      const float4 gq = on ? __ldcs(src + (int64_t)p * nvec) : make_float4(0.f, 0.f, 0.f, 0.f);
-      a0.x += gq.x; a0.y += gq.y; a0.z += gq.z; a0.w += gq.w;
-      a1.x = fmaf(gq.x, gq.x, a1.x); a1.y = fmaf(gq.y, gq.y, a1.y);
-      a1.z = fmaf(gq.z, gq.z, a1.z); a1.w = fmaf(gq.w, gq.w, a1.w);
+      const float4 gt = on ? __ldcs(src + (int64_t)p * nvec) : make_float4(0.f, 0.f, 0.f, 0.f);
+      a0.x += gt.x; a0.y += gt.y; a0.z += gt.z; a0.w += gt.w;
+      a1.x = fmaf(gt.x, gt.x, a1.x); a1.y = fmaf(gt.y, gt.y, a1.y);
+      a1.z = fmaf(gt.z, gt.z, a1.z); a1.w = fmaf(gt.w, gt.w, a1.w);
     }
     // sharded runs: the sum goes to the row's owner unless this rank owns the row and is its only contributor
     const int32_t dst = (ex.on && whole_row) ? ex.dst_at[ci.p0] : -2;
     const int64_t lrow = (int64_t)(ci.key >> ex.log2G);
-    float *row = tab + lrow * rs;
     if (on) {
       if (whole_row && dst >= 0) {
         // one occurrence: sum g^2 = g^2, the owner squares it (half the bytes over NVLink)

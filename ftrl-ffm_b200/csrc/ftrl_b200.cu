@@ -234,7 +234,8 @@ static void swap_idsets(ftrl_handle *h) {
   h->occ_row.swap(a.occ_row); h->chunk_pos.swap(a.chunk_pos); h->n_chunks.swap(a.n_chunks);
   h->sflags.swap(a.sflags); h->fused_sorted.swap(a.fused_sorted);
   h->occ_pos.swap(a.occ_pos); h->batch_flags.swap(a.batch_flags);
-  h->pmask.swap(a.pmask); h->rowmask.swap(a.rowmask); h->scan.swap(a.scan);
+  h->pmask.swap(a.pmask); h->rowmask.swap(a.rowmask); h->scan.swap(a.scan); h->cdesc.swap(a.cdesc);
+  h->ckey.swap(a.ckey); h->csrc.swap(a.csrc); h->cflag.swap(a.cflag); h->n_sel.swap(a.n_sel);
   h->idset_cur ^= 1;
 }
 
@@ -279,10 +280,11 @@ static void ensure_workspace(ftrl_handle *h, int64_t n_rows, int64_t nnz) {
     h->mscan.ensure(nc);
     h->uhead.ensure(nc + 1);
     h->n_uall.ensure(4);
-    h->dst_at.ensure(nc);
-    h->ukey.ensure(nc);
-    h->uinfo.ensure(nc);
-    h->umask.ensure(nc);
+    // published to the peers by the index phase, two sets (parity of the step): [par * nnz_cap + i]
+    h->dst_at.ensure(2 * nc);
+    h->ukey.ensure(2 * nc);
+    h->uinfo.ensure(2 * nc);
+    h->umask.ensure(2 * nc);
     h->rc_w.ensure((size_t)nc * h->dims.ld);
     h->rc_lin.ensure(nc);
     h->inbox.ensure((size_t)oc * 2 * h->dims.ld);
@@ -301,6 +303,7 @@ static void ensure_workspace(ftrl_handle *h, int64_t n_rows, int64_t nnz) {
   }
   h->scan.ensure(nc);
   h->chunk_pos.ensure(nc + 2);
+  if (h->dims.model_type == FTRL_FFM) h->cdesc.ensure(nc + 2);
   h->n_chunks.ensure(4);
   const int64_t slots = 2 * (nc / h->chunk + 2);
   if (h->dims.row_len) h->part.ensure((size_t)slots * 2 * h->dims.ld);
@@ -402,9 +405,9 @@ static void launch_tile(ftrl_handle *h, const Batch &b, const ItemDecode &dec, f
 template <bool PRECISE>
 static void launch_staged_rows(ftrl_handle *h, const Batch &b) {
   const int grid = h->n_sms * 16;
-  k_ffm_staged_rows<PRECISE, 8><<<grid, 256, 0, h->compute>>>(h->dims, h->hyper, (int32_t)b.nnz, h->batch_flags.p, h->tab, h->lin,
-                                                             h->chunk, h->n_chunks.p, h->chunk_pos.p, h->skey.p, h->scan.p,
-                                                             h->staging.p, h->staging_lin.p, h->part.p, h->part_lin.p, h->exportd);
+  k_ffm_staged_rows<PRECISE, 8><<<grid, 256, 0, h->compute>>>(h->dims, h->hyper, h->batch_flags.p, h->tab, h->lin, h->n_chunks.p,
+                                                             h->cdesc.p, h->staging.p, h->staging_lin.p, h->part.p,
+                                                             h->part_lin.p, h->exportd);
   FTRL_CUDA(cudaGetLastError());
   launched(h, PH_ROWS);
 }
@@ -457,9 +460,8 @@ static void run_ffm_batch(ftrl_handle *h, const Batch &b, float *logit_out) {
   if (b.nnz == 0) return;
   {
     PhaseScope ps(h, PH_COMBINE);
-    k_ffm_combine<PRECISE, 256><<<grid, 256, 0, h->compute>>>(d, h->hyper, (int32_t)b.nnz, h->tab, h->lin, h->chunk,
-                                                                   h->n_chunks.p, h->chunk_pos.p, h->skey.p, h->scan.p,
-                                                                   h->part.p, h->part_lin.p, h->exportd);
+    k_ffm_combine<PRECISE, 256><<<grid, 256, 0, h->compute>>>(d, h->hyper, h->tab, h->lin, h->n_chunks.p, h->cdesc.p, h->part.p,
+                                                              h->part_lin.p, h->exportd);
     FTRL_CUDA(cudaGetLastError());
     launched(h, PH_COMBINE);
   }
@@ -501,10 +503,10 @@ static void run_lrfm_batch(ftrl_handle *h, const Batch &b, float *logit_out) {
 // the two halves of the owner-side pre-pass: which slices of the staged rows does the batch touch (ids only) ...
 static void run_row_touch(ftrl_handle *h, int32_t n_sorted, uint32_t sentinel) {
   PhaseScope ps(h, PH_MATERIALISE);
-  const int grid = h->n_sms * 4;
+  const int grid = h->n_sms * 8;  // 64 resident warps per SM: the kernel is a chain of dependent gathers
   FTRL_CUDA(cudaMemsetAsync(h->rowmask.p, 0, sizeof(unsigned long long) * (size_t)(n_sorted + 2), h->compute));
-  k_row_touch<8><<<grid, 256, 0, h->compute>>>(n_sorted, sentinel, h->chunk, h->batch_flags.p, h->n_chunks.p, h->chunk_pos.p,
-                                               h->skey.p, h->socc.p, h->scan.p, h->pmask_src, h->rowmask.p);
+  k_row_touch<8><<<grid, 256, 0, h->compute>>>(sentinel, h->chunk, h->batch_flags.p, h->n_chunks.p, h->cdesc.p, h->socc.p,
+                                               h->pmask_src, h->rowmask.p);
   FTRL_CUDA(cudaGetLastError());
   launched(h, PH_MATERIALISE);
 }
@@ -512,14 +514,13 @@ static void run_row_touch(ftrl_handle *h, int32_t n_sorted, uint32_t sentinel) {
 static void run_row_materialise(ftrl_handle *h, int32_t n_sorted, uint32_t sentinel) {
   PhaseScope ps(h, PH_MATERIALISE);
   const Dims &d = h->dims;
-  const int grid = h->n_sms * 4;
+  const int grid = h->n_sms * 8;
+  (void)n_sorted;
   if (h->precise)
-    k_row_materialise<true, 8><<<grid, 256, 0, h->compute>>>(d, h->hyper, n_sorted, sentinel, h->chunk, h->batch_flags.p,
-                                                             h->n_chunks.p, h->chunk_pos.p, h->skey.p, h->scan.p,
+    k_row_materialise<true, 8><<<grid, 256, 0, h->compute>>>(d, h->hyper, sentinel, h->batch_flags.p, h->n_chunks.p, h->cdesc.p,
                                                              h->rowmask.p, h->tab, h->lin);
   else
-    k_row_materialise<false, 8><<<grid, 256, 0, h->compute>>>(d, h->hyper, n_sorted, sentinel, h->chunk, h->batch_flags.p,
-                                                              h->n_chunks.p, h->chunk_pos.p, h->skey.p, h->scan.p,
+    k_row_materialise<false, 8><<<grid, 256, 0, h->compute>>>(d, h->hyper, sentinel, h->batch_flags.p, h->n_chunks.p, h->cdesc.p,
                                                               h->rowmask.p, h->tab, h->lin);
   FTRL_CUDA(cudaGetLastError());
   launched(h, PH_MATERIALISE);
@@ -563,7 +564,10 @@ static void run_prep(ftrl_handle *h, const Batch &b) {
                                     ChunkHeadPred{h->skey.p, h->scan.p, h->fused_sorted.p, sentinel, h->chunk},
                                     h->compute));
     k_terminate<<<1, 1, 0, h->compute>>>(h->chunk_pos.p, h->n_chunks.p, nnz);
-    launched(h, PH_SEGMENT);
+    if (d.model_type == FTRL_FFM)
+      k_chunk_desc<8><<<h->n_sms * 8, 256, 0, h->compute>>>(nnz, sentinel, h->chunk, h->n_chunks.p, h->chunk_pos.p, h->skey.p,
+                                                           h->scan.p, h->cdesc.p);
+    launched(h, PH_SEGMENT, 2);
     FTRL_CUDA(cudaGetLastError());
   }
   if (d.model_type == FTRL_FFM && h->tile_ok) run_row_touch(h, nnz, sentinel);
@@ -587,7 +591,8 @@ static void run_model(ftrl_handle *h, const Batch &b, float *logit_out) {
 }
 
 template <bool PRECISE>
-static void train_device_sharded(ftrl_handle *h, const Batch &b, float *logit_out, double *loss_sum_out);
+static void train_device_sharded(ftrl_handle *h, const Batch &b, float *logit_out, double *loss_sum_out,
+                                 cudaEvent_t inputs_ready, bool allow_pipe);
 
 // inputs_ready: event after which the CSR arrays of `b` may be read (host path: the slot's copy), or null: the arrays
 // are ready in the order of the compute stream.  With an event (or stable device inputs) the weight-independent
@@ -603,9 +608,8 @@ static void train_device(ftrl_handle *h, const Batch &b, float *logit_out, doubl
     return;
   }
   if (h->G > 1) {
-    if (inputs_ready) FTRL_CUDA(cudaStreamWaitEvent(h->compute, inputs_ready, 0));
-    if (h->precise) train_device_sharded<true>(h, b, logit_out, loss_sum_out);
-    else train_device_sharded<false>(h, b, logit_out, loss_sum_out);
+    if (h->precise) train_device_sharded<true>(h, b, logit_out, loss_sum_out, inputs_ready, true);
+    else train_device_sharded<false>(h, b, logit_out, loss_sum_out, inputs_ready, true);
     return;
   }
   const bool piped = h->pipeline && h->cfg.mode == FTRL_MODE_BATCH && !h->profiling && h->idstream &&
@@ -861,14 +865,39 @@ static void check_device_err(ftrl_handle *h) {
 // ---------------------------------------------------------------------------------------------
 // feature-sharded multi-GPU step (shard.cuh)
 // ---------------------------------------------------------------------------------------------
-static void peer_barrier(ftrl_handle *h) {
-  h->epoch++;
-  k_peer_barrier<<<1, 32, 0, h->compute>>>(h->peers, h->epoch, h->barrier_timeout_cycles, h->d_err);
+// channel 0: weight-dependent phase (compute stream); channel 1: index phase
+static void peer_barrier(ftrl_handle *h, const Peers &pr, int channel) {
+  uint32_t &ep = channel ? h->epoch_id : h->epoch;
+  ep++;
+  k_peer_barrier<<<1, 32, 0, h->compute>>>(pr, channel, ep, h->barrier_timeout_cycles, h->d_err);
   FTRL_CUDA(cudaGetLastError());
 }
 
+// the peers' published lists of the step with parity `par` (two sets in one allocation per rank)
+static Peers peers_of_parity(const ftrl_handle *h, int par) {
+  Peers pr = h->peers;
+  const int64_t off = (int64_t)par * h->nnz_cap;
+  for (int q = 0; q < pr.G; q++) {
+    pr.ukey[q] += off;
+    pr.uinfo[q] += off;
+    pr.umask[q] += off;
+    pr.dst_at[q] += off;
+  }
+  return pr;
+}
+
+// One sharded step = an INDEX phase (ids only: S1, barrier on the index channel, the id part of S2, the local chunk
+// list) and a WEIGHT phase (k_owner_materialise, barrier 2, S3, barrier 3, S4).  With `inputs_ready` (host path) or
+// stable device inputs the index phase of step t+1 runs on the index stream under the weight phase of step t.
+// Everything the index phase writes is double-buffered by the parity of the step (IdSet; the published lists,
+// dst_at and the SyncArea fields): a set is rewritten by the index phase of step t+2, which waits for this rank's
+// weight phase of step t -- and that ends behind barrier 3 of step t, which every rank reaches only after its
+// last read of a peer's set (k_owner_materialise: umask / uinfo; k_ffm_staged_rows / k_ffm_combine: dst_at;
+// k_check_abort: abort_at).  boff / simple are read in the index phase of step t, which every rank has finished
+// before any rank passes the index barrier of step t+1.
 template <bool PRECISE>
-static void train_device_sharded(ftrl_handle *h, const Batch &b, float *logit_out, double *loss_sum_out) {
+static void train_device_sharded(ftrl_handle *h, const Batch &b, float *logit_out, double *loss_sum_out,
+                                 cudaEvent_t inputs_ready, bool allow_pipe) {
   if (!h->attached) throw StateFail{"multi-GPU handle: call ftrl_attach_peers before training"};
   const Dims &d = h->dims;
   if (b.n_rows > h->rows_cap || b.nnz > h->nnz_cap) throw ArgFail{"batch exceeds max_batch_rows / max_batch_nnz of a multi-GPU handle"};
@@ -879,86 +908,128 @@ static void train_device_sharded(ftrl_handle *h, const Batch &b, float *logit_ou
   const int grid = h->n_sms * 4;
   thrust::counting_iterator<int32_t> cnt(0);
   if (!logit_out) logit_out = h->logit_ws.p;
-  const uint32_t step_tag = h->epoch + 1;  // the first barrier epoch of this step: the same on every rank, never 0
-  {
-    PhaseScope ps(h, PH_PREP);
-    FTRL_CUDA(cudaMemsetAsync(h->batch_flags.p, 0x01, sizeof(int32_t), h->compute));
-    if (b.n_rows > 0) {
-      const unsigned pg = (unsigned)((b.n_rows * 32 + 255) / 256);
-      k_prep_rows<<<pg, 256, 0, h->compute>>>(b, d, h->key.p, h->occ_idx.p, h->occ_row.p, h->sflags.p, h->batch_flags.p,
-                                              h->pmask.p);
-      launched(h, PH_PREP);
-    }
-    FTRL_CUDA(cudaGetLastError());
+  const int par = (int)(h->shard_step & 1u);
+  const uint32_t step_tag = ++h->shard_step;  // the same on every rank, never 0
+  if (h->idstream && h->idset_cur != par) swap_idsets(h);
+  const Peers pr = peers_of_parity(h, par);
+  h->exportd.dst_at = h->dst_at.p + (int64_t)par * h->nnz_cap;
+  uint32_t *const ukey = h->ukey.p + (int64_t)par * h->nnz_cap, *const uinfo = h->uinfo.p + (int64_t)par * h->nnz_cap;
+  unsigned long long *const umask = h->umask.p + (int64_t)par * h->nnz_cap;
+  const bool piped = allow_pipe && h->pipeline && h->idstream && !h->profiling && (inputs_ready || h->stable_device_inputs);
+  cudaStream_t main_stream = h->compute;
+
+  // ------------------------------- index phase -------------------------------
+  if (piped) {
+    if (inputs_ready) FTRL_CUDA(cudaStreamWaitEvent(h->idstream, inputs_ready, 0));
+    // this parity's sets were last read by the weight phase two steps ago
+    if (h->hot_recorded[par]) FTRL_CUDA(cudaStreamWaitEvent(h->idstream, h->ev_hot_done[par], 0));
+    h->compute = h->idstream;  // everything below goes to the index stream
+  } else if (inputs_ready) {
+    FTRL_CUDA(cudaStreamWaitEvent(h->compute, inputs_ready, 0));
   }
-  {
-    PhaseScope ps(h, PH_SORT);
-    if (nnz > 0) {
-      size_t bytes = h->cub_bytes;
-      FTRL_CUDA(cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, bytes, h->key.p, h->skey.p, h->occ_idx.p, h->socc.p, nnz, 0,
-                                                key_bits(d.n_feats), h->compute));
+  // index phases run in order, whichever stream the previous one used
+  if (h->id_tail_recorded) FTRL_CUDA(cudaStreamWaitEvent(h->compute, h->ev_id_tail, 0));
+  try {
+    {
+      PhaseScope ps(h, PH_PREP);
+      FTRL_CUDA(cudaMemsetAsync(h->batch_flags.p, 0x01, sizeof(int32_t), h->compute));
+      if (b.n_rows > 0) {
+        const unsigned pg = (unsigned)((b.n_rows * 32 + 255) / 256);
+        k_prep_rows<<<pg, 256, 0, h->compute>>>(b, d, h->key.p, h->occ_idx.p, h->occ_row.p, h->sflags.p, h->batch_flags.p,
+                                                h->pmask.p);
+        launched(h, PH_PREP);
+      }
+      FTRL_CUDA(cudaGetLastError());
     }
+    {
+      PhaseScope ps(h, PH_SORT);
+      if (nnz > 0) {
+        size_t bytes = h->cub_bytes;
+        FTRL_CUDA(cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, bytes, h->key.p, h->skey.p, h->occ_idx.p, h->socc.p, nnz, 0,
+                                                  key_bits(d.n_feats), h->compute));
+      }
+    }
+    {
+      // distinct rows of the local batch, their field masks; tell the peers
+      PhaseScope ps(h, PH_SEGMENT);
+      if (nnz > 0) {
+        k_occ_class<<<(nnz + 255) / 256, 256, 0, h->compute>>>(nnz, sentinel, 0, h->skey.p, h->socc.p, h->occ_row.p, h->sflags.p,
+                                                               h->fused_sorted.p, h->occ_pos.p);
+        size_t bytes = h->cub_bytes;
+        auto mit = thrust::make_transform_iterator(cnt, MaskIn{h->skey.p, h->socc.p, h->pmask.p});
+        FTRL_CUDA(cub::DeviceScan::InclusiveScan(h->cub_tmp.p, bytes, mit, h->mscan.p, MaskScanOp(), nnz, h->compute));
+        bytes = h->cub_bytes;
+        FTRL_CUDA(cub::DeviceSelect::If(h->cub_tmp.p, bytes, cnt, h->uhead.p, h->n_uall.p, nnz, RowHeadPred{h->skey.p}, h->compute));
+      }
+      if (nnz > 0) {
+        // the list goes out bucketed by owner: one stable radix pass over the owner bits
+        k_owner_keys<<<(nnz + 255) / 256, 256, 0, h->compute>>>(nnz, h->G, sentinel, h->uhead.p, h->n_uall.p, h->skey.p, h->bkey.p,
+                                                               h->bidx.p);
+        size_t bytes = h->cub_bytes;
+        FTRL_CUDA(cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, bytes, h->bkey.p, h->bkey_s.p, h->bidx.p, h->perm.p, nnz, 0,
+                                                  h->log2G + 1, h->compute));
+        k_publish_unique<<<(nnz + 255) / 256, 256, 0, h->compute>>>(nnz, h->G, h->bkey_s.p, h->perm.p, h->uhead.p, h->n_uall.p, h->skey.p,
+                                                                   h->mscan.p, ukey, uinfo, umask);
+      }
+      k_publish_bounds<<<1, 32, 0, h->compute>>>(pr, par, nnz, h->bkey_s.p, h->batch_flags.p);
+      FTRL_CUDA(cudaGetLastError());
+      launched(h, PH_SEGMENT, 4);
+      peer_barrier(h, pr, 1);  // 1: every rank's distinct-row list is published
+    }
+    {
+      // owner side: contributions (row, rank) of the rows this rank owns
+      PhaseScope ps(h, PH_EXCHANGE);
+      k_merge_flags<<<1, 1, 0, h->compute>>>(pr, par, h->batch_flags.p, h->d_err);
+      k_fill_owned<<<(oc + 255) / 256, 256, 0, h->compute>>>(pr, par, oc, lsent, step_tag, h->n_sel.p, h->okey.p, h->osrc.p, h->d_err);
+      size_t bytes = h->cub_bytes;
+      FTRL_CUDA(cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, bytes, h->okey.p, h->ckey.p, h->osrc.p, h->csrc.p, oc, 0,
+                                                key_bits((int32_t)h->n_local), h->compute));
+      k_contrib_class<<<(oc + 255) / 256, 256, 0, h->compute>>>(pr, oc, h->n_sel.p, lsent, h->ckey.p, h->csrc.p, h->socc.p,
+                                                               h->cflag.p, h->fused_sorted.p, h->occ_pos.p);
+      FTRL_CUDA(cudaGetLastError());
+      launched(h, PH_EXCHANGE, 3);
+    }
+    {
+      // local chunk list of the rows that are not finalised inside a sample
+      PhaseScope ps(h, PH_SEGMENT);
+      if (nnz > 0) {
+        size_t bytes = h->cub_bytes;
+        auto it = thrust::make_transform_iterator(cnt, HeadFunctor{h->skey.p, h->fused_sorted.p});
+        FTRL_CUDA(cub::DeviceScan::InclusiveScan(h->cub_tmp.p, bytes, it, h->scan.p, SegScanOp(), nnz, h->compute));
+        bytes = h->cub_bytes;
+        FTRL_CUDA(cub::DeviceSelect::If(h->cub_tmp.p, bytes, cnt, h->chunk_pos.p, h->n_chunks.p, nnz,
+                                        ChunkHeadPred{h->skey.p, h->scan.p, h->fused_sorted.p, sentinel, h->chunk}, h->compute));
+        k_terminate<<<1, 1, 0, h->compute>>>(h->chunk_pos.p, h->n_chunks.p, nnz);
+        k_chunk_desc<8><<<h->n_sms * 8, 256, 0, h->compute>>>(nnz, sentinel, h->chunk, h->n_chunks.p, h->chunk_pos.p, h->skey.p,
+                                                             h->scan.p, h->cdesc.p);
+      } else {
+        FTRL_CUDA(cudaMemsetAsync(h->n_chunks.p, 0, sizeof(int32_t), h->compute));
+      }
+      FTRL_CUDA(cudaGetLastError());
+      launched(h, PH_SEGMENT);
+    }
+    if (h->ev_id_tail) {
+      FTRL_CUDA(cudaEventRecord(h->ev_id_tail, h->compute));
+      h->id_tail_recorded = true;
+    }
+    if (piped) FTRL_CUDA(cudaEventRecord(h->ev_id_done[par], h->idstream));
+  } catch (...) {
+    h->compute = main_stream;
+    throw;
   }
+  h->compute = main_stream;
+  if (piped) FTRL_CUDA(cudaStreamWaitEvent(h->compute, h->ev_id_done[par], 0));
+
+  // ------------------------------- weight phase -------------------------------
   {
-    // distinct rows of the local batch, their field masks; tell the peers
-    PhaseScope ps(h, PH_SEGMENT);
-    if (nnz > 0) {
-      k_occ_class<<<(nnz + 255) / 256, 256, 0, h->compute>>>(nnz, sentinel, 0, h->skey.p, h->socc.p, h->occ_row.p, h->sflags.p,
-                                                             h->fused_sorted.p, h->occ_pos.p);
-      size_t bytes = h->cub_bytes;
-      auto mit = thrust::make_transform_iterator(cnt, MaskIn{h->skey.p, h->socc.p, h->pmask.p});
-      FTRL_CUDA(cub::DeviceScan::InclusiveScan(h->cub_tmp.p, bytes, mit, h->mscan.p, MaskScanOp(), nnz, h->compute));
-      bytes = h->cub_bytes;
-      FTRL_CUDA(cub::DeviceSelect::If(h->cub_tmp.p, bytes, cnt, h->uhead.p, h->n_uall.p, nnz, RowHeadPred{h->skey.p}, h->compute));
-    }
-    if (nnz > 0) {
-      // the list goes out bucketed by owner: one stable radix pass over the owner bits
-      k_owner_keys<<<(nnz + 255) / 256, 256, 0, h->compute>>>(nnz, h->G, sentinel, h->uhead.p, h->n_uall.p, h->skey.p, h->bkey.p,
-                                                             h->bidx.p);
-      size_t bytes = h->cub_bytes;
-      FTRL_CUDA(cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, bytes, h->bkey.p, h->bkey_s.p, h->bidx.p, h->perm.p, nnz, 0,
-                                                h->log2G + 1, h->compute));
-      k_publish_unique<<<(nnz + 255) / 256, 256, 0, h->compute>>>(nnz, h->G, h->bkey_s.p, h->perm.p, h->uhead.p, h->n_uall.p, h->skey.p,
-                                                                 h->mscan.p, h->ukey.p, h->uinfo.p, h->umask.p);
-    }
-    k_publish_bounds<<<1, 32, 0, h->compute>>>(h->peers, nnz, h->bkey_s.p, h->batch_flags.p);
-    FTRL_CUDA(cudaGetLastError());
-    launched(h, PH_SEGMENT, 4);
-    peer_barrier(h);  // 1: every rank's distinct-row list is published
-  }
-  {
-    // owner side: contributions (row, rank) of the rows this rank owns
     PhaseScope ps(h, PH_EXCHANGE);
-    k_merge_flags<<<1, 1, 0, h->compute>>>(h->peers, h->batch_flags.p, h->d_err);
-    k_fill_owned<<<(oc + 255) / 256, 256, 0, h->compute>>>(h->peers, oc, lsent, step_tag, h->n_sel.p, h->okey.p, h->osrc.p, h->d_err);
-    size_t bytes = h->cub_bytes;
-    FTRL_CUDA(cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, bytes, h->okey.p, h->ckey.p, h->osrc.p, h->csrc.p, oc, 0,
-                                              key_bits((int32_t)h->n_local), h->compute));
-    k_contrib_class<<<(oc + 255) / 256, 256, 0, h->compute>>>(h->peers, oc, h->n_sel.p, lsent, h->ckey.p, h->csrc.p, h->socc.p,
-                                                             h->cflag.p, h->fused_sorted.p, h->occ_pos.p);
-    k_owner_materialise<PRECISE, 256><<<grid, 256, 0, h->compute>>>(h->peers, d, h->hyper, oc, h->n_sel.p, h->batch_flags.p,
+    // the cub scratch is shared by the two phases' sorts: this phase has none
+    k_owner_materialise<PRECISE, 256><<<grid, 256, 0, h->compute>>>(pr, d, h->hyper, oc, h->n_sel.p, h->batch_flags.p,
                                                                     h->ckey.p, h->csrc.p, h->cflag.p, h->tab, h->lin);
     FTRL_CUDA(cudaGetLastError());
-    launched(h, PH_EXCHANGE, 4);
-  }
-  {
-    // local chunk list of the rows that are not finalised inside a sample
-    PhaseScope ps(h, PH_SEGMENT);
-    if (nnz > 0) {
-      size_t bytes = h->cub_bytes;
-      auto it = thrust::make_transform_iterator(cnt, HeadFunctor{h->skey.p, h->fused_sorted.p});
-      FTRL_CUDA(cub::DeviceScan::InclusiveScan(h->cub_tmp.p, bytes, it, h->scan.p, SegScanOp(), nnz, h->compute));
-      bytes = h->cub_bytes;
-      FTRL_CUDA(cub::DeviceSelect::If(h->cub_tmp.p, bytes, cnt, h->chunk_pos.p, h->n_chunks.p, nnz,
-                                      ChunkHeadPred{h->skey.p, h->scan.p, h->fused_sorted.p, sentinel, h->chunk}, h->compute));
-      k_terminate<<<1, 1, 0, h->compute>>>(h->chunk_pos.p, h->n_chunks.p, nnz);
-    } else {
-      FTRL_CUDA(cudaMemsetAsync(h->n_chunks.p, 0, sizeof(int32_t), h->compute));
-    }
-    FTRL_CUDA(cudaGetLastError());
-    launched(h, PH_SEGMENT);
-    peer_barrier(h);  // 2: classes / inbox slots are known everywhere, w of the touched slices is materialised
-    k_check_abort<<<1, 1, 0, h->compute>>>(h->peers, step_tag, h->batch_flags.p, h->d_err);
+    launched(h, PH_EXCHANGE);
+    peer_barrier(h, pr, 0);  // 2: classes / inbox slots are known everywhere, w of the touched slices is materialised
+    k_check_abort<<<1, 1, 0, h->compute>>>(pr, par, step_tag, h->batch_flags.p, h->d_err);
     FTRL_CUDA(cudaGetLastError());
   }
   const ItemDecode dec = make_item_decode(d.k, 4);
@@ -970,7 +1041,7 @@ static void train_device_sharded(ftrl_handle *h, const Batch &b, float *logit_ou
     PhaseScope ps(h, PH_REDUCE);
     k_batch_reduce<PRECISE><<<reduce_grid(std::max<int64_t>(1, b.n_rows)), 256, 0, h->compute>>>(
         b.n_rows, h->hyper, h->g.p, logit_out, b.label, h->bias, 0, h->red_part.p, h->ticket.p, loss_sum_out, h->red4.p);
-    k_publish_red<<<1, 32, 0, h->compute>>>(h->peers, h->red4.p);
+    k_publish_red<<<1, 32, 0, h->compute>>>(pr, h->red4.p);
     FTRL_CUDA(cudaGetLastError());
     launched(h, PH_REDUCE, 2);
   }
@@ -981,20 +1052,23 @@ static void train_device_sharded(ftrl_handle *h, const Batch &b, float *logit_ou
   }
   {
     PhaseScope ps(h, PH_COMBINE);
-    k_ffm_combine<PRECISE, 256><<<grid, 256, 0, h->compute>>>(d, h->hyper, nnz, h->tab, h->lin, h->chunk, h->n_chunks.p,
-                                                              h->chunk_pos.p, h->skey.p, h->scan.p, h->part.p, h->part_lin.p,
-                                                              h->exportd);
+    k_ffm_combine<PRECISE, 256><<<grid, 256, 0, h->compute>>>(d, h->hyper, h->tab, h->lin, h->n_chunks.p, h->cdesc.p, h->part.p,
+                                                              h->part_lin.p, h->exportd);
     FTRL_CUDA(cudaGetLastError());
     launched(h, PH_COMBINE);
-    peer_barrier(h);  // 3: every contribution is in its owner's inbox, the bias partials are exchanged
+    peer_barrier(h, pr, 0);  // 3: every contribution is in its owner's inbox, the bias partials are exchanged
   }
   {
     PhaseScope ps(h, PH_APPLY);
-    k_owner_apply<PRECISE, 256><<<grid, 256, 0, h->compute>>>(h->peers, d, h->hyper, oc, h->n_sel.p, h->batch_flags.p, h->ckey.p,
+    k_owner_apply<PRECISE, 256><<<grid, 256, 0, h->compute>>>(pr, d, h->hyper, oc, h->n_sel.p, h->batch_flags.p, h->ckey.p,
                                                               h->cflag.p, h->inbox.p, h->inbox_lin.p, h->tab, h->lin);
-    k_bias_apply<PRECISE><<<1, 1, 0, h->compute>>>(h->peers, h->hyper, h->batch_flags.p, h->bias);
+    k_bias_apply<PRECISE><<<1, 1, 0, h->compute>>>(pr, h->hyper, h->batch_flags.p, h->bias);
     FTRL_CUDA(cudaGetLastError());
     launched(h, PH_APPLY, 2);
+  }
+  if (h->ev_hot_done[par]) {
+    FTRL_CUDA(cudaEventRecord(h->ev_hot_done[par], h->compute));
+    h->hot_recorded[par] = true;
   }
   h->stats.kernel_launches = h->launches_this_call;
 }
@@ -1048,7 +1122,8 @@ int ftrl_create(const ftrl_config *cfg, ftrl_handle **out) {
     if (cfg->n_feats <= 0) throw ArgFail{"n_feats must be > 0"};
     if (cfg->model_type != FTRL_LR && cfg->n_factors <= 0) throw ArgFail{"n_factors must be > 0"};
     if (cfg->model_type == FTRL_FFM && cfg->n_fields <= 0) throw ArgFail{"n_fields must be > 0"};
-    if (cfg->model_type == FTRL_FM && cfg->n_factors > 32 * FM_MAX_REGS) throw ArgFail{"FM n_factors > 256 unsupported"};
+    if (cfg->model_type == FTRL_FM && cfg->mode == FTRL_MODE_BATCH && cfg->n_factors > 32 * FM_MAX_REGS)
+      throw ArgFail{"FM n_factors > 256 is unsupported in minibatch mode (sequential mode has no cap)"};
     if (cfg->mode != FTRL_MODE_BATCH && cfg->mode != FTRL_MODE_SEQUENTIAL) throw ArgFail{"bad mode"};
     int n_dev = 0;
     cudaError_t e = cudaGetDeviceCount(&n_dev);
@@ -1142,12 +1217,13 @@ int ftrl_create(const ftrl_config *cfg, ftrl_handle **out) {
     FTRL_CUDA(cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking));
     h->pipeline = env_int("FTRL_B200_PIPELINE", 1);
     h->stable_device_inputs = (cfg->reserved[0] & 1) != 0;
-    if (h->pipeline && cfg->mode == FTRL_MODE_BATCH && h->cfg.world_size <= 1) {
+    if (h->pipeline && cfg->mode == FTRL_MODE_BATCH) {
       FTRL_CUDA(cudaStreamCreateWithFlags(&h->idstream, cudaStreamNonBlocking));
       for (int i = 0; i < 2; i++) {
         FTRL_CUDA(cudaEventCreateWithFlags(&h->ev_id_done[i], cudaEventDisableTiming));
         FTRL_CUDA(cudaEventCreateWithFlags(&h->ev_hot_done[i], cudaEventDisableTiming));
       }
+      FTRL_CUDA(cudaEventCreateWithFlags(&h->ev_id_tail, cudaEventDisableTiming));
     }
     if (h->G > 1 && !h->tile_ok) throw ArgFail{"multi-GPU runs need the tile path (n_factors % 4 == 0, sample tile must fit shared memory)"};
     const int64_t n = std::max<int64_t>(1, h->n_local);
@@ -1227,6 +1303,7 @@ void ftrl_destroy(ftrl_handle *h) {
     if (h->ev_id_done[i]) cudaEventDestroy(h->ev_id_done[i]);
     if (h->ev_hot_done[i]) cudaEventDestroy(h->ev_hot_done[i]);
   }
+  if (h->ev_id_tail) cudaEventDestroy(h->ev_id_tail);
   if (h->idstream) cudaStreamDestroy(h->idstream);
   if (h->compute && h->own_compute) cudaStreamDestroy(h->compute);
   if (h->copy) cudaStreamDestroy(h->copy);
@@ -1828,12 +1905,17 @@ int ftrl_attach_peers(ftrl_handle *h, const void *blobs) {
       FTRL_CUDA(cudaMemcpy(ws.label.p, &lab, sizeof(lab), cudaMemcpyHostToDevice));
       Batch wb{1, 2, ws.row_ptr.p, ws.field.p, ws.feat.p, ws.val.p, ws.label.p};
       h->G = 1;  // one shard: this rank against itself
-      if (h->precise) train_device_sharded<true>(h, wb, nullptr, ws.loss.p); else train_device_sharded<false>(h, wb, nullptr, ws.loss.p);
+      // both parities: the dry run loads every kernel and leaves the step counter even
+      for (int rep = 0; rep < 2; rep++) {
+        if (h->precise) train_device_sharded<true>(h, wb, nullptr, ws.loss.p, nullptr, false);
+        else train_device_sharded<false>(h, wb, nullptr, ws.loss.p, nullptr, false);
+      }
       FTRL_CUDA(cudaStreamSynchronize(h->compute));
       h->G = G; h->log2G = log2G; h->rank = rank;
       FTRL_CUDA(cudaMemcpy(h->bias, &bias_save, sizeof(float4), cudaMemcpyHostToDevice));
       FTRL_CUDA(cudaMemset(h->d_err, 0, sizeof(int32_t)));
-      h->epoch = 0;  // the real SyncArea (zeroed by ftrl_create) has not been touched
+      h->epoch = h->epoch_id = 0;  // the real SyncArea (zeroed by ftrl_create) has not been touched
+      h->shard_step = 0;
     }
     h->shards = sh;
     h->peers = pr;

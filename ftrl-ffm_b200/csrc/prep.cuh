@@ -198,6 +198,41 @@ __device__ __forceinline__ ChunkInfo chunk_info(int32_t c, int32_t nnz, uint32_t
   return ci;
 }
 
+// ---- chunk descriptors ---------------------------------------------------------------------------
+// chunk_info() is a chain of three dependent gathers (chunk_pos -> skey / scan -> end of the run); the FFM row
+// kernels (k_row_touch, k_row_materialise, k_ffm_staged_rows, k_ffm_combine) would each walk it per work item.
+// k_chunk_desc walks it ONCE per chunk, in the index phase (ids only: it overlaps the previous batch), and
+// leaves one 16-byte record per chunk that the row kernels read with a single coalesced load.
+//   x = p0 | row_last << 31      y = key      z = slot | (n_occ - 1) << 27      w = j
+// (p0 < 2^31; slot < 2 * (nnz / ch + 2) < 2^27 for ch = 32; 1 <= n_occ <= 32)
+__device__ __forceinline__ int4 chunk_pack(const ChunkInfo &ci) {
+  return make_int4(ci.p0 | (ci.row_last ? (int)0x80000000u : 0), (int)ci.key, ci.slot | ((ci.p1 - ci.p0 - 1) << 27), ci.j);
+}
+__device__ __forceinline__ ChunkInfo chunk_unpack(const int4 &e, uint32_t sentinel) {
+  ChunkInfo ci;
+  ci.p0 = e.x & 0x7fffffff;
+  ci.row_last = e.x < 0;
+  ci.key = (uint32_t)e.y;
+  ci.valid = ci.key != sentinel;
+  ci.slot = e.z & 0x07ffffff;
+  ci.p1 = ci.p0 + (int)((uint32_t)e.z >> 27) + 1;
+  ci.j = e.w;
+  ci.row_head = e.w == 0;
+  return ci;
+}
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+k_chunk_desc(int32_t nnz, uint32_t sentinel, int32_t ch, const int32_t *__restrict__ n_chunks_p,
+             const int32_t *__restrict__ chunk_pos, const uint32_t *__restrict__ skey, const SegScan *__restrict__ scan,
+             int4 *__restrict__ cdesc) {
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int n_chunks = *n_chunks_p;
+  for (int c = blockIdx.x * WARPS + wib; c < n_chunks; c += gridDim.x * WARPS) {
+    const ChunkInfo ci = chunk_info<true>(c, nnz, sentinel, ch, chunk_pos, skey, scan);
+    if (lane == 0) cdesc[c] = chunk_pack(ci);
+  }
+}
+
 constexpr int SRC_SHIFT = 28;  // source = (rank << 28) | occurrence index  (nnz per rank < 2^28)
 constexpr uint32_t SRC_MASK = (1u << SRC_SHIFT) - 1;
 

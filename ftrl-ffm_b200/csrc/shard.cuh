@@ -34,13 +34,17 @@
 namespace ftrl {
 
 // lives in device memory of every rank, mapped by all peers
+// Two barrier channels: the index phase of step t+1 (ids only: S1 and the id part of S2) runs on its own stream
+// under the weight-dependent phase of step t, so the two phases synchronise independently.  Everything the index
+// phase publishes is double-buffered by the parity of the step (`par`): a set is rewritten two steps later, after
+// the barriers of the step in between have shown that every rank is done reading it (see train_device_sharded).
 struct SyncArea {
-  uint32_t flag[MAX_SHARDS];      // flag[q] = last barrier epoch rank q has reached (written by q)
-  int32_t boff[MAX_SHARDS][MAX_SHARDS + 1];  // boff[q][r] .. boff[q][r+1]: the part of rank q's distinct-row list
-                                             // owned by rank r (the list is published bucketed by owner; written by q)
-  int32_t simple[MAX_SHARDS];     // simple[q] != 0: every sample of rank q's batch has distinct fields
+  uint32_t flag[2][MAX_SHARDS];   // flag[ch][q] = last barrier epoch rank q has reached on channel ch (0: weights, 1: ids)
+  int32_t boff[2][MAX_SHARDS][MAX_SHARDS + 1];  // [par] boff[q][r] .. boff[q][r+1]: the part of rank q's distinct-row list
+                                                // owned by rank r (the list is published bucketed by owner; written by q)
+  int32_t simple[2][MAX_SHARDS];  // [par] simple[q] != 0: every sample of rank q's batch has distinct fields
   double red[MAX_SHARDS][4];      // red[q] = {sum g, sum g^2, sum loss, n_rows} of rank q's batch
-  uint32_t abort_at[MAX_SHARDS];  // abort_at[q] = step tag at which rank q asked every rank to skip the step (written by q)
+  uint32_t abort_at[2][MAX_SHARDS];  // [par] abort_at[q] = step tag at which rank q asked every rank to skip the step
 };
 
 constexpr uint32_t UINFO_SINGLE = 1u << 30;  // uinfo = sorted head position | UINFO_SINGLE
@@ -121,7 +125,7 @@ __global__ void k_publish_unique(int32_t nnz, int G, const uint32_t *__restrict_
 }
 
 // lane r <= G: first slot of bucket r (lower bound in the sorted bucket keys)
-__global__ void k_publish_bounds(Peers pr, int32_t nnz, const uint32_t *__restrict__ bkey_s,
+__global__ void k_publish_bounds(Peers pr, int par, int32_t nnz, const uint32_t *__restrict__ bkey_s,
                                  const int32_t *__restrict__ batch_flags) {
   const int r = threadIdx.x;
   if (r > pr.G) return;
@@ -131,19 +135,19 @@ __global__ void k_publish_bounds(Peers pr, int32_t nnz, const uint32_t *__restri
     if (bkey_s[mid] < (uint32_t)r) lo = mid + 1; else hi = mid;
   }
   for (int q = 0; q < pr.G; q++) {
-    pr.sync[q]->boff[pr.rank][r] = lo;
-    if (r == 0) pr.sync[q]->simple[pr.rank] = batch_flags[0];
+    pr.sync[q]->boff[par][pr.rank][r] = lo;
+    if (r == 0) pr.sync[q]->simple[par][pr.rank] = batch_flags[0];
   }
 }
 
 // all ranks arrive; returns when every rank has reached `epoch`.  A peer that never arrives (crashed
 // process, failed call) must not hang the GPU: after `timeout_cycles` the wait gives up and raises err = 4.
-__global__ void k_peer_barrier(Peers pr, uint32_t epoch, long long timeout_cycles, int32_t *err) {
+__global__ void k_peer_barrier(Peers pr, int channel, uint32_t epoch, long long timeout_cycles, int32_t *err) {
   const int q = threadIdx.x;
   if (q < pr.G) {
     __threadfence_system();
-    *reinterpret_cast<volatile uint32_t *>(&pr.sync[q]->flag[pr.rank]) = epoch;
-    const volatile uint32_t *mine = reinterpret_cast<const volatile uint32_t *>(&pr.sync[pr.rank]->flag[q]);
+    *reinterpret_cast<volatile uint32_t *>(&pr.sync[q]->flag[channel][pr.rank]) = epoch;
+    const volatile uint32_t *mine = reinterpret_cast<const volatile uint32_t *>(&pr.sync[pr.rank]->flag[channel][q]);
     const long long t0 = clock64();
     while ((int32_t)(*mine - epoch) < 0) {
       if (clock64() - t0 > timeout_cycles) {
@@ -156,18 +160,18 @@ __global__ void k_peer_barrier(Peers pr, uint32_t epoch, long long timeout_cycle
 }
 
 // batch_flags[0] = AND over ranks (the tile path needs every rank's batch to have distinct fields)
-__global__ void k_merge_flags(Peers pr, int32_t *batch_flags, int32_t *err) {
+__global__ void k_merge_flags(Peers pr, int par, int32_t *batch_flags, int32_t *err) {
   int all = 1;
-  for (int q = 0; q < pr.G; q++) all = all && pr.sync[pr.rank]->simple[q] != 0;
+  for (int q = 0; q < pr.G; q++) all = all && pr.sync[pr.rank]->simple[par][q] != 0;
   batch_flags[0] = all;
   if (!all) *err = 2;  // sharded mode has no generic fallback yet
 }
 
 // after barrier 2: some rank called the step off (k_fill_owned) -> nothing of this step may change z / n
-__global__ void k_check_abort(Peers pr, uint32_t step_tag, int32_t *batch_flags, int32_t *err) {
+__global__ void k_check_abort(Peers pr, int par, uint32_t step_tag, int32_t *batch_flags, int32_t *err) {
   bool any = false;
   for (int q = 0; q < pr.G; q++)
-    any = any || *reinterpret_cast<const volatile uint32_t *>(&pr.sync[pr.rank]->abort_at[q]) == step_tag;
+    any = any || *reinterpret_cast<const volatile uint32_t *>(&pr.sync[pr.rank]->abort_at[par][q]) == step_tag;
   if (any) {
     batch_flags[0] = 0;
     if (*err == 0) *err = 3;
@@ -180,7 +184,7 @@ __global__ void k_check_abort(Peers pr, uint32_t step_tag, int32_t *batch_flags,
 // called off on EVERY rank before any z / n is touched -- the tag goes to every peer, k_check_abort reads it
 // after barrier 2 and turns the remaining kernels of the step into no-ops (batch_flags[0] = 0).
 // Contribution j is the (j - start_q)-th row of the run rank q published for this owner, runs in rank order.
-__global__ void k_fill_owned(Peers pr, int32_t cap, uint32_t local_sentinel, uint32_t step_tag,
+__global__ void k_fill_owned(Peers pr, int par, int32_t cap, uint32_t local_sentinel, uint32_t step_tag,
                              int32_t *__restrict__ n_sel, uint32_t *__restrict__ okey, uint32_t *__restrict__ osrc,
                              int32_t *__restrict__ err) {
   const int32_t j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -188,7 +192,7 @@ __global__ void k_fill_owned(Peers pr, int32_t cap, uint32_t local_sentinel, uin
   const SyncArea *sa = pr.sync[pr.rank];
   int32_t n = 0, q = -1, u = 0;
   for (int r = 0; r < pr.G; r++) {
-    const int32_t b0 = sa->boff[r][pr.rank], cnt = sa->boff[r][pr.rank + 1] - b0;
+    const int32_t b0 = sa->boff[par][r][pr.rank], cnt = sa->boff[par][r][pr.rank + 1] - b0;
     if (q < 0 && j < n + cnt) {
       q = r;
       u = b0 + (j - n);
@@ -198,7 +202,7 @@ __global__ void k_fill_owned(Peers pr, int32_t cap, uint32_t local_sentinel, uin
   if (j == 0) *n_sel = n;
   if (j == 0 && n > cap) {
     *err = 3;  // owned contributions exceed the workspace (extreme skew)
-    for (int q = 0; q < pr.G; q++) *reinterpret_cast<volatile uint32_t *>(&pr.sync[q]->abort_at[pr.rank]) = step_tag;
+    for (int q = 0; q < pr.G; q++) *reinterpret_cast<volatile uint32_t *>(&pr.sync[q]->abort_at[par][pr.rank]) = step_tag;
   }
   if (j < n) {
     okey[j] = pr.ukey[q][u] >> pr.log2G;

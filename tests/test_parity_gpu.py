@@ -291,6 +291,26 @@ def test_wide_samples_beyond_shared_cache():
     assert_state_close(m.get_state(), o.get_state(), rtol=2e-5, atol=2e-6, atol_z=2e-4, name="wide")
 
 
+@pytest.mark.parametrize("mt,k", [("FFM", 2), ("FM", 3), ("LR", 1), ("FM", 1100)])
+def test_sequential_mode_has_no_sample_width_cap(mt, k):
+    """the reference trains samples of any width (ffm.cpp:57-70, fm.cpp:40-67): beyond the 96 valid features (or
+    1024 FM factors) the sequential kernel keeps in shared memory, a serial path takes over -- same trajectory"""
+    rng = np.random.default_rng(21)
+    nf, nfl = 500, 160
+    m = gpu_model(mt, nf, nfl, k, mode="sequential")
+    o = CpuModel("oracle", mt, nf, nfl, k)
+    st = pkg.synth.random_state(rng, nf, o.row_len)
+    m.set_state(st)
+    o.set_state(st)
+    wide = mt != "FM" or k < 1000
+    b = pkg.synth.random_csr(rng, 5, nf, nfl, max_nnz=150 if wide else 12, min_nnz=100 if wide else 4, oob_frac=0.02)
+    got, gl = m.train(**b)
+    want, wl = o.train_csr(**b)
+    assert_close(got, want, RTOL, 1e-6, "logits")
+    assert abs(gl - wl) <= 1e-9 * max(1.0, abs(wl))
+    assert_state_close(m.get_state(), o.get_state(), RTOL, name=f"wide-seq-{mt}")
+
+
 def test_async_pipeline_three_batches_in_flight():
     rng = np.random.default_rng(4)
     nf, nfl, k = 300, 6, 4

@@ -8,7 +8,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from bench import kernel_source_sha16
 
-HOT = ("k_row_touch", "k_row_materialise", "k_build_canon", "k_ffm_tile", "k_ffm_regrad_rows", "k_ffm_combine",
+HOT = ("k_row_touch", "k_row_materialise", "k_ffm_tile", "k_ffm_staged_rows", "k_ffm_combine",
        "k_lrfm_sample", "k_lrfm_rows", "k_lrfm_combine")
 out = {}
 for arg in sys.argv[1:]:
