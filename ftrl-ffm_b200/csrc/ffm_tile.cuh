@@ -135,13 +135,15 @@ struct RowMeta {   // one 16-byte record per row of a sample
 struct SampleMeta {
   RowMeta *row;     // [f_cap]
   float4 *lin;      // [f_cap] {z, n, w, -} of the linear coordinate, prefetched
-  int32_t *hdr;     // [0] fused rows, [1] label, [2] floats of the row ring the sample needs, [3] staged rows
+  int32_t *hdr;     // [0] fused rows, [1] label, [2] floats of the row ring the sample needs, [3] staged rows,
+                    // [4] fused x fused items, [5] fused x staged items, [6] items, [7] 1 / fused rows (float bits):
+                    // computed once by the metadata warp instead of by every consumer thread
   uint8_t *present; // [n_fields] 1 when some valid row of the sample carries that field
 };
 
 __host__ __device__ inline size_t tile_meta_bytes(int f_cap) {
-  // RowMeta (16 B) + lin (16 B) per row, + header 16 B, + present[f_cap] rounded to 16
-  return (size_t)f_cap * 32 + 16 + 2 * (size_t)((f_cap + 15) / 16) * 16;
+  // RowMeta (16 B) + lin (16 B) per row, + header 32 B, + present[f_cap] rounded to 16
+  return (size_t)f_cap * 32 + 32 + 2 * (size_t)((f_cap + 15) / 16) * 16;
 }
 __host__ __device__ inline size_t tile_stage_bytes(int f_cap, int stride) {
   return (size_t)f_cap * stride * sizeof(float);
@@ -251,7 +253,7 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
     m.lin = reinterpret_cast<float4 *>(p);
     p += (size_t)f_cap * 16;
     m.hdr = reinterpret_cast<int32_t *>(p);
-    p += 16;
+    p += 32;
     m.present = p;
     return m;
   };
@@ -360,6 +362,10 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
         m.hdr[1] = b.label[s];
         m.hdr[2] = need;
         m.hdr[3] = ns;
+        m.hdr[4] = nf * (nf - 1) / 2 * (int)dec.C;
+        m.hdr[5] = nf * ns * (int)dec.C;
+        m.hdr[6] = nv * (nv - 1) / 2 * (int)dec.C;
+        m.hdr[7] = __float_as_int(nf > 0 ? 1.0f / (float)nf : 0.f);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_mfull[slot]);
@@ -488,10 +494,8 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
     float *rows = ring + s_base[st];
     const int nf = m.hdr[0], ns = m.hdr[3], nv = nf + ns;
     // items of the sample in three ranges: fused x fused pairs, fused x staged, staged x staged
-    const uint32_t n_ff = (uint32_t)nf * (uint32_t)(nf - 1) / 2u * dec.C;
-    const uint32_t n_fs = (uint32_t)nf * (uint32_t)ns * dec.C;
-    const uint32_t n_items = (uint32_t)nv * (uint32_t)(nv - 1) / 2u * dec.C;
-    const float inv_nf = nf > 0 ? 1.0f / (float)nf : 0.f;
+    const uint32_t n_ff = (uint32_t)m.hdr[4], n_fs = (uint32_t)m.hdr[5], n_items = (uint32_t)m.hdr[6];
+    const float inv_nf = __int_as_float(m.hdr[7]);
     // (m, n) = row slots of item `item`
     auto item_rows = [&](uint32_t item, int &mi, int &ni, uint32_t &c) {
       uint32_t p;

@@ -1218,6 +1218,8 @@ int ftrl_create(const ftrl_config *cfg, ftrl_handle **out) {
     h->pipeline = env_int("FTRL_B200_PIPELINE", 1);
     h->stable_device_inputs = (cfg->reserved[0] & 1) != 0;
     if (h->pipeline && cfg->mode == FTRL_MODE_BATCH) {
+      // same priority as the compute stream: with a lower one the index phase only runs once the weight-dependent
+      // kernels have no pending CTA left, i.e. not under them at all (measured: the overlap gain vanished)
       FTRL_CUDA(cudaStreamCreateWithFlags(&h->idstream, cudaStreamNonBlocking));
       for (int i = 0; i < 2; i++) {
         FTRL_CUDA(cudaEventCreateWithFlags(&h->ev_id_done[i], cudaEventDisableTiming));

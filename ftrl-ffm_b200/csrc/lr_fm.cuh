@@ -31,8 +31,9 @@ k_lrfm_sample(Batch b, Dims d, Hyper h, float *__restrict__ tab, float4 *__restr
     const int32_t ft = b.feat[r0 + t];
     if (ft < 0 || ft >= d.n_feats) continue;
     const float4 e = lin[ft];
+    // (the stale-by-one w the reference keeps is stored once per row by the row kernels: a store per OCCURRENCE
+    // serialises thousands of writes on the sectors of the hot rows)
     const float w = weight_from<PRECISE>(e.x, f_sqrt<PRECISE>(e.y), h);
-    lin[ft].z = w;
     acc = fmaf(w, b.val[r0 + t], acc);
   }
   if (IS_FM) {
@@ -63,7 +64,6 @@ k_lrfm_sample(Batch b, Dims d, Hyper h, float *__restrict__ tab, float4 *__restr
           sv.v[e] += vx;
           qv.v[e] = fmaf(vx, vx, qv.v[e]);
         }
-        w.store(row + 2 * ld);
       }
       // reduce over the feature slots (lanes with equal lane % Cr); Cr need not be a power of two:
       // gather through shuffles from every slot in a fixed order.
@@ -137,7 +137,9 @@ k_lrfm_rows(Batch b, Dims d, Hyper h, float *__restrict__ tab, float4 *__restric
       for (int r = 0; r < FM_MAX_REGS; r++) {
         a0[r] = a1[r] = 0.f;
         const int f = lane + 32 * r;
-        wv[r] = f < d.k ? row[2 * ld + f] : 0.f;
+        // w = W(n, z) of the pre-update state (what the sample kernel used); stored once per row, by its head chunk
+        wv[r] = f < d.k ? weight_from<PRECISE>(row[f], f_sqrt<PRECISE>(row[ld + f]), h) : 0.f;
+        if (f < d.k && ci.row_head) const_cast<float *>(row)[2 * ld + f] = wv[r];
       }
       for (int p = ci.p0; p < ci.p1; p++) {
         const int64_t t = socc[p];
@@ -170,6 +172,7 @@ k_lrfm_rows(Batch b, Dims d, Hyper h, float *__restrict__ tab, float4 *__restric
       }
       if (lane == 0) {
         float4 e = lin[ci.key];
+        e.z = weight_from<PRECISE>(e.x, f_sqrt<PRECISE>(e.y), h);
         ftrl_apply<PRECISE>(e.x, e.y, e.z, sg, sg2, h);
         lin[ci.key] = e;
       }
@@ -227,6 +230,7 @@ k_lrfm_combine(Dims d, Hyper h, int32_t nnz, float *__restrict__ tab, float4 *__
         sg += t.x; sg2 += t.y;
       }
       float4 e = lin[ci.key];
+      e.z = weight_from<PRECISE>(e.x, f_sqrt<PRECISE>(e.y), h);
       ftrl_apply<PRECISE>(e.x, e.y, e.z, sg, sg2, h);
       lin[ci.key] = e;
     }
