@@ -246,5 +246,6 @@ struct ftrl_handle {
   bool tile_ok = false;
   int tile_ctas_per_sm = 1;
   int tile_f_cap = 0, tile_stride = 0, tile_stride1 = 0, tile_stages = 0, tile_consumers = 0, tile_ipt = 1, tile_meta = 4, tile_dbg = 0, tile_cache = 1, tile_inflight = 4;
+  int tile_ring = 0;  // bytes of the row ring
   size_t tile_smem = 0;
 };

@@ -17,6 +17,7 @@
 //  k_ffm_staged_rows streaming segmented reduction of the staged gradient images: work item = (chunk of
 //                    <= 32 occurrences of one row, 32 float4 vectors); closed-form update, a partial for
 //                    k_ffm_combine, or (sharded runs) the row's sum into its owner's inbox
+//  (the row kernels read one 16-byte descriptor per chunk, built once per batch by k_chunk_desc, prep.cuh)
 //
 // HBM traffic per touched coordinate: rows that occur once: 8 B read (z,n) + 12 B written (z',n',w) = the
 // algorithmic 20 B; other rows: 12 B once (materialise) + 4 B (w) + 4 B (gradient image) per occurrence,
@@ -113,7 +114,8 @@ struct TileGeom {
   int f_cap;        // rows per stage (= n_fields: samples with distinct fields have at most that many)
   int stride;       // floats a fused row (z and n planes) takes in the row ring: 2*ld + pad, conflict-free columns
   int stride1;      // floats a staged row (w plane only) takes: ld + pad1, same residue as `stride` modulo 32 floats
-  int n_stage;      // the row ring holds n_stage * f_cap * stride floats
+  int n_stage;      // the row ring holds at least n_stage * f_cap * stride floats (n_stage all-fused samples) ...
+  int ring_bytes;   // ... and all the shared memory the CTA can get beyond that (multiple of 128)
   int inflight;     // samples that may share the ring (2..TILE_MAX_STAGE)
   int n_meta;       // metadata slots (> n_stage: metadata runs ahead of the row ring)
   int consumers;    // consumer threads (multiple of 32)
@@ -228,19 +230,19 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
   constexpr int NL = 1, NSW = 1;
   const int role = tid < n_cons ? 0 : (tid < n_cons + 32 * NL ? 1 : (tid < n_cons + 32 * (NL + NSW) ? 3 : 2));
   const int ld = d.ld, k = d.k;
-  const int stride = geo.stride, stride1 = geo.stride1, f_cap = geo.f_cap, NS = geo.n_stage, MD = geo.n_meta;
-  const size_t stage_bytes = tile_stage_bytes(f_cap, stride);
-  // The row ring: NS * stage_bytes of shared memory handed out in sample-sized spans.  A fused row takes
-  // `stride` floats (z, n), a staged row `stride1` (w only), so batches with many duplicated rows keep 3-4
-  // samples in flight where all-fused samples keep 2.  Up to TILE_MAX_STAGE samples share the ring.
+  const int stride = geo.stride, stride1 = geo.stride1, f_cap = geo.f_cap, MD = geo.n_meta;
+  // The row ring: geo.ring_bytes of shared memory (at least two all-fused samples; with one CTA per SM everything
+  // the SM has left) handed out in sample-sized spans.  A fused row takes `stride` floats (z, n), a staged row
+  // `stride1` (w only), so batches with many duplicated rows keep 3-4 samples in flight where all-fused samples
+  // keep 2.  Up to TILE_MAX_STAGE samples share the ring.
   constexpr int NSLOT = TILE_MAX_STAGE;
-  const int ring_floats = (int)((size_t)NS * stage_bytes / sizeof(float));
+  const int ring_floats = (int)((size_t)geo.ring_bytes / sizeof(float));
   float *ring = reinterpret_cast<float *>(smem_raw);
   __shared__ int s_base[NSLOT], s_need[NSLOT];
   const size_t meta_bytes = tile_meta_bytes(f_cap);
   const int64_t rs = 3 * (int64_t)ld;
   const uint32_t row_bytes = (uint32_t)(2 * ld * sizeof(float));
-  unsigned char *meta_base = smem_raw + (size_t)NS * stage_bytes;
+  unsigned char *meta_base = smem_raw + (size_t)geo.ring_bytes;
   uint16_t *s_lut = reinterpret_cast<uint16_t *>(meta_base + (size_t)MD * meta_bytes);
 
   auto row_off = [](const RowMeta &rm) { return rm.fk >> 16; };
@@ -284,53 +286,95 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
   if (role == 2) {
     // =========================== metadata warps ===========================
     const int mw = (tid - n_cons - 32 * (NL + NSW)) >> 5;
+    // The per-sample chain of dependent global loads is what bounds a metadata warp (and, with two of them, the
+    // whole CTA: the consumers were waiting for rows a fifth of the time): row_ptr of the NEXT sample is fetched
+    // one iteration ahead, and field / feat / val / occ_pos of a sample are independent loads, so a sample costs
+    // two round trips (CSR entries, then the linear records) instead of four.
     RingCursor mc;
     mc.init(mw, MD);
+    int64_t rp0 = 0, rp1 = 0;
+    if (mw < n_mine) {
+      const int64_t s0 = blockIdx.x + (int64_t)mw * gridDim.x;
+      rp0 = b.row_ptr[s0];
+      rp1 = b.row_ptr[s0 + 1];
+    }
     for (int it = mw; it < n_mine; it += TILE_META_WARPS, mc.advance(TILE_META_WARPS, MD)) {
       const int slot = mc.slot;
+      const int64_t s = blockIdx.x + (int64_t)it * gridDim.x;
+      const int64_t r0 = rp0;
+      const int F = (int)min((int64_t)1 << 20, rp1 - r0);
+      if (it + TILE_META_WARPS < n_mine) {
+        const int64_t sn = s + (int64_t)TILE_META_WARPS * gridDim.x;
+        rp0 = b.row_ptr[sn];
+        rp1 = b.row_ptr[sn + 1];
+      }
+      const int32_t label_s = b.label[s];
       if (mc.round > 0) mbar_wait(&bar_mfree[slot], mc.prev_parity());
       SampleMeta m = sample_meta(slot);
-      const int64_t s = blockIdx.x + (int64_t)it * gridDim.x;
-      const int64_t r0 = b.row_ptr[s];
-      const int F = (int)min((int64_t)1 << 20, b.row_ptr[s + 1] - r0);
       int nf = 0, ns = 0;
       for (int f = lane; f < f_cap; f += 32) m.present[f] = 0;
       __syncwarp();
-      for (int base = 0; base < F; base += 32) {
-        const int t = base + lane;
-        int32_t fl = 0, ft = -1, pos = 0;
-        float x = 0.f;
-        bool ok = false;
-        if (t < F) {
-          fl = b.field[r0 + t];
-          ft = b.feat[r0 + t];
-          x = b.val[r0 + t];
-          ok = feat_valid(d, fl, ft);
-          if (ok) pos = occ_pos[r0 + t];
-        }
-        const bool fz = ok && pos < 0, sg = ok && pos >= 0;
-        const unsigned fm = __ballot_sync(0xffffffffu, fz), sm = __ballot_sync(0xffffffffu, sg);
-        const unsigned below = (1u << lane) - 1;
-        const int idx = fz ? nf + __popc(fm & below) : ns + __popc(sm & below);
-        if (ok && idx < f_cap) {
-          const int sl = fz ? idx : f_cap - 1 - idx;
-          RowMeta rm;
-          rm.fk = fl * k;
-          rm.x = x;
-          rm.pos = pos;
-          if ((ft & rsp.Gm1) == rsp.rank) {
-            rm.loc = ft >> rsp.log2G;
-            m.lin[sl] = rsp.lin[rm.loc];
-          } else {  // remote rows are never fused: pos >= 0, the row's cache slot is its sorted head position
-            const int32_t head = scan[rm.pos].start;
-            rm.loc = -1 - head;
-            m.lin[sl] = make_float4(0.f, 0.f, rsp.rc_lin[head], 0.f);
+      for (int base = 0; base < F; base += 64) {
+        // two blocks of 32 CSR entries at a time: all their loads are issued before the first use
+        int32_t fl[2], ft[2], pos[2];
+        float x[2];
+        bool ok[2];
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+          const int t = base + 32 * u + lane;
+          fl[u] = 0; ft[u] = -1; pos[u] = 0; x[u] = 0.f; ok[u] = false;
+          if (t < F) {
+            fl[u] = b.field[r0 + t];
+            ft[u] = b.feat[r0 + t];
+            x[u] = b.val[r0 + t];
+            pos[u] = occ_pos[r0 + t];  // (written for every occurrence, valid or not: no need to wait for `ok`)
           }
-          m.row[sl] = rm;
-          m.present[fl] = 1;
         }
-        nf += __popc(fm);
-        ns += __popc(sm);
+        int sl[2];
+        bool put[2];
+        RowMeta rm[2];
+        float4 le[2];
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+          ok[u] = base + 32 * u + lane < F && feat_valid(d, fl[u], ft[u]);
+          const bool fz = ok[u] && pos[u] < 0, sg = ok[u] && pos[u] >= 0;
+          const unsigned fm = __ballot_sync(0xffffffffu, fz), sm = __ballot_sync(0xffffffffu, sg);
+          const unsigned below = (1u << lane) - 1;
+          const int idx = fz ? nf + __popc(fm & below) : ns + __popc(sm & below);
+          put[u] = ok[u] && idx < f_cap;
+          sl[u] = fz ? idx : f_cap - 1 - idx;
+          nf += __popc(fm);
+          ns += __popc(sm);
+          rm[u].fk = fl[u] * k;
+          rm[u].x = x[u];
+          rm[u].pos = pos[u];
+          rm[u].loc = 0;
+          le[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+          if (!put[u]) continue;
+          if ((ft[u] & rsp.Gm1) == rsp.rank) {
+            rm[u].loc = ft[u] >> rsp.log2G;
+            le[u] = rsp.lin[rm[u].loc];
+          } else {  // remote rows are never fused: pos >= 0, the row's cache slot is its sorted head position
+            const int32_t head = scan[pos[u]].start;
+            rm[u].loc = -1 - head;
+            le[u].z = rsp.rc_lin[head];
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+          if (!put[u]) continue;
+          m.lin[sl[u]] = le[u];
+          m.row[sl[u]] = rm[u];
+          m.present[fl[u]] = 1;
+          if (geo.dbg & 64) {  // experiment: L2 prefetch of the row several samples before the loader copies it
+            if (rm[u].pos < 0) bulk_prefetch_l2(rsp.tab + (int64_t)rm[u].loc * rs, row_bytes);
+            else if (rm[u].loc >= 0) bulk_prefetch_l2(rsp.tab + (int64_t)rm[u].loc * rs + 2 * ld, row_bytes / 2);
+            else bulk_prefetch_l2(rsp.rc_w + (int64_t)(-1 - rm[u].loc) * ld, row_bytes / 2);
+          }
+        }
       }
       // distinct fields: nf + ns <= f_cap (the clamps only guard malformed input)
       nf = min(nf, f_cap);
@@ -359,7 +403,7 @@ k_ffm_tile(Batch b, Dims d, Hyper h, ItemDecode dec, TileGeom geo, const int32_t
       }
       if (lane == 0) {
         m.hdr[0] = nf;
-        m.hdr[1] = b.label[s];
+        m.hdr[1] = label_s;
         m.hdr[2] = need;
         m.hdr[3] = ns;
         m.hdr[4] = nf * (nf - 1) / 2 * (int)dec.C;

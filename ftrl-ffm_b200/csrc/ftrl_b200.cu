@@ -379,6 +379,7 @@ static void launch_tile(ftrl_handle *h, const Batch &b, const ItemDecode &dec, f
   geo.stride1 = h->tile_stride1;
   geo.inflight = h->tile_inflight;
   geo.n_stage = h->tile_stages;
+  geo.ring_bytes = h->tile_ring;
   geo.n_meta = h->tile_meta;
   geo.consumers = h->tile_consumers;
   geo.dbg = h->tile_dbg;
@@ -1202,6 +1203,14 @@ int ftrl_create(const ftrl_config *cfg, ftrl_handle **out) {
         h->tile_ipt = std::max(1, ipt);
         h->tile_ctas_per_sm = ctas;
         h->tile_smem = tile_smem_bytes(d.n_fields, stride, stages, metas);
+        h->tile_ring = (int)(stage * stages);
+        if (ctas == 1 && env_int("FTRL_B200_TILE_BIGRING", 1)) {
+          // one CTA per SM: the variable-span row ring takes all the shared memory that is left (Zipf batches keep
+          // 3.8 instead of 3.4 samples in flight at cfg4)
+          const size_t extra = (budget - h->tile_smem) / 128 * 128;
+          h->tile_ring += (int)extra;
+          h->tile_smem += extra;
+        }
         const int sm = (int)h->tile_smem;
 #define TILE_ATTR(P, I)                                                                                              \
   FTRL_CUDA(cudaFuncSetAttribute(k_ffm_tile<P, I, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm)); \

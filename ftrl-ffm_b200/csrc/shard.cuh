@@ -3,19 +3,23 @@
 // Row `feat` of lin / tab lives on rank feat mod G at local row feat div G; the samples of a
 // global minibatch are split across ranks.  Every rank runs the single-GPU pipeline on its own samples; what
 // crosses NVLink is one w plane IN and one gradient sum OUT per DISTINCT (row, rank) pair -- not per
-// occurrence -- because duplicates are reduced where the samples live.  Per step, on every rank (all on its
-// stream):
+// occurrence -- because duplicates are reduced where the samples live.  A step has two phases on every rank:
+//
+// INDEX phase (ids only; with early inputs it runs on its own stream and barrier channel, under the weight phase
+// of the PREVIOUS step -- train_device_sharded in ftrl_b200.cu):
 //   S1  k_prep_rows, radix sort by feature id, segmented OR-scan of the field masks, list of the distinct
-//       rows of the local batch (k_publish_unique: feature id, sorted head position, "single occurrence",
-//       field mask); the count goes to every peer
-//   --  barrier 1 (device-side, flags in peer memory)
-//   S2  owner side: DeviceSelect over ALL ranks' distinct-row lists (read over NVLink) keeps the rows this
-//       rank owns, in (rank, row) order -> deterministic; radix sort by local row = the contribution list;
-//       k_contrib_class: a row touched once, by its owner only, is finalised inside that sample ("fused");
-//       a row touched by its owner only is reduced and applied there; every other contribution gets a slot
-//       of the owner's inbox (written into the contributing rank's dst_at); k_owner_materialise writes
-//       w = W(n,z) for the slices the global batch touches into the table and pushes it into the row cache
-//       of every remote rank that touches the row (one NVLink store stream per distinct (row, rank))
+//       rows of the local batch, published BUCKETED BY OWNER (k_owner_keys, one radix pass, k_publish_unique:
+//       feature id, sorted head position, "single occurrence", field mask; k_publish_bounds: bucket bounds)
+//   --  barrier 1 (device-side, flags in peer memory, index channel)
+//   S2a owner side: k_fill_owned copies the run every rank published for this owner (rank order -> deterministic),
+//       radix sort by local row = the contribution list; k_contrib_class: a row touched once, by its owner only,
+//       is finalised inside that sample ("fused"); a row touched by its owner only is reduced and applied there;
+//       every other contribution gets a slot of the owner's inbox (written into the contributing rank's dst_at);
+//       then the local chunk list and its descriptors (k_chunk_desc)
+// WEIGHT phase (compute stream, weight channel):
+//   S2b k_owner_materialise writes w = W(n,z) for the slices the global batch touches into the table and pushes
+//       it into the row cache of every remote rank that touches the row (one NVLink store stream per distinct
+//       (row, rank))
 //   --  barrier 2
 //   S3  k_ffm_tile over the local samples (all addresses local: shard rows, row cache, staging);
 //       k_ffm_staged_rows / k_ffm_combine reduce the local duplicates and store each row's (sum g, sum g^2)
