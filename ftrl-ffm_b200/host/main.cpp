@@ -15,6 +15,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <deque>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <future>
 #include <numeric>
 #include <random>
@@ -134,14 +137,23 @@ class Trainer {
       PinnedCsr &p = rk.pin[pin];
       const size_t rows = b1 - b0;
       size_t nnz = 0;
-      for (size_t i = b0; i < b1; i++) {
-        const size_t r = order ? (size_t)order[i] : i;
-        nnz += (size_t)(data.row_ptr[r + 1] - data.row_ptr[r]);
+      if (order) {
+        for (size_t i = b0; i < b1; i++) nnz += (size_t)(data.row_ptr[order[i] + 1] - data.row_ptr[order[i]]);
+      } else {
+        nnz = (size_t)(data.row_ptr[b1] - data.row_ptr[b0]);
       }
       p.ensure(rows, nnz);
       size_t w = 0;
       p.row_ptr[0] = 0;
-      for (size_t i = b0; i < b1; i++) {
+      if (!order && rows) {  // file order: the share is one contiguous span of every array
+        const size_t a = (size_t)data.row_ptr[b0];
+        memcpy(p.field, data.field.data() + a, nnz * sizeof(int32_t));
+        memcpy(p.feat, data.feat.data() + a, nnz * sizeof(int32_t));
+        memcpy(p.val, data.val.data() + a, nnz * sizeof(float));
+        memcpy(p.label, data.label.data() + b0, rows * sizeof(int32_t));
+        for (size_t i = 0; i < rows; i++) p.row_ptr[i + 1] = data.row_ptr[b0 + i + 1] - (int64_t)a;
+      }
+      for (size_t i = b0; order && i < b1; i++) {
         const size_t r = order ? (size_t)order[i] : i;
         const size_t a = (size_t)data.row_ptr[r], n = (size_t)data.row_ptr[r + 1] - a;
         memcpy(p.field + w, data.field.data() + a, n * sizeof(int32_t));
@@ -298,17 +310,55 @@ double stream_file(Trainer &tr, const std::string &path, bool libffm, int n_thre
     fprintf(stderr, "open file <%s> error. \n", path.c_str());  // pc_task.cpp:8
     exit(EXIT_FAILURE);
   }
-  std::vector<char> buf(32u << 20);
+  constexpr size_t kBlock = 32u << 20;
+  // A regular file is read with one pread per parser thread, in parallel, into a buffer that is reused from block
+  // to block (no page faults after the first block, no serial 32 MB read); anything else (a pipe, a FIFO) goes
+  // through fread.  The parser threads are persistent (host::WorkerPool).
+  off_t file_len = -1, file_pos = 0;
+  {
+    struct stat st;
+    if (fstat(fileno(f), &st) == 0 && S_ISREG(st.st_mode)) file_len = st.st_size;
+  }
+  host::WorkerPool pool(std::max(1, n_threads));
+  const int fd = fileno(f);
+  std::vector<char> buf(kBlock + (1u << 20));
   size_t have = 0;
   bool eof = false;
+  std::vector<host::Csr> scratch;  // per-thread parts, reused from block to block
   // producer: next block of complete lines -> CSR; false when the file is exhausted
   auto produce = [&](host::Csr *out) -> bool {
     out->clear();
     while (!eof || have) {
       if (!eof) {
-        const size_t got = fread(buf.data() + have, 1, buf.size() - have, f);
+        size_t got = 0;
+        const size_t room = buf.size() - have;
+        if (file_len >= 0) {
+          const size_t want = (size_t)std::min<off_t>((off_t)room, file_len - file_pos);
+          const int nt = pool.size();
+          const size_t per = (want + nt - 1) / nt;
+          std::vector<size_t> done(nt, 0);
+          pool.run(nt, [&](int i) {
+            const size_t o0 = std::min(want, per * (size_t)i), o1 = std::min(want, o0 + per);
+            size_t d = 0;
+            while (o0 + d < o1) {
+              const ssize_t r = pread(fd, buf.data() + have + o0 + d, o1 - o0 - d, file_pos + (off_t)(o0 + d));
+              if (r <= 0) break;
+              d += (size_t)r;
+            }
+            done[i] = d;
+          });
+          for (int i = 0; i < nt; i++) {  // a short read (file truncated meanwhile) ends the stream there
+            const size_t o0 = std::min(want, per * (size_t)i), o1 = std::min(want, o0 + per);
+            got += done[i];
+            if (done[i] < o1 - o0) break;
+          }
+          file_pos += (off_t)got;
+          if (got == 0 || file_pos >= file_len) eof = true;
+        } else {
+          got = fread(buf.data() + have, 1, room, f);
+          if (got == 0) eof = true;
+        }
         have += got;
-        if (got == 0) eof = true;
       }
       size_t use = have;
       if (!eof) {  // cut at the last complete line
@@ -319,7 +369,7 @@ double stream_file(Trainer &tr, const std::string &path, bool libffm, int n_thre
         }
       }
       if (use == 0) return false;
-      host::parse_buffer(buf.data(), use, libffm, n_threads, *out);
+      host::parse_buffer(buf.data(), use, libffm, n_threads, *out, &scratch, &pool);
       memmove(buf.data(), buf.data() + use, have - use);
       have -= use;
       return true;
