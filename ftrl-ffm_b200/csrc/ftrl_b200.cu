@@ -285,9 +285,10 @@ static void ensure_workspace(ftrl_handle *h, int64_t n_rows, int64_t nnz) {
     h->ukey.ensure(2 * nc);
     h->uinfo.ensure(2 * nc);
     h->umask.ensure(2 * nc);
-    h->rc_w.ensure((size_t)nc * h->dims.ld);
+    // (LR has no latent row: the buffers the peers map still have to exist)
+    h->rc_w.ensure(std::max<size_t>(64, (size_t)nc * h->dims.ld));
     h->rc_lin.ensure(nc);
-    h->inbox.ensure((size_t)oc * 2 * h->dims.ld);
+    h->inbox.ensure(std::max<size_t>(64, (size_t)oc * 2 * h->dims.ld));
     h->inbox_lin.ensure(oc);
   }
   h->fused_sorted.ensure(nc);
@@ -484,17 +485,55 @@ static void run_lrfm_batch(ftrl_handle *h, const Batch &b, float *logit_out) {
   const int grid = h->n_sms * 4;
   {
     PhaseScope ps(h, PH_ROWS);
-    k_lrfm_rows<PRECISE, IS_FM, 8><<<grid, 256, 0, h->compute>>>(b, d, h->hyper, h->tab, h->lin, h->chunk, h->n_chunks.p,
-                                                                 h->chunk_pos.p, h->skey.p, h->socc.p, h->scan.p,
-                                                                 h->occ_row.p, h->g.p, h->S.p, h->part.p, h->part_lin.p);
+    k_lrfm_rows<PRECISE, IS_FM, 8, false><<<grid, 256, 0, h->compute>>>(b, d, h->hyper, h->tab, h->lin, h->chunk, h->n_chunks.p,
+                                                                        h->chunk_pos.p, h->skey.p, h->socc.p, h->scan.p,
+                                                                        h->occ_row.p, h->g.p, h->S.p, h->part.p, h->part_lin.p,
+                                                                        RowSpace{}, Export{});
     FTRL_CUDA(cudaGetLastError());
     launched(h, PH_ROWS);
   }
   {
     PhaseScope ps(h, PH_COMBINE);
-    k_lrfm_combine<PRECISE, IS_FM, 8><<<grid, 256, 0, h->compute>>>(d, h->hyper, (int32_t)b.nnz, h->tab, h->lin, h->chunk,
-                                                                    h->n_chunks.p, h->chunk_pos.p, h->skey.p, h->scan.p,
-                                                                    h->part.p, h->part_lin.p);
+    k_lrfm_combine<PRECISE, IS_FM, 8, false><<<grid, 256, 0, h->compute>>>(d, h->hyper, (int32_t)b.nnz, h->tab, h->lin, h->chunk,
+                                                                           h->n_chunks.p, h->chunk_pos.p, h->skey.p, h->scan.p,
+                                                                           h->part.p, h->part_lin.p, Export{});
+    FTRL_CUDA(cudaGetLastError());
+    launched(h, PH_COMBINE);
+  }
+}
+
+// sharded LR / FM: sample kernel over the materialised w (shard rows + row cache), row kernels with Export
+template <int VEC, bool PRECISE, bool IS_FM>
+static void run_lrfm_batch_sharded(ftrl_handle *h, const Batch &b, float *logit_out) {
+  const Dims &d = h->dims;
+  if (b.n_rows > 0) {
+    PhaseScope ps(h, PH_SAMPLE);
+    const unsigned grid = (unsigned)((b.n_rows * 32 + 255) / 256);
+    k_lrfm_sample_sh<VEC, PRECISE, IS_FM><<<grid, 256, 0, h->compute>>>(b, d, h->hyper, h->rowspace, h->occ_pos.p, h->scan.p,
+                                                                        h->bias, h->S.p, h->g.p, logit_out);
+    FTRL_CUDA(cudaGetLastError());
+    launched(h, PH_SAMPLE);
+  }
+}
+template <bool PRECISE, bool IS_FM>
+static void run_lrfm_rows_sharded(ftrl_handle *h, const Batch &b) {
+  const Dims &d = h->dims;
+  if (b.nnz == 0) return;
+  const int grid = h->n_sms * 4;
+  {
+    PhaseScope ps(h, PH_ROWS);
+    k_lrfm_rows<PRECISE, IS_FM, 8, true><<<grid, 256, 0, h->compute>>>(b, d, h->hyper, h->tab, h->lin, h->chunk, h->n_chunks.p,
+                                                                       h->chunk_pos.p, h->skey.p, h->socc.p, h->scan.p,
+                                                                       h->occ_row.p, h->g.p, h->S.p, h->part.p, h->part_lin.p,
+                                                                       h->rowspace, h->exportd);
+    FTRL_CUDA(cudaGetLastError());
+    launched(h, PH_ROWS);
+  }
+  {
+    PhaseScope ps(h, PH_COMBINE);
+    k_lrfm_combine<PRECISE, IS_FM, 8, true><<<grid, 256, 0, h->compute>>>(d, h->hyper, (int32_t)b.nnz, h->tab, h->lin, h->chunk,
+                                                                          h->n_chunks.p, h->chunk_pos.p, h->skey.p, h->scan.p,
+                                                                          h->part.p, h->part_lin.p, h->exportd);
     FTRL_CUDA(cudaGetLastError());
     launched(h, PH_COMBINE);
   }
@@ -690,8 +729,8 @@ static void predict_device(ftrl_handle *h, const Batch &b, int output_prob, floa
     else k_ffm_predict<1, 256><<<grid, 256, 0, h->compute>>>(b, d, make_item_decode(d.k, 1), h->shards, h->bias, h->pair_lut, output_prob, out, lg_side);
   } else {
     const unsigned grid = (unsigned)((b.n_rows * 32 + 255) / 256);
-    if (d.model_type == FTRL_FM) k_lrfm_predict<true><<<grid, 256, 0, h->compute>>>(b, d, h->tab, h->lin, h->bias, output_prob, out, lg_side);
-    else k_lrfm_predict<false><<<grid, 256, 0, h->compute>>>(b, d, h->tab, h->lin, h->bias, output_prob, out, lg_side);
+    if (d.model_type == FTRL_FM) k_lrfm_predict<true><<<grid, 256, 0, h->compute>>>(b, d, h->shards, h->bias, output_prob, out, lg_side);
+    else k_lrfm_predict<false><<<grid, 256, 0, h->compute>>>(b, d, h->shards, h->bias, output_prob, out, lg_side);
   }
   FTRL_CUDA(cudaGetLastError());
   launched(h, PH_PREDICT);
@@ -918,6 +957,7 @@ static void train_device_sharded(ftrl_handle *h, const Batch &b, float *logit_ou
   unsigned long long *const umask = h->umask.p + (int64_t)par * h->nnz_cap;
   const bool piped = allow_pipe && h->pipeline && h->idstream && !h->profiling && (inputs_ready || h->stable_device_inputs);
   cudaStream_t main_stream = h->compute;
+  const bool is_ffm = d.model_type == FTRL_FFM;
 
   // ------------------------------- index phase -------------------------------
   if (piped) {
@@ -957,8 +997,10 @@ static void train_device_sharded(ftrl_handle *h, const Batch &b, float *logit_ou
         k_occ_class<<<(nnz + 255) / 256, 256, 0, h->compute>>>(nnz, sentinel, 0, h->skey.p, h->socc.p, h->occ_row.p, h->sflags.p,
                                                                h->fused_sorted.p, h->occ_pos.p);
         size_t bytes = h->cub_bytes;
-        auto mit = thrust::make_transform_iterator(cnt, MaskIn{h->skey.p, h->socc.p, h->pmask.p});
-        FTRL_CUDA(cub::DeviceScan::InclusiveScan(h->cub_tmp.p, bytes, mit, h->mscan.p, MaskScanOp(), nnz, h->compute));
+        if (is_ffm) {  // which field slices of a row does this rank's batch touch (LR / FM rows have no slices)
+          auto mit = thrust::make_transform_iterator(cnt, MaskIn{h->skey.p, h->socc.p, h->pmask.p});
+          FTRL_CUDA(cub::DeviceScan::InclusiveScan(h->cub_tmp.p, bytes, mit, h->mscan.p, MaskScanOp(), nnz, h->compute));
+        }
         bytes = h->cub_bytes;
         FTRL_CUDA(cub::DeviceSelect::If(h->cub_tmp.p, bytes, cnt, h->uhead.p, h->n_uall.p, nnz, RowHeadPred{h->skey.p}, h->compute));
       }
@@ -970,7 +1012,7 @@ static void train_device_sharded(ftrl_handle *h, const Batch &b, float *logit_ou
         FTRL_CUDA(cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, bytes, h->bkey.p, h->bkey_s.p, h->bidx.p, h->perm.p, nnz, 0,
                                                   h->log2G + 1, h->compute));
         k_publish_unique<<<(nnz + 255) / 256, 256, 0, h->compute>>>(nnz, h->G, h->bkey_s.p, h->perm.p, h->uhead.p, h->n_uall.p, h->skey.p,
-                                                                   h->mscan.p, ukey, uinfo, umask);
+                                                                   is_ffm ? h->mscan.p : nullptr, ukey, uinfo, umask);
       }
       k_publish_bounds<<<1, 32, 0, h->compute>>>(pr, par, nnz, h->bkey_s.p, h->batch_flags.p);
       FTRL_CUDA(cudaGetLastError());
@@ -980,13 +1022,13 @@ static void train_device_sharded(ftrl_handle *h, const Batch &b, float *logit_ou
     {
       // owner side: contributions (row, rank) of the rows this rank owns
       PhaseScope ps(h, PH_EXCHANGE);
-      k_merge_flags<<<1, 1, 0, h->compute>>>(pr, par, h->batch_flags.p, h->d_err);
+      k_merge_flags<<<1, 1, 0, h->compute>>>(pr, par, is_ffm ? 1 : 0, h->batch_flags.p, h->d_err);
       k_fill_owned<<<(oc + 255) / 256, 256, 0, h->compute>>>(pr, par, oc, lsent, step_tag, h->n_sel.p, h->okey.p, h->osrc.p, h->d_err);
       size_t bytes = h->cub_bytes;
       FTRL_CUDA(cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, bytes, h->okey.p, h->ckey.p, h->osrc.p, h->csrc.p, oc, 0,
                                                 key_bits((int32_t)h->n_local), h->compute));
-      k_contrib_class<<<(oc + 255) / 256, 256, 0, h->compute>>>(pr, oc, h->n_sel.p, lsent, h->ckey.p, h->csrc.p, h->socc.p,
-                                                               h->cflag.p, h->fused_sorted.p, h->occ_pos.p);
+      k_contrib_class<<<(oc + 255) / 256, 256, 0, h->compute>>>(pr, oc, h->n_sel.p, lsent, is_ffm ? 1 : 0, h->ckey.p, h->csrc.p,
+                                                               h->socc.p, h->cflag.p, h->fused_sorted.p, h->occ_pos.p);
       FTRL_CUDA(cudaGetLastError());
       launched(h, PH_EXCHANGE, 3);
     }
@@ -1001,8 +1043,9 @@ static void train_device_sharded(ftrl_handle *h, const Batch &b, float *logit_ou
         FTRL_CUDA(cub::DeviceSelect::If(h->cub_tmp.p, bytes, cnt, h->chunk_pos.p, h->n_chunks.p, nnz,
                                         ChunkHeadPred{h->skey.p, h->scan.p, h->fused_sorted.p, sentinel, h->chunk}, h->compute));
         k_terminate<<<1, 1, 0, h->compute>>>(h->chunk_pos.p, h->n_chunks.p, nnz);
-        k_chunk_desc<8><<<h->n_sms * 8, 256, 0, h->compute>>>(nnz, sentinel, h->chunk, h->n_chunks.p, h->chunk_pos.p, h->skey.p,
-                                                             h->scan.p, h->cdesc.p);
+        if (is_ffm)
+          k_chunk_desc<8><<<h->n_sms * 8, 256, 0, h->compute>>>(nnz, sentinel, h->chunk, h->n_chunks.p, h->chunk_pos.p, h->skey.p,
+                                                               h->scan.p, h->cdesc.p);
       } else {
         FTRL_CUDA(cudaMemsetAsync(h->n_chunks.p, 0, sizeof(int32_t), h->compute));
       }
@@ -1025,18 +1068,26 @@ static void train_device_sharded(ftrl_handle *h, const Batch &b, float *logit_ou
   {
     PhaseScope ps(h, PH_EXCHANGE);
     // the cub scratch is shared by the two phases' sorts: this phase has none
-    k_owner_materialise<PRECISE, 256><<<grid, 256, 0, h->compute>>>(pr, d, h->hyper, oc, h->n_sel.p, h->batch_flags.p,
-                                                                    h->ckey.p, h->csrc.p, h->cflag.p, h->tab, h->lin);
+    k_owner_materialise<PRECISE, 256><<<grid, 256, 0, h->compute>>>(pr, d, h->hyper, is_ffm ? 0 : 1, oc, h->n_sel.p,
+                                                                    h->batch_flags.p, h->ckey.p, h->csrc.p, h->cflag.p, h->tab,
+                                                                    h->lin);
     FTRL_CUDA(cudaGetLastError());
     launched(h, PH_EXCHANGE);
     peer_barrier(h, pr, 0);  // 2: classes / inbox slots are known everywhere, w of the touched slices is materialised
     k_check_abort<<<1, 1, 0, h->compute>>>(pr, par, step_tag, h->batch_flags.p, h->d_err);
     FTRL_CUDA(cudaGetLastError());
   }
-  const ItemDecode dec = make_item_decode(d.k, 4);
-  {
+  if (is_ffm) {
+    const ItemDecode dec = make_item_decode(d.k, 4);
     PhaseScope ps(h, PH_SAMPLE);
     if (b.n_rows > 0) launch_tile<PRECISE>(h, b, dec, logit_out);
+  } else if (d.model_type == FTRL_FM) {
+    const int vec = pick_vec(d.k);
+    if (vec == 4) run_lrfm_batch_sharded<4, PRECISE, true>(h, b, logit_out);
+    else if (vec == 2) run_lrfm_batch_sharded<2, PRECISE, true>(h, b, logit_out);
+    else run_lrfm_batch_sharded<1, PRECISE, true>(h, b, logit_out);
+  } else {
+    run_lrfm_batch_sharded<1, PRECISE, false>(h, b, logit_out);
   }
   {
     PhaseScope ps(h, PH_REDUCE);
@@ -1046,19 +1097,23 @@ static void train_device_sharded(ftrl_handle *h, const Batch &b, float *logit_ou
     FTRL_CUDA(cudaGetLastError());
     launched(h, PH_REDUCE, 2);
   }
-  {
-    // local duplicates are reduced here; each row's sum goes to its owner's inbox (or is applied here)
-    PhaseScope ps(h, PH_ROWS);
-    launch_staged_rows<PRECISE>(h, b);
-  }
-  {
+  if (is_ffm) {
+    {
+      // local duplicates are reduced here; each row's sum goes to its owner's inbox (or is applied here)
+      PhaseScope ps(h, PH_ROWS);
+      launch_staged_rows<PRECISE>(h, b);
+    }
     PhaseScope ps(h, PH_COMBINE);
     k_ffm_combine<PRECISE, 256><<<grid, 256, 0, h->compute>>>(d, h->hyper, h->tab, h->lin, h->n_chunks.p, h->cdesc.p, h->part.p,
                                                               h->part_lin.p, h->exportd);
     FTRL_CUDA(cudaGetLastError());
     launched(h, PH_COMBINE);
-    peer_barrier(h, pr, 0);  // 3: every contribution is in its owner's inbox, the bias partials are exchanged
+  } else if (d.model_type == FTRL_FM) {
+    run_lrfm_rows_sharded<PRECISE, true>(h, b);
+  } else {
+    run_lrfm_rows_sharded<PRECISE, false>(h, b);
   }
+  peer_barrier(h, pr, 0);  // 3: every contribution is in its owner's inbox, the bias partials are exchanged
   {
     PhaseScope ps(h, PH_APPLY);
     k_owner_apply<PRECISE, 256><<<grid, 256, 0, h->compute>>>(pr, d, h->hyper, oc, h->n_sel.p, h->batch_flags.p, h->ckey.p,
@@ -1150,8 +1205,7 @@ int ftrl_create(const ftrl_config *cfg, ftrl_handle **out) {
     if (h->G > 1) {
       if (h->G > MAX_SHARDS || (h->G & (h->G - 1))) throw ArgFail{"world_size must be 1, 2, 4 or 8"};
       if (h->rank < 0 || h->rank >= h->G) throw ArgFail{"rank out of range"};
-      if (cfg->model_type != FTRL_FFM || cfg->mode != FTRL_MODE_BATCH)
-        throw ArgFail{"feature-sharded multi-GPU runs support FFM in minibatch mode only"};
+      if (cfg->mode != FTRL_MODE_BATCH) throw ArgFail{"feature-sharded multi-GPU runs are minibatch mode only"};
       if (cfg->max_batch_rows <= 0 || cfg->max_batch_nnz <= 0)
         throw ArgFail{"multi-GPU runs need max_batch_rows / max_batch_nnz (buffers are mapped by peers, they cannot grow)"};
       if (cfg->max_batch_nnz >= (1ll << SRC_SHIFT)) throw ArgFail{"max_batch_nnz must be < 2^28 in multi-GPU runs"};
@@ -1236,7 +1290,8 @@ int ftrl_create(const ftrl_config *cfg, ftrl_handle **out) {
       }
       FTRL_CUDA(cudaEventCreateWithFlags(&h->ev_id_tail, cudaEventDisableTiming));
     }
-    if (h->G > 1 && !h->tile_ok) throw ArgFail{"multi-GPU runs need the tile path (n_factors % 4 == 0, sample tile must fit shared memory)"};
+    if (h->G > 1 && d.model_type == FTRL_FFM && !h->tile_ok)
+      throw ArgFail{"multi-GPU FFM runs need the tile path (n_factors % 4 == 0, n_fields <= 64, sample tile must fit shared memory)"};
     const int64_t n = std::max<int64_t>(1, h->n_local);
     FTRL_CUDA(cudaMalloc(&h->lin, page_round(sizeof(float4) * n)));
     FTRL_CUDA(cudaMalloc(&h->bias, sizeof(float4)));
@@ -1246,6 +1301,10 @@ int ftrl_create(const ftrl_config *cfg, ftrl_handle **out) {
     FTRL_CUDA(cudaMalloc(&h->pair_lut, sizeof(uint32_t) * PAIR_LUT_N));
     k_build_pair_lut<<<(PAIR_LUT_N + 255) / 256, 256, 0, h->compute>>>(h->pair_lut);
     k_init_lin<<<(unsigned)((n + 255) / 256), 256, 0, h->compute>>>(h->lin, n, cfg->init_mean, cfg->init_stddev, cfg->seed, h->G, h->rank);
+    if (!d.row_len && h->G > 1) {  // sharded LR: a placeholder the peers can map (no latent table)
+      FTRL_CUDA(cudaMalloc(&h->tab, page_round(64)));
+      FTRL_CUDA(cudaMemsetAsync(h->tab, 0, 64, h->compute));
+    }
     if (d.row_len) {
       FTRL_CUDA(cudaMalloc(&h->tab, page_round(sizeof(float) * 3 * (size_t)d.ld * (size_t)n)));
       const int64_t q = n * (d.ld / 4);

@@ -96,20 +96,117 @@ k_lrfm_sample(Batch b, Dims d, Hyper h, float *__restrict__ tab, float4 *__restr
 }
 
 // ---------------------------------------------------------------------------------------------
+// sharded runs (shard.cuh): the same sample kernel over materialised w.  The owner of every row the GLOBAL batch
+// touches has written w = W(n,z) into its shard (lin.z, the w plane of tab) and pushed it into the row cache of
+// every remote rank that touches the row (rc_lin / rc_w, indexed by the row's sorted head position on that rank),
+// so a sample only reads local memory: shard rows for the ids this rank owns, the cache for the others.
+// ---------------------------------------------------------------------------------------------
+template <int VEC, bool PRECISE, bool IS_FM>
+__global__ void __launch_bounds__(256)
+k_lrfm_sample_sh(Batch b, Dims d, Hyper h, const __grid_constant__ RowSpace rsp, const int32_t *__restrict__ occ_pos,
+                 const SegScan *__restrict__ scan, const float4 *__restrict__ bias, float *__restrict__ S,
+                 float *__restrict__ g_out, float *__restrict__ logit_out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (s >= b.n_rows) return;
+  const int64_t r0 = b.row_ptr[s];
+  const int F = (int)(b.row_ptr[s + 1] - r0);
+  const int64_t ld = d.ld, rs = 3 * ld;
+  // w of occurrence t: (linear w, latent w row)
+  auto locate = [&](int64_t t, int32_t ft, float &wl, const float *&wrow) {
+    if ((ft & rsp.Gm1) == rsp.rank) {
+      const int64_t loc = ft >> rsp.log2G;
+      wl = rsp.lin[loc].z;
+      wrow = rsp.tab + loc * rs + 2 * ld;
+    } else {
+      const int32_t head = scan[occ_pos[t]].start;
+      wl = rsp.rc_lin[head];
+      wrow = rsp.rc_w + (int64_t)head * ld;
+    }
+  };
+  float acc = 0.f;
+  for (int t = lane; t < F; t += 32) {
+    const int32_t ft = b.feat[r0 + t];
+    if (ft < 0 || ft >= d.n_feats) continue;
+    float wl;
+    const float *wrow;
+    locate(r0 + t, ft, wl, wrow);
+    acc = fmaf(wl, b.val[r0 + t], acc);
+  }
+  if (IS_FM) {
+    const int C = d.k / VEC;
+    for (int cb = 0; cb < C; cb += 32) {
+      const int Cr = min(C - cb, 32);
+      const int slots = 32 / Cr;
+      const int j = lane / Cr, c = cb + lane % Cr;
+      const bool lane_on = j < slots;
+      Vec<VEC> sv, qv;
+#pragma unroll
+      for (int e = 0; e < VEC; e++) sv.v[e] = qv.v[e] = 0.f;
+      for (int t0 = 0; t0 < F; t0 += slots) {
+        const int t = t0 + j;
+        if (!lane_on || t >= F) continue;
+        const int32_t ft = b.feat[r0 + t];
+        if (ft < 0 || ft >= d.n_feats) continue;
+        const float x = b.val[r0 + t];
+        float wl;
+        const float *wrow;
+        locate(r0 + t, ft, wl, wrow);
+        Vec<VEC> w;
+        w.load(wrow + c * VEC);
+#pragma unroll
+        for (int e = 0; e < VEC; e++) {
+          const float vx = w.v[e] * x;
+          sv.v[e] += vx;
+          qv.v[e] = fmaf(vx, vx, qv.v[e]);
+        }
+      }
+      Vec<VEC> st, qt;
+#pragma unroll
+      for (int e = 0; e < VEC; e++) st.v[e] = qt.v[e] = 0.f;
+      for (int jj = 0; jj < slots; jj++) {
+        const int src = jj * Cr + lane % Cr;
+#pragma unroll
+        for (int e = 0; e < VEC; e++) {
+          st.v[e] += __shfl_sync(0xffffffffu, sv.v[e], src);
+          qt.v[e] += __shfl_sync(0xffffffffu, qv.v[e], src);
+        }
+      }
+      if (lane < Cr) {
+#pragma unroll
+        for (int e = 0; e < VEC; e++) acc += 0.5f * (st.v[e] * st.v[e] - qt.v[e]);
+        st.store(S + s * (int64_t)d.k + (int64_t)(cb + lane) * VEC);
+      }
+    }
+  }
+  float logit = warp_sum(acc);
+  if (lane == 0) {
+    const float4 bz = *bias;
+    logit += weight_from<PRECISE>(bz.x, f_sqrt<PRECISE>(bz.y), h);
+    const int y = b.label[s];
+    g_out[s] = sigmoid_f(logit) - (float)y;
+    logit_out[s] = logit;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // row kernel, warp per chunk of one feature's occurrences (sorted list).  Linear coordinate:
 // lanes stride over occurrences, fixed-order shuffle reduction.  FM latent row: lane owns
 // coordinate(s) f = lane, lane+32, ...; gv = g (x S_f - (v x) x)  (fm.cpp:89).
 // ---------------------------------------------------------------------------------------------
 constexpr int FM_MAX_REGS = 8;  // latent coordinates per lane kept in registers (k <= 256)
 
-template <bool PRECISE, bool IS_FM, int WARPS>
+// SH (sharded runs): w is the materialised one (shard w plane / row cache), and a row's sum goes where
+// Export::dst_at says: the owner's inbox, or -- this rank owns the row and is its only contributor -- applied here.
+template <bool PRECISE, bool IS_FM, int WARPS, bool SH = false>
 __global__ void __launch_bounds__(WARPS * 32)
 k_lrfm_rows(Batch b, Dims d, Hyper h, float *__restrict__ tab, float4 *__restrict__ lin, int32_t ch,
             const int32_t *__restrict__ n_chunks_p, const int32_t *__restrict__ chunk_pos,
             const uint32_t *__restrict__ skey, const uint32_t *__restrict__ socc,
             const SegScan *__restrict__ scan, const int32_t *__restrict__ occ_row,
             const float *__restrict__ g_in, const float *__restrict__ S, float *__restrict__ part,
-            float2 *__restrict__ part_lin) {
+            float2 *__restrict__ part_lin, const __grid_constant__ RowSpace rsp = RowSpace{},
+            const __grid_constant__ Export ex = Export{}) {
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t ld = d.ld, rs = 3 * ld;
   const int n_chunks = *n_chunks_p;
@@ -129,17 +226,25 @@ k_lrfm_rows(Batch b, Dims d, Hyper h, float *__restrict__ tab, float4 *__restric
     }
     sg = warp_sum(sg);
     sg2 = warp_sum(sg2);
+    // sharded: the row's sorted head position (its slot in the row cache / dst_at), its owner and local index
+    const int32_t head = SH ? scan[ci.p0].start : 0;
+    const bool mine = !SH || (int)(ci.key & (uint32_t)rsp.Gm1) == rsp.rank;
+    const int64_t lrow = SH ? (int64_t)(ci.key >> rsp.log2G) : (int64_t)ci.key;
     // FM latent row
     float a0[FM_MAX_REGS], a1[FM_MAX_REGS], wv[FM_MAX_REGS];
     if (IS_FM) {
-      const float *row = tab + (int64_t)ci.key * rs;
+      const float *row = tab + lrow * rs;
 #pragma unroll
       for (int r = 0; r < FM_MAX_REGS; r++) {
         a0[r] = a1[r] = 0.f;
         const int f = lane + 32 * r;
-        // w = W(n, z) of the pre-update state (what the sample kernel used); stored once per row, by its head chunk
-        wv[r] = f < d.k ? weight_from<PRECISE>(row[f], f_sqrt<PRECISE>(row[ld + f]), h) : 0.f;
-        if (f < d.k && ci.row_head) const_cast<float *>(row)[2 * ld + f] = wv[r];
+        if (SH) {
+          wv[r] = f < d.k ? (mine ? row[2 * ld + f] : rsp.rc_w[(int64_t)head * ld + f]) : 0.f;
+        } else {
+          // w = W(n, z) of the pre-update state (what the sample kernel used); stored once per row, by its head chunk
+          wv[r] = f < d.k ? weight_from<PRECISE>(row[f], f_sqrt<PRECISE>(row[ld + f]), h) : 0.f;
+          if (f < d.k && ci.row_head) const_cast<float *>(row)[2 * ld + f] = wv[r];
+        }
       }
       for (int p = ci.p0; p < ci.p1; p++) {
         const int64_t t = socc[p];
@@ -156,9 +261,25 @@ k_lrfm_rows(Batch b, Dims d, Hyper h, float *__restrict__ tab, float4 *__restric
         }
       }
     }
-    if (whole_row) {
+    const int32_t dst = (SH && whole_row) ? ex.dst_at[head] : -2;
+    if (whole_row && dst >= 0) {
+      // (sum g, sum g^2) into the owner's inbox
+      const int q = (int)(ci.key & (uint32_t)ex.Gm1);
       if (IS_FM) {
-        float *row = tab + (int64_t)ci.key * rs;
+        float *o = ex.inbox[q] + (int64_t)dst * 2 * ld;
+#pragma unroll
+        for (int r = 0; r < FM_MAX_REGS; r++) {
+          const int f = lane + 32 * r;
+          if (f < d.k) {
+            o[f] = a0[r];
+            o[ld + f] = a1[r];
+          }
+        }
+      }
+      if (lane == 0) ex.inbox_lin[q][dst] = make_float2(sg, sg2);
+    } else if (whole_row) {
+      if (IS_FM) {
+        float *row = tab + lrow * rs;
 #pragma unroll
         for (int r = 0; r < FM_MAX_REGS; r++) {
           const int f = lane + 32 * r;
@@ -171,10 +292,10 @@ k_lrfm_rows(Batch b, Dims d, Hyper h, float *__restrict__ tab, float4 *__restric
         }
       }
       if (lane == 0) {
-        float4 e = lin[ci.key];
-        e.z = weight_from<PRECISE>(e.x, f_sqrt<PRECISE>(e.y), h);
+        float4 e = lin[lrow];
+        if (!SH) e.z = weight_from<PRECISE>(e.x, f_sqrt<PRECISE>(e.y), h);  // (sharded: materialised by the owner kernel)
         ftrl_apply<PRECISE>(e.x, e.y, e.z, sg, sg2, h);
-        lin[ci.key] = e;
+        lin[lrow] = e;
       }
     } else {
       if (IS_FM) {
@@ -193,12 +314,13 @@ k_lrfm_rows(Batch b, Dims d, Hyper h, float *__restrict__ tab, float4 *__restric
   }
 }
 
-template <bool PRECISE, bool IS_FM, int WARPS>
+template <bool PRECISE, bool IS_FM, int WARPS, bool SH = false>
 __global__ void __launch_bounds__(WARPS * 32)
 k_lrfm_combine(Dims d, Hyper h, int32_t nnz, float *__restrict__ tab, float4 *__restrict__ lin, int32_t ch,
                const int32_t *__restrict__ n_chunks_p, const int32_t *__restrict__ chunk_pos,
                const uint32_t *__restrict__ skey, const SegScan *__restrict__ scan,
-               const float *__restrict__ part, const float2 *__restrict__ part_lin) {
+               const float *__restrict__ part, const float2 *__restrict__ part_lin,
+               const __grid_constant__ Export ex = Export{}) {
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t ld = d.ld, rs = 3 * ld;
   const int n_chunks = *n_chunks_p;
@@ -208,8 +330,12 @@ k_lrfm_combine(Dims d, Hyper h, int32_t nnz, float *__restrict__ tab, float4 *__
     if (!ci.valid || !ci.row_head || ci.row_last) continue;
     int J = 1;
     while (c + J < n_chunks && skey[chunk_pos[c + J]] == ci.key) J++;
+    const int32_t dst = SH ? ex.dst_at[ci.p0] : -2;  // (ci.p0 of a head chunk = the row's sorted head position)
+    const int q = SH ? (int)(ci.key & (uint32_t)ex.Gm1) : 0;
+    const int64_t lrow = SH ? (int64_t)(ci.key >> ex.log2G) : (int64_t)ci.key;
     if (IS_FM) {
-      float *row = tab + (int64_t)ci.key * rs;
+      float *row = tab + lrow * rs;
+      float *o = dst >= 0 ? ex.inbox[q] + (int64_t)dst * 2 * ld : nullptr;
       const float *p0 = part + (int64_t)ci.slot * 2 * ld;
       for (int f = lane; f < d.k; f += 32) {
         float a0 = 0.f, a1 = 0.f;
@@ -217,10 +343,15 @@ k_lrfm_combine(Dims d, Hyper h, int32_t nnz, float *__restrict__ tab, float4 *__
           a0 += p0[(int64_t)j * 2 * ld + f];
           a1 += p0[(int64_t)j * 2 * ld + ld + f];
         }
-        float z = row[f], n = row[ld + f];
-        ftrl_apply<PRECISE>(z, n, row[2 * ld + f], a0, a1, h);
-        row[f] = z;
-        row[ld + f] = n;
+        if (o) {
+          o[f] = a0;
+          o[ld + f] = a1;
+        } else {
+          float z = row[f], n = row[ld + f];
+          ftrl_apply<PRECISE>(z, n, row[2 * ld + f], a0, a1, h);
+          row[f] = z;
+          row[ld + f] = n;
+        }
       }
     }
     if (lane == 0) {
@@ -229,10 +360,14 @@ k_lrfm_combine(Dims d, Hyper h, int32_t nnz, float *__restrict__ tab, float4 *__
         const float2 t = part_lin[ci.slot + j];
         sg += t.x; sg2 += t.y;
       }
-      float4 e = lin[ci.key];
-      e.z = weight_from<PRECISE>(e.x, f_sqrt<PRECISE>(e.y), h);
-      ftrl_apply<PRECISE>(e.x, e.y, e.z, sg, sg2, h);
-      lin[ci.key] = e;
+      if (dst >= 0) {
+        ex.inbox_lin[q][dst] = make_float2(sg, sg2);
+      } else {
+        float4 e = lin[lrow];
+        if (!SH) e.z = weight_from<PRECISE>(e.x, f_sqrt<PRECISE>(e.y), h);
+        ftrl_apply<PRECISE>(e.x, e.y, e.z, sg, sg2, h);
+        lin[lrow] = e;
+      }
     }
   }
 }
@@ -240,9 +375,8 @@ k_lrfm_combine(Dims d, Hyper h, int32_t nnz, float *__restrict__ tab, float4 *__
 // predict (lr.cpp:20-24, fm.cpp:34-38): warp per sample, stored w only
 template <bool IS_FM>
 __global__ void __launch_bounds__(256)
-k_lrfm_predict(Batch b, Dims d, const float *__restrict__ tab, const float4 *__restrict__ lin,
-               const float4 *__restrict__ bias, int output_prob, float *__restrict__ out,
-               float *__restrict__ logit_out) {
+k_lrfm_predict(Batch b, Dims d, const __grid_constant__ Shards sh, const float4 *__restrict__ bias, int output_prob,
+               float *__restrict__ out, float *__restrict__ logit_out) {
   const int lane = threadIdx.x & 31;
   const int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (s >= b.n_rows) return;
@@ -252,7 +386,7 @@ k_lrfm_predict(Batch b, Dims d, const float *__restrict__ tab, const float4 *__r
   float acc = 0.f;
   for (int t = lane; t < F; t += 32) {
     const int32_t ft = b.feat[r0 + t];
-    if (ft >= 0 && ft < d.n_feats) acc = fmaf(lin[ft].z, b.val[r0 + t], acc);
+    if (ft >= 0 && ft < d.n_feats) acc = fmaf(sh.linp(ft)->z, b.val[r0 + t], acc);
   }
   if (IS_FM) {
     for (int f = lane; f < d.k; f += 32) {
@@ -260,7 +394,7 @@ k_lrfm_predict(Batch b, Dims d, const float *__restrict__ tab, const float4 *__r
       for (int t = 0; t < F; t++) {
         const int32_t ft = b.feat[r0 + t];
         if (ft < 0 || ft >= d.n_feats) continue;
-        const float vx = tab[(int64_t)ft * rs + 2 * ld + f] * b.val[r0 + t];
+        const float vx = sh.row(ft, rs)[2 * ld + f] * b.val[r0 + t];
         sv += vx;
         qv = fmaf(vx, vx, qv);
       }

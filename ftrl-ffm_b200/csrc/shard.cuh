@@ -125,7 +125,7 @@ __global__ void k_publish_unique(int32_t nnz, int G, const uint32_t *__restrict_
   const int32_t next = u + 1 < n_uall ? uhead[u + 1] : nnz;
   ukey[v] = skey[p];
   uinfo[v] = (uint32_t)p | (next - p == 1 ? UINFO_SINGLE : 0u);
-  umask[v] = mscan[next - 1].mask;
+  umask[v] = mscan ? mscan[next - 1].mask : ~0ull;  // LR / FM: a row has no field slices, everything is touched
 }
 
 // lane r <= G: first slot of bucket r (lower bound in the sorted bucket keys)
@@ -164,11 +164,12 @@ __global__ void k_peer_barrier(Peers pr, int channel, uint32_t epoch, long long 
 }
 
 // batch_flags[0] = AND over ranks (the tile path needs every rank's batch to have distinct fields)
-__global__ void k_merge_flags(Peers pr, int par, int32_t *batch_flags, int32_t *err) {
+// (LR / FM have no such requirement: need_simple == 0)
+__global__ void k_merge_flags(Peers pr, int par, int need_simple, int32_t *batch_flags, int32_t *err) {
   int all = 1;
-  for (int q = 0; q < pr.G; q++) all = all && pr.sync[pr.rank]->simple[par][q] != 0;
+  for (int q = 0; q < pr.G && need_simple; q++) all = all && pr.sync[pr.rank]->simple[par][q] != 0;
   batch_flags[0] = all;
-  if (!all) *err = 2;  // sharded mode has no generic fallback yet
+  if (!all) *err = 2;  // sharded FFM has no generic (repeated-field) fallback yet
 }
 
 // after barrier 2: some rank called the step off (k_fill_owned) -> nothing of this step may change z / n
@@ -224,7 +225,9 @@ enum : uint8_t {
 };
 
 // one thread per sorted contribution c (ckey sorted, contributions of one row in rank order)
-__global__ void k_contrib_class(Peers pr, int32_t cap, const int32_t *__restrict__ n_sel, uint32_t lsent,
+// allow_fuse == 0 (LR / FM: the sample kernel finalises no row): a row touched once, by its owner only, is reduced and
+// applied by the owner's row kernels like every other owner-only row
+__global__ void k_contrib_class(Peers pr, int32_t cap, const int32_t *__restrict__ n_sel, uint32_t lsent, int allow_fuse,
                                 const uint32_t *__restrict__ ckey, const uint32_t *__restrict__ csrc,
                                 const uint32_t *__restrict__ socc, uint8_t *__restrict__ cflag,
                                 uint8_t *__restrict__ fused_sorted, int32_t *__restrict__ occ_pos) {
@@ -244,7 +247,7 @@ __global__ void k_contrib_class(Peers pr, int32_t cap, const int32_t *__restrict
   const int32_t p_head = (int32_t)(info & UINFO_POS);
   const bool single = (info & UINFO_SINGLE) != 0;
   if (head && last && q == pr.rank) {
-    if (single) {  // finalised inside its sample by k_ffm_tile
+    if (single && allow_fuse) {  // finalised inside its sample by k_ffm_tile
       fused_sorted[p_head] = 1;
       occ_pos[socc[p_head]] = -1;
       cflag[c] = 0;
@@ -264,7 +267,7 @@ __global__ void k_contrib_class(Peers pr, int32_t cap, const int32_t *__restrict
 // transfer per distinct (row, rank), overlapped with the table reads of the other rows.
 template <bool PRECISE, int THREADS>
 __global__ void __launch_bounds__(THREADS)
-k_owner_materialise(Peers pr, Dims d, Hyper h, int32_t cap, const int32_t *__restrict__ n_sel,
+k_owner_materialise(Peers pr, Dims d, Hyper h, int all_slices, int32_t cap, const int32_t *__restrict__ n_sel,
                     const int32_t *__restrict__ batch_flags, const uint32_t *__restrict__ ckey,
                     const uint32_t *__restrict__ csrc, const uint8_t *__restrict__ cflag, float *__restrict__ tab,
                     float4 *__restrict__ lin) {
@@ -275,7 +278,9 @@ k_owner_materialise(Peers pr, Dims d, Hyper h, int32_t cap, const int32_t *__res
   const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
   const int32_t n = min(*n_sel, cap);
   const int64_t ld = d.ld, rs = 3 * ld;
-  const int vpf = d.k >> 2;
+  // FFM: the vectors of the field slices the batch touches; LR / FM (all_slices): the whole latent row (none for LR)
+  const int vpf = all_slices ? 1 : d.k >> 2;
+  const int n_vec = all_slices ? (int)(ld >> 2) : d.n_fields * vpf;
   for (int base = blockIdx.x * THREADS; base < n; base += gridDim.x * THREADS) {
     if (tid == 0) s_n = 0;
     __syncthreads();
@@ -296,7 +301,7 @@ k_owner_materialise(Peers pr, Dims d, Hyper h, int32_t cap, const int32_t *__res
       }
       const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)m);
       const unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(m >> 32));
-      const unsigned long long mask = ((unsigned long long)hi << 32) | lo;
+      const unsigned long long mask = all_slices ? ~0ull : (((unsigned long long)hi << 32) | lo);
       const unsigned remote = __ballot_sync(0xffffffffu, my_q >= 0 && my_q != pr.rank);
       // the remote contributors' caches, broadcast once (warp-uniform; the loop below diverges on the mask)
       float *rcw[MAX_SHARDS];
@@ -307,8 +312,8 @@ k_owner_materialise(Peers pr, Dims d, Hyper h, int32_t cap, const int32_t *__res
         if ((remote >> j) & 1u) rcw[j] = pr.rc_w[q] + (int64_t)head * ld;
       }
       float *row = tab + (int64_t)k * rs;
-      for (int v = lane; v < d.n_fields * vpf; v += 32) {
-        if (!((mask >> (v / vpf)) & 1ull)) continue;
+      for (int v = lane; v < n_vec; v += 32) {
+        if (!all_slices && !((mask >> (v / vpf)) & 1ull)) continue;
         const float4 z = reinterpret_cast<const float4 *>(row)[v], nn = reinterpret_cast<const float4 *>(row + ld)[v];
         const float4 w = weight4<PRECISE>(z, nn, h);
         reinterpret_cast<float4 *>(row + 2 * ld)[v] = w;
@@ -346,7 +351,7 @@ k_owner_apply(Peers pr, Dims d, Hyper h, int32_t cap, const int32_t *__restrict_
   const int32_t n = min(*n_sel, cap);
   const int64_t ld = d.ld, rs = 3 * ld;
   const int nvec = (int)(ld >> 2);
-  const int parts = (nvec + 31) >> 5;
+  const int parts = max(1, (nvec + 31) >> 5);  // (LR: no latent row, part 0 still updates the linear coordinate)
   for (int base = blockIdx.x * THREADS; base < n; base += gridDim.x * THREADS) {
     if (tid == 0) s_n = 0;
     __syncthreads();

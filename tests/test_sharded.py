@@ -101,6 +101,43 @@ def test_shard_count_invariance_on_one_gpu(world):
     sharded.close()
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("mt,k", [("LR", 1), ("FM", 8), ("FM", 5)])
+def test_lr_fm_shard_count_invariance_on_one_gpu(mt, k, world):
+    """LR and FM shard like FFM (lr.cpp:9-18, fm.cpp:21-32 train any sample on any model): the owner materialises
+    the linear w / latent row of every row the global batch touches and pushes it to the ranks that touch it, the
+    ranks reduce their duplicates and send one (sum g, sum g^2) per row back.  Hot rows (Zipf ids: thousands of
+    occurrences, several chunks per row) and rows only their owner touches are both in these batches; prediction
+    reads every shard."""
+    rng = np.random.default_rng(8)
+    nf, nfl, B = 3000, 13, 700
+    kw = dict(model_type=mt, n_feats=nf, n_fields=nfl, n_factors=k)
+    single = pkg.FtrlModel(**kw)
+    sharded = pkg.LogicalShards(world, max_batch_rows=B, max_batch_nnz=B * nfl, **kw)
+    st = pkg.synth.random_state(rng, nf, 0 if mt == "LR" else k)
+    single.set_state(st)
+    sharded.set_state(st)
+    for step in range(3):
+        parts = [pkg.synth.criteo_batch(B, nfl, nf, seed=100 * step + r, dist="zipf" if step % 2 == 0 else "uniform")
+                 for r in range(world)]
+        glob = {"row_ptr": np.concatenate([[0]] + [p["row_ptr"][1:] + i * B * nfl for i, p in enumerate(parts)]),
+                "field": np.concatenate([p["field"] for p in parts]), "feat": np.concatenate([p["feat"] for p in parts]),
+                "val": np.concatenate([p["val"] for p in parts]), "label": np.concatenate([p["label"] for p in parts])}
+        lg1, loss1 = single.train(**glob)
+        outs = sharded.train(parts)
+        lgG = np.concatenate([o[0] for o in outs])
+        assert_close(lgG, lg1, 1e-5, 2e-6, f"logits step {step}")
+        assert abs(sum(o[1] for o in outs) - loss1) <= 1e-6 * max(1.0, abs(loss1))
+        assert_state_close(sharded.get_state(), single.get_state(), rtol=2e-5, atol=2e-6, atol_z=2e-4,
+                           name=f"{mt} G={world} step {step}")
+    p = parts[0]
+    want, _ = single.predict(p["row_ptr"], p["field"], p["feat"], p["val"], p["label"])
+    got, _ = sharded.models[1].predict(p["row_ptr"], p["field"], p["feat"], p["val"], p["label"])
+    assert_close(got, want, 1e-5, 2e-6, "predict through the shards")
+    sharded.close()
+
+
 def _ragged(b, rng, nf, drop=0.3, oob=0.02):
     """criteo-shaped batch -> samples with a random SUBSET of the fields (still distinct), a few out-of-range ids"""
     keep = rng.random(len(b["feat"])) >= drop
