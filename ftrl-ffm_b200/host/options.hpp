@@ -38,7 +38,7 @@ static const char *kHelp =
     "--batch_size <n>: samples per GPU minibatch; 1 = reference-exact sequential mode\tdefault:1024\n"
     "--device <ordinal>: CUDA device (first device of a multi-GPU run)\tdefault:0\n"
     "--n_gpus <n>: 1, 2, 4 or 8 GPUs of this box; the tables are sharded by feature id, every minibatch is split "
-    "across the GPUs (FFM, data in memory: --online false or --csr_cache true)\tdefault:1\n"
+    "across the GPUs (data in memory: --online false or --csr_cache true)\tdefault:1\n"
     "--seed <n>: shuffle / init seed (0 = from std::random_device)\tdefault:0\n"
     "--csr_cache <bool>: keep a binary image <file>.csr of each parsed data file and reuse it while the text is "
     "unchanged\tdefault:false\n"
