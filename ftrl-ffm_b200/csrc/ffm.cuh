@@ -82,13 +82,17 @@ struct SampleCache {
 // the batch, in a sample with distinct fields, are finalised here: z', n' written in place (20 B
 // per coordinate, the algorithmic minimum).  All other rows are left to k_ffm_rows.
 // ---------------------------------------------------------------------------------------------
-template <int VEC, bool PRECISE, int THREADS>
+// SH (sharded runs, the generic fallback of shard.cuh): w is the materialised one -- the w plane of the shard row for
+// the ids this rank owns, the row cache (by sorted head position) for the others; nothing is stored or finalised.
+template <int VEC, bool PRECISE, int THREADS, bool SH = false>
 __global__ void __launch_bounds__(THREADS)
 k_ffm_sample(Batch b, Dims d, Hyper h, ItemDecode dec, float *__restrict__ tab, float4 *__restrict__ lin,
              const float4 *__restrict__ bias, const uint32_t *__restrict__ pair_lut,
              const int32_t *__restrict__ occ_pos, int fuse, const int32_t *__restrict__ batch_flags,
-             int skip_if_simple, float *__restrict__ g_out, float *__restrict__ logit_out) {
+             int skip_if_simple, float *__restrict__ g_out, float *__restrict__ logit_out,
+             const __grid_constant__ RowSpace rsp, const SegScan *__restrict__ scan) {
   if (skip_if_simple && batch_flags[0] != 0) return;  // the tile kernels (ffm_tile.cuh) took this batch
+  if (SH && batch_flags[1] != 0) return;               // sharded run: the step was called off
   __shared__ SampleCache sc;
   __shared__ float red[33];
   __shared__ float s_g;
@@ -98,12 +102,18 @@ k_ffm_sample(Batch b, Dims d, Hyper h, ItemDecode dec, float *__restrict__ tab, 
   __syncthreads();  // shared sample cache / reduction scratch of the previous sample are free
   const int64_t r0 = b.row_ptr[s];
   int F = (int)min((int64_t)FFM_MAX_F, b.row_ptr[s + 1] - r0);
-  const bool fusable = fuse != 0;  // per occurrence: occ_pos < 0 <=> finalised here
+  const bool fusable = !SH && fuse != 0;  // per occurrence: occ_pos < 0 <=> finalised here
   const int64_t ld = d.ld, rs = 3 * ld;
+  // base of the row of occurrence t such that base + 2 ld is its w plane (sharded: only that plane is ever read)
+  auto row_of = [&](int64_t t, int32_t ft) -> float * {
+    if (!SH) return tab + (int64_t)ft * rs;
+    if ((ft & rsp.Gm1) == rsp.rank) return rsp.tab + (int64_t)(ft >> rsp.log2G) * rs;
+    return const_cast<float *>(rsp.rc_w) + (int64_t)scan[occ_pos[t]].start * ld - 2 * ld;
+  };
   for (int t = tid; t < F && t < FFM_CAP; t += THREADS) {
     const int32_t fl = b.field[r0 + t], ft = b.feat[r0 + t];
     const bool ok = feat_valid(d, fl, ft);
-    sc.row[t] = ok ? tab + (int64_t)ft * rs : nullptr;
+    sc.row[t] = ok ? row_of(r0 + t, ft) : nullptr;
     sc.fk[t] = fl * d.k;
     sc.x[t] = b.val[r0 + t];
     sc.fused[t] = fusable && ok && occ_pos[r0 + t] < 0;
@@ -114,7 +124,7 @@ k_ffm_sample(Batch b, Dims d, Hyper h, ItemDecode dec, float *__restrict__ tab, 
       row = sc.row[m]; fk = sc.fk[m]; x = sc.x[m]; fz = sc.fused[m];
     } else {
       const int32_t fl = b.field[r0 + m], ft = b.feat[r0 + m];
-      row = feat_valid(d, fl, ft) ? tab + (int64_t)ft * rs : nullptr;
+      row = feat_valid(d, fl, ft) ? row_of(r0 + m, ft) : nullptr;
       fk = fl * d.k;
       x = b.val[r0 + m];
       fz = fusable && row != nullptr && occ_pos[r0 + m] < 0;
@@ -138,26 +148,39 @@ k_ffm_sample(Batch b, Dims d, Hyper h, ItemDecode dec, float *__restrict__ tab, 
     if (ra == nullptr || rb == nullptr) continue;
     float *pa = ra + fkn + c * VEC;
     float *pb = rb + fkm + c * VEC;
-    Vec<VEC> zA, nA, zB, nB, wA, wB;
-    zA.load(pa); nA.load(pa + ld); zB.load(pb); nB.load(pb + ld);
+    Vec<VEC> wA, wB;
     float dot = 0.f;
+    if (SH) {
+      wA.load(pa + 2 * ld);
+      wB.load(pb + 2 * ld);
 #pragma unroll
-    for (int e = 0; e < VEC; e++) {
-      wA.v[e] = weight_from<PRECISE>(zA.v[e], f_sqrt<PRECISE>(nA.v[e]), h);
-      wB.v[e] = weight_from<PRECISE>(zB.v[e], f_sqrt<PRECISE>(nB.v[e]), h);
-      dot = fmaf(wA.v[e], wB.v[e], dot);
+      for (int e = 0; e < VEC; e++) dot = fmaf(wA.v[e], wB.v[e], dot);
+    } else {
+      Vec<VEC> zA, nA, zB, nB;
+      zA.load(pa); nA.load(pa + ld); zB.load(pb); nB.load(pb + ld);
+#pragma unroll
+      for (int e = 0; e < VEC; e++) {
+        wA.v[e] = weight_from<PRECISE>(zA.v[e], f_sqrt<PRECISE>(nA.v[e]), h);
+        wB.v[e] = weight_from<PRECISE>(zB.v[e], f_sqrt<PRECISE>(nB.v[e]), h);
+        dot = fmaf(wA.v[e], wB.v[e], dot);
+      }
+      wA.store(pa + 2 * ld);
+      wB.store(pb + 2 * ld);
     }
-    wA.store(pa + 2 * ld);
-    wB.store(pb + 2 * ld);
     acc = fmaf(dot, xm * xn, acc);
   }
   // linear part (ftrl_model.cpp:44-59): thread t handles feature t
   for (int t = tid; t < F; t += THREADS) {
     const int32_t ft = b.feat[r0 + t];
     if (!feat_valid(d, b.field[r0 + t], ft)) continue;
-    const float4 e = lin[ft];
-    const float w = weight_from<PRECISE>(e.x, f_sqrt<PRECISE>(e.y), h);
-    lin[ft].z = w;
+    float w;
+    if (SH) {
+      w = (ft & rsp.Gm1) == rsp.rank ? rsp.lin[ft >> rsp.log2G].z : rsp.rc_lin[scan[occ_pos[r0 + t]].start];
+    } else {
+      const float4 e = lin[ft];
+      w = weight_from<PRECISE>(e.x, f_sqrt<PRECISE>(e.y), h);
+      lin[ft].z = w;
+    }
     acc = fmaf(w, b.val[r0 + t], acc);
   }
   float logit = block_sum(acc, red);
@@ -240,15 +263,18 @@ k_ffm_sample(Batch b, Dims d, Hyper h, ItemDecode dec, float *__restrict__ tab, 
 // ---------------------------------------------------------------------------------------------
 constexpr int GATHER_U = 4;
 
-template <int VEC, bool PRECISE, int WARPS>
+template <int VEC, bool PRECISE, int WARPS, bool SH = false>
 __global__ void __launch_bounds__(WARPS * 32)
 k_ffm_rows(Batch b, Dims d, Hyper h, ItemDecode dec, float *__restrict__ tab, float4 *__restrict__ lin, int32_t ch,
            const int32_t *__restrict__ n_chunks_p, const int32_t *__restrict__ chunk_pos,
            const uint32_t *__restrict__ skey, const uint32_t *__restrict__ socc,
            const SegScan *__restrict__ scan, const int32_t *__restrict__ occ_row,
            const uint8_t *__restrict__ sflags, const int32_t *__restrict__ batch_flags, int skip_if_simple,
-           const float *__restrict__ g_in, float *__restrict__ part, float2 *__restrict__ part_lin) {
+           const float *__restrict__ g_in, float *__restrict__ part, float2 *__restrict__ part_lin,
+           const __grid_constant__ RowSpace rsp, const __grid_constant__ Export ex,
+           const int32_t *__restrict__ occ_pos) {
   if (skip_if_simple && batch_flags[0] != 0) return;  // the tile kernels (ffm_tile.cuh) took this batch
+  if (SH && batch_flags[1] != 0) return;               // sharded run: the step was called off
   extern __shared__ __align__(16) float smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t ld = d.ld, rs = 3 * ld;
@@ -310,7 +336,11 @@ k_ffm_rows(Batch b, Dims d, Hyper h, ItemDecode dec, float *__restrict__ tab, fl
               const float xn = b.val[r0 + n];
               act[u] = feat_valid(d, fn, in);
               if (act[u]) {
-                src[u] = tab + (int64_t)in * rs + 2 * ld + fmk + c4 * VEC;
+                const float *wrow;  // w plane of the partner row
+                if (!SH) wrow = tab + (int64_t)in * rs + 2 * ld;
+                else if ((in & rsp.Gm1) == rsp.rank) wrow = rsp.tab + (int64_t)(in >> rsp.log2G) * rs + 2 * ld;
+                else wrow = rsp.rc_w + (int64_t)scan[occ_pos[r0 + n]].start * ld;
+                src[u] = wrow + fmk + c4 * VEC;
                 off[u] = fn * d.k + c4 * VEC;
                 gx[u] = gxm * xn;
               }
@@ -353,8 +383,16 @@ k_ffm_rows(Batch b, Dims d, Hyper h, ItemDecode dec, float *__restrict__ tab, fl
     }
     sg = warp_sum(sg);
     sg2 = warp_sum(sg2);
-    if (whole_row) {
-      float *row = tab + (int64_t)ci.key * rs;
+    // sharded: a row held by one chunk goes to its owner's inbox unless this rank owns it and is its only contributor
+    const int32_t dst = (SH && whole_row) ? ex.dst_at[ci.p0] : -2;
+    const int64_t lrow = SH ? (int64_t)(ci.key >> ex.log2G) : (int64_t)ci.key;
+    if (whole_row && dst >= 0) {
+      const int q = (int)(ci.key & (uint32_t)ex.Gm1);
+      float *o = ex.inbox[q] + (int64_t)dst * 2 * ld;
+      for (int64_t v = lane; v < 2 * ld; v += 32) o[v] = acc0[v];
+      if (lane == 0) ex.inbox_lin[q][dst] = make_float2(sg, sg2);
+    } else if (whole_row) {
+      float *row = tab + lrow * rs;
       for (int64_t v = lane * VEC; v < d.row_len; v += 32 * VEC) {
         Vec<VEC> a0, a1;
         a0.load(acc0 + v); a1.load(acc1 + v);
@@ -369,13 +407,13 @@ k_ffm_rows(Batch b, Dims d, Hyper h, ItemDecode dec, float *__restrict__ tab, fl
         z.store(row + v); n.store(row + ld + v);
       }
       if (lane == 0) {
-        float4 e = lin[ci.key];
+        float4 e = lin[lrow];
         ftrl_apply<PRECISE>(e.x, e.y, e.z, sg, sg2, h);
-        lin[ci.key] = e;
+        lin[lrow] = e;
       }
     } else {
-      float *dst = part + (int64_t)ci.slot * 2 * ld;
-      for (int64_t v = lane; v < 2 * ld; v += 32) dst[v] = acc0[v];
+      float *pdst = part + (int64_t)ci.slot * 2 * ld;
+      for (int64_t v = lane; v < 2 * ld; v += 32) pdst[v] = acc0[v];
       if (lane == 0) part_lin[ci.slot] = make_float2(sg, sg2);
     }
     __syncwarp();
@@ -395,7 +433,9 @@ template <bool PRECISE, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 k_ffm_combine(Dims d, Hyper h, float *__restrict__ tab, float4 *__restrict__ lin,
               const int32_t *__restrict__ n_chunks_p, const int4 *__restrict__ cdesc,
-              const float *__restrict__ part, const float2 *__restrict__ part_lin, const __grid_constant__ Export ex) {
+              const float *__restrict__ part, const float2 *__restrict__ part_lin, const __grid_constant__ Export ex,
+              const int32_t *__restrict__ batch_flags) {
+  if (ex.on && batch_flags[1] != 0) return;  // sharded run: the step was called off (shard.cuh: k_check_abort)
   constexpr int WARPS = THREADS / 32;
   constexpr int VB = 32 * COMB_VPL;  // vectors per block
   __shared__ int s_list[THREADS];

@@ -351,18 +351,21 @@ static int pick_vec(int k) { return k % 4 == 0 ? 4 : k % 2 == 0 ? 2 : 1; }
 // ---------------------------------------------------------------------------------------------
 // batch training, device-resident CSR
 // ---------------------------------------------------------------------------------------------
-template <int VEC, bool PRECISE>
+template <int VEC, bool PRECISE, bool SH = false>
 static void launch_ffm_sample(ftrl_handle *h, const Batch &b, float *logit_out, int skip_if_simple) {
   const Dims &d = h->dims;
   const double fbar = b.n_rows ? (double)b.nnz / (double)b.n_rows : 0.0;
   const double items = fbar * (fbar - 1) * 0.5 * (d.k / VEC);
   int threads = h->sample_threads ? h->sample_threads : items <= 64 ? 64 : items <= 256 ? 128 : items <= 1024 ? 256 : 512;
+  // sharded runs: ONE instantiation, the one the dry run of ftrl_attach_peers has loaded (a first-time kernel load is
+  // deferred while the spinning barrier kernels of the step are running)
+  if (SH) threads = 256;
   const dim3 grid((unsigned)((b.n_rows + FFM_SPB - 1) / FFM_SPB));
   const ItemDecode dec = make_item_decode(d.k, VEC);
 #define FFM_SAMPLE(T)                                                                                          \
-  k_ffm_sample<VEC, PRECISE, T><<<grid, T, 0, h->compute>>>(b, d, h->hyper, dec, h->tab, h->lin, h->bias, h->pair_lut, \
-                                                           h->occ_pos.p, h->fuse, h->batch_flags.p, skip_if_simple, \
-                                                           h->g.p, logit_out)
+  k_ffm_sample<VEC, PRECISE, T, SH><<<grid, T, 0, h->compute>>>(b, d, h->hyper, dec, h->tab, h->lin, h->bias, h->pair_lut, \
+                                                               h->occ_pos.p, h->fuse, h->batch_flags.p, skip_if_simple, \
+                                                               h->g.p, logit_out, h->rowspace, h->scan.p)
   if (threads <= 64) FFM_SAMPLE(64);
   else if (threads <= 128) FFM_SAMPLE(128);
   else if (threads <= 256) FFM_SAMPLE(256);
@@ -415,6 +418,32 @@ static void launch_staged_rows(ftrl_handle *h, const Batch &b) {
 }
 
 // FFM minibatch: when every sample of the batch has distinct fields (device-side flag) the tile kernels
+// the generic row kernel (any samples; SH: sharded runs, rows resolved through RowSpace, sums through Export)
+template <int VEC, bool PRECISE, bool SH>
+static void launch_ffm_rows(ftrl_handle *h, const Batch &b, const ItemDecode &dec, int skip_if_simple) {
+  const Dims &d = h->dims;
+  const int grid = h->n_sms * 4;
+  const size_t smem8 = (size_t)8 * 2 * d.ld * sizeof(float);
+  if (smem8 <= 160 * 1024) {
+    auto kern = k_ffm_rows<VEC, PRECISE, 8, SH>;
+    if (smem8 > 48 * 1024) FTRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
+    kern<<<grid, 256, smem8, h->compute>>>(b, d, h->hyper, dec, h->tab, h->lin, h->chunk, h->n_chunks.p, h->chunk_pos.p,
+                                           h->skey.p, h->socc.p, h->scan.p, h->occ_row.p, h->sflags.p,
+                                           h->batch_flags.p, skip_if_simple, h->g.p, h->part.p, h->part_lin.p, h->rowspace,
+                                           h->exportd, h->occ_pos.p);
+  } else {
+    const size_t smem1 = (size_t)2 * d.ld * sizeof(float);
+    if (smem1 > 200 * 1024) throw ArgFail{"n_fields*n_factors too large for the row kernel"};
+    auto kern = k_ffm_rows<VEC, PRECISE, 1, SH>;
+    FTRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+    kern<<<grid * 4, 32, smem1, h->compute>>>(b, d, h->hyper, dec, h->tab, h->lin, h->chunk, h->n_chunks.p,
+                                              h->chunk_pos.p, h->skey.p, h->socc.p, h->scan.p, h->occ_row.p,
+                                              h->sflags.p, h->batch_flags.p, skip_if_simple, h->g.p, h->part.p,
+                                              h->part_lin.p, h->rowspace, h->exportd, h->occ_pos.p);
+  }
+  FTRL_CUDA(cudaGetLastError());
+}
+
 // (ffm_tile.cuh) process it; otherwise the generic LDG kernels do.  Both sets are enqueued, the one that
 // does not apply returns at once -- no host round trip.
 template <int VEC, bool PRECISE>
@@ -438,24 +467,7 @@ static void run_ffm_batch(ftrl_handle *h, const Batch &b, float *logit_out) {
     launch_ffm_sample<VEC, PRECISE>(h, b, logit_out, tile ? 1 : 0);
     launched(h, PH_GENERIC);
     if (b.nnz > 0) {
-      const size_t smem8 = (size_t)8 * 2 * d.ld * sizeof(float);
-      if (smem8 <= 160 * 1024) {
-        auto kern = k_ffm_rows<VEC, PRECISE, 8>;
-        if (smem8 > 48 * 1024) FTRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
-        kern<<<grid, 256, smem8, h->compute>>>(b, d, h->hyper, dec, h->tab, h->lin, h->chunk, h->n_chunks.p, h->chunk_pos.p,
-                                               h->skey.p, h->socc.p, h->scan.p, h->occ_row.p, h->sflags.p,
-                                               h->batch_flags.p, tile ? 1 : 0, h->g.p, h->part.p, h->part_lin.p);
-      } else {
-        const size_t smem1 = (size_t)2 * d.ld * sizeof(float);
-        if (smem1 > 200 * 1024) throw ArgFail{"n_fields*n_factors too large for the row kernel"};
-        auto kern = k_ffm_rows<VEC, PRECISE, 1>;
-        FTRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-        kern<<<grid * 4, 32, smem1, h->compute>>>(b, d, h->hyper, dec, h->tab, h->lin, h->chunk, h->n_chunks.p,
-                                                  h->chunk_pos.p, h->skey.p, h->socc.p, h->scan.p, h->occ_row.p,
-                                                  h->sflags.p, h->batch_flags.p, tile ? 1 : 0, h->g.p, h->part.p,
-                                                  h->part_lin.p);
-      }
-      FTRL_CUDA(cudaGetLastError());
+      launch_ffm_rows<VEC, PRECISE, false>(h, b, dec, tile ? 1 : 0);
       launched(h, PH_GENERIC);
     }
   }
@@ -463,7 +475,7 @@ static void run_ffm_batch(ftrl_handle *h, const Batch &b, float *logit_out) {
   {
     PhaseScope ps(h, PH_COMBINE);
     k_ffm_combine<PRECISE, 256><<<grid, 256, 0, h->compute>>>(d, h->hyper, h->tab, h->lin, h->n_chunks.p, h->cdesc.p, h->part.p,
-                                                              h->part_lin.p, h->exportd);
+                                                              h->part_lin.p, h->exportd, h->batch_flags.p);
     FTRL_CUDA(cudaGetLastError());
     launched(h, PH_COMBINE);
   }
@@ -488,7 +500,7 @@ static void run_lrfm_batch(ftrl_handle *h, const Batch &b, float *logit_out) {
     k_lrfm_rows<PRECISE, IS_FM, 8, false><<<grid, 256, 0, h->compute>>>(b, d, h->hyper, h->tab, h->lin, h->chunk, h->n_chunks.p,
                                                                         h->chunk_pos.p, h->skey.p, h->socc.p, h->scan.p,
                                                                         h->occ_row.p, h->g.p, h->S.p, h->part.p, h->part_lin.p,
-                                                                        RowSpace{}, Export{});
+                                                                        RowSpace{}, Export{}, h->batch_flags.p);
     FTRL_CUDA(cudaGetLastError());
     launched(h, PH_ROWS);
   }
@@ -496,7 +508,7 @@ static void run_lrfm_batch(ftrl_handle *h, const Batch &b, float *logit_out) {
     PhaseScope ps(h, PH_COMBINE);
     k_lrfm_combine<PRECISE, IS_FM, 8, false><<<grid, 256, 0, h->compute>>>(d, h->hyper, (int32_t)b.nnz, h->tab, h->lin, h->chunk,
                                                                            h->n_chunks.p, h->chunk_pos.p, h->skey.p, h->scan.p,
-                                                                           h->part.p, h->part_lin.p, Export{});
+                                                                           h->part.p, h->part_lin.p, Export{}, h->batch_flags.p);
     FTRL_CUDA(cudaGetLastError());
     launched(h, PH_COMBINE);
   }
@@ -525,7 +537,7 @@ static void run_lrfm_rows_sharded(ftrl_handle *h, const Batch &b) {
     k_lrfm_rows<PRECISE, IS_FM, 8, true><<<grid, 256, 0, h->compute>>>(b, d, h->hyper, h->tab, h->lin, h->chunk, h->n_chunks.p,
                                                                        h->chunk_pos.p, h->skey.p, h->socc.p, h->scan.p,
                                                                        h->occ_row.p, h->g.p, h->S.p, h->part.p, h->part_lin.p,
-                                                                       h->rowspace, h->exportd);
+                                                                       h->rowspace, h->exportd, h->batch_flags.p);
     FTRL_CUDA(cudaGetLastError());
     launched(h, PH_ROWS);
   }
@@ -533,7 +545,7 @@ static void run_lrfm_rows_sharded(ftrl_handle *h, const Batch &b) {
     PhaseScope ps(h, PH_COMBINE);
     k_lrfm_combine<PRECISE, IS_FM, 8, true><<<grid, 256, 0, h->compute>>>(d, h->hyper, (int32_t)b.nnz, h->tab, h->lin, h->chunk,
                                                                           h->n_chunks.p, h->chunk_pos.p, h->skey.p, h->scan.p,
-                                                                          h->part.p, h->part_lin.p, h->exportd);
+                                                                          h->part.p, h->part_lin.p, h->exportd, h->batch_flags.p);
     FTRL_CUDA(cudaGetLastError());
     launched(h, PH_COMBINE);
   }
@@ -573,6 +585,7 @@ static void run_prep(ftrl_handle *h, const Batch &b) {
   {
     PhaseScope ps(h, PH_PREP);
     FTRL_CUDA(cudaMemsetAsync(h->batch_flags.p, 0x01, sizeof(int32_t), h->compute));  // != 0: all samples simple
+    FTRL_CUDA(cudaMemsetAsync(h->batch_flags.p + 1, 0, sizeof(int32_t), h->compute));  // [1]: step called off (sharded)
     const unsigned grid = (unsigned)((b.n_rows * 32 + 255) / 256);
     k_prep_rows<<<grid, 256, 0, h->compute>>>(b, d, h->key.p, h->occ_idx.p, h->occ_row.p, h->sflags.p,
                                               h->batch_flags.p, h->tile_ok ? h->pmask.p : nullptr);
@@ -974,6 +987,7 @@ static void train_device_sharded(ftrl_handle *h, const Batch &b, float *logit_ou
     {
       PhaseScope ps(h, PH_PREP);
       FTRL_CUDA(cudaMemsetAsync(h->batch_flags.p, 0x01, sizeof(int32_t), h->compute));
+      FTRL_CUDA(cudaMemsetAsync(h->batch_flags.p + 1, 0, sizeof(int32_t), h->compute));
       if (b.n_rows > 0) {
         const unsigned pg = (unsigned)((b.n_rows * 32 + 255) / 256);
         k_prep_rows<<<pg, 256, 0, h->compute>>>(b, d, h->key.p, h->occ_idx.p, h->occ_row.p, h->sflags.p, h->batch_flags.p,
@@ -1022,13 +1036,14 @@ static void train_device_sharded(ftrl_handle *h, const Batch &b, float *logit_ou
     {
       // owner side: contributions (row, rank) of the rows this rank owns
       PhaseScope ps(h, PH_EXCHANGE);
-      k_merge_flags<<<1, 1, 0, h->compute>>>(pr, par, is_ffm ? 1 : 0, h->batch_flags.p, h->d_err);
+      k_merge_flags<<<1, 1, 0, h->compute>>>(pr, par, is_ffm ? 1 : 0, h->batch_flags.p);
       k_fill_owned<<<(oc + 255) / 256, 256, 0, h->compute>>>(pr, par, oc, lsent, step_tag, h->n_sel.p, h->okey.p, h->osrc.p, h->d_err);
       size_t bytes = h->cub_bytes;
       FTRL_CUDA(cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, bytes, h->okey.p, h->ckey.p, h->osrc.p, h->csrc.p, oc, 0,
                                                 key_bits((int32_t)h->n_local), h->compute));
-      k_contrib_class<<<(oc + 255) / 256, 256, 0, h->compute>>>(pr, oc, h->n_sel.p, lsent, is_ffm ? 1 : 0, h->ckey.p, h->csrc.p,
-                                                               h->socc.p, h->cflag.p, h->fused_sorted.p, h->occ_pos.p);
+      k_contrib_class<<<(oc + 255) / 256, 256, 0, h->compute>>>(pr, oc, h->n_sel.p, lsent, is_ffm ? 1 : 0, h->batch_flags.p,
+                                                               h->ckey.p, h->csrc.p, h->socc.p, h->cflag.p,
+                                                               h->fused_sorted.p, h->occ_pos.p);
       FTRL_CUDA(cudaGetLastError());
       launched(h, PH_EXCHANGE, 3);
     }
@@ -1077,10 +1092,18 @@ static void train_device_sharded(ftrl_handle *h, const Batch &b, float *logit_ou
     k_check_abort<<<1, 1, 0, h->compute>>>(pr, par, step_tag, h->batch_flags.p, h->d_err);
     FTRL_CUDA(cudaGetLastError());
   }
+  const ItemDecode dec4 = make_item_decode(d.k, 4);
   if (is_ffm) {
-    const ItemDecode dec = make_item_decode(d.k, 4);
-    PhaseScope ps(h, PH_SAMPLE);
-    if (b.n_rows > 0) launch_tile<PRECISE>(h, b, dec, logit_out);
+    {
+      PhaseScope ps(h, PH_SAMPLE);
+      if (b.n_rows > 0) launch_tile<PRECISE>(h, b, dec4, logit_out);
+    }
+    // a batch in which some sample (of any rank) repeats a field: the generic kernels take it (device-side flag)
+    PhaseScope ps(h, PH_GENERIC);
+    if (b.n_rows > 0) {
+      launch_ffm_sample<4, PRECISE, true>(h, b, logit_out, 1);
+      launched(h, PH_GENERIC);
+    }
   } else if (d.model_type == FTRL_FM) {
     const int vec = pick_vec(d.k);
     if (vec == 4) run_lrfm_batch_sharded<4, PRECISE, true>(h, b, logit_out);
@@ -1103,9 +1126,14 @@ static void train_device_sharded(ftrl_handle *h, const Batch &b, float *logit_ou
       PhaseScope ps(h, PH_ROWS);
       launch_staged_rows<PRECISE>(h, b);
     }
+    if (nnz > 0) {
+      PhaseScope ps(h, PH_GENERIC);
+      launch_ffm_rows<4, PRECISE, true>(h, b, dec4, 1);
+      launched(h, PH_GENERIC);
+    }
     PhaseScope ps(h, PH_COMBINE);
     k_ffm_combine<PRECISE, 256><<<grid, 256, 0, h->compute>>>(d, h->hyper, h->tab, h->lin, h->n_chunks.p, h->cdesc.p, h->part.p,
-                                                              h->part_lin.p, h->exportd);
+                                                              h->part_lin.p, h->exportd, h->batch_flags.p);
     FTRL_CUDA(cudaGetLastError());
     launched(h, PH_COMBINE);
   } else if (d.model_type == FTRL_FM) {

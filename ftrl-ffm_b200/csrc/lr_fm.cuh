@@ -205,8 +205,9 @@ k_lrfm_rows(Batch b, Dims d, Hyper h, float *__restrict__ tab, float4 *__restric
             const uint32_t *__restrict__ skey, const uint32_t *__restrict__ socc,
             const SegScan *__restrict__ scan, const int32_t *__restrict__ occ_row,
             const float *__restrict__ g_in, const float *__restrict__ S, float *__restrict__ part,
-            float2 *__restrict__ part_lin, const __grid_constant__ RowSpace rsp = RowSpace{},
-            const __grid_constant__ Export ex = Export{}) {
+            float2 *__restrict__ part_lin, const __grid_constant__ RowSpace rsp, const __grid_constant__ Export ex,
+            const int32_t *__restrict__ batch_flags) {
+  if (SH && batch_flags[1] != 0) return;  // sharded run: the step was called off (shard.cuh: k_check_abort)
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t ld = d.ld, rs = 3 * ld;
   const int n_chunks = *n_chunks_p;
@@ -320,7 +321,8 @@ k_lrfm_combine(Dims d, Hyper h, int32_t nnz, float *__restrict__ tab, float4 *__
                const int32_t *__restrict__ n_chunks_p, const int32_t *__restrict__ chunk_pos,
                const uint32_t *__restrict__ skey, const SegScan *__restrict__ scan,
                const float *__restrict__ part, const float2 *__restrict__ part_lin,
-               const __grid_constant__ Export ex = Export{}) {
+               const __grid_constant__ Export ex, const int32_t *__restrict__ batch_flags) {
+  if (SH && batch_flags[1] != 0) return;  // sharded run: the step was called off
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t ld = d.ld, rs = 3 * ld;
   const int n_chunks = *n_chunks_p;

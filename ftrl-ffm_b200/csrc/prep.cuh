@@ -71,7 +71,8 @@ __device__ __forceinline__ bool feat_valid(const Dims &d, int32_t fld, int32_t f
 
 // warp per sample.  batch_flags[0] is cleared to 0 when some sample repeats a field.
 // pmask[t] (FFM, n_fields <= 64): bit f set iff some OTHER valid feature of t's sample carries field f,
-// i.e. the slices of t's row this sample touches (ffm.cpp:72-88 touches (feat_m, field_n) for n != m).
+// i.e. the slices of t's row this sample touches (ffm.cpp:72-88 touches (feat_m, field_n) for n != m) -- also
+// exact for samples that repeat a field (`dup`: the fields carried by two or more features of the sample).
 __global__ void k_prep_rows(Batch b, Dims d, uint32_t *__restrict__ key, uint32_t *__restrict__ occ_idx,
                             int32_t *__restrict__ occ_row, uint8_t *__restrict__ sflags,
                             int32_t *__restrict__ batch_flags, uint64_t *__restrict__ pmask) {
@@ -81,6 +82,7 @@ __global__ void k_prep_rows(Batch b, Dims d, uint32_t *__restrict__ key, uint32_
   const int64_t r0 = b.row_ptr[warp], r1 = b.row_ptr[warp + 1];
   bool simple = true;
   uint64_t seen = 0;  // field bitmask when n_fields <= 64
+  uint64_t dup = 0;   // fields carried by more than one valid feature
   for (int64_t base = r0; base < r1; base += 32) {
     const int64_t t = base + lane;
     int32_t fld = -1;
@@ -101,6 +103,10 @@ __global__ void k_prep_rows(Batch b, Dims d, uint32_t *__restrict__ key, uint32_
       if (d.n_fields <= 64) {
         const uint64_t bit = ok ? (1ull << fld) : 0ull;
         if (bit & seen) simple = false;
+        const uint64_t dbit = (ok && (__popc(same & okmask) > 1 || (bit & seen))) ? bit : 0ull;
+        const unsigned dlo = __reduce_or_sync(0xffffffffu, (unsigned)dbit);
+        const unsigned dhi = __reduce_or_sync(0xffffffffu, (unsigned)(dbit >> 32));
+        dup |= ((uint64_t)dhi << 32) | dlo;
         const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)bit);
         const unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(bit >> 32));
         seen |= ((uint64_t)hi << 32) | lo;
@@ -122,8 +128,8 @@ __global__ void k_prep_rows(Batch b, Dims d, uint32_t *__restrict__ key, uint32_
     for (int64_t t = r0 + lane; t < r1; t += 32) {
       const int32_t fld = b.field[t];
       const bool ok = feat_valid(d, fld, b.feat[t]);
-      // with distinct fields the own field is carried by this feature only
-      pmask[t] = ok ? (seen & ~(1ull << fld)) : 0ull;
+      // the own field counts only when another feature of the sample carries it too
+      pmask[t] = ok ? ((seen & ~(1ull << fld)) | (dup & (1ull << fld))) : 0ull;
     }
   }
 }

@@ -164,12 +164,14 @@ __global__ void k_peer_barrier(Peers pr, int channel, uint32_t epoch, long long 
 }
 
 // batch_flags[0] = AND over ranks (the tile path needs every rank's batch to have distinct fields)
-// (LR / FM have no such requirement: need_simple == 0)
-__global__ void k_merge_flags(Peers pr, int par, int need_simple, int32_t *batch_flags, int32_t *err) {
+// (LR / FM have no such requirement: need_simple == 0).  A batch that is not simple on some rank takes the generic
+// kernels on EVERY rank (k_ffm_sample / k_ffm_rows, SH variants), and the owners fuse nothing.
+// batch_flags[1] = "the step was called off" (k_check_abort), cleared here.
+__global__ void k_merge_flags(Peers pr, int par, int need_simple, int32_t *batch_flags) {
   int all = 1;
   for (int q = 0; q < pr.G && need_simple; q++) all = all && pr.sync[pr.rank]->simple[par][q] != 0;
   batch_flags[0] = all;
-  if (!all) *err = 2;  // sharded FFM has no generic (repeated-field) fallback yet
+  batch_flags[1] = 0;
 }
 
 // after barrier 2: some rank called the step off (k_fill_owned) -> nothing of this step may change z / n
@@ -178,7 +180,8 @@ __global__ void k_check_abort(Peers pr, int par, uint32_t step_tag, int32_t *bat
   for (int q = 0; q < pr.G; q++)
     any = any || *reinterpret_cast<const volatile uint32_t *>(&pr.sync[pr.rank]->abort_at[par][q]) == step_tag;
   if (any) {
-    batch_flags[0] = 0;
+    batch_flags[0] = 0;  // the tile kernels skip the batch ...
+    batch_flags[1] = 1;  // ... and so does everything else of the step
     if (*err == 0) *err = 3;
   }
 }
@@ -228,7 +231,8 @@ enum : uint8_t {
 // allow_fuse == 0 (LR / FM: the sample kernel finalises no row): a row touched once, by its owner only, is reduced and
 // applied by the owner's row kernels like every other owner-only row
 __global__ void k_contrib_class(Peers pr, int32_t cap, const int32_t *__restrict__ n_sel, uint32_t lsent, int allow_fuse,
-                                const uint32_t *__restrict__ ckey, const uint32_t *__restrict__ csrc,
+                                const int32_t *__restrict__ batch_flags, const uint32_t *__restrict__ ckey,
+                                const uint32_t *__restrict__ csrc,
                                 const uint32_t *__restrict__ socc, uint8_t *__restrict__ cflag,
                                 uint8_t *__restrict__ fused_sorted, int32_t *__restrict__ occ_pos) {
   const int32_t c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -245,7 +249,10 @@ __global__ void k_contrib_class(Peers pr, int32_t cap, const int32_t *__restrict
   const int q = (int)(src >> SRC_SHIFT);
   const uint32_t info = pr.uinfo[q][src & SRC_MASK];
   const int32_t p_head = (int32_t)(info & UINFO_POS);
-  const bool single = (info & UINFO_SINGLE) != 0;
+  // in a batch with repeated fields one occurrence can collect several gradients per coordinate: its sum of squares
+  // is not the square of its sum, so nothing is "single" (and nothing fused) there
+  const bool simple = batch_flags[0] != 0;
+  const bool single = (info & UINFO_SINGLE) != 0 && simple;
   if (head && last && q == pr.rank) {
     if (single && allow_fuse) {  // finalised inside its sample by k_ffm_tile
       fused_sorted[p_head] = 1;
@@ -271,14 +278,14 @@ k_owner_materialise(Peers pr, Dims d, Hyper h, int all_slices, int32_t cap, cons
                     const int32_t *__restrict__ batch_flags, const uint32_t *__restrict__ ckey,
                     const uint32_t *__restrict__ csrc, const uint8_t *__restrict__ cflag, float *__restrict__ tab,
                     float4 *__restrict__ lin) {
-  if (batch_flags[0] == 0) return;
   constexpr int WARPS = THREADS / 32;
   __shared__ int s_list[THREADS];
   __shared__ int s_n;
   const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
   const int32_t n = min(*n_sel, cap);
   const int64_t ld = d.ld, rs = 3 * ld;
-  // FFM: the vectors of the field slices the batch touches; LR / FM (all_slices): the whole latent row (none for LR)
+  // FFM: the vectors of the field slices the batch touches (w of the other slices keeps its stored, stale value like
+  // in the reference); LR / FM: the whole latent row (none for LR)
   const int vpf = all_slices ? 1 : d.k >> 2;
   const int n_vec = all_slices ? (int)(ld >> 2) : d.n_fields * vpf;
   for (int base = blockIdx.x * THREADS; base < n; base += gridDim.x * THREADS) {
@@ -343,7 +350,7 @@ k_owner_apply(Peers pr, Dims d, Hyper h, int32_t cap, const int32_t *__restrict_
               const int32_t *__restrict__ batch_flags, const uint32_t *__restrict__ ckey,
               const uint8_t *__restrict__ cflag, const float *__restrict__ inbox, const float2 *__restrict__ inbox_lin,
               float *__restrict__ tab, float4 *__restrict__ lin) {
-  if (batch_flags[0] == 0) return;
+  if (batch_flags[1] != 0) return;  // the step was called off
   constexpr int WARPS = THREADS / 32;
   __shared__ int s_list[THREADS];
   __shared__ int s_n;
@@ -416,7 +423,7 @@ __global__ void k_publish_red(Peers pr, const double *__restrict__ local4) {
 // bias update from the G partials, in rank order (identical on every rank)
 template <bool PRECISE>
 __global__ void k_bias_apply(Peers pr, Hyper h, const int32_t *__restrict__ batch_flags, float4 *__restrict__ bias) {
-  if (batch_flags[0] == 0) return;  // the step was called off
+  if (batch_flags[1] != 0) return;  // the step was called off
   double a = 0.0, q2 = 0.0, n = 0.0;
   for (int q = 0; q < pr.G; q++) {
     a += pr.sync[pr.rank]->red[q][0];

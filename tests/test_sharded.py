@@ -138,6 +138,40 @@ def test_lr_fm_shard_count_invariance_on_one_gpu(mt, k, world):
     sharded.close()
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_generic_fallback_repeated_fields(world):
+    """samples that repeat a field (the reference trains any sample: ffm.cpp:90-136): when ANY rank's batch has one,
+    every rank takes the generic kernels for that step (device-side flag, no host round trip) and the owners fuse
+    nothing; the field masks stay exact, so untouched slices keep their stored w.  Steps with and without such
+    samples alternate."""
+    rng = np.random.default_rng(12)
+    nf, nfl, k, B = 400, 6, 4, 160
+    kw = dict(model_type="FFM", n_feats=nf, n_fields=nfl, n_factors=k)
+    single = pkg.FtrlModel(**kw)
+    sharded = pkg.LogicalShards(world, max_batch_rows=B, max_batch_nnz=B * 8, **kw)
+    st = pkg.synth.random_state(rng, nf, nfl * k)
+    single.set_state(st)
+    sharded.set_state(st)
+    for step in range(4):
+        dup = step % 2 == 0
+        # only ONE rank's share repeats fields in the "dup" steps: the flag has to travel
+        parts = [pkg.synth.random_csr(rng, B, nf, nfl, max_nnz=8 if (dup and r == world - 1) else nfl, min_nnz=1,
+                                      dup_field=dup and r == world - 1, dup_feat=dup and r == 0) for r in range(world)]
+        off = np.cumsum([0] + [int(p["row_ptr"][-1]) for p in parts])
+        glob = {"row_ptr": np.concatenate([[0]] + [p["row_ptr"][1:] + off[i] for i, p in enumerate(parts)]),
+                "field": np.concatenate([p["field"] for p in parts]), "feat": np.concatenate([p["feat"] for p in parts]),
+                "val": np.concatenate([p["val"] for p in parts]), "label": np.concatenate([p["label"] for p in parts])}
+        lg1, loss1 = single.train(**glob)
+        outs = sharded.train(parts)
+        lgG = np.concatenate([o[0] for o in outs])
+        assert_close(lgG, lg1, 1e-5, 2e-6, f"logits step {step}")
+        assert abs(sum(o[1] for o in outs) - loss1) <= 1e-6 * max(1.0, abs(loss1))
+        assert_state_close(sharded.get_state(), single.get_state(), rtol=2e-5, atol=2e-6, atol_z=2e-4,
+                           name=f"generic G={world} step {step}")
+    sharded.close()
+
+
 def _ragged(b, rng, nf, drop=0.3, oob=0.02):
     """criteo-shaped batch -> samples with a random SUBSET of the fields (still distinct), a few out-of-range ids"""
     keep = rng.random(len(b["feat"])) >= drop
