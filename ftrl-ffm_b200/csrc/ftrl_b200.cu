@@ -905,7 +905,6 @@ static void check_device_err(ftrl_handle *h) {
   FTRL_CUDA(cudaMemcpy(&e, h->d_err, sizeof(e), cudaMemcpyDeviceToHost));
   if (e) {
     FTRL_CUDA(cudaMemset(h->d_err, 0, sizeof(e)));
-    if (e == 2) throw ArgFail{"multi-GPU run: a sample repeats a field (the sharded path needs distinct fields per sample)"};
     if (e == 3) throw ArgFail{"multi-GPU run: the rows owned by one rank exceed its workspace (extreme id skew): the step was skipped on every rank, no state was changed"};
     if (e == 4) throw StateFail{"multi-GPU run: a peer did not reach the device barrier in time"};
     throw ArgFail{"sequential mode: a sample exceeds the supported size (more than 96 valid features, or FM n_factors > 1024)"};

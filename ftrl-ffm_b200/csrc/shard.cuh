@@ -21,7 +21,9 @@
 //       it into the row cache of every remote rank that touches the row (one NVLink store stream per distinct
 //       (row, rank))
 //   --  barrier 2
-//   S3  k_ffm_tile over the local samples (all addresses local: shard rows, row cache, staging);
+//   S3  k_ffm_tile over the local samples (all addresses local: shard rows, row cache, staging) -- or, when some
+//       sample of some rank repeats a field, the generic k_ffm_sample / k_ffm_rows (SH variants) on every rank;
+//       LR / FM: k_lrfm_sample_sh, k_lrfm_rows / k_lrfm_combine (SH);
 //       k_ffm_staged_rows / k_ffm_combine reduce the local duplicates and store each row's (sum g, sum g^2)
 //       into the owner's inbox (Export); the local (sum g, sum g^2, loss) of the bias goes to every peer
 //   --  barrier 3

@@ -216,8 +216,8 @@ int ftrl_randomize_state(ftrl_handle *h, uint64_t seed, float z_scale, float n_l
 /* ---- multi-GPU (feature-sharded tables, peer memory over NVLink) ----------------- */
 /* Replaces the shared-memory Hogwild workers of src/task/ftrl_offline.cpp:63-103 across GPUs: the samples of a
  * global minibatch are split over the ranks, rows live on rank feat % world_size (config.rank / world_size,
- * LR, FM or FFM in minibatch mode, max_batch_rows / max_batch_nnz fixed at ftrl_create; FFM batches must have
- * distinct fields per sample, else the step is refused with FTRL_ERR_ARG).  After ftrl_attach_peers every
+ * LR, FM or FFM in minibatch mode, max_batch_rows / max_batch_nnz fixed at ftrl_create; any samples: an FFM
+ * batch in which a sample repeats a field takes the generic kernels on every rank).  After ftrl_attach_peers every
  * ftrl_train_batch(_device) call is COLLECTIVE: all ranks call it once per step with their share of the
  * minibatch; the result equals one GPU training on the concatenated minibatch up to fp32 re-association of
  * the per-rank partial sums (deterministic for a given world_size).  A rank that stops calling makes the
