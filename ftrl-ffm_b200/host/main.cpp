@@ -15,9 +15,6 @@
 #include <cstdlib>
 #include <cstring>
 #include <deque>
-#include <sys/stat.h>
-#include <unistd.h>
-
 #include <future>
 #include <numeric>
 #include <random>
@@ -305,77 +302,13 @@ void run_offline(const host::Options &o) {
 // Like the reference's producer / consumer pair, reading + parsing of block i+1 (a producer task on the parser
 // threads) overlaps the submission and the GPU work of block i (this thread).
 double stream_file(Trainer &tr, const std::string &path, bool libffm, int n_threads, bool train) {
-  FILE *f = fopen(path.c_str(), "rb");
-  if (!f) {
+  host::TextBlockReader reader(path, libffm, n_threads);
+  if (!reader.ok()) {
     fprintf(stderr, "open file <%s> error. \n", path.c_str());  // pc_task.cpp:8
     exit(EXIT_FAILURE);
   }
-  constexpr size_t kBlock = 32u << 20;
-  // A regular file is read with one pread per parser thread, in parallel, into a buffer that is reused from block
-  // to block (no page faults after the first block, no serial 32 MB read); anything else (a pipe, a FIFO) goes
-  // through fread.  The parser threads are persistent (host::WorkerPool).
-  off_t file_len = -1, file_pos = 0;
-  {
-    struct stat st;
-    if (fstat(fileno(f), &st) == 0 && S_ISREG(st.st_mode)) file_len = st.st_size;
-  }
-  host::WorkerPool pool(std::max(1, n_threads));
-  const int fd = fileno(f);
-  std::vector<char> buf(kBlock + (1u << 20));
-  size_t have = 0;
-  bool eof = false;
-  std::vector<host::Csr> scratch;  // per-thread parts, reused from block to block
   // producer: next block of complete lines -> CSR; false when the file is exhausted
-  auto produce = [&](host::Csr *out) -> bool {
-    out->clear();
-    while (!eof || have) {
-      if (!eof) {
-        size_t got = 0;
-        const size_t room = buf.size() - have;
-        if (file_len >= 0) {
-          const size_t want = (size_t)std::min<off_t>((off_t)room, file_len - file_pos);
-          const int nt = pool.size();
-          const size_t per = (want + nt - 1) / nt;
-          std::vector<size_t> done(nt, 0);
-          pool.run(nt, [&](int i) {
-            const size_t o0 = std::min(want, per * (size_t)i), o1 = std::min(want, o0 + per);
-            size_t d = 0;
-            while (o0 + d < o1) {
-              const ssize_t r = pread(fd, buf.data() + have + o0 + d, o1 - o0 - d, file_pos + (off_t)(o0 + d));
-              if (r <= 0) break;
-              d += (size_t)r;
-            }
-            done[i] = d;
-          });
-          for (int i = 0; i < nt; i++) {  // a short read (file truncated meanwhile) ends the stream there
-            const size_t o0 = std::min(want, per * (size_t)i), o1 = std::min(want, o0 + per);
-            got += done[i];
-            if (done[i] < o1 - o0) break;
-          }
-          file_pos += (off_t)got;
-          if (got == 0 || file_pos >= file_len) eof = true;
-        } else {
-          got = fread(buf.data() + have, 1, room, f);
-          if (got == 0) eof = true;
-        }
-        have += got;
-      }
-      size_t use = have;
-      if (!eof) {  // cut at the last complete line
-        while (use > 0 && buf[use - 1] != '\n') use--;
-        if (use == 0) {
-          if (have == buf.size()) buf.resize(buf.size() * 2);
-          continue;
-        }
-      }
-      if (use == 0) return false;
-      host::parse_buffer(buf.data(), use, libffm, n_threads, *out, &scratch, &pool);
-      memmove(buf.data(), buf.data() + use, have - use);
-      have -= use;
-      return true;
-    }
-    return false;
-  };
+  auto produce = [&](host::Csr *out) -> bool { return reader.next(*out); };
   long lines = 0, next_log = 1000000;
   host::Csr blocks[2];
   tr.begin_epoch(1u << 16);
@@ -392,7 +325,6 @@ double stream_file(Trainer &tr, const std::string &path, bool libffm, int n_thre
       next_log += 1000000;
     }
   }
-  fclose(f);
   return tr.take_loss();
 }
 

@@ -29,6 +29,20 @@ int64_t host_load_file(const char *path, int libffm, int n_threads, int use_cach
   if (use_cache) host::save_csr_cache(path, libffm != 0, g_csr);
   return (int64_t)g_csr.rows();
 }
+// the file streamed in blocks of `block_bytes` (host::TextBlockReader: parallel pread, persistent parser threads),
+// the blocks appended in order; *n_blocks tells how many there were
+int64_t host_stream_file(const char *path, int libffm, int n_threads, int64_t block_bytes, int *n_blocks) {
+  g_csr.clear();
+  if (n_blocks) *n_blocks = 0;
+  host::TextBlockReader rd(path, libffm != 0, n_threads, (size_t)block_bytes);
+  if (!rd.ok()) return -1;
+  host::Csr blk;
+  while (rd.next(blk)) {
+    g_csr.append(blk);
+    if (n_blocks) ++*n_blocks;
+  }
+  return (int64_t)g_csr.rows();
+}
 int64_t host_parse_nnz() { return (int64_t)g_csr.feat.size(); }
 void host_parse_fetch(int64_t *row_ptr, int32_t *field, int32_t *feat, float *val, int32_t *label) {
   memcpy(row_ptr, g_csr.row_ptr.data(), sizeof(int64_t) * g_csr.row_ptr.size());

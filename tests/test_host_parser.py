@@ -177,3 +177,44 @@ def test_decimal_fast_path_is_correctly_rounded():
     keep = want != 0
     np.testing.assert_array_equal(d["val"], want[keep])
     assert list(d["feat"]) == [i + 1 for i in range(len(toks)) if keep[i]]
+
+
+def _fetch(lib, n):
+    nnz = lib.host_parse_nnz()
+    rp = np.zeros(n + 1, np.int64)
+    fi, fe, va, la = np.zeros(nnz, np.int32), np.zeros(nnz, np.int32), np.zeros(nnz, np.float32), np.zeros(n, np.int32)
+    lib.host_parse_fetch(*(a.ctypes.data_as(C.c_void_p) for a in (rp, fi, fe, va, la)))
+    return {"row_ptr": rp, "field": fi, "feat": fe, "val": va, "label": la}
+
+
+@pytest.mark.parametrize("trailing_newline", [True, False])
+@pytest.mark.parametrize("threads,block", [(1, 1 << 16), (4, 1 << 16), (7, 70_000), (3, 1 << 22)])
+def test_streamed_blocks_equal_whole_file_parse(tmp_path, threads, block, trailing_newline):
+    """the streaming front end of `main` (host::TextBlockReader: blocks of complete lines, parallel pread into a
+    reused buffer, persistent parser threads, per-thread parts reused) yields the same CSR, in file order, as one
+    parse of the whole text -- for blocks much smaller than the file, a last line without newline, and lines of very
+    different lengths (one longer than a block's slice per thread)"""
+    rng = np.random.default_rng(threads * 1000 + block % 97)
+    b = pkg.synth.criteo_batch(3000, 39, 100_000, seed=5)
+    path = str(tmp_path / "s.ffm")
+    pkg.synth.write_text(b, path)
+    text = open(path).read()
+    lines = text.rstrip("\n").split("\n")
+    # a few short, empty and very long lines in between
+    long_line = "1 " + " ".join(f"{i % 39}:{i}:1.5" for i in range(6000))
+    for pos in sorted(rng.integers(0, len(lines), 6).tolist(), reverse=True):
+        lines.insert(pos, rng.choice(["0 3:17:1", "", long_line]))
+    text = "\n".join(lines) + ("\n" if trailing_newline else "")
+    open(path, "w").write(text)
+    want = parse(text, True, 1)
+    lib = parser_lib()
+    lib.host_stream_file.restype = C.c_int64
+    lib.host_stream_file.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int64, C.POINTER(C.c_int)]
+    nb = C.c_int(0)
+    n = lib.host_stream_file(path.encode(), 1, threads, block, C.byref(nb))
+    assert n == len(want["label"])
+    got = _fetch(lib, n)
+    for key in want:
+        assert np.array_equal(got[key], want[key]), key
+    assert nb.value >= max(1, len(text) // (block + (block >> 5) + 4096))
+    assert lib.host_stream_file(str(tmp_path / "missing").encode(), 1, 2, block, None) == -1
